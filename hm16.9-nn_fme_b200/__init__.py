@@ -1,0 +1,252 @@
+"""fme_b200 -- Python host-side mirror of the C ABI in include/fme_b200.h.
+
+The product is libfme_b200.so (hand-written sm_100a CUDA kernels behind a C ABI); this module is the thin
+ctypes binding the tests and bench use, mirroring the reference's operator surface for the fractional-ME
+path (names follow HM: frac_dif = TEncSearch::xPatternSearchFracDIF, nn_pred = NN_pred, filter_hor/ver =
+TComInterpolationFilter::filterHor/filterVer, dist = DistParam::DistFunc).
+
+There is NO CPU fallback: importing works anywhere (so host-side helpers can be tested), but creating an
+`Fme` context raises unless the CUDA library loads and an sm_100 device is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import nn_weights  # noqa: F401  (re-export)
+from .pu_list import PU_DTYPE, RESULT_DTYPE, MC_PU_DTYPE  # noqa: F401
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libfme_b200.so")
+
+MODE_STD, MODE_NN, MODE_BOTH = 1, 2, 3
+PU_LOSSLESS, PU_ERR_ON_GPU = 0x01, 0x02
+
+# every symbol include/fme_b200.h declares (checked by tests/test_abi.py against the header)
+EXPORTS = [
+    "fme_create", "fme_destroy", "fme_last_error", "fme_version", "fme_set_stream", "fme_synchronize",
+    "fme_set_nn_weights", "fme_load_nn_csv_dir", "fme_set_slice", "fme_upload_ref", "fme_upload_ref_u8",
+    "fme_upload_org", "fme_upload_org_u8", "fme_submit", "fme_submit_async", "fme_submit_device", "fme_interp_slot",
+    "fme_upload_ref_device_u8", "fme_upload_org_device_u8", "fme_int_surface_device", "fme_filter_hor",
+    "fme_filter_ver", "fme_dist", "fme_mv_cost", "fme_upload_ref_chroma", "fme_mc", "fme_download_plane",
+    "fme_last_kernel_ms", "fme_launch_count", "fme_set_profiling",
+]
+
+
+class FmeConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("margin", C.c_int32),
+                ("bitDepth", C.c_int32), ("numRefSlots", C.c_int32), ("maxPUs", C.c_int32), ("useHadME", C.c_int32),
+                ("fen", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+
+class FmeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """Load libfme_b200.so; fails loudly when the extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FmeError("libfme_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                       "this engine has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, sp, u8p = C.c_void_p, C.c_int, C.POINTER(C.c_short), C.POINTER(C.c_uint8)
+    lib.fme_last_error.restype = C.c_char_p
+    lib.fme_version.restype = C.c_char_p
+    lib.fme_launch_count.restype = C.c_int64
+    lib.fme_launch_count.argtypes = [vp]
+    lib.fme_create.argtypes = [C.POINTER(FmeConfig), C.POINTER(vp)]
+    lib.fme_destroy.argtypes = [vp]
+    lib.fme_destroy.restype = None
+    lib.fme_set_stream.argtypes = [vp, vp]
+    lib.fme_synchronize.argtypes = [vp]
+    lib.fme_set_nn_weights.argtypes = [vp, vp, C.c_size_t]
+    lib.fme_load_nn_csv_dir.argtypes = [vp, C.c_char_p]
+    lib.fme_set_slice.argtypes = [vp, C.c_double]
+    lib.fme_upload_ref.argtypes = [vp, i32, vp, i32]
+    lib.fme_upload_ref_u8.argtypes = [vp, i32, vp, i32]
+    lib.fme_upload_org.argtypes = [vp, vp, i32]
+    lib.fme_upload_org_u8.argtypes = [vp, vp, i32]
+    lib.fme_submit.argtypes = [vp, vp, i32, vp, i32]
+    lib.fme_submit_async.argtypes = [vp, vp, i32, vp, i32]
+    lib.fme_submit_device.argtypes = [vp, vp, i32, vp, i32]
+    lib.fme_interp_slot.argtypes = [vp, i32]
+    lib.fme_upload_ref_device_u8.argtypes = [vp, i32, vp, i32]
+    lib.fme_upload_org_device_u8.argtypes = [vp, vp, i32]
+    lib.fme_int_surface_device.argtypes = [vp, vp, i32]
+    lib.fme_filter_hor.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32]
+    lib.fme_filter_ver.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32]
+    lib.fme_dist.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.fme_mv_cost.argtypes = [vp, i32, i32, i32, i32, i32, C.POINTER(C.c_uint32)]
+    lib.fme_upload_ref_chroma.argtypes = [vp, i32, vp, vp, i32]
+    lib.fme_mc.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.fme_download_plane.argtypes = [vp, i32, i32, i32, vp, i32]
+    lib.fme_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
+    lib.fme_set_profiling.argtypes = [vp, i32]
+    _lib = lib
+    return lib
+
+
+def _addr(a, off_elems=0):
+    return C.c_void_p(a.ctypes.data + off_elems * a.itemsize)
+
+
+class Fme:
+    """One engine context (= one encoder instance's TEncSearch for the fractional-ME path)."""
+
+    def __init__(self, width, height, num_ref_slots=4, max_pus=1 << 20, margin=80, use_had=True, fen=True, device=0):
+        self.lib = load_library()
+        self.cfg = FmeConfig(device=device, width=width, height=height, margin=margin, bitDepth=8,
+                             numRefSlots=num_ref_slots, maxPUs=max_pus, useHadME=int(use_had), fen=int(fen))
+        self.h = C.c_void_p()
+        self._check(self.lib.fme_create(C.byref(self.cfg), C.byref(self.h)))
+        self.width, self.height, self.margin = width, height, margin
+
+    def _check(self, rc):
+        if rc != 0:
+            raise FmeError("fme error %d: %s" % (rc, self.lib.fme_last_error().decode()))
+
+    def close(self):
+        if self.h:
+            self.lib.fme_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state ----
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.fme_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self._check(self.lib.fme_synchronize(self.h))
+
+    def set_nn_weights(self, blob):
+        buf = C.create_string_buffer(bytes(blob), len(blob))
+        self._check(self.lib.fme_set_nn_weights(self.h, C.cast(buf, C.c_void_p), len(blob)))
+
+    def load_nn_csv_dir(self, path):
+        self._check(self.lib.fme_load_nn_csv_dir(self.h, path.encode()))
+
+    def set_slice(self, lam):
+        self._check(self.lib.fme_set_slice(self.h, float(lam)))
+
+    def set_profiling(self, on):
+        self._check(self.lib.fme_set_profiling(self.h, int(on)))
+
+    # ---- frames ----
+    def upload_ref(self, slot, pic):
+        """pic: (H, W) int16 (Pel) or uint8 array, picture area only."""
+        pic = np.ascontiguousarray(pic)
+        assert pic.shape == (self.height, self.width)
+        if pic.dtype == np.uint8:
+            self._check(self.lib.fme_upload_ref_u8(self.h, slot, _addr(pic), pic.shape[1]))
+        else:
+            assert pic.dtype == np.int16
+            self._check(self.lib.fme_upload_ref(self.h, slot, _addr(pic), pic.shape[1]))
+
+    def upload_ref_padded(self, slot, padded, margin):
+        """padded: TComPicYuv-style int16 plane with `margin` replicated samples around the picture."""
+        assert padded.dtype == np.int16 and padded.flags.c_contiguous
+        stride = padded.shape[1]
+        self._check(self.lib.fme_upload_ref(self.h, slot, _addr(padded, margin * stride + margin), stride))
+
+    def upload_org(self, pic):
+        pic = np.ascontiguousarray(pic)
+        assert pic.shape == (self.height, self.width)
+        if pic.dtype == np.uint8:
+            self._check(self.lib.fme_upload_org_u8(self.h, _addr(pic), pic.shape[1]))
+        else:
+            assert pic.dtype == np.int16
+            self._check(self.lib.fme_upload_org(self.h, _addr(pic), pic.shape[1]))
+
+    def upload_ref_device_u8(self, slot, dev_ptr, pitch):
+        self._check(self.lib.fme_upload_ref_device_u8(self.h, slot, C.c_void_p(dev_ptr), pitch))
+
+    def upload_org_device_u8(self, dev_ptr, pitch):
+        self._check(self.lib.fme_upload_org_device_u8(self.h, C.c_void_p(dev_ptr), pitch))
+
+    def interp_slot(self, slot):
+        self._check(self.lib.fme_interp_slot(self.h, slot))
+
+    def upload_ref_chroma(self, slot, cb, cr):
+        cb, cr = np.ascontiguousarray(cb, np.int16), np.ascontiguousarray(cr, np.int16)
+        assert cb.shape == cr.shape == (self.height // 2, self.width // 2)
+        self._check(self.lib.fme_upload_ref_chroma(self.h, slot, _addr(cb), _addr(cr), cb.shape[1]))
+
+    def download_plane(self, slot, fy, fx):
+        wp, hp = self.width + 2 * self.margin, self.height + 2 * self.margin
+        out = np.zeros((hp, wp), np.uint8)
+        self._check(self.lib.fme_download_plane(self.h, slot, fy, fx, _addr(out), wp))
+        return out
+
+    # ---- search ----
+    def submit(self, pus, mode=MODE_BOTH):
+        pus = np.ascontiguousarray(pus, dtype=PU_DTYPE)
+        out = np.zeros(len(pus), RESULT_DTYPE)
+        self._check(self.lib.fme_submit(self.h, _addr(pus), len(pus), _addr(out), mode))
+        return out
+
+    def submit_async(self, pus_ptr, n, out_ptr, mode=MODE_BOTH):
+        self._check(self.lib.fme_submit_async(self.h, C.c_void_p(pus_ptr), n, C.c_void_p(out_ptr), mode))
+
+    def submit_device(self, d_pus_ptr, n, d_out_ptr, mode=MODE_BOTH):
+        self._check(self.lib.fme_submit_device(self.h, C.c_void_p(d_pus_ptr), n, C.c_void_p(d_out_ptr), mode))
+
+    def int_surface_device(self, d_pus_ptr, n):
+        self._check(self.lib.fme_int_surface_device(self.h, C.c_void_p(d_pus_ptr), n))
+
+    # ---- block-level (reference operator names) ----
+    def filter_hor(self, comp, src, src_off, src_stride, w, h, frac, is_last, bit_depth=8):
+        dst = np.zeros((h, w), np.int16)
+        self._check(self.lib.fme_filter_hor(self.h, comp, _addr(src, src_off), src_stride, _addr(dst), w, w, h, frac,
+                                            int(is_last), bit_depth))
+        return dst
+
+    def filter_ver(self, comp, src, src_off, src_stride, w, h, frac, is_first, is_last, bit_depth=8):
+        dst = np.zeros((h, w), np.int16)
+        self._check(self.lib.fme_filter_ver(self.h, comp, _addr(src, src_off), src_stride, _addr(dst), w, w, h, frac,
+                                            int(is_first), int(is_last), bit_depth))
+        return dst
+
+    def dist(self, kind, org_blocks, cur_blocks, w, h, bit_depth=8, sub_shift=0):
+        """org_blocks/cur_blocks: (n, h, stride) int16 arrays."""
+        org_blocks = np.ascontiguousarray(org_blocks, np.int16)
+        cur_blocks = np.ascontiguousarray(cur_blocks, np.int16)
+        n = org_blocks.shape[0]
+        out = np.zeros(n, np.uint32)
+        self._check(self.lib.fme_dist(self.h, kind, _addr(org_blocks), org_blocks.shape[2], _addr(cur_blocks),
+                                      cur_blocks.shape[2], w, h, bit_depth, sub_shift, n, _addr(out)))
+        return out
+
+    def mv_cost(self, x, y, scale, px, py):
+        v = C.c_uint32()
+        self._check(self.lib.fme_mv_cost(self.h, x, y, scale, px, py, C.byref(v)))
+        return v.value
+
+    def mc(self, pus, chroma=True):
+        pus = np.ascontiguousarray(pus, dtype=MC_PU_DTYPE)
+        n = len(pus)
+        y = np.zeros((n, 64, 64), np.int16)
+        cb = np.zeros((n, 32, 32), np.int16)
+        cr = np.zeros((n, 32, 32), np.int16)
+        self._check(self.lib.fme_mc(self.h, _addr(pus), n, _addr(y), _addr(cb) if chroma else None,
+                                    _addr(cr) if chroma else None))
+        return y, cb, cr
+
+    # ---- introspection ----
+    def last_kernel_ms(self):
+        k = (C.c_float * 4)()
+        self._check(self.lib.fme_last_kernel_ms(self.h, C.byref(k)))
+        return dict(k1_interp=k[0], k2_refine=k[1], k3_nn=k[2], k0_surface=k[3])
+
+    def launch_count(self):
+        return int(self.lib.fme_launch_count(self.h))

@@ -1,0 +1,687 @@
+// C ABI of libfme_b200.so (include/fme_b200.h): context, device memory, streams, launch sequencing.
+// There is deliberately no CPU path in this file: every entry point either runs CUDA work on an
+// sm_100 device or fails with an error code.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fme_common.cuh"
+
+namespace {
+
+thread_local std::string t_lastError;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  t_lastError = buf;
+  return code;
+}
+
+#define CU_CHECK(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) return fail(FME_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                       __FILE__, __LINE__);                                         \
+  } while (0)
+
+inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct fme_ctx {
+  fme_config cfg;
+  FmeGeom g;
+  int numSMs = 0;
+  cudaStream_t ownStream = nullptr, stream = nullptr;
+  // device memory
+  uint8_t* d_planes = nullptr;   // [slots][16][Hp][pitch]
+  uint8_t* d_org = nullptr;      // [H + 1][orgPitch]
+  uint8_t* d_pic = nullptr;      // raw u8 picture staging [H][picPitch]
+  int picPitch = 0;
+  int16_t* d_pel = nullptr;      // Pel staging for uploads / block-level calls
+  size_t pelCapacity = 0;        // in samples
+  int16_t* d_pel2 = nullptr;
+  size_t pel2Capacity = 0;
+  uint8_t* d_cb = nullptr;       // [slots][Hcp][cPitch]
+  uint8_t* d_cr = nullptr;
+  fme_pu* d_pus = nullptr;
+  fme_result* d_res = nullptr;
+  float* d_nn = nullptr;
+  size_t nnBytes = 0;
+  uint32_t* d_costLut = nullptr;
+  uint32_t* d_scratchU32 = nullptr;
+  size_t scratchU32Capacity = 0;
+  FmeK2Scratch k2{};
+  // pinned host staging
+  void* h_stage = nullptr;
+  size_t h_stageBytes = 0;
+  // state
+  std::vector<char> refValid;
+  bool orgValid = false, sliceValid = false, nnValid = false;
+  double lambda = 0.0;
+  uint32_t costLut[FME_COST_LUT_SIZE];
+  // profiling
+  bool profiling = false;
+  cudaEvent_t ev[8] = {};
+  float lastMs[4] = {0, 0, 0, 0};
+  int64_t launches = 0;
+};
+
+namespace {
+
+int ensure_pinned(fme_ctx* c, size_t bytes) {
+  if (c->h_stageBytes >= bytes) return FME_OK;
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  c->h_stage = nullptr;
+  c->h_stageBytes = 0;
+  CU_CHECK(cudaMallocHost(&c->h_stage, bytes));
+  c->h_stageBytes = bytes;
+  return FME_OK;
+}
+
+int ensure_pel(int16_t** p, size_t* cap, size_t samples) {
+  if (*cap >= samples) return FME_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  CU_CHECK(cudaMalloc(p, samples * sizeof(int16_t)));
+  *cap = samples;
+  return FME_OK;
+}
+
+int ensure_u32(fme_ctx* c, size_t n) {
+  if (c->scratchU32Capacity >= n) return FME_OK;
+  if (c->d_scratchU32) cudaFree(c->d_scratchU32);
+  c->d_scratchU32 = nullptr;
+  c->scratchU32Capacity = 0;
+  CU_CHECK(cudaMalloc(&c->d_scratchU32, n * sizeof(uint32_t)));
+  c->scratchU32Capacity = n;
+  return FME_OK;
+}
+
+// Copy a host picture (Pel or u8, w x h, given stride in samples) into the ctx's u8 staging picture.
+template <typename T>
+int stage_picture(fme_ctx* c, const T* src, int stride, int w, int h, uint8_t* d_dst, int dstPitch) {
+  if (!src || stride < w) return fail(FME_ERR_INVALID, "picture pointer/stride invalid");
+  size_t bytes = (size_t)w * h;
+  // the previous async copy out of the pinned buffer must have drained before we reuse or grow it
+  CU_CHECK(cudaStreamSynchronize(c->stream));
+  int rc = ensure_pinned(c, bytes);
+  if (rc) return rc;
+  uint8_t* hs = static_cast<uint8_t*>(c->h_stage);
+  for (int y = 0; y < h; ++y) {
+    const T* s = src + (size_t)y * stride;
+    uint8_t* d = hs + (size_t)y * w;
+    for (int x = 0; x < w; ++x) d[x] = (uint8_t)s[x];
+  }
+  CU_CHECK(cudaMemcpy2DAsync(d_dst, dstPitch, hs, w, w, h, cudaMemcpyHostToDevice, c->stream));
+  return FME_OK;
+}
+
+int check_slot(fme_ctx* c, int slot) {
+  if (!c) return fail(FME_ERR_INVALID, "null ctx");
+  if (slot < 0 || slot >= c->cfg.numRefSlots) return fail(FME_ERR_INVALID, "slot %d out of range", slot);
+  return FME_OK;
+}
+
+struct StageTimer {
+  fme_ctx* c;
+  int idx;
+  StageTimer(fme_ctx* c_, int i) : c(c_), idx(i) {
+    if (c->profiling) cudaEventRecord(c->ev[2 * idx], c->stream);
+  }
+  ~StageTimer() {
+    if (c->profiling) cudaEventRecord(c->ev[2 * idx + 1], c->stream);
+  }
+};
+
+int run_k1(fme_ctx* c, int slot) {
+  StageTimer t(c, 0);
+  CU_CHECK(fme_launch_k1(c->g, c->d_pic, c->picPitch, c->d_planes + (size_t)slot * c->g.slotBytes, c->stream,
+                         &c->launches));
+  c->refValid[slot] = 1;
+  return FME_OK;
+}
+
+int run_search(fme_ctx* c, fme_pu* d_pus, int n, fme_result* d_out, int mode) {
+  if (mode < 1 || mode > 3) return fail(FME_ERR_INVALID, "mode must be FME_MODE_STD|NN|BOTH");
+  if ((mode & FME_MODE_STD) && (!c->orgValid || !c->sliceValid))
+    return fail(FME_ERR_STATE, "fme_submit(STD) needs fme_upload_org and fme_set_slice first");
+  if ((mode & FME_MODE_NN) && !c->nnValid) return fail(FME_ERR_STATE, "fme_submit(NN) needs fme_set_nn_weights first");
+  if (mode != FME_MODE_BOTH) CU_CHECK(fme_launch_clear_results(d_out, n, c->stream, &c->launches));
+  if (mode & FME_MODE_STD) {
+    StageTimer t(c, 1);
+    CU_CHECK(fme_launch_k2(c->g, c->d_planes, c->d_org, d_pus, n, d_out, c->d_costLut, c->cfg.useHadME, c->k2,
+                           c->numSMs, c->stream, &c->launches));
+  }
+  if (mode & FME_MODE_NN) {
+    StageTimer t(c, 2);
+    CU_CHECK(fme_launch_k3(d_pus, n, d_out, c->d_nn, c->nnBytes, c->stream, &c->launches));
+  }
+  return FME_OK;
+}
+
+void collect_ms(fme_ctx* c) {
+  if (!c->profiling) return;
+  for (int i = 0; i < 4; ++i) {
+    float ms = 0.f;
+    if (cudaEventQuery(c->ev[2 * i + 1]) == cudaSuccess && cudaEventElapsedTime(&ms, c->ev[2 * i], c->ev[2 * i + 1]) == cudaSuccess)
+      c->lastMs[i] = ms;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fme_last_error(void) { return t_lastError.c_str(); }
+const char* fme_version(void) { return "fme_b200 0.1 (sm_100a)"; }
+
+int fme_create(const fme_config* cfg, fme_ctx** out) {
+  if (!cfg || !out) return fail(FME_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->width < 8 || cfg->height < 8 || cfg->width > 16384 || cfg->height > 16384)
+    return fail(FME_ERR_INVALID, "unsupported picture size %dx%d", cfg->width, cfg->height);
+  if (cfg->margin < 16 || (cfg->margin & 15)) return fail(FME_ERR_INVALID, "margin must be a multiple of 16, >= 16");
+  if (cfg->bitDepth != 8) return fail(FME_ERR_INVALID, "frame-level passes support bitDepth 8 only");
+  if (cfg->numRefSlots < 1 || cfg->numRefSlots > 64) return fail(FME_ERR_INVALID, "numRefSlots out of range");
+  if (cfg->maxPUs < 1) return fail(FME_ERR_INVALID, "maxPUs must be positive");
+
+  int nDev = 0;
+  if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) {
+    cudaGetLastError();
+    return fail(FME_ERR_NO_DEVICE, "no CUDA device visible; this engine has no CPU path");
+  }
+  if (cfg->device < 0 || cfg->device >= nDev) return fail(FME_ERR_INVALID, "device %d out of range", cfg->device);
+  cudaDeviceProp prop;
+  CU_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10)
+    return fail(FME_ERR_NO_DEVICE, "device %d is sm_%d%d; libfme_b200 is built for sm_100a only", cfg->device, prop.major,
+                prop.minor);
+  CU_CHECK(cudaSetDevice(cfg->device));
+
+  fme_ctx* c = new fme_ctx();
+  c->cfg = *cfg;
+  c->numSMs = prop.multiProcessorCount;
+  FmeGeom& g = c->g;
+  g.W = cfg->width; g.H = cfg->height; g.M = cfg->margin;
+  g.Wp = g.W + 2 * g.M; g.Hp = g.H + 2 * g.M;
+  g.pitch = round_up(g.Wp, 128);
+  g.planeBytes = (size_t)g.Hp * g.pitch;
+  g.slotBytes = g.planeBytes * FME_NUM_PLANES;
+  g.orgPitch = round_up(g.W + 16, 128);
+  g.Wc = g.W / 2; g.Hc = g.H / 2; g.Mc = g.M / 2;
+  g.Wcp = g.Wc + 2 * g.Mc; g.Hcp = g.Hc + 2 * g.Mc;
+  g.cPitch = round_up(g.Wcp, 128);
+  g.cPlaneBytes = (size_t)g.Hcp * g.cPitch;
+  g.numSlots = cfg->numRefSlots;
+  c->picPitch = round_up(g.W, 256);
+  c->refValid.assign(cfg->numRefSlots, 0);
+
+#define CREATE_CHECK(expr)                                                                    \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      int rc = fail(FME_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));                   \
+      fme_destroy(c);                                                                         \
+      return rc;                                                                              \
+    }                                                                                         \
+  } while (0)
+  CREATE_CHECK(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
+  c->stream = c->ownStream;
+  for (auto& e : c->ev) CREATE_CHECK(cudaEventCreate(&e));
+  // +1 plane of slack so that word-granular staging reads past the last row stay inside the allocation
+  CREATE_CHECK(cudaMalloc(&c->d_planes, g.slotBytes * cfg->numRefSlots + g.pitch * 2));
+  CREATE_CHECK(cudaMemsetAsync(c->d_planes, 0, g.slotBytes * cfg->numRefSlots + g.pitch * 2, c->stream));
+  CREATE_CHECK(cudaMalloc(&c->d_org, (size_t)(g.H + 2) * g.orgPitch));
+  CREATE_CHECK(cudaMemsetAsync(c->d_org, 0, (size_t)(g.H + 2) * g.orgPitch, c->stream));
+  CREATE_CHECK(cudaMalloc(&c->d_pic, (size_t)g.H * c->picPitch));
+  CREATE_CHECK(cudaMalloc(&c->d_pus, sizeof(fme_pu) * (size_t)cfg->maxPUs));
+  CREATE_CHECK(cudaMalloc(&c->d_res, sizeof(fme_result) * (size_t)cfg->maxPUs));
+  CREATE_CHECK(cudaMalloc(&c->d_costLut, sizeof(uint32_t) * FME_COST_LUT_SIZE));
+  CREATE_CHECK(cudaMalloc(&c->k2.classCount, sizeof(int) * (4 * FME_MAX_CLASSES + 16)));
+  c->k2.classCursor = c->k2.classCount + FME_MAX_CLASSES;
+  c->k2.classOffset = c->k2.classCursor + FME_MAX_CLASSES;
+  c->k2.packOffset = c->k2.classOffset + FME_MAX_CLASSES + 1;
+  c->k2.workCounter = c->k2.packOffset + FME_MAX_CLASSES + 1;
+  CREATE_CHECK(cudaMalloc(&c->k2.order, sizeof(int) * (size_t)cfg->maxPUs));
+  CREATE_CHECK(cudaStreamSynchronize(c->stream));
+#undef CREATE_CHECK
+  *out = c;
+  return FME_OK;
+}
+
+void fme_destroy(fme_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_planes); cudaFree(c->d_org); cudaFree(c->d_pic); cudaFree(c->d_pel); cudaFree(c->d_pel2);
+  cudaFree(c->d_cb); cudaFree(c->d_cr); cudaFree(c->d_pus); cudaFree(c->d_res); cudaFree(c->d_nn);
+  cudaFree(c->d_costLut); cudaFree(c->d_scratchU32); cudaFree(c->k2.classCount); cudaFree(c->k2.order);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  for (auto& e : c->ev)
+    if (e) cudaEventDestroy(e);
+  if (c->ownStream) cudaStreamDestroy(c->ownStream);
+  delete c;
+}
+
+int fme_set_stream(fme_ctx* c, void* s) {
+  if (!c) return fail(FME_ERR_INVALID, "null ctx");
+  CU_CHECK(cudaStreamSynchronize(c->stream));
+  c->stream = s ? static_cast<cudaStream_t>(s) : c->ownStream;
+  return FME_OK;
+}
+
+int fme_synchronize(fme_ctx* c) {
+  if (!c) return fail(FME_ERR_INVALID, "null ctx");
+  CU_CHECK(cudaStreamSynchronize(c->stream));
+  collect_ms(c);
+  return FME_OK;
+}
+
+int fme_set_profiling(fme_ctx* c, int on) {
+  if (!c) return fail(FME_ERR_INVALID, "null ctx");
+  c->profiling = on != 0;
+  return FME_OK;
+}
+
+int fme_last_kernel_ms(fme_ctx* c, float k[4]) {
+  if (!c || !k) return fail(FME_ERR_INVALID, "null argument");
+  collect_ms(c);
+  for (int i = 0; i < 4; ++i) k[i] = c->lastMs[i];
+  return FME_OK;
+}
+
+int64_t fme_launch_count(fme_ctx* c) { return c ? c->launches : 0; }
+
+// ---- NN weights ----------------------------------------------------------------------------
+static size_t nn_payload_floats(const FmeNnHeader& h) {
+  size_t n = 3 * (size_t)h.nErr + (size_t)h.nEmb * h.embRows * h.embDim;
+  int in = h.nErr + h.nEmb * h.embDim;
+  for (int l = 0; l < h.nHidden; ++l) {
+    n += (size_t)h.hidden[l] * in + 3 * (size_t)h.hidden[l];
+    in = h.hidden[l];
+  }
+  return n + (size_t)h.nOut * in + h.nOut;
+}
+
+int fme_set_nn_weights(fme_ctx* c, const void* blob, size_t bytes) {
+  if (!c || !blob || bytes < sizeof(FmeNnHeader)) return fail(FME_ERR_INVALID, "bad weight blob");
+  FmeNnHeader h;
+  memcpy(&h, blob, sizeof(h));
+  if (h.magic != FME_NN_MAGIC) return fail(FME_ERR_INVALID, "weight blob: bad magic");
+  if (h.nErr != 9 || (h.nEmb != 0 && h.nEmb != 2) || h.nHidden < 1 || h.nHidden > 4 || h.nOut < 1 || h.nOut > 64 ||
+      (h.nEmb == 2 && (h.embRows != 8 || h.embDim < 1 || h.embDim > 8)))
+    return fail(FME_ERR_INVALID, "weight blob: unsupported architecture");
+  for (int l = 0; l < h.nHidden; ++l)
+    if (h.hidden[l] < 1 || h.hidden[l] > 64) return fail(FME_ERR_INVALID, "weight blob: hidden width out of range");
+  size_t need = sizeof(FmeNnHeader) + 4 * nn_payload_floats(h);
+  if (bytes != need) return fail(FME_ERR_INVALID, "weight blob: size %zu, expected %zu", bytes, need);
+  if (need > 200 * 1024) return fail(FME_ERR_INVALID, "weight blob too large for shared memory");
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  CU_CHECK(cudaStreamSynchronize(c->stream));
+  if (c->d_nn) cudaFree(c->d_nn);
+  c->d_nn = nullptr;
+  CU_CHECK(cudaMalloc(&c->d_nn, need));
+  CU_CHECK(cudaMemcpy(c->d_nn, blob, need, cudaMemcpyHostToDevice));
+  c->nnBytes = need;
+  c->nnValid = true;
+  return FME_OK;
+}
+
+// DL/blowing/<qp> layout: files "<k>.<name>.csv", k = 1..14 (DL/edit.sh:13-17)
+static int read_csv(const std::string& path, std::vector<std::vector<double>>& rows) {
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) return fail(FME_ERR_IO, "cannot open %s", path.c_str());
+  std::string text;
+  char buf[4096];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, n);
+  fclose(f);
+  rows.clear();
+  std::vector<double> cur;
+  const char* p = text.c_str();
+  while (*p) {
+    if (*p == '\n') {
+      if (!cur.empty()) rows.push_back(cur);
+      cur.clear();
+      ++p;
+    } else if (*p == ',' || *p == ';' || *p == ' ' || *p == '\t' || *p == '\r') {
+      ++p;
+    } else {
+      char* end = nullptr;
+      double v = strtod(p, &end);
+      if (end == p) return fail(FME_ERR_IO, "parse error in %s", path.c_str());
+      cur.push_back(v);
+      p = end;
+    }
+  }
+  if (!cur.empty()) rows.push_back(cur);
+  return FME_OK;
+}
+
+int fme_load_nn_csv_dir(fme_ctx* c, const char* dir) {
+  if (!c || !dir) return fail(FME_ERR_INVALID, "null argument");
+  static const char* names[14] = {"1.emb0-weight", "2.emb1-weight", "3.lins0-weight", "4.lins1-weight", "5.outp-weight",
+                                  "6.lins0-bias", "7.lins1-bias", "8.outp-bias", "9.bn-weight", "10.bns0-weight",
+                                  "11.bns1-weight", "12.bns0-bias", "13.bns1-bias", nullptr};
+  std::vector<std::vector<double>> t[14];
+  for (int i = 0; i < 13; ++i) {
+    int rc = read_csv(std::string(dir) + "/" + names[i] + ".csv", t[i]);
+    if (rc) return rc;
+  }
+  // 14.mapper_<qp>.csv: the QP is part of the name; try the four shipped ones
+  int rc = FME_ERR_IO;
+  for (int qp : {22, 27, 32, 37}) {
+    rc = read_csv(std::string(dir) + "/14.mapper_" + std::to_string(qp) + ".csv", t[13]);
+    if (rc == FME_OK) break;
+  }
+  if (rc) return rc;
+  auto flat = [](const std::vector<std::vector<double>>& r, std::vector<float>& out) {
+    for (auto& row : r)
+      for (double v : row) out.push_back((float)v);
+  };
+  if (t[13].size() != 2 || t[13][0].size() != 9) return fail(FME_ERR_IO, "mapper csv malformed");
+  FmeNnHeader h{};
+  h.magic = FME_NN_MAGIC; h.version = 1; h.nErr = 9; h.nEmb = 2; h.embRows = 8; h.embDim = 4; h.nHidden = 2;
+  h.hidden[0] = (int)t[2].size(); h.hidden[1] = (int)t[3].size(); h.nOut = (int)t[4].size();
+  std::vector<float> p;
+  flat({t[13][0]}, p); flat({t[13][1]}, p); flat(t[8], p);       // mean, stdev, gammaIn
+  flat(t[0], p); flat(t[1], p);                                    // embeddings
+  flat(t[2], p); flat(t[5], p); flat(t[9], p); flat(t[11], p);     // layer 0: W b gamma beta
+  flat(t[3], p); flat(t[6], p); flat(t[10], p); flat(t[12], p);    // layer 1
+  flat(t[4], p); flat(t[7], p);                                    // output
+  if (p.size() != nn_payload_floats(h)) return fail(FME_ERR_IO, "csv directory has unexpected shapes");
+  std::vector<char> blob(sizeof(h) + 4 * p.size());
+  memcpy(blob.data(), &h, sizeof(h));
+  memcpy(blob.data() + sizeof(h), p.data(), 4 * p.size());
+  return fme_set_nn_weights(c, blob.data(), blob.size());
+}
+
+// ---- slice lambda ----------------------------------------------------------------------------
+int fme_set_slice(fme_ctx* c, double lambda) {
+  if (!c || !(lambda > 0.0)) return fail(FME_ERR_INVALID, "lambda must be positive");
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  c->lambda = lambda;
+  // TComRdCost.cpp:108 m_dLambdaMotionSAD[0]; TComRdCost.h:159 selectMotionLambda(true, 0, false);
+  // TComRdCost.h:165-169 Distortion((m_motionLambda * bits) / 65536.0)
+  const double motionLambda = 65536.0 * sqrt(lambda);
+  for (unsigned b = 0; b < FME_COST_LUT_SIZE; ++b) c->costLut[b] = (uint32_t)((motionLambda * b) / 65536.0);
+  CU_CHECK(cudaStreamSynchronize(c->stream));
+  CU_CHECK(cudaMemcpyAsync(c->d_costLut, c->costLut, sizeof(c->costLut), cudaMemcpyHostToDevice, c->stream));
+  CU_CHECK(cudaStreamSynchronize(c->stream));
+  c->sliceValid = true;
+  return FME_OK;
+}
+
+int fme_mv_cost(fme_ctx* c, int x, int y, int scale, int predX, int predY, uint32_t* out) {
+  if (!c || !out) return fail(FME_ERR_INVALID, "null argument");
+  if (!c->sliceValid) return fail(FME_ERR_STATE, "fme_set_slice not called");
+  auto bits = [](int v) {
+    unsigned len = 1, t = (v <= 0) ? (((unsigned)(-v)) << 1) + 1 : ((unsigned)v << 1);
+    while (t != 1) { t >>= 1; len += 2; }
+    return len;
+  };
+  unsigned b = bits((x << scale) - predX) + bits((y << scale) - predY);
+  if (b >= FME_COST_LUT_SIZE) return fail(FME_ERR_INVALID, "vector out of range");
+  *out = c->costLut[b];
+  return FME_OK;
+}
+
+// ---- frame data ----------------------------------------------------------------------------
+int fme_upload_ref(fme_ctx* c, int slot, const int16_t* y, int stride) {
+  int rc = check_slot(c, slot);
+  if (rc) return rc;
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  rc = stage_picture(c, y, stride, c->g.W, c->g.H, c->d_pic, c->picPitch);
+  if (rc) return rc;
+  return run_k1(c, slot);
+}
+
+int fme_upload_ref_u8(fme_ctx* c, int slot, const uint8_t* y, int stride) {
+  int rc = check_slot(c, slot);
+  if (rc) return rc;
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  rc = stage_picture(c, y, stride, c->g.W, c->g.H, c->d_pic, c->picPitch);
+  if (rc) return rc;
+  return run_k1(c, slot);
+}
+
+int fme_upload_ref_device_u8(fme_ctx* c, int slot, const uint8_t* d_y, int pitch) {
+  int rc = check_slot(c, slot);
+  if (rc) return rc;
+  if (!d_y || pitch < c->g.W) return fail(FME_ERR_INVALID, "bad device picture");
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  CU_CHECK(cudaMemcpy2DAsync(c->d_pic, c->picPitch, d_y, pitch, c->g.W, c->g.H, cudaMemcpyDeviceToDevice, c->stream));
+  return run_k1(c, slot);
+}
+
+int fme_interp_slot(fme_ctx* c, int slot) {
+  int rc = check_slot(c, slot);
+  if (rc) return rc;
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  return run_k1(c, slot);
+}
+
+int fme_upload_org(fme_ctx* c, const int16_t* y, int stride) {
+  if (!c) return fail(FME_ERR_INVALID, "null ctx");
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  int rc = stage_picture(c, y, stride, c->g.W, c->g.H, c->d_org, c->g.orgPitch);
+  if (rc) return rc;
+  c->orgValid = true;
+  return FME_OK;
+}
+
+int fme_upload_org_u8(fme_ctx* c, const uint8_t* y, int stride) {
+  if (!c) return fail(FME_ERR_INVALID, "null ctx");
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  int rc = stage_picture(c, y, stride, c->g.W, c->g.H, c->d_org, c->g.orgPitch);
+  if (rc) return rc;
+  c->orgValid = true;
+  return FME_OK;
+}
+
+int fme_upload_org_device_u8(fme_ctx* c, const uint8_t* d_y, int pitch) {
+  if (!c || !d_y || pitch < c->g.W) return fail(FME_ERR_INVALID, "bad device picture");
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  CU_CHECK(cudaMemcpy2DAsync(c->d_org, c->g.orgPitch, d_y, pitch, c->g.W, c->g.H, cudaMemcpyDeviceToDevice, c->stream));
+  c->orgValid = true;
+  return FME_OK;
+}
+
+int fme_upload_ref_chroma(fme_ctx* c, int slot, const int16_t* cb, const int16_t* cr, int stride) {
+  int rc = check_slot(c, slot);
+  if (rc) return rc;
+  if (!cb || !cr) return fail(FME_ERR_INVALID, "null chroma plane");
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  const FmeGeom& g = c->g;
+  if (!c->d_cb) {
+    CU_CHECK(cudaMalloc(&c->d_cb, g.cPlaneBytes * c->cfg.numRefSlots + g.cPitch));
+    CU_CHECK(cudaMalloc(&c->d_cr, g.cPlaneBytes * c->cfg.numRefSlots + g.cPitch));
+  }
+  for (int k = 0; k < 2; ++k) {
+    rc = stage_picture(c, k ? cr : cb, stride, g.Wc, g.Hc, c->d_pic, c->picPitch);
+    if (rc) return rc;
+    CU_CHECK(fme_launch_pad_chroma(g, c->d_pic, c->picPitch, (k ? c->d_cr : c->d_cb) + (size_t)slot * g.cPlaneBytes,
+                                   c->stream, &c->launches));
+  }
+  return FME_OK;
+}
+
+// ---- the batched search ------------------------------------------------------------------------
+static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, int mode, bool sync) {
+  if (!c || !pus || !out) return fail(FME_ERR_INVALID, "null argument");
+  if (n < 0 || n > c->cfg.maxPUs) return fail(FME_ERR_INVALID, "n=%d exceeds maxPUs=%d", n, c->cfg.maxPUs);
+  if (n == 0) return FME_OK;
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  CU_CHECK(cudaMemcpyAsync(c->d_pus, pus, sizeof(fme_pu) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  bool needK0 = false;
+  if (sync) {  // full validation on the synchronous path
+    for (int i = 0; i < n; ++i) {
+      if (pus[i].flags & FME_PU_ERR_ON_GPU) needK0 = true;
+      if ((mode & FME_MODE_STD) || (pus[i].flags & FME_PU_ERR_ON_GPU)) {
+        if (pus[i].refSlot >= c->cfg.numRefSlots || !c->refValid[pus[i].refSlot])
+          return fail(FME_ERR_STATE, "PU %d references slot %d which holds no picture", i, pus[i].refSlot);
+        if (fme_dim_index(pus[i].w) < 0 || fme_dim_index(pus[i].h) < 0)
+          return fail(FME_ERR_INVALID, "PU %d: %dx%d is not an HEVC PU size", i, pus[i].w, pus[i].h);
+      }
+    }
+  } else {
+    needK0 = (pus[0].flags & FME_PU_ERR_ON_GPU) != 0;
+  }
+  if (needK0) {
+    if (!c->orgValid) return fail(FME_ERR_STATE, "FME_PU_ERR_ON_GPU needs fme_upload_org first");
+    StageTimer t(c, 3);
+    CU_CHECK(fme_launch_k0(c->g, c->d_planes, c->d_org, c->d_pus, n, c->cfg.fen, c->stream, &c->launches));
+  }
+  int rc = run_search(c, c->d_pus, n, c->d_res, mode);
+  if (rc) return rc;
+  CU_CHECK(cudaMemcpyAsync(out, c->d_res, sizeof(fme_result) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  if (sync) {
+    CU_CHECK(cudaStreamSynchronize(c->stream));
+    collect_ms(c);
+  }
+  return FME_OK;
+}
+
+int fme_submit(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, int mode) {
+  return submit_common(c, pus, n, out, mode, true);
+}
+int fme_submit_async(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, int mode) {
+  return submit_common(c, pus, n, out, mode, false);
+}
+
+int fme_submit_device(fme_ctx* c, const fme_pu* d_pus, int n, fme_result* d_out, int mode) {
+  if (!c || !d_pus || !d_out) return fail(FME_ERR_INVALID, "null argument");
+  if (n < 0 || n > c->cfg.maxPUs) return fail(FME_ERR_INVALID, "n=%d exceeds maxPUs=%d", n, c->cfg.maxPUs);
+  if (n == 0) return FME_OK;
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  return run_search(c, const_cast<fme_pu*>(d_pus), n, d_out, mode);
+}
+
+int fme_int_surface_device(fme_ctx* c, fme_pu* d_pus, int n) {
+  if (!c || !d_pus) return fail(FME_ERR_INVALID, "null argument");
+  if (!c->orgValid) return fail(FME_ERR_STATE, "fme_int_surface_device needs fme_upload_org first");
+  if (n <= 0) return FME_OK;
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  StageTimer t(c, 3);
+  CU_CHECK(fme_launch_k0(c->g, c->d_planes, c->d_org, d_pus, n, c->cfg.fen, c->stream, &c->launches));
+  return FME_OK;
+}
+
+// ---- block-level parity entry points -------------------------------------------------------------
+static int filter_common(fme_ctx* c, int isVertical, int comp, const int16_t* src, int srcStride, int16_t* dst,
+                         int dstStride, int w, int h, int frac, int isFirst, int isLast, int bitDepth) {
+  if (!c || !src || !dst) return fail(FME_ERR_INVALID, "null argument");
+  if (w < 1 || h < 1 || w > 4096 || h > 4096 || srcStride < w || dstStride < w) return fail(FME_ERR_INVALID, "bad block geometry");
+  if (bitDepth < 8 || bitDepth > 12) return fail(FME_ERR_INVALID, "bitDepth out of range");
+  bool isLuma = comp == 0;
+  int ntaps = isLuma ? 8 : 4;
+  if (frac < 0 || frac >= (isLuma ? 4 : 8)) return fail(FME_ERR_INVALID, "frac out of range");
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  // copy the block plus the taps' support; like the reference, the caller guarantees it is readable
+  int before = frac ? ntaps / 2 - 1 : 0, after = frac ? ntaps / 2 : 0;
+  int bx = isVertical ? 0 : before, ax = isVertical ? 0 : after;
+  int by = isVertical ? before : 0, ay = isVertical ? after : 0;
+  int sw = w + bx + ax, sh = h + by + ay;
+  int rc = ensure_pel(&c->d_pel, &c->pelCapacity, (size_t)sw * sh);
+  if (rc) return rc;
+  rc = ensure_pel(&c->d_pel2, &c->pel2Capacity, (size_t)w * h);
+  if (rc) return rc;
+  const int16_t* s0 = src - (ptrdiff_t)by * srcStride - bx;
+  CU_CHECK(cudaMemcpy2DAsync(c->d_pel, sw * 2, s0, (size_t)srcStride * 2, (size_t)sw * 2, sh, cudaMemcpyHostToDevice, c->stream));
+  CU_CHECK(fme_launch_filter(isVertical, ntaps, isFirst, isLast, bitDepth, c->d_pel + (size_t)by * sw + bx, sw, c->d_pel2,
+                             w, w, h, frac, isLuma, c->stream, &c->launches));
+  CU_CHECK(cudaMemcpy2DAsync(dst, (size_t)dstStride * 2, c->d_pel2, (size_t)w * 2, (size_t)w * 2, h, cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(cudaStreamSynchronize(c->stream));
+  return FME_OK;
+}
+
+int fme_filter_hor(fme_ctx* c, int comp, const int16_t* src, int srcStride, int16_t* dst, int dstStride, int w, int h,
+                   int frac, int isLast, int bitDepth) {
+  return filter_common(c, 0, comp, src, srcStride, dst, dstStride, w, h, frac, 1, isLast, bitDepth);
+}
+int fme_filter_ver(fme_ctx* c, int comp, const int16_t* src, int srcStride, int16_t* dst, int dstStride, int w, int h,
+                   int frac, int isFirst, int isLast, int bitDepth) {
+  return filter_common(c, 1, comp, src, srcStride, dst, dstStride, w, h, frac, isFirst, isLast, bitDepth);
+}
+
+int fme_dist(fme_ctx* c, int kind, const int16_t* org, int orgStride, const int16_t* cur, int curStride, int w, int h,
+             int bitDepth, int subShift, int nBlocks, uint32_t* out) {
+  if (!c || !org || !cur || !out) return fail(FME_ERR_INVALID, "null argument");
+  if (kind < 0 || kind > 2 || w < 2 || h < 2 || w > 64 || h > 64 || orgStride < w || curStride < w || nBlocks < 1 ||
+      bitDepth < 8 || bitDepth > 12 || subShift < 0 || subShift > 4)
+    return fail(FME_ERR_INVALID, "bad fme_dist arguments");
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  size_t no = (size_t)nBlocks * h * orgStride, nc = (size_t)nBlocks * h * curStride;
+  int rc = ensure_pel(&c->d_pel, &c->pelCapacity, no);
+  if (rc) return rc;
+  rc = ensure_pel(&c->d_pel2, &c->pel2Capacity, nc);
+  if (rc) return rc;
+  rc = ensure_u32(c, nBlocks);
+  if (rc) return rc;
+  CU_CHECK(cudaMemcpyAsync(c->d_pel, org, no * 2, cudaMemcpyHostToDevice, c->stream));
+  CU_CHECK(cudaMemcpyAsync(c->d_pel2, cur, nc * 2, cudaMemcpyHostToDevice, c->stream));
+  CU_CHECK(fme_launch_dist(kind, c->d_pel, orgStride, c->d_pel2, curStride, w, h, bitDepth, subShift, nBlocks,
+                           c->d_scratchU32, c->stream, &c->launches));
+  CU_CHECK(cudaMemcpyAsync(out, c->d_scratchU32, sizeof(uint32_t) * nBlocks, cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(cudaStreamSynchronize(c->stream));
+  return FME_OK;
+}
+
+// ---- motion compensation ---------------------------------------------------------------------------
+int fme_mc(fme_ctx* c, const fme_mc_pu* pus, int n, int16_t* dstY, int16_t* dstCb, int16_t* dstCr) {
+  if (!c || !pus || !dstY) return fail(FME_ERR_INVALID, "null argument");
+  if (n < 0 || n > c->cfg.maxPUs) return fail(FME_ERR_INVALID, "n out of range");
+  if (n == 0) return FME_OK;
+  bool chroma = dstCb && dstCr;
+  if (chroma && !c->d_cb) return fail(FME_ERR_STATE, "fme_mc with chroma needs fme_upload_ref_chroma first");
+  for (int i = 0; i < n; ++i) {
+    if (pus[i].refSlot >= c->cfg.numRefSlots || !c->refValid[pus[i].refSlot])
+      return fail(FME_ERR_STATE, "PU %d references slot %d which holds no picture", i, pus[i].refSlot);
+    if (pus[i].w > 64 || pus[i].h > 64 || pus[i].w < 4 || pus[i].h < 4) return fail(FME_ERR_INVALID, "PU %d: bad size", i);
+  }
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  size_t ySamples = (size_t)n * 64 * 64, cSamples = (size_t)n * 32 * 32;
+  int rc = ensure_pel(&c->d_pel, &c->pelCapacity, ySamples);
+  if (rc) return rc;
+  if (chroma) {
+    rc = ensure_pel(&c->d_pel2, &c->pel2Capacity, 2 * cSamples);
+    if (rc) return rc;
+  }
+  static_assert(sizeof(fme_mc_pu) <= sizeof(fme_pu), "record staging reuses d_pus");
+  CU_CHECK(cudaMemcpyAsync(c->d_pus, pus, sizeof(fme_mc_pu) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CU_CHECK(fme_launch_mc(c->g, c->d_planes, chroma ? c->d_cb : nullptr, chroma ? c->d_cr : nullptr,
+                         reinterpret_cast<const fme_mc_pu*>(c->d_pus), n, c->d_pel, chroma ? c->d_pel2 : nullptr,
+                         chroma ? c->d_pel2 + cSamples : nullptr, c->stream, &c->launches));
+  CU_CHECK(cudaMemcpyAsync(dstY, c->d_pel, ySamples * 2, cudaMemcpyDeviceToHost, c->stream));
+  if (chroma) {
+    CU_CHECK(cudaMemcpyAsync(dstCb, c->d_pel2, cSamples * 2, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(cudaMemcpyAsync(dstCr, c->d_pel2 + cSamples, cSamples * 2, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU_CHECK(cudaStreamSynchronize(c->stream));
+  return FME_OK;
+}
+
+// ---- introspection -----------------------------------------------------------------------------------
+int fme_download_plane(fme_ctx* c, int slot, int fy, int fx, uint8_t* dst, int dstStride) {
+  int rc = check_slot(c, slot);
+  if (rc) return rc;
+  if (!dst || fy < 0 || fy > 3 || fx < 0 || fx > 3 || dstStride < c->g.Wp) return fail(FME_ERR_INVALID, "bad argument");
+  if (!c->refValid[slot]) return fail(FME_ERR_STATE, "slot %d holds no picture", slot);
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  const uint8_t* src = c->d_planes + (size_t)slot * c->g.slotBytes + (size_t)(fy * 4 + fx) * c->g.planeBytes;
+  CU_CHECK(cudaMemcpy2DAsync(dst, dstStride, src, c->g.pitch, c->g.Wp, c->g.Hp, cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(cudaStreamSynchronize(c->stream));
+  return FME_OK;
+}
+
+}  // extern "C"

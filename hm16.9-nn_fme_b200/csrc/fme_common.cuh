@@ -1,0 +1,85 @@
+// Shared declarations of the B200 fractional-ME engine (device + host side of libfme_b200.so).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fme_b200.h"
+
+#define FME_NUM_PLANES 16     // P[fy][fx], fy,fx in 0..3; plane 0 = padded integer-pel copy
+#define FME_COST_LUT_SIZE 160 // MV bit counts: 2 * (1 + 2*17) = 70 max for 16-bit components, padded
+#define FME_MAX_CLASSES 64    // (w index) * 8 + (h index), w,h in {4,8,12,16,24,32,48,64}
+
+// Geometry of one padded plane set (all slots share it).
+struct FmeGeom {
+  int W, H;        // picture
+  int M;           // margin
+  int Wp, Hp;      // padded: W + 2M, H + 2M
+  int pitch;       // bytes per padded row (multiple of 128)
+  size_t planeBytes;  // Hp * pitch
+  size_t slotBytes;   // 16 * planeBytes
+  int orgPitch;    // bytes per row of the source picture
+  int Wc, Hc, Mc, Wcp, Hcp, cPitch;  // chroma (4:2:0) padded geometry
+  size_t cPlaneBytes;
+  int numSlots;     // reference slots allocated (records with a larger refSlot are clamped)
+};
+
+// NN weight header as laid out in the FMNN blob (see nn_weights.py / oracle header).
+struct FmeNnHeader {
+  int32_t magic, version, nErr, nEmb, embRows, embDim, nHidden, hidden[4], nOut, outSigmoid, reserved[3];
+};
+#define FME_NN_MAGIC 0x4e4e4d46
+
+__host__ __device__ inline int fme_dim_index(int v) {
+  // {4,8,12,16,24,32,48,64} -> 0..7, anything else -> -1
+  switch (v) {
+    case 4: return 0;
+    case 8: return 1;
+    case 12: return 2;
+    case 16: return 3;
+    case 24: return 4;
+    case 32: return 5;
+    case 48: return 6;
+    case 64: return 7;
+    default: return -1;
+  }
+}
+__host__ __device__ inline int fme_index_dim(int i) {
+  const int t[8] = {4, 8, 12, 16, 24, 32, 48, 64};
+  return t[i & 7];
+}
+
+// ---- launchers implemented in the kernel translation units ----------------------------------
+struct FmeK2Scratch {
+  int* classCount;   // [FME_MAX_CLASSES]
+  int* classCursor;  // [FME_MAX_CLASSES]
+  int* classOffset;  // [FME_MAX_CLASSES + 1]
+  int* packOffset;   // [FME_MAX_CLASSES + 1] cumulative number of packs
+  int* order;        // [maxPUs] PU indices grouped by class
+  int* workCounter;  // [1] dynamic pack scheduler
+};
+
+cudaError_t fme_launch_k1(const FmeGeom& g, const uint8_t* d_pic, int picPitch, uint8_t* d_planes, cudaStream_t s,
+                          int64_t* launches);
+cudaError_t fme_launch_pad_chroma(const FmeGeom& g, const uint8_t* d_pic, int picPitch, uint8_t* d_plane,
+                                  cudaStream_t s, int64_t* launches);
+cudaError_t fme_launch_k2(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_pu* d_pus, int n,
+                          fme_result* d_res, const uint32_t* d_costLut, int useHad, const FmeK2Scratch& sc,
+                          int numSMs, cudaStream_t s, int64_t* launches);
+cudaError_t fme_launch_k3(const fme_pu* d_pus, int n, fme_result* d_res, const float* d_nn, size_t nnBytes,
+                          cudaStream_t s, int64_t* launches);
+cudaError_t fme_launch_k0(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, fme_pu* d_pus, int n,
+                          int fen, cudaStream_t s, int64_t* launches);
+cudaError_t fme_launch_clear_results(fme_result* d_res, int n, cudaStream_t s, int64_t* launches);
+
+cudaError_t fme_launch_filter(int isVertical, int ntaps, int isFirst, int isLast, int bitDepth, const int16_t* d_src,
+                              int srcStride, int16_t* d_dst, int dstStride, int w, int h, int frac, int isLuma,
+                              cudaStream_t s, int64_t* launches);
+cudaError_t fme_launch_dist(int kind, const int16_t* d_org, int orgStride, const int16_t* d_cur, int curStride, int w,
+                            int h, int bitDepth, int subShift, int nBlocks, uint32_t* d_out, cudaStream_t s,
+                            int64_t* launches);
+cudaError_t fme_launch_pel_to_u8(const int16_t* d_src, int srcStride, uint8_t* d_dst, int dstPitch, int w, int h,
+                                 cudaStream_t s, int64_t* launches);
+cudaError_t fme_launch_mc(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_cb, const uint8_t* d_cr,
+                          const fme_mc_pu* d_pus, int n, int16_t* d_y, int16_t* d_cbOut, int16_t* d_crOut,
+                          cudaStream_t s, int64_t* launches);

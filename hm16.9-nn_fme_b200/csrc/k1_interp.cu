@@ -1,0 +1,216 @@
+// K1: sub-pel plane generation (replaces xExtDIFUpSamplingH/Q + filterHor/filterVer for whole
+// reference pictures; reference: TEncSearch.cpp:6331-6532, TComInterpolationFilter.cpp:172-257).
+//
+// For an 8-bit picture R (edge-replicated to infinity, which is what TComPicYuv::extendPicBorder
+// stores in the 80-sample margin) and HEVC luma taps c_f, the 16 planes are
+//   T_fx(x,y)    = sum_k c_fx[k] R(x+k-3, y) - 8192            (first stage, shift 0 at 8 bit, int16)
+//   P[fy][fx]    = clip255((sum_k c_fy[k] T_fx(x, y+k-3) + 2048 + (8192<<6)) >> 12)      fy != 0
+//   P[0][fx]     = clip255((T_fx + 8192 + 32) >> 6)
+// which is bit-identical to what the reference's per-PU two-stage filtering produces at every
+// position.  Layout in HBM: planes[p = fy*4+fx][Hp][pitch] u8, picture sample (0,0) at [M][M].
+//
+// One CTA produces a 128 x 32 tile of all 16 planes:
+//   stage A  (136 x 39) u8 input tile -> shared memory, coordinates clamped to the picture
+//   stage B  horizontal 8-tap for fx = 0..3 with dp4a (u8 samples x s8 taps) -> int16 in shared memory
+//   stage C  vertical 8-tap for fy = 1..3 with dp2a (s16 x s8 tap pairs), fy = 0 by shift; u8x4 stores
+// Algorithmic HBM bytes: 1 B read + 16 B written per padded sample (plane 0 is the padded copy).
+#include "fme_common.cuh"
+
+namespace {
+
+constexpr int TW = 128;           // output tile width  (one 128-byte line per plane row)
+constexpr int TH = 32;            // output tile height
+constexpr int IN_W = TW + 8;      // input columns x0-4 .. x0+TW+3 (word aligned)
+constexpr int IN_H = TH + 7;      // input rows    y0-3 .. y0+TH+3
+constexpr int K1_THREADS = 256;
+
+__device__ __forceinline__ int dp4a_u8s8(unsigned a, int b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp2a_lo(int a, int b, int c) {
+  int d;
+  asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp2a_hi(int a, int b, int c) {
+  int d;
+  asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+#define PACK4(a, b, c, d) \
+  ((int)(((unsigned)(a)&0xffu) | (((unsigned)(b)&0xffu) << 8) | (((unsigned)(c)&0xffu) << 16) | (((unsigned)(d)&0xffu) << 24)))
+// TComInterpolationFilter.cpp:57-63 luma taps, packed as s8x4 (low half, high half)
+__constant__ int c_lumaLo[4] = {PACK4(0, 0, 0, 64), PACK4(-1, 4, -10, 58), PACK4(-1, 4, -11, 40), PACK4(0, 1, -5, 17)};
+__constant__ int c_lumaHi[4] = {PACK4(0, 0, 0, 0), PACK4(17, -5, 1, 0), PACK4(40, -11, 4, -1), PACK4(58, -10, 4, -1)};
+
+__device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
+
+__global__ void __launch_bounds__(K1_THREADS) k1_interp_planes(const uint8_t* __restrict__ pic, int picPitch, int W,
+                                                               int H, int M, int Wp, int Hp, int pitch,
+                                                               size_t planeBytes, uint8_t* __restrict__ planes) {
+  __shared__ __align__(16) uint8_t s_in[IN_H][IN_W];
+  __shared__ __align__(16) int16_t s_t[4][IN_H][TW];
+
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * TW;  // padded-plane coordinates of the tile
+  const int y0 = blockIdx.y * TH;
+
+  // ---- stage A: input tile, clamped to the picture --------------------------------------------
+  {
+    const int pxBase = x0 - M - 4;  // picture x of input column 0 (multiple of 4)
+    const int pyBase = y0 - M - 3;
+    for (int i = tid; i < IN_H * (IN_W / 4); i += K1_THREADS) {
+      int r = i / (IN_W / 4), wq = i - r * (IN_W / 4);
+      int py = min(max(pyBase + r, 0), H - 1);
+      int px = pxBase + wq * 4;
+      const uint8_t* row = pic + (size_t)py * picPitch;
+      unsigned v;
+      if (px >= 0 && px + 3 <= W - 1) {
+        v = *reinterpret_cast<const unsigned*>(row + px);
+      } else {
+        unsigned b0 = row[min(max(px + 0, 0), W - 1)], b1 = row[min(max(px + 1, 0), W - 1)];
+        unsigned b2 = row[min(max(px + 2, 0), W - 1)], b3 = row[min(max(px + 3, 0), W - 1)];
+        v = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+      }
+      *reinterpret_cast<unsigned*>(&s_in[r][wq * 4]) = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- stage B: horizontal filters -> int16 T_fx ---------------------------------------------
+  // item = (row, quad of 4 output columns).  Output column x uses input columns x+1 .. x+8
+  // (input column index = picture x + 4, taps reach x-3 .. x+4).
+  for (int i = tid; i < IN_H * (TW / 4); i += K1_THREADS) {
+    int r = i / (TW / 4), q = i - r * (TW / 4);
+    const unsigned* src = reinterpret_cast<const unsigned*>(&s_in[r][q * 4]);
+    unsigned w0 = src[0], w1 = src[1], w2 = src[2];
+    unsigned lo[4], hi[4];
+    lo[0] = __funnelshift_r(w0, w1, 8);  hi[0] = __funnelshift_r(w1, w2, 8);
+    lo[1] = __funnelshift_r(w0, w1, 16); hi[1] = __funnelshift_r(w1, w2, 16);
+    lo[2] = __funnelshift_r(w0, w1, 24); hi[2] = __funnelshift_r(w1, w2, 24);
+    lo[3] = w1;                          hi[3] = w2;
+    // fx = 0: (s << 6) - 8192, s = input column x+4 = byte 0 of w1 + ...
+    {
+      int t0 = (int)((w1)&0xff) * 64 - 8192, t1 = (int)((w1 >> 8) & 0xff) * 64 - 8192;
+      int t2 = (int)((w1 >> 16) & 0xff) * 64 - 8192, t3 = (int)((w1 >> 24) & 0xff) * 64 - 8192;
+      int2 o;
+      o.x = (t0 & 0xffff) | (t1 << 16);
+      o.y = (t2 & 0xffff) | (t3 << 16);
+      *reinterpret_cast<int2*>(&s_t[0][r][q * 4]) = o;
+    }
+#pragma unroll
+    for (int f = 1; f < 4; ++f) {
+      int t[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) t[k] = dp4a_u8s8(hi[k], c_lumaHi[f], dp4a_u8s8(lo[k], c_lumaLo[f], -8192));
+      int2 o;
+      o.x = (t[0] & 0xffff) | (t[1] << 16);
+      o.y = (t[2] & 0xffff) | (t[3] << 16);
+      *reinterpret_cast<int2*>(&s_t[f][r][q * 4]) = o;
+    }
+  }
+  __syncthreads();
+
+  // ---- stage C: vertical filters, 16 planes, u8x4 stores -------------------------------------
+  for (int i = tid; i < TH * (TW / 4); i += K1_THREADS) {
+    int r = i / (TW / 4), q = i - r * (TW / 4);
+    int gy = y0 + r, gx = x0 + q * 4;
+    if (gy >= Hp || gx >= Wp) continue;  // Wp is a multiple of 4
+    uint8_t* outBase = planes + (size_t)gy * pitch + gx;
+#pragma unroll
+    for (int fx = 0; fx < 4; ++fx) {
+      // rows r .. r+7 of T_fx (output row r is centred on input row r+3)
+      int2 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = *reinterpret_cast<const int2*>(&s_t[fx][r + k][q * 4]);
+      // fy = 0: (T + 8192 + 32) >> 6 on the centre row
+      {
+        int2 c = v[3];
+        int a0 = (int)(short)(c.x & 0xffff), a1 = c.x >> 16, a2 = (int)(short)(c.y & 0xffff), a3 = c.y >> 16;
+        unsigned o = clip255((a0 + 8224) >> 6) | (clip255((a1 + 8224) >> 6) << 8) |
+                     (clip255((a2 + 8224) >> 6) << 16) | (clip255((a3 + 8224) >> 6) << 24);
+        *reinterpret_cast<unsigned*>(outBase + (size_t)(0 * 4 + fx) * planeBytes) = o;
+      }
+      // vertical pairs (T(x,k), T(x,k+1)) for the four columns
+      int p[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        p[0][k] = __byte_perm(v[2 * k].x, v[2 * k + 1].x, 0x5410);
+        p[1][k] = __byte_perm(v[2 * k].x, v[2 * k + 1].x, 0x7632);
+        p[2][k] = __byte_perm(v[2 * k].y, v[2 * k + 1].y, 0x5410);
+        p[3][k] = __byte_perm(v[2 * k].y, v[2 * k + 1].y, 0x7632);
+      }
+#pragma unroll
+      for (int fy = 1; fy < 4; ++fy) {
+        int tl = c_lumaLo[fy], th = c_lumaHi[fy];
+        int o[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          int acc = 2048 + (8192 << 6);
+          acc = dp2a_lo(p[c][0], tl, acc);
+          acc = dp2a_hi(p[c][1], tl, acc);
+          acc = dp2a_lo(p[c][2], th, acc);
+          acc = dp2a_hi(p[c][3], th, acc);
+          o[c] = clip255(acc >> 12);
+        }
+        unsigned ov = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+        *reinterpret_cast<unsigned*>(outBase + (size_t)(fy * 4 + fx) * planeBytes) = ov;
+      }
+    }
+  }
+}
+
+// Edge-replicating copy of a chroma picture into its padded plane (used by MC only).
+__global__ void k_pad_plane(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int M, int Wp, int Hp,
+                            int pitch, uint8_t* __restrict__ dst) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= Wp || y >= Hp) return;
+  int px = min(max(x - M, 0), W - 1), py = min(max(y - M, 0), H - 1);
+  dst[(size_t)y * pitch + x] = pic[(size_t)py * picPitch + px];
+}
+
+// Pel (int16) picture -> u8 picture (8-bit content).
+__global__ void k_pel_to_u8(const int16_t* __restrict__ src, int srcStride, uint8_t* __restrict__ dst, int dstPitch,
+                            int w, int h) {
+  int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  const int16_t* s = src + (size_t)y * srcStride + x;
+  uint8_t* d = dst + (size_t)y * dstPitch + x;
+  if (x + 3 < w) {
+    unsigned v = (unsigned)(s[0] & 0xff) | ((unsigned)(s[1] & 0xff) << 8) | ((unsigned)(s[2] & 0xff) << 16) |
+                 ((unsigned)(s[3] & 0xff) << 24);
+    *reinterpret_cast<unsigned*>(d) = v;
+  } else {
+    for (int k = 0; x + k < w; ++k) d[k] = (uint8_t)s[k];
+  }
+}
+
+}  // namespace
+
+cudaError_t fme_launch_k1(const FmeGeom& g, const uint8_t* d_pic, int picPitch, uint8_t* d_planes, cudaStream_t s,
+                          int64_t* launches) {
+  dim3 grid((g.Wp + TW - 1) / TW, (g.Hp + TH - 1) / TH);
+  k1_interp_planes<<<grid, K1_THREADS, 0, s>>>(d_pic, picPitch, g.W, g.H, g.M, g.Wp, g.Hp, g.pitch, g.planeBytes,
+                                                d_planes);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t fme_launch_pad_chroma(const FmeGeom& g, const uint8_t* d_pic, int picPitch, uint8_t* d_plane,
+                                  cudaStream_t s, int64_t* launches) {
+  dim3 grid((g.Wcp + 127) / 128, g.Hcp);
+  k_pad_plane<<<grid, 128, 0, s>>>(d_pic, picPitch, g.Wc, g.Hc, g.Mc, g.Wcp, g.Hcp, g.cPitch, d_plane);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t fme_launch_pel_to_u8(const int16_t* d_src, int srcStride, uint8_t* d_dst, int dstPitch, int w, int h,
+                                 cudaStream_t s, int64_t* launches) {
+  dim3 grid(((w + 3) / 4 + 127) / 128, h);
+  k_pel_to_u8<<<grid, 128, 0, s>>>(d_src, srcStride, d_dst, dstPitch, w, h);
+  ++*launches;
+  return cudaGetLastError();
+}

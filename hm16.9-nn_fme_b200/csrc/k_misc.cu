@@ -1,0 +1,320 @@
+// K0 (integer 3x3 error surface), block-level filter / distortion parity kernels and motion compensation.
+#include "fme_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// K0: 3x3 integer error surface around the best integer MV.
+// Metric of xTZSearchHelp (TEncSearch.cpp:1085-1090, 1156-1166) as selected by
+// TComRdCost::setDistParam(pattern, ref, stride, dp) (TComRdCost.cpp:200-229): SSE for widths
+// 4/8/16/32/64, SAD12/24/48 otherwise, the SADs on every second row (<< 1) when FEN is on and rows > 8.
+// Raster order [TL,T,TR,L,C,R,BL,B,BR] = array_e[0..3], C, array_e[4..7] (TEncSearch.cpp:88, 1341-1376).
+// One warp per PU; lanes stride over the PU's 4-sample groups; plane 0 is the padded integer-pel copy.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k0_int_surface(fme_pu* __restrict__ pus, int n, const uint8_t* __restrict__ planes,
+                                                      const uint8_t* __restrict__ org, const FmeGeom g, int fen) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int nWarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = warp; i < n; i += nWarps) {
+    fme_pu p = pus[i];
+    if (!(p.flags & FME_PU_ERR_ON_GPU)) continue;
+    int w = p.w, h = p.h;
+    bool useSad = (w == 12 || w == 24 || w == 48);
+    int step = (useSad && fen && h > 8) ? 2 : 1;
+    int X = min(max(p.x + p.mvIntX, -(g.M - 8)), g.W + g.M - 8 - w);
+    int Y = min(max(p.y + p.mvIntY, -(g.M - 8)), g.H + g.M - 8 - h);
+    int ox = min(max((int)p.x, 0), g.W - w), oy = min(max((int)p.y, 0), g.H - h);
+    const uint8_t* ref = planes + (size_t)min((int)p.refSlot, g.numSlots - 1) * g.slotBytes + (size_t)(Y + g.M) * g.pitch + (X + g.M);
+    const uint8_t* src = org + (size_t)oy * g.orgPitch + ox;
+    unsigned acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = 0;
+    int groups = w >> 2;  // 4-sample groups per row
+    int rows = h / step;
+    for (int t = lane; t < groups * rows; t += 32) {
+      int r = (t / groups) * step, c = (t % groups) * 4;
+      int o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = src[(size_t)r * g.orgPitch + c + k];
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        const uint8_t* rr = ref + (ptrdiff_t)(r + dy) * g.pitch + c;
+        int v[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[k] = rr[k - 1];
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          unsigned s = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            int d = o[k] - v[k + 1 + dx];
+            s += useSad ? (unsigned)abs(d) : (unsigned)(d * d);
+          }
+          acc[(dy + 1) * 3 + dx + 1] += s;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      unsigned v = __reduce_add_sync(0xffffffffu, acc[k]);
+      if (step == 2) v <<= 1;  // uiSum <<= iSubShift (TComRdCost.cpp, xGetSAD12/24/48)
+      acc[k] = v;
+    }
+    if (lane < 9) {
+      unsigned v = acc[0];
+#pragma unroll
+      for (int k = 1; k < 9; ++k)
+        if (lane == k) v = acc[k];
+      pus[i].err[lane] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block-level TComInterpolationFilter::filter / filterCopy (TComInterpolationFilter.cpp:94-257)
+// ------------------------------------------------------------------------------------------------
+__constant__ int8_t c_luma[4][8] = {{0, 0, 0, 64, 0, 0, 0, 0},
+                                    {-1, 4, -10, 58, 17, -5, 1, 0},
+                                    {-1, 4, -11, 40, 40, -11, 4, -1},
+                                    {0, 1, -5, 17, 58, -10, 4, -1}};
+__constant__ int8_t c_chroma[8][4] = {{0, 64, 0, 0},   {-2, 58, 10, -2}, {-4, 54, 16, -2}, {-6, 46, 28, -4},
+                                      {-4, 36, 36, -4}, {-4, 28, 46, -6}, {-2, 16, 54, -4}, {-2, 10, 58, -2}};
+
+// src points at the block's first sample; the halo (N/2-1 before, N/2 after) must be present.
+__global__ void k_filter_block(int isVertical, int ntaps, int isFirst, int isLast, int bitDepth,
+                               const int16_t* __restrict__ src, int srcStride, int16_t* __restrict__ dst,
+                               int dstStride, int w, int h, int frac, int isLuma) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  const int headRoom = max(2, 14 - bitDepth);
+  const int16_t* s = src + (ptrdiff_t)y * srcStride + x;
+  int16_t out;
+  if (frac == 0) {  // filterCopy, TComInterpolationFilter.cpp:94-154
+    int v = s[0];
+    if (isFirst == isLast) {
+      out = (int16_t)v;
+    } else if (isFirst) {
+      int16_t t = (int16_t)(v << headRoom);
+      out = (int16_t)(t - 8192);
+    } else {
+      int16_t t = (int16_t)((v + 8192 + (1 << (headRoom - 1))) >> headRoom);
+      int maxVal = (1 << bitDepth) - 1;
+      if (t < 0) t = 0;
+      if (t > maxVal) t = (int16_t)maxVal;
+      out = t;
+    }
+  } else {  // filter<N,...>, TComInterpolationFilter.cpp:172-257
+    int cStride = isVertical ? srcStride : 1;
+    s -= (ntaps / 2 - 1) * cStride;
+    int shift = 6, offset, maxVal;
+    if (isLast) {
+      shift += isFirst ? 0 : headRoom;
+      offset = 1 << (shift - 1);
+      offset += isFirst ? 0 : (8192 << 6);
+      maxVal = (1 << bitDepth) - 1;
+    } else {
+      shift -= isFirst ? headRoom : 0;
+      offset = isFirst ? -(8192 << shift) : 0;
+      maxVal = 0;
+    }
+    int sum = 0;
+    for (int k = 0; k < ntaps; ++k) {
+      int c = isLuma ? c_luma[frac][k] : c_chroma[frac][k];
+      sum += (int)s[(ptrdiff_t)k * cStride] * c;
+    }
+    int16_t v = (int16_t)((sum + offset) >> shift);
+    if (isLast) {
+      if (v < 0) v = 0;
+      if (v > maxVal) v = (int16_t)maxVal;
+    }
+    out = v;
+  }
+  dst[(ptrdiff_t)y * dstStride + x] = out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block-level distortion (TComRdCost.cpp:359-1495) on Pel buffers, one warp per block pair.
+// kind 0: SSE (or SAD12/24/48 with subShift), 1: HADs, 2: SADs with subShift.
+// ------------------------------------------------------------------------------------------------
+__device__ int had_tile_generic(const int16_t* org, int os, const int16_t* cur, int cs, int n) {
+  int d[64];
+  for (int r = 0; r < n; ++r)
+    for (int c = 0; c < n; ++c) d[r * n + c] = (int)org[r * os + c] - (int)cur[r * cs + c];
+  for (int len = 1; len < n; len <<= 1) {
+    for (int r = 0; r < n; ++r)
+      for (int i = 0; i < n; i += 2 * len)
+        for (int j = i; j < i + len; ++j) {
+          int a = d[r * n + j], b = d[r * n + j + len];
+          d[r * n + j] = a + b;
+          d[r * n + j + len] = a - b;
+        }
+  }
+  for (int len = 1; len < n; len <<= 1) {
+    for (int c = 0; c < n; ++c)
+      for (int i = 0; i < n; i += 2 * len)
+        for (int j = i; j < i + len; ++j) {
+          int a = d[j * n + c], b = d[(j + len) * n + c];
+          d[j * n + c] = a + b;
+          d[(j + len) * n + c] = a - b;
+        }
+  }
+  int s = 0;
+  for (int i = 0; i < n * n; ++i) s += abs(d[i]);
+  if (n == 8) return (s + 2) >> 2;
+  if (n == 4) return (s + 1) >> 1;
+  return s;
+}
+
+__global__ void __launch_bounds__(128) k_dist_blocks(int kind, const int16_t* __restrict__ org, int os,
+                                                     const int16_t* __restrict__ cur, int cs, int w, int h,
+                                                     int bitDepth, int subShift, int nBlocks,
+                                                     uint32_t* __restrict__ out) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= nBlocks) return;
+  const int16_t* o = org + (size_t)warp * h * os;
+  const int16_t* c = cur + (size_t)warp * h * cs;
+  bool sadIntMe = (kind == 0) && (w == 12 || w == 24 || w == 48);
+  unsigned acc = 0;
+  if (kind == 1) {
+    int n = ((h % 8 == 0) && (w % 8 == 0)) ? 8 : ((h % 4 == 0) && (w % 4 == 0)) ? 4 : 2;
+    int tx = w / n, tiles = tx * (h / n);
+    for (int t = lane; t < tiles; t += 32) {
+      int x = (t % tx) * n, y = (t / tx) * n;
+      acc += (unsigned)had_tile_generic(o + y * os + x, os, c + y * cs + x, cs, n);
+    }
+    acc = __reduce_add_sync(0xffffffffu, acc);
+    acc >>= (bitDepth - 8);
+  } else if (kind == 2 || sadIntMe) {
+    int step = 1 << subShift;
+    int rows = h / step;
+    for (int t = lane; t < rows * w; t += 32) {
+      int r = (t / w) * step, x = t % w;
+      acc += (unsigned)abs((int)o[r * os + x] - (int)c[r * cs + x]);
+    }
+    acc = __reduce_add_sync(0xffffffffu, acc);
+    acc <<= subShift;
+    acc >>= (bitDepth - 8);
+  } else {
+    int sh = (bitDepth - 8) << 1;
+    for (int t = lane; t < h * w; t += 32) {
+      int r = t / w, x = t % w;
+      int d = (int)o[r * os + x] - (int)c[r * cs + x];
+      acc += (unsigned)((d * d) >> sh);
+    }
+    acc = __reduce_add_sync(0xffffffffu, acc);
+  }
+  if (lane == 0) out[warp] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Motion compensation, uni-prediction (TComPrediction::xPredInterBlk, TComPrediction.cpp:643-681).
+// Luma: the clipped MC sample at quarter-pel MV equals plane P[mvY&3][mvX&3] at the integer offset
+// (SURVEY.md A.1), so luma MC is a gather.  Chroma (4:2:0): 4-tap at 1/8 pel with the reference's
+// two-stage rounding; chroma planes are padded copies.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int chroma_sample(const uint8_t* plane, int pitch, int x, int y, int xFrac, int yFrac) {
+  const uint8_t* p = plane + (ptrdiff_t)y * pitch + x;
+  if (yFrac == 0) {
+    if (xFrac == 0) return p[0];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s += c_chroma[xFrac][k] * (int)p[k - 1];
+    return min(max((s + 32) >> 6, 0), 255);
+  }
+  if (xFrac == 0) {
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s += c_chroma[yFrac][k] * (int)p[(ptrdiff_t)(k - 1) * pitch];
+    return min(max((s + 32) >> 6, 0), 255);
+  }
+  int acc = 2048 + (8192 << 6);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint8_t* q = p + (ptrdiff_t)(j - 1) * pitch;
+    int t = -8192;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t += c_chroma[xFrac][k] * (int)q[k - 1];
+    acc += c_chroma[yFrac][j] * t;
+  }
+  return min(max(acc >> 12, 0), 255);
+}
+
+__global__ void __launch_bounds__(256) k_mc(const fme_mc_pu* __restrict__ pus, int n, const uint8_t* __restrict__ planes,
+                                            const uint8_t* __restrict__ cb, const uint8_t* __restrict__ cr,
+                                            const FmeGeom g, int16_t* __restrict__ dstY, int16_t* __restrict__ dstCb,
+                                            int16_t* __restrict__ dstCr) {
+  int i = blockIdx.x;
+  if (i >= n) return;
+  fme_mc_pu p = pus[i];
+  int w = p.w, h = p.h;
+  // luma
+  {
+    int fx = p.mvX & 3, fy = p.mvY & 3;
+    int X = min(max(p.x + (p.mvX >> 2), -(g.M - 8)), g.W + g.M - 8 - w);
+    int Y = min(max(p.y + (p.mvY >> 2), -(g.M - 8)), g.H + g.M - 8 - h);
+    const uint8_t* src = planes + (size_t)min((int)p.refSlot, g.numSlots - 1) * g.slotBytes + (size_t)(fy * 4 + fx) * g.planeBytes +
+                         (size_t)(Y + g.M) * g.pitch + (X + g.M);
+    int16_t* d = dstY + (size_t)i * 64 * 64;
+    for (int t = threadIdx.x; t < w * h; t += blockDim.x) {
+      int r = t / w, c = t % w;
+      d[r * 64 + c] = src[(size_t)r * g.pitch + c];
+    }
+  }
+  // chroma
+  if (cb && cr && dstCb && dstCr) {
+    int cw = w >> 1, ch = h >> 1;
+    int xFrac = p.mvX & 7, yFrac = p.mvY & 7;
+    int X = min(max((p.x >> 1) + (p.mvX >> 3), -(g.Mc - 4)), g.Wc + g.Mc - 4 - cw) + g.Mc;
+    int Y = min(max((p.y >> 1) + (p.mvY >> 3), -(g.Mc - 4)), g.Hc + g.Mc - 4 - ch) + g.Mc;
+    const uint8_t* pcb = cb + (size_t)min((int)p.refSlot, g.numSlots - 1) * g.cPlaneBytes;
+    const uint8_t* pcr = cr + (size_t)min((int)p.refSlot, g.numSlots - 1) * g.cPlaneBytes;
+    int16_t* dcb = dstCb + (size_t)i * 32 * 32;
+    int16_t* dcr = dstCr + (size_t)i * 32 * 32;
+    for (int t = threadIdx.x; t < cw * ch; t += blockDim.x) {
+      int r = t / cw, c = t % cw;
+      dcb[r * 32 + c] = (int16_t)chroma_sample(pcb, g.cPitch, X + c, Y + r, xFrac, yFrac);
+      dcr[r * 32 + c] = (int16_t)chroma_sample(pcr, g.cPitch, X + c, Y + r, xFrac, yFrac);
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t fme_launch_k0(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, fme_pu* d_pus, int n,
+                          int fen, cudaStream_t s, int64_t* launches) {
+  if (n <= 0) return cudaSuccess;
+  int blocks = (n + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k0_int_surface<<<blocks, 256, 0, s>>>(d_pus, n, d_planes, d_org, g, fen);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t fme_launch_filter(int isVertical, int ntaps, int isFirst, int isLast, int bitDepth, const int16_t* d_src,
+                              int srcStride, int16_t* d_dst, int dstStride, int w, int h, int frac, int isLuma,
+                              cudaStream_t s, int64_t* launches) {
+  dim3 grid((w + 63) / 64, h);
+  k_filter_block<<<grid, 64, 0, s>>>(isVertical, ntaps, isFirst, isLast, bitDepth, d_src, srcStride, d_dst, dstStride,
+                                     w, h, frac, isLuma);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t fme_launch_dist(int kind, const int16_t* d_org, int orgStride, const int16_t* d_cur, int curStride, int w,
+                            int h, int bitDepth, int subShift, int nBlocks, uint32_t* d_out, cudaStream_t s,
+                            int64_t* launches) {
+  int blocks = (nBlocks + 3) / 4;
+  k_dist_blocks<<<blocks, 128, 0, s>>>(kind, d_org, orgStride, d_cur, curStride, w, h, bitDepth, subShift, nBlocks,
+                                       d_out);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t fme_launch_mc(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_cb, const uint8_t* d_cr,
+                          const fme_mc_pu* d_pus, int n, int16_t* d_y, int16_t* d_cbOut, int16_t* d_crOut,
+                          cudaStream_t s, int64_t* launches) {
+  if (n <= 0) return cudaSuccess;
+  k_mc<<<n, 256, 0, s>>>(d_pus, n, d_planes, d_cb, d_cr, g, d_y, d_cbOut, d_crOut);
+  ++*launches;
+  return cudaGetLastError();
+}

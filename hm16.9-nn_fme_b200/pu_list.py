@@ -1,0 +1,133 @@
+"""PU batch records and the synthetic workloads of SURVEY.md section 8d.
+
+The record layouts mirror `fme_pu` / `fme_result` / `fme_mc_pu` in include/fme_b200.h.  The PU list is
+what the reference's RD recursion visits for every fully-inside CU at depths 0-3 (TEncCu.cpp:451-614):
+2Nx2N, 2NxN x2, Nx2N x2 (5 PUs per CU; counts 10 295 / 214 500 / 860 100 per frame and reference for
+416x240 / 1080p / 2160p), optionally plus the AMP shapes.
+"""
+import numpy as np
+
+PU_DTYPE = np.dtype(
+    [("x", "<i2"), ("y", "<i2"), ("w", "u1"), ("h", "u1"), ("refSlot", "u1"), ("flags", "u1"),
+     ("mvIntX", "<i2"), ("mvIntY", "<i2"), ("mvPredX", "<i2"), ("mvPredY", "<i2"), ("err", "<u4", (9,))],
+    align=True)
+RESULT_DTYPE = np.dtype(
+    [("halfX", "i1"), ("halfY", "i1"), ("qterX", "i1"), ("qterY", "i1"), ("cost", "<u4"),
+     ("nnHalfX", "i1"), ("nnHalfY", "i1"), ("nnQterX", "i1"), ("nnQterY", "i1"), ("nnClass", "u1"),
+     ("pad", "u1", (3,))],
+    align=True)
+MC_PU_DTYPE = np.dtype(
+    [("x", "<i2"), ("y", "<i2"), ("w", "u1"), ("h", "u1"), ("refSlot", "u1"), ("flags", "u1"),
+     ("mvX", "<i2"), ("mvY", "<i2")], align=True)
+assert PU_DTYPE.itemsize == 52 and RESULT_DTYPE.itemsize == 16 and MC_PU_DTYPE.itemsize == 12
+
+# lowdelay_P GOP entry QP offsets / factors (cfg/encoder_lowdelay_P_main.cfg:24-27)
+LOWDELAY_P_QP_OFFSETS = (3, 2, 3, 1)
+LOWDELAY_P_QP_FACTORS = (0.4624, 0.4624, 0.4624, 0.578)
+
+
+def slice_lambda(qp, qp_offset=3, qp_factor=0.4624, depth=0, had_me=True):
+    """TEncSlice.cpp:290-325: lambda = QPfactor * 2^((QP + offset - 12)/3) [* clip(2,4,(qp-12)/6) if depth>0]
+    [* 0.95 if HadamardME is off]."""
+    qp_temp = float(qp + qp_offset) - 12.0
+    lam = qp_factor * 2.0 ** (qp_temp / 3.0)
+    if depth > 0:
+        lam *= min(max(qp_temp / 6.0, 2.0), 4.0)
+    if not had_me:
+        lam *= 0.95
+    return lam
+
+
+def enumerate_pus(width, height, ctu=64, min_cu=8, amp=False):
+    """(x, y, w, h) int arrays for one frame and one reference."""
+    xs, ys, ws, hs = [], [], [], []
+
+    def add(x, y, w, h):
+        xs.append(x.ravel()); ys.append(y.ravel())
+        ws.append(np.full(x.size, w)); hs.append(np.full(x.size, h))
+
+    cu = ctu
+    while cu >= min_cu:
+        nx, ny = width // cu, height // cu
+        gy, gx = np.meshgrid(np.arange(ny) * cu, np.arange(nx) * cu, indexing="ij")
+        add(gx, gy, cu, cu)                                   # 2Nx2N
+        add(gx, gy, cu, cu // 2); add(gx, gy + cu // 2, cu, cu // 2)   # 2NxN
+        add(gx, gy, cu // 2, cu); add(gx + cu // 2, gy, cu // 2, cu)   # Nx2N
+        if amp and cu >= 16:
+            q = cu // 4
+            add(gx, gy, cu, q); add(gx, gy + q, cu, cu - q)            # 2NxnU
+            add(gx, gy, cu, cu - q); add(gx, gy + cu - q, cu, q)       # 2NxnD
+            add(gx, gy, q, cu); add(gx + q, gy, cu - q, cu)            # nLx2N
+            add(gx, gy, cu - q, cu); add(gx + cu - q, gy, q, cu)       # nRx2N
+        cu //= 2
+    return (np.concatenate(xs).astype(np.int16), np.concatenate(ys).astype(np.int16),
+            np.concatenate(ws).astype(np.uint8), np.concatenate(hs).astype(np.uint8))
+
+
+def _lowpass_noise(h, w, rng):
+    """Low-pass-filtered uniform noise in 0..255 (three separable box blurs via running sums)."""
+    a = rng.uniform(0.0, 1.0, (h, w)).astype(np.float32)
+    for r in (9, 5, 3):
+        for axis in (1, 0):
+            p = np.concatenate([np.take(a, range(-r, 0), axis=axis), a, np.take(a, range(0, r + 1), axis=axis)], axis=axis)
+            cs = np.cumsum(p, axis=axis, dtype=np.float64)
+            n = a.shape[axis]
+            hi = np.take(cs, range(2 * r + 1, 2 * r + 1 + n), axis=axis)
+            lo = np.take(cs, range(0, n), axis=axis)
+            a = ((hi - lo) / (2 * r + 1)).astype(np.float32)
+    a = (a - a.min()) / max(float(a.max() - a.min()), 1e-6)
+    return a * 255.0
+
+
+def synth_frames(width, height, n_refs=4, seed=1000):
+    """Source frame + n_refs reference frames (uint8) and the true motion (dx, dy) in pixels of each
+    reference relative to the source: ref_k(x, y) ~ org(x - dx_k, y - dy_k), (dx, dy) = (1.25, 0.75)*(k+1)."""
+    rng = np.random.default_rng(seed)
+    pad = 16
+    base = _lowpass_noise(height + 2 * pad, width + 2 * pad, rng)
+    # add texture so that SATD/SSE surfaces are not degenerate
+    base = np.clip(base + rng.normal(0.0, 6.0, base.shape), 0, 255).astype(np.float32)
+    org = np.clip(np.rint(base[pad:pad + height, pad:pad + width]), 0, 255).astype(np.uint8)
+    refs, motions = [], []
+    for k in range(n_refs):
+        dx, dy = 1.25 * (k + 1), 0.75 * (k + 1)
+        ix, iy = int(np.floor(dx)), int(np.floor(dy))
+        fx, fy = dx - ix, dy - iy
+        # ref(x, y) = base(x - dx, y - dy), bilinear
+        y0, x0 = pad - iy - 1, pad - ix - 1
+        a = base[y0:y0 + height + 1, x0:x0 + width + 1]
+        top = a[:-1, :-1] * fx + a[:-1, 1:] * (1 - fx)
+        bot = a[1:, :-1] * fx + a[1:, 1:] * (1 - fx)
+        r = top * fy + bot * (1 - fy)
+        r = r + rng.normal(0.0, 2.0, r.shape)
+        refs.append(np.clip(np.rint(r), 0, 255).astype(np.uint8))
+        motions.append((dx, dy))
+    return org, refs, motions
+
+
+def make_records(width, height, motions, seed=0, amp=False, err_on_gpu=False):
+    """The per-frame PU batch: every PU of enumerate_pus() against every reference slot.
+    intMV = round(true motion) + U{-1,0,1}; mvPred = 4*intMV + U{-6..6}."""
+    rng = np.random.default_rng(seed)
+    x, y, w, h = enumerate_pus(width, height, amp=amp)
+    n1 = len(x)
+    recs = np.zeros(n1 * len(motions), PU_DTYPE)
+    for s, (dx, dy) in enumerate(motions):
+        r = recs[s * n1:(s + 1) * n1]
+        r["x"], r["y"], r["w"], r["h"] = x, y, w, h
+        r["refSlot"] = s
+        r["flags"] = 0x02 if err_on_gpu else 0
+        mx = int(np.rint(dx)) + rng.integers(-1, 2, n1)
+        my = int(np.rint(dy)) + rng.integers(-1, 2, n1)
+        r["mvIntX"], r["mvIntY"] = mx, my
+        r["mvPredX"] = mx * 4 + rng.integers(-6, 7, n1)
+        r["mvPredY"] = my * 4 + rng.integers(-6, 7, n1)
+    return recs
+
+
+def band_of_pus(recs, band, n_bands, height, ctu=64):
+    """CTU-row band sharding: band b owns CTU rows [b*R, (b+1)*R), R = ceil(rows/n_bands)."""
+    rows = (height + ctu - 1) // ctu
+    per = (rows + n_bands - 1) // n_bands
+    ctu_row = recs["y"] // ctu
+    return recs[(ctu_row >= band * per) & (ctu_row < (band + 1) * per)]

@@ -1,0 +1,180 @@
+/* fme_b200.h -- C ABI of the B200-native fractional-pel motion-estimation engine.
+ *
+ * Drop-in boundary for the fractional-ME hot path of HM-16.9-NN_FME.
+ * The reference has no FFI; its "API" for this path is a set of C++ member functions.  Each
+ * entry point below names the reference interface it replaces (paths relative to
+ * /root/reference/source/Lib).  A header-only C++ adaptor that reproduces the reference's own
+ * signatures on top of these calls is in hm16.9-nn_fme_b200/adaptor/fme_hm_adaptor.h;
+ * INTEGRATION.md shows the binding a maintainer would add to TEncSearch.cpp.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Every call returns FME_OK (0) or a
+ * negative fme_status; fme_last_error() gives the text of the last failure on the calling thread.
+ * All host buffers are caller-owned.  One fme_ctx per encoder instance; calls on one ctx are
+ * serialised by the caller (the reference is single-threaded, TEncSearch.cpp:55-77).
+ * There is NO CPU fallback: if no sm_100 device is usable, fme_create fails.
+ *
+ * Sample types: Pel = int16_t (TLibCommon/TypeDef.h:228), Distortion = uint32_t (TypeDef.h:239),
+ * TComMv components = int16_t (TLibCommon/TComMv.h:53-54).  Frame-level passes are 8-bit 4:2:0
+ * (RExt__HIGH_BIT_DEPTH_SUPPORT = 0, TypeDef.h:118); block-level filters accept bitDepth 8..12.
+ */
+#ifndef FME_B200_H
+#define FME_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fme_ctx fme_ctx;
+
+typedef enum fme_status {
+  FME_OK = 0,
+  FME_ERR_INVALID = -1,   /* bad argument */
+  FME_ERR_CUDA = -2,      /* CUDA runtime/driver failure (text in fme_last_error) */
+  FME_ERR_NO_DEVICE = -3, /* no usable sm_100 GPU: the engine has no CPU path */
+  FME_ERR_STATE = -4,     /* call order violated (e.g. submit before upload_ref / set_slice) */
+  FME_ERR_IO = -5         /* weight file could not be read / parsed */
+} fme_status;
+
+/* fme_submit modes (SURVEY.md section 7 "both run" quirk, TEncSearch.cpp:4534-4597) */
+#define FME_MODE_STD 1  /* standard interpolate-and-search FME: half/qter MV + cost              */
+#define FME_MODE_NN 2   /* NN_pred only                                                            */
+#define FME_MODE_BOTH 3 /* master behaviour: standard cost AND NN MV                               */
+
+/* fme_pu.flags */
+#define FME_PU_LOSSLESS 0x01 /* bIsLosslessCoded: SAD instead of Hadamard (TEncSearch.cpp:5258, 1604) */
+#define FME_PU_ERR_ON_GPU 0x02 /* err[] is ignored; the 3x3 integer error surface is computed on the
+                                  device by the K0 pass (TEncSearch.cpp:5037-5050 semantics)         */
+
+typedef struct fme_config {
+  int32_t device;       /* CUDA device ordinal */
+  int32_t width;        /* luma picture width  (TComPicYuv) */
+  int32_t height;       /* luma picture height */
+  int32_t margin;       /* luma margin of the padded reference planes; reference uses 80
+                           (TComPicYuv.cpp:94-95).  Must be a multiple of 16, >= 16. */
+  int32_t bitDepth;     /* 8 */
+  int32_t numRefSlots;  /* reference pictures resident at once (lowdelay_P: 4) */
+  int32_t maxPUs;       /* capacity of one fme_submit batch */
+  int32_t useHadME;     /* HadamardME cfg flag (TEncCfg getUseHADME, TEncSearch.cpp:1604) */
+  int32_t fen;          /* FEN / FastInterSearchMode 1|3: row-subsampled SAD in integer ME
+                           (TEncSearch.cpp:1158-1164); only used by the K0 error-surface pass */
+  int32_t reserved[7];
+} fme_config;
+
+/* One PU's integer-ME hand-off: what xMotionEstimation has in hand at
+ * TEncSearch.cpp:4534 / 4541.  err[] is the raster 3x3 integer error grid [TL,T,TR,L,C,R,BL,B,BR]:
+ * array_e[0..3], C, array_e[4..7] (TEncSearch.cpp:88, 1341-1376, 5049-5050). */
+typedef struct fme_pu {
+  int16_t x, y;             /* PU top-left luma sample in the picture */
+  uint8_t w, h;             /* PU size (iRoiWidth, iRoiHeight, TEncSearch.cpp:4460) */
+  uint8_t refSlot;          /* which uploaded reference picture */
+  uint8_t flags;            /* FME_PU_* */
+  int16_t mvIntX, mvIntY;   /* best integer MV, full-pel units (rcMv at TEncSearch.cpp:4534) */
+  int16_t mvPredX, mvPredY; /* predictor in quarter-pel units (m_mvPredictor, TComRdCost.h:163) */
+  uint32_t err[9];
+} fme_pu; /* 52 bytes */
+
+typedef struct fme_result {
+  int8_t halfX, halfY, qterX, qterY;         /* rcMvHalf, rcMvQter in {-1,0,1} (TEncSearch.h:423-432) */
+  uint32_t cost;                             /* ruiCost: best quarter-stage cost incl. MV bits         */
+  int8_t nnHalfX, nnHalfY, nnQterX, nnQterY; /* MVX_HALF.. (TEncSearch.cpp:55, 136-193)                */
+  uint8_t nnClass;                           /* NN_out, 0..48                                          */
+  uint8_t pad[3];
+} fme_result; /* 16 bytes */
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+int fme_create(const fme_config* cfg, fme_ctx** out);
+void fme_destroy(fme_ctx* ctx);
+const char* fme_last_error(void);
+const char* fme_version(void);
+/* Use an existing CUDA stream (cudaStream_t passed as void*) for all work of this ctx; NULL
+ * restores the ctx's own stream.  Lets a host framework time the kernels with its own events. */
+int fme_set_stream(fme_ctx* ctx, void* cudaStream);
+int fme_synchronize(fme_ctx* ctx);
+
+/* ---- per-sequence / per-slice state ------------------------------------------------------ */
+/* NN weights: replaces the Eigen comma initialisers of TEncSearch::init (TEncSearch.cpp:470-1073).
+ * blob = "FMNN" container (see hm16.9-nn_fme_b200/nn_weights.py); csv dir = DL/blowing/<qp>. */
+int fme_set_nn_weights(fme_ctx* ctx, const void* blob, size_t bytes);
+int fme_load_nn_csv_dir(fme_ctx* ctx, const char* dir);
+/* Motion lambda: replaces TComRdCost::setLambda + selectMotionLambda(true,0,false)
+ * (TComRdCost.cpp:104-117, TComRdCost.h:159).  Builds cost[bits] = uint32((65536*sqrt(lambda)*bits)/65536.0)
+ * on the host with the reference's exact double expression (TComRdCost.h:165-169). */
+int fme_set_slice(fme_ctx* ctx, double lambda);
+
+/* ---- frame data --------------------------------------------------------------------------- */
+/* Reference picture: y points at picture sample (0,0) of a TComPicYuv luma plane (Pel, stride in
+ * samples).  Only the width x height picture area is read; the margin is regenerated on the device
+ * by edge replication, which is what TComPicYuv::extendPicBorder (TComPicYuv.cpp:229-276) stores.
+ * Runs the K1 pass: all 15 sub-pel planes of SURVEY.md A.1 (replaces xExtDIFUpSamplingH/Q,
+ * TEncSearch.cpp:6331-6532, and their filterHor/filterVer calls). */
+int fme_upload_ref(fme_ctx* ctx, int slot, const int16_t* y, int stride);
+int fme_upload_ref_u8(fme_ctx* ctx, int slot, const uint8_t* y, int stride);
+/* Source picture (pcYuvOrg / TComPattern key, TEncSearch.cpp:4474-4479). */
+int fme_upload_org(fme_ctx* ctx, const int16_t* y, int stride);
+int fme_upload_org_u8(fme_ctx* ctx, const uint8_t* y, int stride);
+
+/* ---- the batched search -------------------------------------------------------------------- */
+/* Replaces, for n PUs at once, xPatternSearchFracDIF (TEncSearch.cpp:5232-5269, mode bit 0) and
+ * NN_pred (TEncSearch.cpp:85-204, mode bit 1).  Synchronous: host records in, host results out. */
+int fme_submit(fme_ctx* ctx, const fme_pu* pus, int n, fme_result* out, int mode);
+/* Asynchronous halves for pipelining: records/results in pinned host memory owned by the caller.
+ * fme_submit_async enqueues H2D + kernels + D2H on the ctx stream; fme_synchronize completes it. */
+int fme_submit_async(fme_ctx* ctx, const fme_pu* pus, int n, fme_result* out, int mode);
+/* Device-resident variant: d_pus / d_out are device pointers; nothing is copied. */
+int fme_submit_device(fme_ctx* ctx, const fme_pu* d_pus, int n, fme_result* d_out, int mode);
+/* Re-run K1 on the reference already resident in `slot` (device-resident benchmarking). */
+int fme_interp_slot(fme_ctx* ctx, int slot);
+/* Device-to-device upload of an 8-bit picture (d_y: device pointer, pitch in bytes), then K1.
+ * Used with torch/NCCL buffers in the multi-GPU banded mode. */
+int fme_upload_ref_device_u8(fme_ctx* ctx, int slot, const uint8_t* d_y, int pitch);
+int fme_upload_org_device_u8(fme_ctx* ctx, const uint8_t* d_y, int pitch);
+/* K0: fill fme_pu.err[] of device-resident records from the 3x3 integer error surface
+ * (xTZ8PointSquareSearch(save=true) metric, TEncSearch.cpp:1085-1166, 5037-5050). */
+int fme_int_surface_device(fme_ctx* ctx, fme_pu* d_pus, int n);
+
+/* ---- block-level parity entry points ------------------------------------------------------- */
+/* TComInterpolationFilter::filterHor / filterVer (TComInterpolationFilter.cpp:341-394).
+ * comp: 0 = luma (8-tap, frac 0..3), 1/2 = chroma 4:2:0 (4-tap, frac 0..7).  src must be readable
+ * over the taps' support exactly as in the reference (3 left/4 right, 1/2 for chroma). */
+int fme_filter_hor(fme_ctx* ctx, int comp, const int16_t* src, int srcStride, int16_t* dst, int dstStride, int w,
+                   int h, int frac, int isLast, int bitDepth);
+int fme_filter_ver(fme_ctx* ctx, int comp, const int16_t* src, int srcStride, int16_t* dst, int dstStride, int w,
+                   int h, int frac, int isFirst, int isLast, int bitDepth);
+/* DistParam::DistFunc (TComRdCost.h:60-108; TComRdCost.cpp:359-1495) for nBlocks independent block
+ * pairs of one shape.  kind: 0 = integer-ME metric (SSE, or SAD12/24/48 with subShift), 1 = HADs,
+ * 2 = SADs.  org/cur hold nBlocks blocks back to back, each h rows of `stride` samples. */
+int fme_dist(fme_ctx* ctx, int kind, const int16_t* org, int orgStride, const int16_t* cur, int curStride, int w,
+             int h, int bitDepth, int subShift, int nBlocks, uint32_t* out);
+/* getCostOfVectorWithPredictor (TComRdCost.h:165-174) with the current slice lambda. */
+int fme_mv_cost(fme_ctx* ctx, int x, int y, int scale, int predX, int predY, uint32_t* out);
+
+/* ---- motion compensation ("next" row f2) ------------------------------------ */
+/* Chroma reference planes for MC (Pel, picture sample (0,0), chroma stride; 4:2:0). */
+int fme_upload_ref_chroma(fme_ctx* ctx, int slot, const int16_t* cb, const int16_t* cr, int stride);
+/* xPredInterBlk, uni-prediction (TComPrediction.cpp:643-681) for n PUs: mv = quarter-pel luma MV.
+ * dstY: n blocks back to back, each 64x64 Pel (stride 64); dstCb/dstCr: each 32x32 (stride 32). */
+typedef struct fme_mc_pu {
+  int16_t x, y;
+  uint8_t w, h, refSlot, flags;
+  int16_t mvX, mvY;
+} fme_mc_pu; /* 12 bytes */
+int fme_mc(fme_ctx* ctx, const fme_mc_pu* pus, int n, int16_t* dstY, int16_t* dstCb, int16_t* dstCr);
+
+/* ---- introspection (parity tests, profiling) ------------------------------------------------ */
+/* Copy padded sub-pel plane P[fy][fx] of `slot` to host: (height+2*margin) rows of (width+2*margin) bytes. */
+int fme_download_plane(fme_ctx* ctx, int slot, int fy, int fx, uint8_t* dst, int dstStride);
+/* Milliseconds spent in the kernels of the last fme_submit* / fme_upload_ref* / fme_interp_slot call
+ * (CUDA events on the ctx stream): k[0]=K1 interp, k[1]=K2 refine, k[2]=K3 NN, k[3]=K0 surface. */
+int fme_last_kernel_ms(fme_ctx* ctx, float k[4]);
+/* Number of kernel launches issued by this ctx since creation. */
+int64_t fme_launch_count(fme_ctx* ctx);
+/* Enable/disable per-kernel event timing (adds event records; default off). */
+int fme_set_profiling(fme_ctx* ctx, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

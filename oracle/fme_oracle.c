@@ -423,6 +423,15 @@ int orc_nn_pred(const void* blob, const uint32_t err9[9], int puHeight, int puWi
 
 /* ---------------------------------------------------------------- PU-list runner */
 
+/* fill err[] of every record with the 3x3 integer error surface around its integer MV */
+void orc_fill_surface(const orc_pel* org, int os, const orc_pel* const* refs, int rs, orc_pu* pus, int n, int fen) {
+  for (int i = 0; i < n; ++i) {
+    orc_pu* p = &pus[i];
+    orc_int_surface(org + p->y * os + p->x, os, p->w, p->h,
+                    refs[p->refSlot] + (p->y + p->mvIntY) * rs + p->x + p->mvIntX, rs, fen, p->err);
+  }
+}
+
 void orc_run_pu_list(const orc_pel* org, int os, const orc_pel* const* refs, int rs, const orc_pu* pus, int n, int mode,
                      double lambda, int useHad, const void* nnBlob, orc_result* out) {
   for (int i = 0; i < n; ++i) {

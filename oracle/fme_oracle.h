@@ -104,6 +104,8 @@ typedef struct {
   int8_t nnHalfX, nnHalfY, nnQterX, nnQterY;
   uint8_t nnClass, pad[3];
 } orc_result;
+void orc_fill_surface(const orc_pel* org, int orgStride, const orc_pel* const* refs, int refStride, orc_pu* pus, int n,
+                      int fen);
 /* mode bit0 = standard FME, bit1 = NN_pred.  refs[s] -> picture sample (0,0) of padded plane s. */
 void orc_run_pu_list(const orc_pel* org, int orgStride, const orc_pel* const* refs, int refStride, const orc_pu* pus,
                      int n, int mode, double lambda, int useHad, const void* nnBlob, orc_result* out);

@@ -76,6 +76,7 @@ class Oracle:
                                       C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_subpel_plane.argtypes = [c_short_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                        c_short_p, C.c_int]
+        L.orc_fill_surface.argtypes = [c_short_p, C.c_int, C.POINTER(c_short_p), C.c_int, C.c_void_p, C.c_int, C.c_int]
         L.orc_int_surface.argtypes = [c_short_p, C.c_int, C.c_int, C.c_int, c_short_p, C.c_int, C.c_int, c_uint_p]
 
     def filter_hor(self, is_luma, src, src_off, sstride, w, h, frac, is_last, bit_depth=8):
@@ -129,6 +130,12 @@ class Oracle:
         buf = C.create_string_buffer(bytes(blob), len(blob))
         cls = self.L.orc_nn_pred(buf, e, h, w, logits, hxy, qxy)
         return cls, np.array(logits[:49], np.float32), (hxy[0], hxy[1]), (qxy[0], qxy[1])
+
+    def fill_surface(self, org, ostride, refs, ref_offs, rstride, pus, fen=1):
+        arr = (c_short_p * len(refs))(*[_ptr(r, o) for r, o in zip(refs, ref_offs)])
+        assert pus.flags.c_contiguous and pus.dtype == PU_DTYPE
+        self.L.orc_fill_surface(_ptr(org), ostride, arr, rstride, C.c_void_p(pus.ctypes.data), len(pus), fen)
+        return pus
 
     def run_pu_list(self, org, ostride, refs, ref_offs, rstride, pus, mode, lam, use_had, blob):
         """org: int16 plane with picture (0,0) at flat offset 0; refs: list of padded int16 planes."""
@@ -234,3 +241,30 @@ def reference():
         p = build_reference()
         _REFERENCE = Reference(p) if p else None
     return _REFERENCE
+
+
+def pad_plane(pic, margin):
+    """TComPicYuv-style padded Pel plane: picture + `margin` edge-replicated samples (TComPicYuv.cpp:229-276)."""
+    return np.ascontiguousarray(np.pad(np.asarray(pic).astype(np.int16), margin, mode="edge"))
+
+
+class CpuFrame:
+    """Host-side frame set shared by the oracle / reference runners in the tests and the CPU baseline."""
+
+    def __init__(self, org_u8, refs_u8, margin=80):
+        self.margin = margin
+        self.h, self.w = org_u8.shape
+        self.org = np.ascontiguousarray(org_u8.astype(np.int16))
+        self.refs = [pad_plane(r, margin) for r in refs_u8]
+        self.rstride = self.w + 2 * margin
+        self.ref_offs = [margin * self.rstride + margin] * len(self.refs)
+
+    def oracle_fill_surface(self, pus, fen=1):
+        return oracle().fill_surface(self.org, self.w, self.refs, self.ref_offs, self.rstride, pus, fen)
+
+    def oracle_run(self, pus, mode, lam, use_had, blob):
+        return oracle().run_pu_list(self.org, self.w, self.refs, self.ref_offs, self.rstride, pus, mode, lam,
+                                    int(use_had), blob)
+
+    def reference_run(self, pus, mode):
+        return reference().run_pu_list(self.org, self.w, self.refs, self.ref_offs, self.rstride, pus, mode)

@@ -1,0 +1,75 @@
+"""CPU: the C-ABI library loads and exports every symbol include/fme_b200.h declares; record layouts match;
+the product refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from common import fme
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "fme_b200.h")
+
+
+def header_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fme_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported():
+    import __graft_entry__ as ge
+    ge.build()
+    lib = fme.load_library()
+    names = header_functions()
+    assert len(names) >= 28
+    for n in names:
+        assert hasattr(lib, n), "missing export: " + n
+    assert sorted(fme.EXPORTS) == names
+
+
+def test_record_layouts_match_header():
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "fme_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(fme_pu), offsetof(fme_pu, mvIntX), offsetof(fme_pu, err),
+         sizeof(fme_result), offsetof(fme_result, cost), offsetof(fme_result, nnClass), sizeof(fme_mc_pu), sizeof(fme_config));
+  return 0;
+}'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+        vals = list(map(int, subprocess.check_output([os.path.join(d, "t")]).split()))
+    dt, rt = fme.PU_DTYPE, fme.RESULT_DTYPE
+    assert vals == [dt.itemsize, dt.fields["mvIntX"][1], dt.fields["err"][1], rt.itemsize, rt.fields["cost"][1],
+                    rt.fields["nnClass"][1], fme.MC_PU_DTYPE.itemsize, C.sizeof(fme.FmeConfig)]
+
+
+def test_oracle_record_layout_matches_product():
+    import oracle_bindings as ob
+    assert ob.PU_DTYPE == fme.PU_DTYPE and ob.RESULT_DTYPE == fme.RESULT_DTYPE
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the engine must fail loudly, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(fme.FmeError) as e:
+        fme.Fme(64, 64)
+    assert "no CPU path" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_never_references_the_oracle():
+    pkg = os.path.join(ROOT, "hm16.9-nn_fme_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dp, f), errors="ignore").read()
+                assert "libfme_oracle" not in text and "libhmref" not in text and "oracle_bindings" not in text, f

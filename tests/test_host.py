@@ -1,0 +1,77 @@
+"""CPU: host-side logic (PU lists, weight containers, lambda, sharding incl. a 2-rank gloo run)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from common import fme
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_pu_list_counts_match_survey():
+    for (w, h), n in (((416, 240), 10295), ((1920, 1080), 214500), ((3840, 2160), 860100)):
+        x, y, pw, ph = fme.pu_list.enumerate_pus(w, h)
+        assert len(x) == n
+        assert int((x.astype(int) + pw <= w).all()) and int((y.astype(int) + ph <= h).all())
+    # measured PU histogram of the reference encode: 8x4 == 4x8 == 2 * 8x8 etc.
+    x, y, pw, ph = fme.pu_list.enumerate_pus(416, 240)
+    cnt = lambda a, b: int(((pw == a) & (ph == b)).sum())
+    assert cnt(8, 4) == cnt(4, 8) == 2 * cnt(8, 8) and cnt(64, 64) == 18 and cnt(8, 8) == 1560
+
+
+def test_amp_shapes_are_hevc_pu_sizes():
+    x, y, pw, ph = fme.pu_list.enumerate_pus(128, 128, amp=True)
+    shapes = set(zip(pw.tolist(), ph.tolist()))
+    for s in ((64, 16), (64, 48), (16, 64), (48, 64), (32, 8), (32, 24), (8, 32), (24, 32), (16, 4), (16, 12), (4, 16), (12, 16)):
+        assert s in shapes
+
+
+def test_slice_lambda_matches_reference_formula():
+    assert abs(fme.pu_list.slice_lambda(22) - 9.3213998955) < 1e-9
+    import oracle_bindings as ob
+    L = ob.oracle().L
+    for qp in (22, 27, 32, 37):
+        for off, fac in zip(fme.pu_list.LOWDELAY_P_QP_OFFSETS, fme.pu_list.LOWDELAY_P_QP_FACTORS):
+            for had in (True, False):
+                assert fme.pu_list.slice_lambda(qp, off, fac, 0, had) == L.orc_slice_lambda(qp + off, fac, 0, int(had))
+
+
+def test_weight_blobs():
+    nw = fme.nn_weights
+    for qp in nw.QPS:
+        blob = nw.load_blob(qp)
+        h = nw.parse_header(blob)
+        assert h["hidden"] == [22, 20] and h["nOut"] == 49 and h["nEmb"] == 2
+        assert nw.flops_per_pu(blob) == 3588
+        assert len(blob) == 64 + 4 * (27 + 64 + 22 * 17 + 66 + 20 * 22 + 60 + 49 * 20 + 49)
+    assert nw.select_qp(30) == 22 and nw.select_qp(27) == 27  # TEncSearch.cpp:925 fallback
+    b3 = nw.synthetic_blob((40, 40, 40), n_emb=0, seed=1)
+    assert nw.parse_header(b3)["hidden"] == [40, 40, 40] and nw.flops_per_pu(b3) == 11040
+    if os.path.isdir("/root/reference/DL/blowing/22"):
+        assert nw.blob_from_csv_dir("/root/reference/DL/blowing/22") == nw.load_blob(22)
+
+
+def test_band_sharding_partitions_the_list():
+    org, refs, motions = fme.pu_list.synth_frames(256, 192, n_refs=1, seed=3)
+    recs = fme.pu_list.make_records(256, 192, motions)
+    for nb in (1, 2, 3, 4, 8):
+        parts = [fme.pu_list.band_of_pus(recs, b, nb, 192) for b in range(nb)]
+        assert sum(len(p) for p in parts) == len(recs)
+        for b, p in enumerate(parts):
+            if len(p):
+                per = (3 + nb - 1) // nb
+                assert (p["y"] // 64 >= b * per).all() and (p["y"] // 64 < (b + 1) * per).all()
+
+
+def test_two_rank_gloo_band_merge():
+    """world_size-2 run of the banded host logic over gloo: each rank owns a CTU-row band, computes its PUs
+    (oracle as the stand-in compute on CPU), results gathered on rank 0 equal the single-process run."""
+    script = os.path.join(ROOT, "tests", "gloo_band_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29541")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29541", script],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "BAND_MERGE_OK" in out.stdout
