@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py -- fractional-ME throughput of the B200 engine on BASELINE.json's headline workload.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode replica|banded]
+
+A "step" is one pass of the hot path over one coded frame of the 1080p QP22 lowdelay_P workload
+(BASELINE.json configs[2] at QP22): K1 interpolates the one reference picture that is new for
+this frame, then K2 (standard FME: 9 half + 8 quarter SATD candidates) and K3 (NN_pred) run over the frame's
+PU batch, 4 references x 214 500 PUs = 858 000 PUs, mode BOTH (what the reference's master does for every PU,
+TEncSearch.cpp:4534-4541).
+
+  value      whole-job PUs/s with inputs resident in HBM (device pointers; nothing copied)
+  e2e        the same through the host-buffer C ABI calls a reference adaptor makes (fme_upload_ref,
+             fme_upload_org, fme_submit_async + fme_synchronize), pinned host memory, copies inside the timed region
+  roofline   dominant kernel (K2) and per-kernel figures, algorithmic bytes/flops from DESIGN.md
+  cpu_baseline  the reference's own compiled xPatternSearchFracDIF + NN_pred (oracle/_ref/libhmref.so), or the
+             C port when that library is absent, single thread, bounded sample, rank 0 at N=1 only
+
+--impl reference times the reference's CPU implementation on all host cores (one process per core, the
+reference is single-threaded with global state) on the same workload and prints the same JSON line.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, N_REFS, QP = 1920, 1080, 4, 22
+W4K, H4K = 3840, 2160
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def build_workload(fme, width, height, n_sets, seed):
+    """n_sets independent frame sets (source + 4 references + PU batch).  err[] is left for the K0 pass
+    (run once, outside the timed region, so that the records the timed region consumes are complete)."""
+    sets = []
+    for i in range(n_sets):
+        org, refs, motions = fme.pu_list.synth_frames(width, height, n_refs=N_REFS, seed=seed + i)
+        recs = fme.pu_list.make_records(width, height, motions, seed=seed + 100 + i, err_on_gpu=True)
+        sets.append((org, refs, recs))
+    return sets
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import fme_loader
+    fme = fme_loader.load()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 through torch.distributed.run (see module docstring)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    banded = args.mode == "banded"
+    width, height = (W4K, H4K) if banded else (W, H)
+
+    n_sets = 3
+    seed = 2000 + QP if not banded else 3000
+    # replica mode: every GPU runs an independent (sequence, QP) job -> different content per rank
+    sets = build_workload(fme, width, height, n_sets, seed + (0 if banded else 1000 * rank))
+    n_full = len(sets[0][2])
+    if banded:
+        sets = [(o, r, np.ascontiguousarray(fme.pu_list.band_of_pus(rc, rank, world, height))) for (o, r, rc) in sets]
+    n_pus = max(len(s[2]) for s in sets)
+    lam = fme.pu_list.slice_lambda(QP)
+    blob = fme.nn_weights.load_blob(QP)
+
+    eng = fme.Fme(width, height, num_ref_slots=N_REFS, max_pus=n_pus, device=local)
+    # a dedicated (non-default) stream shared by torch and the engine, so that torch's CUDA events see the kernels
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_nn_weights(blob)
+    eng.set_slice(lam)
+
+    # ---- device-resident inputs (torch owns the memory; the engine gets raw pointers) ----
+    d_org = [torch.from_numpy(o).to(dev) for (o, _, _) in sets]
+    d_refs = [[torch.from_numpy(r).to(dev) for r in refs] for (_, refs, _) in sets]
+    d_recs = [torch.from_numpy(rc.view(np.uint8).reshape(len(rc), -1).copy()).to(dev) for (_, _, rc) in sets]
+    d_res = torch.zeros((n_pus, 16), dtype=torch.uint8, device=dev)
+    # references of set 0 resident in all slots; K0 fills err[] of every record set once (untimed)
+    for i, (o, refs, rc) in enumerate(sets):
+        eng.upload_org_device_u8(d_org[i].data_ptr(), width)
+        for s in range(N_REFS):
+            eng.upload_ref_device_u8(s, d_refs[i][s].data_ptr(), width)
+        eng.int_surface_device(d_recs[i].data_ptr(), len(rc))
+    torch.cuda.synchronize(dev)
+    # clear the ERR_ON_GPU flag: the timed region consumes complete records, as a host adaptor would send them
+    h_recs = []
+    for i, (_, _, rc) in enumerate(sets):
+        full = d_recs[i].cpu().numpy().view(fme.PU_DTYPE).reshape(-1).copy()
+        full["flags"] = 0
+        h_recs.append(full)
+        d_recs[i].copy_(torch.from_numpy(full.view(np.uint8).reshape(len(full), -1)))
+    torch.cuda.synchronize(dev)
+
+    def step_device(i):
+        k = i % n_sets
+        slot = i % N_REFS
+        if banded and world > 1:
+            # the rank that "reconstructed" the new reference broadcasts it over NVLink
+            dist.broadcast(d_refs[k][slot], src=i % world)
+        eng.upload_ref_device_u8(slot, d_refs[k][slot].data_ptr(), width)   # D2D + K1
+        eng.upload_org_device_u8(d_org[k].data_ptr(), width)
+        eng.submit_device(d_recs[k].data_ptr(), len(sets[k][2]), d_res.data_ptr(), fme.MODE_BOTH)  # K2 + K3
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        l0 = eng.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, eng.launch_count() - l0
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches = timed(step_device, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+
+    pus_per_step = sum(len(s[2]) for s in sets) / n_sets  # this rank
+    if world > 1:
+        t = torch.tensor([pus_per_step], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        pus_per_step_all = float(t.item())
+    else:
+        pus_per_step_all = pus_per_step
+    value = pus_per_step_all * args.steps / (ms_dev / 1e3)
+    frames_per_step = world if not banded else 1
+
+    # ---- e2e: host buffers through the reference-facing calls ----
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_org16 = [pin(o.astype(np.int16)) for (o, _, _) in sets]           # Pel planes, as TComPicYuv holds them
+    h_ref16 = [[pin(r.astype(np.int16)) for r in refs] for (_, refs, _) in sets]
+    h_pus = [pin(r.view(np.uint8).reshape(len(r), -1)) for r in h_recs]
+    h_out = torch.zeros((n_pus, 16), dtype=torch.uint8).pin_memory()
+    lib, hnd = eng.lib, eng.h
+
+    def step_e2e(i):
+        k = i % n_sets
+        slot = i % N_REFS
+        if banded and world > 1:
+            dist.broadcast(d_refs[k][slot], src=i % world)
+            eng.upload_ref_device_u8(slot, d_refs[k][slot].data_ptr(), width)
+        else:
+            eng._check(lib.fme_upload_ref(hnd, slot, ctypes.c_void_p(h_ref16[k][slot].data_ptr()), width))
+        eng._check(lib.fme_upload_org(hnd, ctypes.c_void_p(h_org16[k].data_ptr()), width))
+        n = len(sets[k][2])
+        eng.submit_async(h_pus[k].data_ptr(), n, h_out.data_ptr(), fme.MODE_BOTH)
+        eng.synchronize()   # the caller reads the step's results here
+        return int(h_out[0, 4])
+
+    ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+    e2e_value = pus_per_step_all * args.steps / (ms_e2e / 1e3)
+    h2d = width * height * 2 * (1 if banded and world > 1 else 2) + int(pus_per_step) * 52
+    d2h = int(pus_per_step) * 16
+
+    # ---- per-kernel times (separate short pass with event pairs around each stage) ----
+    eng.set_profiling(True)
+    kms = {"k1_interp": [], "k2_refine": [], "k3_nn": []}
+    for i in range(6):
+        step_device(i)
+        eng.synchronize()
+        m = eng.last_kernel_ms()
+        if i >= 2:
+            for k in kms:
+                kms[k].append(m[k])
+    eng.set_profiling(False)
+    kavg = {k: float(np.mean(v)) for k, v in kms.items()}
+
+    out = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        wp, hp = width + 160, height + 160
+        k1_bytes = wp * hp * 16                                   # 1 B in + 15 B out per padded sample
+        rc = sets[0][2]
+        pu_px = float((rc["w"].astype(np.int64) * rc["h"]).sum())
+        k2_bytes = 18.0 * pu_px                                   # org once + 17 distinct candidate blocks, u8
+        k3_flops = fme.nn_weights.flops_per_pu(blob) * len(rc)
+        gbs = lambda b, ms: b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        kernels = {
+            "k1_interp": {"ms": kavg["k1_interp"], "bound": "hbm", "achieved": gbs(k1_bytes, kavg["k1_interp"]),
+                          "peak": peak, "unit": "GB/s", "frac": gbs(k1_bytes, kavg["k1_interp"]) / peak,
+                          "alg_bytes": k1_bytes, "note": "incl. the D2D picture copy that precedes the kernel"},
+            "k2_refine": {"ms": kavg["k2_refine"], "bound": "hbm", "achieved": gbs(k2_bytes, kavg["k2_refine"]),
+                          "peak": peak, "unit": "GB/s", "frac": gbs(k2_bytes, kavg["k2_refine"]) / peak,
+                          "alg_bytes": k2_bytes, "int_ops_per_s": 144.0 * pu_px / (kavg["k2_refine"] * 1e-3) if kavg["k2_refine"] > 0 else 0,
+                          "note": "issue-bound integer SATD; HBM fraction reported because the contract asks for it"},
+            "k3_nn": {"ms": kavg["k3_nn"], "bound": "fp32", "achieved": k3_flops / (kavg["k3_nn"] * 1e-3) / 1e12 if kavg["k3_nn"] > 0 else 0,
+                      "unit": "TFLOP/s"},
+        }
+        dom = max(("k1_interp", "k2_refine"), key=lambda k: kavg[k])
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved"], "peak": peak, "unit": "GB/s",
+                    "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src}
+        out = {
+            "metric": "FME PUs/sec at 1080p QP22 (xPatternSearchFracDIF + NN_pred per PU)" if not banded else
+                      "FME PUs/sec at 2160p QP22, CTU-row bands",
+            "value": value, "unit": "PU/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "strong" if banded else "weak", "vs_baseline": None, "dtype": "u8/int32 (SATD), fp32 (NN_pred)",
+            "data": "synthetic", "impl": "b200",
+            "config": {"workload": ("1920x1080 class-B-shaped synthetic, lowdelay_P, QP22, 4 refs, 858000 PUs/frame, mode BOTH"
+                                    if not banded else "3840x2160 synthetic, 4 refs, 3440400 PUs/frame, CTU-row bands + NCCL ref broadcast"),
+                       "pus_per_step_per_gpu": int(pus_per_step), "frames_per_step": frames_per_step,
+                       "parallelism": ("replica x%d (independent sequence jobs, no collective)" % world) if not banded
+                       else ("ctu-row bands x%d, ncclBroadcast of the new reference per frame" % world),
+                       "l2_policy": "inputs larger than L2: each step reads 4x16 planes (%.0f MB) + records, ring of %d frame sets"
+                                    % (4 * 16 * wp * hp / 1e6, n_sets)},
+            "frames_per_sec": frames_per_step * args.steps / (ms_dev / 1e3),
+            "interp_gb_s": kernels["k1_interp"]["achieved"],
+            "e2e": {"value": e2e_value, "unit": "PU/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps, "frames_per_sec": frames_per_step * args.steps / (ms_e2e / 1e3)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "kernels": kernels,
+        }
+        if world == 1:
+            out["cpu_baseline"] = cpu_baseline_single(fme, sets[0], h_recs[0], lam, blob)
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baselines
+# ------------------------------------------------------------------------------------------------
+def _cpu_runner():
+    """(kind, run(frame, recs) -> results) using the reference's compiled code when present, else the C port."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_bindings as ob
+    return ob
+
+
+def cpu_baseline_single(fme, wset, recs, lam, blob, max_pus=214500):
+    """Single-thread reference path on a bounded sample: the PU list of one reference picture."""
+    ob = _cpu_runner()
+    org, refs, _ = wset
+    sample = np.ascontiguousarray(recs[:max_pus])
+    frame = ob.CpuFrame(org, refs)
+    R = ob.reference()
+    t0 = time.perf_counter()
+    if R is not None:
+        R.init(QP, 1, 1)
+        R.set_lambda(lam)
+        frame.reference_run(sample, 3)
+        kind = "reference"
+    else:
+        frame.oracle_run(sample, 3, lam, 1, blob)
+        kind = "port"
+    dt = time.perf_counter() - t0
+    return {"value": len(sample) / dt, "unit": "PU/s", "cores": 1, "kind": kind, "seconds": dt,
+            "host_cpus": os.cpu_count(),
+            "sample": "%d PUs = the 1080p PU list of one reference picture (all 12 PU shapes in frame proportion), "
+                      "xPatternSearchFracDIF then NN_pred per PU%s" % (len(sample), " (NN_pred over the Eigen stand-in)" if kind == "reference" else "")}
+
+
+_REF_JOB = {}
+
+
+def _ref_worker(bounds):
+    """Runs in a forked child: the frame set is inherited through _REF_JOB, only the PU range is passed."""
+    lo, hi = bounds
+    J = _REF_JOB
+    ob = _cpu_runner()
+    if "frame" not in J:
+        J["frame"] = ob.CpuFrame(J["org"], J["refs"])
+        J["R"] = ob.reference()
+        if J["R"] is not None:
+            J["R"].init(QP, 1, 1)
+            J["R"].set_lambda(J["lam"])
+    sub = J["sample"][lo:hi]
+    if J["R"] is not None:
+        J["frame"].reference_run(sub, 3)
+    else:
+        J["frame"].oracle_run(sub, 3, J["lam"], 1, J["blob"])
+    return hi - lo
+
+
+def run_reference(args):
+    """The reference's CPU implementation on all host cores: one process per core over disjoint PU ranges
+    (the reference is single-threaded with process-global NN state, TEncSearch.cpp:55-77)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import fme_loader
+    fme = fme_loader.load()
+    ob = _cpu_runner()
+    org, refs, motions = fme.pu_list.synth_frames(W, H, n_refs=N_REFS, seed=2000 + QP)
+    recs = fme.pu_list.make_records(W, H, motions, seed=2100 + QP)
+    frame = ob.CpuFrame(org, refs)
+    # bounded sample per step: the PU list of one reference picture (214 500 PUs), errors from the CPU path
+    sample = np.ascontiguousarray(recs[:214500])
+    frame.oracle_fill_surface(sample)
+    lam = fme.pu_list.slice_lambda(QP)
+    cores = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    kind = "reference" if ob.reference() is not None else "port"
+    bounds = np.linspace(0, len(sample), cores + 1).astype(int)
+    # interleave shapes across workers: the list is ordered by depth, so stride it instead of slicing
+    perm = np.argsort(np.arange(len(sample)) % cores, kind="stable")
+    sample = np.ascontiguousarray(sample[perm])
+    jobs = [(int(bounds[i]), int(bounds[i + 1])) for i in range(cores)]
+    _REF_JOB.update(org=org, refs=refs, sample=sample, lam=lam, blob=fme.nn_weights.load_blob(QP))
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(cores) as pool:
+        for s in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            pool.map(_ref_worker, jobs)
+            dt = time.perf_counter() - t0
+            if s >= args.warmup:
+                times.append(dt)
+    total = float(np.sum(times))
+    value = len(sample) * len(times) / total
+    print(json.dumps({
+        "impl": "reference", "metric": "FME PUs/sec at 1080p QP22 (xPatternSearchFracDIF + NN_pred per PU)",
+        "value": value, "unit": "PU/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int16/int32 (SATD), fp32 (NN_pred)", "data": "synthetic",
+        "config": {"workload": "1920x1080 class-B-shaped synthetic, lowdelay_P, QP22, 4 refs, 858000 PUs/frame, mode BOTH",
+                   "sample_pus_per_step": int(len(sample))},
+        "frames_per_sec": value / 858000.0,
+        "cpu_baseline": {"value": value, "unit": "PU/s", "cores": cores, "kind": kind,
+                         "sample": "%d PUs per step = the 1080p PU list of one reference picture, split over %d processes"
+                                   % (len(sample), cores)},
+        "e2e": {"value": value, "unit": "PU/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="replica", choices=["replica", "banded"])
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

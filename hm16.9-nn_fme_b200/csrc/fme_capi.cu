@@ -50,6 +50,8 @@ struct fme_ctx {
   size_t pelCapacity = 0;        // in samples
   int16_t* d_pel2 = nullptr;
   size_t pel2Capacity = 0;
+  int16_t* d_pelPic = nullptr;   // Pel picture staging for fme_upload_ref / fme_upload_org
+  size_t pelPicCapacity = 0;
   uint8_t* d_cb = nullptr;       // [slots][Hcp][cPitch]
   uint8_t* d_cr = nullptr;
   fme_pu* d_pus = nullptr;
@@ -60,9 +62,6 @@ struct fme_ctx {
   uint32_t* d_scratchU32 = nullptr;
   size_t scratchU32Capacity = 0;
   FmeK2Scratch k2{};
-  // pinned host staging
-  void* h_stage = nullptr;
-  size_t h_stageBytes = 0;
   // state
   std::vector<char> refValid;
   bool orgValid = false, sliceValid = false, nnValid = false;
@@ -77,19 +76,9 @@ struct fme_ctx {
 
 namespace {
 
-int ensure_pinned(fme_ctx* c, size_t bytes) {
-  if (c->h_stageBytes >= bytes) return FME_OK;
-  if (c->h_stage) cudaFreeHost(c->h_stage);
-  c->h_stage = nullptr;
-  c->h_stageBytes = 0;
-  CU_CHECK(cudaMallocHost(&c->h_stage, bytes));
-  c->h_stageBytes = bytes;
-  return FME_OK;
-}
-
 int ensure_pel(int16_t** p, size_t* cap, size_t samples) {
   if (*cap >= samples) return FME_OK;
-  if (*p) cudaFree(*p);
+  if (*p) cudaFree(*p);  // cudaFree synchronises the device, so in-flight users of the old buffer have drained
   *p = nullptr;
   *cap = 0;
   CU_CHECK(cudaMalloc(p, samples * sizeof(int16_t)));
@@ -107,22 +96,21 @@ int ensure_u32(fme_ctx* c, size_t n) {
   return FME_OK;
 }
 
-// Copy a host picture (Pel or u8, w x h, given stride in samples) into the ctx's u8 staging picture.
-template <typename T>
-int stage_picture(fme_ctx* c, const T* src, int stride, int w, int h, uint8_t* d_dst, int dstPitch) {
+// Copy a host picture (w x h, stride in samples) into a device u8 picture.  No CPU pass over the samples:
+// u8 input is DMA'd straight into place; Pel (int16) input is DMA'd into a device staging plane and narrowed
+// by a kernel.  With pinned caller memory both copies are fully asynchronous.
+int stage_picture(fme_ctx* c, const uint8_t* src, int stride, int w, int h, uint8_t* d_dst, int dstPitch) {
   if (!src || stride < w) return fail(FME_ERR_INVALID, "picture pointer/stride invalid");
-  size_t bytes = (size_t)w * h;
-  // the previous async copy out of the pinned buffer must have drained before we reuse or grow it
-  CU_CHECK(cudaStreamSynchronize(c->stream));
-  int rc = ensure_pinned(c, bytes);
+  CU_CHECK(cudaMemcpy2DAsync(d_dst, dstPitch, src, stride, w, h, cudaMemcpyHostToDevice, c->stream));
+  return FME_OK;
+}
+int stage_picture(fme_ctx* c, const int16_t* src, int stride, int w, int h, uint8_t* d_dst, int dstPitch) {
+  if (!src || stride < w) return fail(FME_ERR_INVALID, "picture pointer/stride invalid");
+  int rc = ensure_pel(&c->d_pelPic, &c->pelPicCapacity, (size_t)w * h);
   if (rc) return rc;
-  uint8_t* hs = static_cast<uint8_t*>(c->h_stage);
-  for (int y = 0; y < h; ++y) {
-    const T* s = src + (size_t)y * stride;
-    uint8_t* d = hs + (size_t)y * w;
-    for (int x = 0; x < w; ++x) d[x] = (uint8_t)s[x];
-  }
-  CU_CHECK(cudaMemcpy2DAsync(d_dst, dstPitch, hs, w, w, h, cudaMemcpyHostToDevice, c->stream));
+  CU_CHECK(cudaMemcpy2DAsync(c->d_pelPic, (size_t)w * 2, src, (size_t)stride * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice,
+                             c->stream));
+  CU_CHECK(fme_launch_pel_to_u8(c->d_pelPic, w, d_dst, dstPitch, w, h, c->stream, &c->launches));
   return FME_OK;
 }
 
@@ -263,10 +251,9 @@ void fme_destroy(fme_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  cudaFree(c->d_planes); cudaFree(c->d_org); cudaFree(c->d_pic); cudaFree(c->d_pel); cudaFree(c->d_pel2);
+  cudaFree(c->d_planes); cudaFree(c->d_org); cudaFree(c->d_pic); cudaFree(c->d_pel); cudaFree(c->d_pel2); cudaFree(c->d_pelPic);
   cudaFree(c->d_cb); cudaFree(c->d_cr); cudaFree(c->d_pus); cudaFree(c->d_res); cudaFree(c->d_nn);
   cudaFree(c->d_costLut); cudaFree(c->d_scratchU32); cudaFree(c->k2.classCount); cudaFree(c->k2.order);
-  if (c->h_stage) cudaFreeHost(c->h_stage);
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
   if (c->ownStream) cudaStreamDestroy(c->ownStream);

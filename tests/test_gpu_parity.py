@@ -1,0 +1,356 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the CPU oracle, the committed reference fixtures and
+size-independent properties at full size.  Bit-exact everywhere (integer work; NN_pred uses the oracle's
+operation order, so classes are compared exactly and the mismatch rate is asserted to be 0)."""
+import numpy as np
+import pytest
+
+import oracle_bindings as ob
+from common import (FILT_OFF, FILT_STRIDE, filter_case_iter, filter_src, fme, golden, golden_recs, golden_res,
+                    nn_fields, std_fields)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def small():
+    """The golden small frame loaded into an engine."""
+    g = golden()
+    recs = golden_recs(g)
+    eng = fme.Fme(128, 96, num_ref_slots=2, max_pus=len(recs) + 64)
+    eng.set_slice(float(g["small_lambda"][0]))
+    eng.upload_org(g["small_org"])
+    for s in range(2):
+        eng.upload_ref(s, g["small_refs"][s])
+    yield eng, g, recs
+    eng.close()
+
+
+# ---------------------------------------------------------------- K1 planes
+def test_k1_planes_bit_exact_small(small, orc):
+    eng, g, _ = small
+    M = 80
+    padded = ob.pad_plane(g["small_refs"][1], M + 8)  # extra ring so that the oracle can filter the whole padded plane
+    S = padded.shape[1]
+    Wp, Hp = 128 + 2 * M, 96 + 2 * M
+    for fy in range(4):
+        for fx in range(4):
+            got = eng.download_plane(1, fy, fx)
+            want = orc.subpel_plane(padded, (M + 8) * S + (M + 8), S, -M, -M, Wp, Hp, fy, fx)
+            assert np.array_equal(got.astype(np.int16), want), (fy, fx)
+
+
+def test_k1_planes_bit_exact_416x240(orc):
+    """Config C2, interpolation half: all 16 planes of a 416x240 reference, incl. the replicated margin."""
+    org, refs, _ = fme.pu_list.synth_frames(416, 240, n_refs=1, seed=1000)
+    eng = fme.Fme(416, 240, num_ref_slots=1, max_pus=16)
+    # upload through the Pel (int16) TComPicYuv-style padded plane this time
+    M = 80
+    eng.upload_ref_padded(0, ob.pad_plane(refs[0], M), M)
+    padded = ob.pad_plane(refs[0], M + 8)
+    S = padded.shape[1]
+    for fy in range(4):
+        for fx in range(4):
+            got = eng.download_plane(0, fy, fx)
+            want = orc.subpel_plane(padded, (M + 8) * S + (M + 8), S, -M, -M, 416 + 2 * M, 240 + 2 * M, fy, fx)
+            assert np.array_equal(got.astype(np.int16), want), (fy, fx)
+    eng.close()
+
+
+def test_k1_extreme_content(orc):
+    """Saturating content (0/255 checkerboards and steps) exercises the clip and the int16 intermediate range."""
+    rng = np.random.default_rng(9)
+    pic = np.where(rng.integers(0, 2, (64, 128)) > 0, 255, 0).astype(np.uint8)
+    pic[:, 64:] = (np.indices((64, 64)).sum(0) % 2 * 255).astype(np.uint8)
+    eng = fme.Fme(128, 64, num_ref_slots=1, max_pus=16, margin=16)
+    eng.upload_ref(0, pic)
+    padded = ob.pad_plane(pic, 24)
+    S = padded.shape[1]
+    for fy in range(4):
+        for fx in range(4):
+            got = eng.download_plane(0, fy, fx)
+            want = orc.subpel_plane(padded, 24 * S + 24, S, -16, -16, 160, 96, fy, fx)
+            assert np.array_equal(got.astype(np.int16), want), (fy, fx)
+    eng.close()
+
+
+# ---------------------------------------------------------------- block-level entry points
+def test_block_filters_match_reference_fixture(small):
+    eng, g, _ = small
+    for (is_ver, luma, frac, w, h, first, last, bd, want) in filter_case_iter(g):
+        src = filter_src(g, is_ver, first, bd)
+        comp = 0 if luma else 1
+        if is_ver:
+            got = eng.filter_ver(comp, src, FILT_OFF, FILT_STRIDE, w, h, frac, first, last, bd)
+        else:
+            got = eng.filter_hor(comp, src, FILT_OFF, FILT_STRIDE, w, h, frac, last, bd)
+        assert np.array_equal(got, want), (is_ver, luma, frac, w, h, first, last, bd)
+
+
+def test_block_dist_matches_reference_fixture(small):
+    eng, g, _ = small
+    for (w, h, kind, ss, pair), want in zip(g["dist_meta"], g["dist_val"]):
+        o, c = (g["dist_org"], g["dist_cur"]) if pair == 0 else (g["dist_org2"], g["dist_cur2"])
+        got = eng.dist(int(kind), o[None, :int(h), :], c[None, :int(h), :], int(w), int(h), 8, int(ss))
+        assert int(got[0]) == int(want), (w, h, kind, ss, pair)
+
+
+def test_block_dist_batch_vs_oracle(small, orc):
+    eng, _, _ = small
+    rng = np.random.default_rng(3)
+    for (w, h) in ((8, 8), (16, 16), (12, 16), (64, 64), (4, 8)):
+        org = rng.integers(0, 256, (37, h, 64)).astype(np.int16)
+        cur = rng.integers(0, 256, (37, h, 72)).astype(np.int16)
+        for kind in (0, 1, 2):
+            got = eng.dist(kind, org, cur, w, h)
+            want = [orc.dist(kind, org[i], 0, 64, cur[i], 0, 72, w, h) for i in range(37)]
+            assert got.tolist() == want, (w, h, kind)
+
+
+def test_mv_cost_matches_reference_fixture(small):
+    eng, g, _ = small
+    for (lam, x, y, sc, px, py), want in list(zip(g["mv_meta"], g["mv_val"]))[:200]:
+        eng.set_slice(float(lam))
+        assert eng.mv_cost(int(x), int(y), int(sc), int(px), int(py)) == int(want)
+    eng.set_slice(float(g["small_lambda"][0]))
+
+
+# ---------------------------------------------------------------- K2 / K3 / K0 on the golden frame
+def test_k2_matches_reference_fixture_hadamard(small):
+    eng, g, recs = small
+    got = eng.submit(recs, fme.MODE_STD)
+    mv_g, cost_g = std_fields(got)
+    mv_w, cost_w = std_fields(golden_res(g, "small_res_had"))
+    bad = np.nonzero((mv_g != mv_w).any(1) | (cost_g != cost_w))[0]
+    assert len(bad) == 0, (len(bad), recs[bad[:5]], got[bad[:5]], golden_res(g, "small_res_had")[bad[:5]])
+
+
+def test_k2_matches_reference_fixture_sad():
+    g = golden()
+    recs = golden_recs(g)
+    eng = fme.Fme(128, 96, num_ref_slots=2, max_pus=len(recs), use_had=False)
+    eng.set_slice(float(g["small_lambda"][0]))
+    eng.upload_org(g["small_org"])
+    for s in range(2):
+        eng.upload_ref(s, g["small_refs"][s])
+    got = eng.submit(recs, fme.MODE_STD)
+    mv_g, cost_g = std_fields(got)
+    mv_w, cost_w = std_fields(golden_res(g, "small_res_sad"))
+    assert np.array_equal(mv_g, mv_w) and np.array_equal(cost_g, cost_w)
+    # the lossless flag selects SAD per PU even when HadamardME is on (TEncSearch.cpp:5258)
+    eng.close()
+    eng = fme.Fme(128, 96, num_ref_slots=2, max_pus=len(recs), use_had=True)
+    eng.set_slice(float(g["small_lambda"][0]))
+    eng.upload_org(g["small_org"])
+    for s in range(2):
+        eng.upload_ref(s, g["small_refs"][s])
+    r2 = recs.copy()
+    r2["flags"] |= fme.PU_LOSSLESS
+    got = eng.submit(r2, fme.MODE_STD)
+    mv_g, cost_g = std_fields(got)
+    assert np.array_equal(mv_g, mv_w) and np.array_equal(cost_g, cost_w)
+    eng.close()
+
+
+def test_k3_matches_reference_fixture_all_qps(small):
+    eng, g, recs = small
+    for qp in (22, 27, 32, 37):
+        eng.set_nn_weights(fme.nn_weights.load_blob(qp))
+        got = eng.submit(recs, fme.MODE_NN)
+        want = golden_res(g, "small_res_nn%d" % qp)
+        mism = int((nn_fields(got) != nn_fields(want)).any(1).sum())
+        assert mism == 0, "QP%d: %d of %d PUs differ (mismatch rate %.4f%%)" % (qp, mism, len(recs), 100.0 * mism / len(recs))
+        # hand-made grids, incl. SURVEY appendix B
+        grids = g["nn_grids"]
+        r = np.zeros(len(grids), fme.PU_DTYPE)
+        r["err"] = grids[:, :9].astype(np.uint32)
+        r["h"], r["w"] = grids[:, 9], grids[:, 10]
+        got = eng.submit(r, fme.MODE_NN)
+        want = g["nn_out%d" % qp]
+        assert np.array_equal(nn_fields(got), want[:, [1, 2, 3, 4, 0]])
+
+
+def test_k3_three_layer_variant(small, orc):
+    """Config C4: generic layer list (9 -> 40 -> 40 -> 40 -> 49, no embeddings); oracle = same generic forward."""
+    eng, g, recs = small
+    blob = fme.nn_weights.synthetic_blob((40, 40, 40), n_emb=0, seed=4)
+    eng.set_nn_weights(blob)
+    got = eng.submit(recs, fme.MODE_NN)
+    frame = ob.CpuFrame(g["small_org"], list(g["small_refs"]))
+    want = frame.oracle_run(recs, 2, 1.0, 1, blob)
+    assert np.array_equal(nn_fields(got), nn_fields(want))
+    blob4 = fme.nn_weights.synthetic_blob((40, 40, 40, 40), n_emb=2, seed=5)
+    eng.set_nn_weights(blob4)
+    got = eng.submit(recs, fme.MODE_NN)
+    want = frame.oracle_run(recs, 2, 1.0, 1, blob4)
+    assert np.array_equal(nn_fields(got), nn_fields(want))
+
+
+def test_k0_surface_matches_reference_fixture(small):
+    eng, g, recs = small
+    eng.set_nn_weights(fme.nn_weights.load_blob(22))
+    r = recs.copy()
+    r["err"] = 0
+    r["flags"] |= fme.PU_ERR_ON_GPU
+    got = eng.submit(r, fme.MODE_BOTH)
+    # errors computed on the device feed NN_pred: classes equal the fixture's (its err[] came from the reference)
+    assert np.array_equal(nn_fields(got), nn_fields(golden_res(g, "small_res_nn22")))
+    mv_g, cost_g = std_fields(got)
+    mv_w, cost_w = std_fields(golden_res(g, "small_res_had"))
+    assert np.array_equal(mv_g, mv_w) and np.array_equal(cost_g, cost_w)
+
+
+def test_mode_both_equals_std_plus_nn(small):
+    eng, g, recs = small
+    eng.set_nn_weights(fme.nn_weights.load_blob(22))
+    both = eng.submit(recs, fme.MODE_BOTH)
+    std = eng.submit(recs, fme.MODE_STD)
+    nn = eng.submit(recs, fme.MODE_NN)
+    assert np.array_equal(std_fields(both)[0], std_fields(std)[0]) and np.array_equal(both["cost"], std["cost"])
+    assert np.array_equal(nn_fields(both), nn_fields(nn))
+    assert (std["nnClass"] == 0).all() and (nn["cost"] == 0).all()
+
+
+# ---------------------------------------------------------------- config C1/C2: the full 416x240 list
+@pytest.mark.parametrize("use_had", [True, False])
+def test_full_416x240_list_vs_oracle(use_had):
+    W, H = 416, 240
+    org, refs, motions = fme.pu_list.synth_frames(W, H, n_refs=4, seed=1000)
+    recs = fme.pu_list.make_records(W, H, motions, seed=1, amp=True)
+    frame = ob.CpuFrame(org, refs)
+    frame.oracle_fill_surface(recs)
+    blob = fme.nn_weights.load_blob(22)
+    for k, (off, fac) in enumerate(zip(fme.pu_list.LOWDELAY_P_QP_OFFSETS[:2], fme.pu_list.LOWDELAY_P_QP_FACTORS[:2])):
+        lam = fme.pu_list.slice_lambda(22, off, fac, had_me=use_had)
+        eng = fme.Fme(W, H, num_ref_slots=4, max_pus=len(recs), use_had=use_had)
+        eng.set_nn_weights(blob)
+        eng.set_slice(lam)
+        eng.upload_org(org)
+        for s in range(4):
+            eng.upload_ref(s, refs[s])
+        got = eng.submit(recs, fme.MODE_BOTH)
+        want = frame.oracle_run(recs, 3, lam, use_had, blob)
+        for f in ("halfX", "halfY", "qterX", "qterY", "cost", "nnHalfX", "nnHalfY", "nnQterX", "nnQterY", "nnClass"):
+            bad = np.nonzero(got[f] != want[f])[0]
+            assert len(bad) == 0, (f, len(bad), recs[bad[:4]], got[bad[:4]], want[bad[:4]])
+        eng.close()
+
+
+def test_edge_cases(small):
+    eng, g, recs = small
+    eng.set_nn_weights(fme.nn_weights.load_blob(22))
+    assert len(eng.submit(recs[:0], fme.MODE_BOTH)) == 0                 # empty batch
+    one = eng.submit(recs[5:6], fme.MODE_STD)                            # single PU
+    assert np.array_equal(one.view(np.uint8), eng.submit(recs, fme.MODE_STD)[5:6].view(np.uint8))
+    # ragged: a batch that is not a multiple of any pack size, in shuffled order
+    idx = np.random.default_rng(0).permutation(len(recs))[:1237]
+    a = eng.submit(recs[idx], fme.MODE_STD)
+    b = eng.submit(recs, fme.MODE_STD)[idx]
+    assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    with pytest.raises(fme.FmeError):
+        eng.submit(np.zeros(eng.cfg.maxPUs + 1, fme.PU_DTYPE), fme.MODE_STD)  # over capacity
+    bad = recs[:4].copy()
+    bad["refSlot"] = 7
+    with pytest.raises(fme.FmeError):
+        eng.submit(bad, fme.MODE_STD)                                     # slot without a picture
+    bad = recs[:4].copy()
+    bad["w"] = 20
+    with pytest.raises(fme.FmeError):
+        eng.submit(bad, fme.MODE_STD)                                     # not an HEVC PU size
+
+
+def test_state_errors():
+    eng = fme.Fme(64, 64, num_ref_slots=1, max_pus=8)
+    r = np.zeros(1, fme.PU_DTYPE)
+    r["w"], r["h"] = 8, 8
+    with pytest.raises(fme.FmeError):
+        eng.submit(r, fme.MODE_STD)  # nothing uploaded
+    with pytest.raises(fme.FmeError):
+        eng.submit(r, fme.MODE_NN)   # no weights
+    with pytest.raises(fme.FmeError):
+        eng.set_nn_weights(b"\0" * 100)
+    eng.close()
+
+
+# ---------------------------------------------------------------- motion compensation (a14)
+def test_mc_luma_and_chroma_vs_oracle(small, orc):
+    eng, g, recs = small
+    rng = np.random.default_rng(6)
+    H, W = 96, 128
+    cb = rng.integers(0, 256, (H // 2, W // 2)).astype(np.int16)
+    cr = rng.integers(0, 256, (H // 2, W // 2)).astype(np.int16)
+    eng.upload_ref_chroma(1, cb, cr)
+    n = 200
+    pus = np.zeros(n, fme.MC_PU_DTYPE)
+    sel = rng.integers(0, len(recs), n)
+    pus["x"], pus["y"], pus["w"], pus["h"] = recs["x"][sel], recs["y"][sel], recs["w"][sel], recs["h"][sel]
+    pus["refSlot"] = 1
+    pus["mvX"] = rng.integers(-40, 41, n)
+    pus["mvY"] = rng.integers(-40, 41, n)
+    y, ocb, ocr = eng.mc(pus)
+    M = 80
+    luma = ob.pad_plane(g["small_refs"][1], M)
+    S = luma.shape[1]
+    pcb, pcr = ob.pad_plane(cb, M // 2), ob.pad_plane(cr, M // 2)
+    Sc = pcb.shape[1]
+    for i in range(n):
+        p = pus[i]
+        w, h, mvx, mvy = int(p["w"]), int(p["h"]), int(p["mvX"]), int(p["mvY"])
+        # luma: xPredInterBlk three cases (TComPrediction.cpp:661-680)
+        off = (M + int(p["y"]) + (mvy >> 2)) * S + M + int(p["x"]) + (mvx >> 2)
+        fx, fy = mvx & 3, mvy & 3
+        if fy == 0:
+            want = orc.filter_hor(1, luma, off, S, w, h, fx, 1)
+        elif fx == 0:
+            want = orc.filter_ver(1, luma, off, S, w, h, fy, 1, 1)
+        else:
+            tmp = orc.filter_hor(1, luma, off - 3 * S, S, w, h + 7, fx, 0)
+            want = orc.filter_ver(1, tmp, 3 * w, w, w, h, fy, 0, 1)
+        assert np.array_equal(y[i, :h, :w], want), ("luma", i, p)
+        cw, ch = w // 2, h // 2
+        offc = (M // 2 + (int(p["y"]) >> 1) + (mvy >> 3)) * Sc + M // 2 + (int(p["x"]) >> 1) + (mvx >> 3)
+        fx, fy = mvx & 7, mvy & 7
+        for plane, got in ((pcb, ocb), (pcr, ocr)):
+            if fy == 0:
+                want = orc.filter_hor(0, plane, offc, Sc, cw, ch, fx, 1)
+            elif fx == 0:
+                want = orc.filter_ver(0, plane, offc, Sc, cw, ch, fy, 1, 1)
+            else:
+                tmp = orc.filter_hor(0, plane, offc - Sc, Sc, cw, ch + 3, fx, 0)
+                want = orc.filter_ver(0, tmp, cw, cw, cw, ch, fy, 0, 1)
+            assert np.array_equal(got[i, :ch, :cw], want), ("chroma", i, p)
+
+
+# ---------------------------------------------------------------- full-size properties (config C3 shape)
+def test_1080p_properties(orc):
+    """1920x1080, 4 references, 858 000 PUs: (1) a 3 000-PU random sample agrees with the oracle bit for bit,
+    (2) results are independent of batch order and of how the batch is split."""
+    W, H = 1920, 1080
+    org, refs, motions = fme.pu_list.synth_frames(W, H, n_refs=4, seed=2022)
+    recs = fme.pu_list.make_records(W, H, motions, seed=2, err_on_gpu=True)
+    assert len(recs) == 858000
+    lam = fme.pu_list.slice_lambda(22)
+    blob = fme.nn_weights.load_blob(22)
+    eng = fme.Fme(W, H, num_ref_slots=4, max_pus=len(recs))
+    eng.set_nn_weights(blob)
+    eng.set_slice(lam)
+    eng.upload_org(org)
+    for s in range(4):
+        eng.upload_ref(s, refs[s])
+    full = eng.submit(recs, fme.MODE_BOTH)
+    rng = np.random.default_rng(0)
+    idx = np.sort(rng.choice(len(recs), 3000, replace=False))
+    frame = ob.CpuFrame(org, refs)
+    sample = np.ascontiguousarray(recs[idx])
+    frame.oracle_fill_surface(sample)
+    want = frame.oracle_run(sample, 3, lam, 1, blob)
+    for f in ("halfX", "halfY", "qterX", "qterY", "cost", "nnHalfX", "nnHalfY", "nnQterX", "nnQterY", "nnClass"):
+        assert np.array_equal(full[f][idx], want[f]), f
+    # order / split independence
+    perm = rng.permutation(len(recs))
+    shuffled = eng.submit(recs[perm], fme.MODE_BOTH)
+    assert np.array_equal(shuffled.view(np.uint8), full[perm].view(np.uint8))
+    halves = np.concatenate([eng.submit(recs[:400001], fme.MODE_BOTH), eng.submit(recs[400001:], fme.MODE_BOTH)])
+    assert np.array_equal(halves.view(np.uint8), full.view(np.uint8))
+    # checksum of the result fields, printed for the record
+    print("1080p checksum cost=%d classes=%d" % (int(full["cost"].astype(np.uint64).sum()), int(full["nnClass"].astype(np.uint64).sum())))
+    eng.close()
