@@ -239,17 +239,27 @@ def run_gpu(args):
     h2d = width * height * 2 * (1 if banded and world > 1 else 2) + int(pus_per_step) * 52
     d2h = int(pus_per_step) * 16
 
-    # ---- per-kernel times (separate short pass with event pairs around each stage) ----
-    eng.set_profiling(True)
+    # ---- per-kernel times: CUDA events on the launching stream around each pass of a step ----
+    # (K2 and K3 are launched by separate submit calls here so that an event fits between them; the STD call
+    #  includes K2's three tiny binning kernels and a result-clear kernel.)
     kms = {"k1_interp": [], "k2_refine": [], "k3_nn": []}
-    for i in range(6):
-        step_device(i)
-        eng.synchronize()
-        m = eng.last_kernel_ms()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    for i in range(2 + 6):
+        k, slot = i % n_sets, i % N_REFS
+        n = len(sets[k][2])
+        eng.upload_org_device_u8(d_org[k].data_ptr(), width)
+        ev[0].record(stream)
+        eng.upload_ref_device_u8(slot, d_refs[k][slot].data_ptr(), width)
+        ev[1].record(stream)
+        eng.submit_device(d_recs[k].data_ptr(), n, d_res.data_ptr(), fme.MODE_STD)
+        ev[2].record(stream)
+        eng.submit_device(d_recs[k].data_ptr(), n, d_res.data_ptr(), fme.MODE_NN)
+        ev[3].record(stream)
+        torch.cuda.synchronize(dev)
         if i >= 2:
-            for k in kms:
-                kms[k].append(m[k])
-    eng.set_profiling(False)
+            kms["k1_interp"].append(ev[0].elapsed_time(ev[1]))
+            kms["k2_refine"].append(ev[1].elapsed_time(ev[2]))
+            kms["k3_nn"].append(ev[2].elapsed_time(ev[3]))
     kavg = {k: float(np.mean(v)) for k, v in kms.items()}
 
     out = None

@@ -120,15 +120,22 @@ int check_slot(fme_ctx* c, int slot) {
   return FME_OK;
 }
 
+// Event pair around one pass.  Events belong to this library's CUDA runtime instance; recording them on a
+// stream created by another runtime instance (e.g. torch's) is rejected by the driver with "invalid resource
+// handle", so a failed record switches profiling off instead of poisoning the next launch check.
 struct StageTimer {
   fme_ctx* c;
   int idx;
-  StageTimer(fme_ctx* c_, int i) : c(c_), idx(i) {
-    if (c->profiling) cudaEventRecord(c->ev[2 * idx], c->stream);
+  void rec(int e) {
+    if (!c->profiling) return;
+    if (cudaEventRecord(c->ev[e], c->stream) != cudaSuccess) {
+      cudaGetLastError();
+      c->profiling = false;
+      for (float& m : c->lastMs) m = -1.f;
+    }
   }
-  ~StageTimer() {
-    if (c->profiling) cudaEventRecord(c->ev[2 * idx + 1], c->stream);
-  }
+  StageTimer(fme_ctx* c_, int i) : c(c_), idx(i) { rec(2 * idx); }
+  ~StageTimer() { rec(2 * idx + 1); }
 };
 
 int run_k1(fme_ctx* c, int slot) {
