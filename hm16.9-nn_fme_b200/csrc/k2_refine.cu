@@ -11,8 +11,10 @@
 //   * a prepass groups PU indices by shape class (w,h) so that a warp always works on same-shape PUs;
 //   * one warp = one "pack" of P PUs whose tiles (8x8, or 4x4 when w or h is not a multiple of 8,
 //     TComRdCost.cpp:1446-1492) fill the 32 lanes: lane = (PU in pack, tile in PU);
-//   * per refinement stage the warp stages the candidate regions of its PUs from the HBM/L2-resident
-//     planes into shared memory with 4-byte cp.async (rows stay source-aligned), then every lane
+//   * the warp walks 12 staging steps per pack (4 half-pel planes, then one plane per quarter-pel candidate):
+//     the candidate regions of all its PUs are copied from the HBM/L2-resident planes into shared memory
+//     with 4/8/16-byte cp.async into one of two buffers while the previous step's candidates are evaluated
+//     from the other (rows stay source-aligned, readers funnel-shift); every lane
 //     computes the SATD of its own tile in registers: two 16-bit residuals per 32-bit register (SWAR),
 //     butterflies as plain 32-bit adds, |a+b|+|a-b| = 2 max(|a|,|b|) for the intra-register stage;
 //   * per-PU sums by __reduce_add_sync over the PU's lane group, MV cost from an exact host-built LUT,
@@ -21,9 +23,12 @@
 
 namespace {
 
-constexpr int K2_WARPS = 8;
+#ifndef FME_K2_WARPS
+#define FME_K2_WARPS 16
+#endif
+constexpr int K2_WARPS = FME_K2_WARPS;
 constexpr int K2_THREADS = K2_WARPS * 32;
-constexpr int K2_SMEM_PER_WARP = 17920;  // max over shape classes of one staging step (64x64 half stage: 4*65*68)
+constexpr int K2_SMEM_PER_WARP = 10496;  // two staging buffers of max P*(h+1)*RW + 16 bytes (64x64: 65*80 = 5200)
 constexpr int K2_MAX_PACK = 32;
 
 // TEncSearch.cpp:212-236
@@ -35,6 +40,7 @@ struct ClassInfo {
   int ts;        // tile size 8 or 4
   int tilesX;    // tiles per PU row
   int tiles;     // tiles per PU
+  int units;     // lane work units per PU: one 8x8 tile, or a pair of 4x4 tiles
   int P;         // PUs per pack
 };
 
@@ -45,7 +51,8 @@ __host__ __device__ inline ClassInfo class_info(int cls) {
   c.ts = ((c.w & 7) == 0 && (c.h & 7) == 0) ? 8 : 4;
   c.tilesX = c.w / c.ts;
   c.tiles = c.tilesX * (c.h / c.ts);
-  c.P = c.tiles >= 32 ? 1 : 32 / c.tiles;
+  c.units = c.ts == 8 ? c.tiles : c.tiles / 2;  // 4x4-tiled PUs always have an even tile count
+  c.P = c.units >= 32 ? 1 : 32 / c.units;
   return c;
 }
 
@@ -120,10 +127,12 @@ __device__ __forceinline__ unsigned abs2(unsigned a) {
   unsigned s = ((a >> 15) & 0x10001u) * 0xffffu;
   return (a + s) ^ s;
 }
-// max of the two 16-bit fields of m, zero-extended
-__device__ __forceinline__ unsigned hmax2(unsigned m) {
-  unsigned sw = __byte_perm(m, 0, 0x1032);
-  return __vmaxu2(m, sw) & 0xffffu;
+// acc + max of the two 16-bit fields of m: swap halves, packed max, then one dp2a picks the low field
+__device__ __forceinline__ unsigned acc_hmax2(unsigned m, unsigned acc) {
+  unsigned mx = __vmaxu2(m, __byte_perm(m, 0, 0x1032));
+  unsigned d;
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(mx), "r"(1u), "r"(acc));
+  return d;
 }
 
 // Read 8 bytes at arbitrary byte address from shared memory (3 aligned words + 2 funnel shifts).
@@ -144,16 +153,18 @@ __device__ __forceinline__ unsigned lds_row4(const uint8_t* base) {
 
 // SATD of one 8x8 tile: xCalcHADs8x8 (TComRdCost.cpp:1330-1425).  o[] holds the source tile as
 // 16 words of u8x4 (row r -> o[2r], o[2r+1]); cand points at the candidate tile's row 0 in smem.
-__device__ __forceinline__ unsigned satd8x8(const unsigned (&o)[16], const uint8_t* cand, int candPitch) {
+template <typename OrgRow>
+__device__ __forceinline__ unsigned satd8x8(OrgRow orgRow, const uint8_t* cand, int candPitch) {
   unsigned d[32];  // d[4r + j] = (res(r,2j), res(r,2j+1)) packed lo/hi
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
-    unsigned c0, c1;
+    unsigned c0, c1, o0, o1;
     lds_row8(cand + r * candPitch, c0, c1);
-    d[4 * r + 0] = __byte_perm(o[2 * r], 0, 0x4140) - __byte_perm(c0, 0, 0x4140);
-    d[4 * r + 1] = __byte_perm(o[2 * r], 0, 0x4342) - __byte_perm(c0, 0, 0x4342);
-    d[4 * r + 2] = __byte_perm(o[2 * r + 1], 0, 0x4140) - __byte_perm(c1, 0, 0x4140);
-    d[4 * r + 3] = __byte_perm(o[2 * r + 1], 0, 0x4342) - __byte_perm(c1, 0, 0x4342);
+    orgRow(r, o0, o1);
+    d[4 * r + 0] = __byte_perm(o0, 0, 0x4140) - __byte_perm(c0, 0, 0x4140);
+    d[4 * r + 1] = __byte_perm(o0, 0, 0x4342) - __byte_perm(c0, 0, 0x4342);
+    d[4 * r + 2] = __byte_perm(o1, 0, 0x4140) - __byte_perm(c1, 0, 0x4140);
+    d[4 * r + 3] = __byte_perm(o1, 0, 0x4342) - __byte_perm(c1, 0, 0x4342);
   }
   // horizontal: column-index bits 1 and 2 (bit 0 lives inside a word and is folded into the final max)
 #pragma unroll
@@ -185,7 +196,7 @@ __device__ __forceinline__ unsigned satd8x8(const unsigned (&o)[16], const uint8
   // last horizontal stage + abs: |lo+hi| + |lo-hi| = 2 max(|lo|,|hi|)
   unsigned sum = 0;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) sum += hmax2(abs2(d[i]));
+  for (int i = 0; i < 32; ++i) sum = acc_hmax2(abs2(d[i]), sum);
   return (2 * sum + 2) >> 2;  // TComRdCost.cpp:1421
 }
 
@@ -212,18 +223,20 @@ __device__ __forceinline__ unsigned satd4x4(const unsigned (&o)[4], const uint8_
   }
   unsigned sum = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) sum += hmax2(abs2(d[i]));
+  for (int i = 0; i < 8; ++i) sum = acc_hmax2(abs2(d[i]), sum);
   return (2 * sum + 1) >> 1;  // TComRdCost.cpp:1325
 }
 
-__device__ __forceinline__ unsigned sad8x8(const unsigned (&o)[16], const uint8_t* cand, int candPitch) {
+template <typename OrgRow>
+__device__ __forceinline__ unsigned sad8x8(OrgRow orgRow, const uint8_t* cand, int candPitch) {
   unsigned s = 0;
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
-    unsigned c0, c1;
+    unsigned c0, c1, o0, o1;
     lds_row8(cand + r * candPitch, c0, c1);
-    s = __vsadu4(o[2 * r], c0) + s;
-    s = __vsadu4(o[2 * r + 1], c1) + s;
+    orgRow(r, o0, o1);
+    s = __vsadu4(o0, c0) + s;
+    s = __vsadu4(o1, c1) + s;
   }
   return s;
 }
@@ -232,17 +245,6 @@ __device__ __forceinline__ unsigned sad4x4(const unsigned (&o)[4], const uint8_t
 #pragma unroll
   for (int r = 0; r < 4; ++r) s += __vsadu4(o[r], lds_row4(cand + r * candPitch));
   return s;
-}
-
-template <int TS>
-__device__ __forceinline__ unsigned tile_dist(const unsigned* o, const uint8_t* cand, int candPitch, bool had) {
-  if constexpr (TS == 8) {
-    const unsigned(&oo)[16] = *reinterpret_cast<const unsigned(*)[16]>(o);
-    return had ? satd8x8(oo, cand, candPitch) : sad8x8(oo, cand, candPitch);
-  } else {
-    const unsigned(&oo)[4] = *reinterpret_cast<const unsigned(*)[4]>(o);
-    return had ? satd4x4(oo, cand, candPitch) : sad4x4(oo, cand, candPitch);
-  }
 }
 
 // 8 / 4 bytes at an arbitrary byte address in global memory (aligned 32-bit loads + funnel shift)
@@ -267,35 +269,90 @@ __device__ __forceinline__ int golomb_bits(int v) {
   return 1 + 2 * (31 - __clz(u));
 }
 
-__device__ __forceinline__ void cp_async4(void* smemDst, const void* gsrc) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smemDst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
 // ------------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------------
-struct PackPu {      // per-PU state of the pack, kept in shared memory (one per PU in the pack)
-  int pu;            // global PU index, -1 = padding
-  int X, Y;          // PU origin + integer MV, picture coordinates
-  int planeBase;     // byte offset of the slot's plane 0 (as 32-bit units of 16 B to fit: see below)
-};
+template <int A>
+__device__ __forceinline__ void cp_async_g(void* smemDst, const void* gsrc) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smemDst);
+  if constexpr (A == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+  else if constexpr (A == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Per-pack staging geometry (uniform across the warp).
+struct StageGeom {
+  int RW;   // staged row bytes (multiple of the copy granule A)
+  int G;    // granules per row
+  int RB;   // bytes per staged region = (h + 1) * RW
+};
+// Mixed-radix position of a lane's current copy item (PU j, row, granule) and its +32 step.
+struct ItemPos {
+  int j, row, gi;
+  int dJ, dRow, dG;
+};
+__device__ __forceinline__ ItemPos item_pos(int lane, int rows, int G) {
+  ItemPos p;
+  const int items = rows * G;
+  p.j = lane / items;
+  int r = lane - p.j * items;
+  p.row = r / G;
+  p.gi = r - p.row * G;
+  p.dJ = 32 / items;
+  r = 32 - p.dJ * items;
+  p.dRow = r / G;
+  p.dG = r - p.dRow * G;
+  return p;
+}
+
+// One staging step: copy `rows` rows of RW bytes of every PU's region (source base pointers in s_base) into
+// buf + j*RB.  The pack's regions form one flat item space (count * rows * G granules) walked by all 32 lanes;
+// rows keep the source's alignment modulo A (readers funnel-shift).  No divisions in the loop.
+template <int A>
+__device__ __forceinline__ void stage_regions(uint8_t* buf, const StageGeom sg, int rows, int count, int pitch,
+                                              const unsigned long long* s_base, ItemPos p) {
+  while (p.j < count) {
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(s_base[p.j]) + (size_t)(p.row * pitch + p.gi * A);
+    cp_async_g<A>(buf + p.j * sg.RB + p.row * sg.RW + p.gi * A, src);
+    p.gi += p.dG; p.row += p.dRow; p.j += p.dJ;
+    if (p.gi >= sg.G) { p.gi -= sg.G; ++p.row; }
+    if (p.row >= rows) { p.row -= rows; ++p.j; }
+  }
+}
+
+// Distortion of one lane unit against the candidate at `cand` (row 0 of the unit's first tile).
 template <int TS>
-__device__ __forceinline__ void k2_pack(const ClassInfo ci, const int* __restrict__ order, int first, int count,
-                                        const fme_pu* __restrict__ pus, fme_result* __restrict__ res,
-                                        const uint8_t* __restrict__ planes, const uint8_t* __restrict__ org,
-                                        const FmeGeom g, const uint32_t* __restrict__ costLut, int useHad,
-                                        uint8_t* smem, int* s_pu, int* s_X, int* s_Y, long long* s_slotOff, int* s_win) {
+__device__ __forceinline__ unsigned unit_dist(const unsigned* o, const uint8_t* cand, int candPitch, int tile1Off,
+                                              bool had) {
+  if constexpr (TS == 8) {
+    auto row = [&](int r, unsigned& lo, unsigned& hi) { lo = o[2 * r]; hi = o[2 * r + 1]; };
+    return had ? satd8x8(row, cand, candPitch) : sad8x8(row, cand, candPitch);
+  } else {
+    const unsigned(&oa)[4] = *reinterpret_cast<const unsigned(*)[4]>(o);
+    const unsigned(&ob)[4] = *reinterpret_cast<const unsigned(*)[4]>(o + 4);
+    return had ? satd4x4(oa, cand, candPitch) + satd4x4(ob, cand + tile1Off, candPitch)
+               : sad4x4(oa, cand, candPitch) + sad4x4(ob, cand + tile1Off, candPitch);
+  }
+}
+
+template <int TS, int A>
+__device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__ order, int first, int count,
+                                     const fme_pu* __restrict__ pus, fme_result* __restrict__ res,
+                                     const uint8_t* __restrict__ planes, const uint8_t* __restrict__ org,
+                                     const FmeGeom& g, const uint32_t* __restrict__ costLut, int useHad,
+                                     uint8_t* smem, int* s_pu, int* s_X, int* s_Y, long long* s_slotOff, int* s_win,
+                                     unsigned long long* s_base) {
   const int lane = threadIdx.x & 31;
   const int w = ci.w, h = ci.h;
-  const int T = ci.tiles;
-  const int rounds = (T + 31) / 32;           // > 1 only when a single PU has more than 32 tiles (P == 1)
-  const int lanesPerPu = T >= 32 ? 32 : T;
-  const int myPu = lane / lanesPerPu;         // PU slot in the pack served by this lane
+  const int U = ci.units;                      // lane units per PU
+  const int rounds = (U + 31) >> 5;            // 2 only when a single PU has more than 32 units (then P == 1)
+  const int lanesPerPu = U >= 32 ? 32 : U;
+  const int myPu = U >= 32 ? 0 : lane / lanesPerPu;   // PU slot in the pack served by this lane
   const bool laneActive = myPu < count && myPu < ci.P;
-  const int tile0 = lane - myPu * lanesPerPu;  // tile index in round 0
+  const int unit0 = lane - myPu * lanesPerPu;  // unit index in round 0
   const unsigned groupMask =
       lanesPerPu == 32 ? 0xffffffffu : (((1u << lanesPerPu) - 1u) << (myPu * lanesPerPu));
 
@@ -314,154 +371,170 @@ __device__ __forceinline__ void k2_pack(const ClassInfo ci, const int* __restric
   }
   __syncwarp();
 
+  // ---- staging geometry ----
+  StageGeom sg;
+  sg.RW = ((w + A + A - 1) / A) * A;  // covers [x0 & ~(A-1), x0 + w + 1)
+  sg.G = sg.RW / A;
+  sg.RB = (h + 1) * sg.RW;
+  const ItemPos posHalf = item_pos(lane, h + 1, sg.G);  // a handful of divisions per pack, none per item
+  const ItemPos posQter = item_pos(lane, h, sg.G);
+  const int bufBytes = (ci.P * sg.RB + 16 + 15) & ~15;
+  uint8_t* const bufA = smem;
+  uint8_t* const bufB = smem + bufBytes;
+
+  // Region of step s for PU j.  Steps 0..3: half-pel planes (0,0) (0,2) (2,0) (2,2), origin (X-1, Y-1),
+  // h+1 rows.  Steps 4..11: quarter-pel candidate s-3 of s_acMvRefineQ around the PU's half-pel winner, h rows.
+  auto publishBases = [&](int s) {
+    if (lane < count) {
+      int plane, x0, y0;
+      if (s < 4) {
+        plane = (s & 1) * 2 + (s >> 1) * 8;
+        x0 = s_X[lane] - 1;
+        y0 = s_Y[lane] - 1;
+      } else {
+        int wv = s_win[lane];
+        int jhx = (int)(int8_t)(wv & 0xff), jhy = (int)(int8_t)((wv >> 8) & 0xff);
+        int qx = 2 * jhx + c_refineQ[s - 3][0], qy = 2 * jhy + c_refineQ[s - 3][1];
+        plane = (qy & 3) * 4 + (qx & 3);
+        x0 = s_X[lane] + (qx >> 2);
+        y0 = s_Y[lane] + (qy >> 2);
+      }
+      s_base[lane] = (unsigned long long)(planes + s_slotOff[lane] + (size_t)plane * g.planeBytes +
+                                          (size_t)(y0 + g.M) * g.pitch + ((x0 + g.M) & ~(A - 1)));
+    }
+    __syncwarp();
+  };
+  auto stage = [&](int s) {
+    publishBases(s);
+    stage_regions<A>((s & 1) ? bufB : bufA, sg, s < 4 ? h + 1 : h, count, g.pitch, s_base, s < 4 ? posHalf : posQter);
+    cp_async_commit();
+  };
+  stage(0);  // in flight while the source tiles are fetched
+
   // ---- source tile(s) of this lane into registers ----
-  constexpr int OW = TS == 8 ? 16 : 4;  // words per tile
-  unsigned o[2][OW];
-  int predX = 0, predY = 0, mvIntX = 0, mvIntY = 0, lossless = 0, puIdx = -1;
+  constexpr int OW = 16 / 2 * 2 / (TS == 8 ? 1 : 2);  // 16 words (one 8x8 tile) or 8 words (two 4x4 tiles)
+  unsigned o[OW];
+  int predX = 0, predY = 0, mvIntX = 0, mvIntY = 0, lossless = 0, puIdx = -1, alignX = 0;
+  int ox = 0, oy = 0;
   if (laneActive) {
     puIdx = s_pu[myPu];
     fme_pu p = pus[puIdx];
     predX = p.mvPredX; predY = p.mvPredY; mvIntX = p.mvIntX; mvIntY = p.mvIntY;
     lossless = p.flags & FME_PU_LOSSLESS;
-#pragma unroll
-    for (int rd = 0; rd < 2; ++rd) {
-      int t = tile0 + 32 * rd;
-      if (rd < rounds && t < T) {
-        int tx = t % ci.tilesX, ty = t / ci.tilesX;
-        int ox = min(max((int)p.x, 0), g.W - w), oy = min(max((int)p.y, 0), g.H - h);
-        const uint8_t* src = org + (size_t)(oy + ty * TS) * g.orgPitch + ox + tx * TS;
-#pragma unroll
-        for (int r = 0; r < TS; ++r) {
-          if constexpr (TS == 8) ldg_row8(src + (size_t)r * g.orgPitch, o[rd][2 * r], o[rd][2 * r + 1]);
-          else o[rd][r] = ldg_row4(src + (size_t)r * g.orgPitch);
-        }
-      }
-    }
+    alignX = s_X[myPu] + g.M;
+    ox = min(max((int)p.x, 0), g.W - w);
+    oy = min(max((int)p.y, 0), g.H - h);
   }
   const bool had = useHad && !lossless;
-
-  // region geometry for staging
-  const int RW = w + 4;                 // staged row bytes: covers [x0 & ~3, x0 + w + 1)
-  const int wordsPerRow = RW >> 2;
-
-  // ================= half-pel stage: planes (0,0) (0,2) (2,0) (2,2), origin (X-1, Y-1), (w+1) x (h+1)
-  {
-    const int rows = h + 1;
-    const int regionBytes = rows * RW;
-    const int perPu = 4 * regionBytes;
-    const int wordsPerRegion = rows * wordsPerRow;
-    const int total = count * 4 * wordsPerRegion;
-    for (int i = lane; i < total; i += 32) {
-      int j = i / (4 * wordsPerRegion);
-      int rem = i - j * 4 * wordsPerRegion;
-      int k = rem / wordsPerRegion;
-      rem -= k * wordsPerRegion;
-      int row = rem / wordsPerRow, wd = rem - row * wordsPerRow;
-      int plane = (k & 1) * 2 + (k >> 1) * 8;  // k: 0->(0,0) 1->(0,2) 2->(2,0) 3->(2,2); index fy*4+fx
-      int x0 = s_X[j] - 1, y0 = s_Y[j] - 1;
-      const uint8_t* src = planes + s_slotOff[j] + (size_t)plane * g.planeBytes +
-                           (size_t)(y0 + g.M + row) * g.pitch + ((x0 + g.M) & ~3) + wd * 4;
-      cp_async4(smem + j * perPu + k * regionBytes + row * RW + wd * 4, src);
-    }
-    cp_async_wait_all();
-    __syncwarp();
-
-    unsigned best = 0xffffffffu;
-    int bestI = 0;
-    const int align = laneActive ? ((s_X[myPu] - 1 + g.M) & 3) : 0;
-#pragma unroll 1
-    for (int i = 0; i < 9; ++i) {
-      int hx = c_refineH[i][0], hy = c_refineH[i][1];
-      int qx = 2 * hx, qy = 2 * hy;
-      int k = ((qx & 3) ? 1 : 0) + ((qy & 3) ? 2 : 0);
-      int dx = 1 + (qx >> 2), dy = 1 + (qy >> 2);  // offset inside the staged region (origin X-1, Y-1)
-      unsigned dist = 0;
-      if (laneActive) {
+  // unit -> byte offset of its (first) tile inside a staged region, offset of the second 4x4 tile, source load
+  int uOff = 0, u1Off = 0;
+  bool uOn = false;
+  auto loadUnit = [&](int u) {
+    uOn = laneActive && u < U;
+    if (!uOn) return;
+    if constexpr (TS == 8) {
+      int ty = u / ci.tilesX, tx = u - ty * ci.tilesX;
+      uOff = ty * 8 * sg.RW + tx * 8;
+      const uint8_t* src = org + (size_t)(oy + ty * 8) * g.orgPitch + ox + tx * 8;
 #pragma unroll
-        for (int rd = 0; rd < 2; ++rd) {
-          int t = tile0 + 32 * rd;
-          if (rd < rounds && t < T) {
-            int tx = t % ci.tilesX, ty = t / ci.tilesX;
-            const uint8_t* c = smem + myPu * perPu + k * regionBytes + (dy + ty * TS) * RW + align + dx + tx * TS;
-            dist += tile_dist<TS>(o[rd], c, RW, had);
-          }
-        }
+      for (int r = 0; r < 8; ++r) ldg_row8(src + (size_t)r * g.orgPitch, o[2 * r], o[2 * r + 1]);
+    } else {
+      int t0 = 2 * u, t1 = 2 * u + 1;
+      int ty0 = t0 / ci.tilesX, tx0 = t0 - ty0 * ci.tilesX;
+      int ty1 = t1 / ci.tilesX, tx1 = t1 - ty1 * ci.tilesX;
+      uOff = ty0 * 4 * sg.RW + tx0 * 4;
+      u1Off = (ty1 * 4 * sg.RW + tx1 * 4) - uOff;
+      const uint8_t* s0 = org + (size_t)(oy + ty0 * 4) * g.orgPitch + ox + tx0 * 4;
+      const uint8_t* s1 = org + (size_t)(oy + ty1 * 4) * g.orgPitch + ox + tx1 * 4;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        o[r] = ldg_row4(s0 + (size_t)r * g.orgPitch);
+        o[4 + r] = ldg_row4(s1 + (size_t)r * g.orgPitch);
+      }
+    }
+  };
+  if (rounds == 1) loadUnit(unit0);
+
+  // ---- 12 steps: prefetch step s+1 while evaluating the candidates served by step s ----
+  unsigned cost[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) cost[i] = 0xffffffffu;
+  unsigned qBest = 0xffffffffu;
+  int qBestI = 0, bhx = 0, bhy = 0;
+#pragma unroll 1
+  for (int s = 0; s < 12; ++s) {
+    const bool prefetch = (s != 3) && (s != 11);  // step 4 depends on the half-pel winner found after step 3
+    if (prefetch) {
+      stage(s + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncwarp();
+    const uint8_t* region = ((s & 1) ? bufB : bufA) + myPu * sg.RB;
+    // candidates served by this step, in table order (TEncSearch.cpp:212-236):
+    // s=0: H0 | s=1 (fx=2): H3 (-1,0), H4 (1,0) | s=2 (fy=2): H1 (0,-1), H2 (0,1) | s=3: H5..H8 | s>=4: Q(s-3)
+    const int iFirst = (s == 0) ? 0 : (s == 1) ? 3 : (s == 2) ? 1 : (s == 3) ? 5 : s - 3;
+    const int iCount = (s == 0 || s >= 4) ? 1 : (s == 3) ? 4 : 2;
+#pragma unroll 1
+    for (int c = 0; c < iCount; ++c) {
+      const int i = iFirst + c;
+      int candOff, vx, vy;
+      if (s < 4) {
+        const int hx = c_refineH[i][0], hy = c_refineH[i][1];
+        // inside the region (origin X-1, Y-1): x offset 1 + ((2hx)>>2), y offset 1 + ((2hy)>>2)
+        candOff = (1 + ((2 * hy) >> 2)) * sg.RW + ((alignX - 1) & (A - 1)) + 1 + ((2 * hx) >> 2);
+        // cost scale 1 (TEncSearch.cpp:4531): ((int<<1)+h) << 1 - pred
+        vx = ((mvIntX << 1) + hx) << 1;
+        vy = ((mvIntY << 1) + hy) << 1;
+      } else {
+        const int qx = 2 * bhx + c_refineQ[i][0];
+        candOff = (alignX + (qx >> 2)) & (A - 1);
+        // cost scale 0 (TEncSearch.cpp:5260): (((int<<1)+half)<<1) + q - pred
+        vx = (((mvIntX << 1) + bhx) << 1) + c_refineQ[i][0];
+        vy = (((mvIntY << 1) + bhy) << 1) + c_refineQ[i][1];
+      }
+      unsigned dist = 0;
+#pragma unroll 1
+      for (int rd = 0; rd < rounds; ++rd) {
+        if (rounds > 1) loadUnit(unit0 + 32 * rd);  // PUs with more than 32 units: source tile re-fetched per round
+        if (uOn) dist += unit_dist<TS>(o, region + uOff + candOff, sg.RW, u1Off, had);
       }
       if (laneActive) {
         dist = __reduce_add_sync(groupMask, dist);
-        // cost scale 1 (TEncSearch.cpp:4531): ((int<<1)+h) << 1 - pred
-        int bits = golomb_bits((((mvIntX << 1) + hx) << 1) - predX) + golomb_bits((((mvIntY << 1) + hy) << 1) - predY);
-        dist += costLut[bits];
-        if (dist < best) { best = dist; bestI = i; }
-      }
-    }
-    __syncwarp();
-
-    // ================= quarter-pel stage: 8 candidates around the half-pel winner, two steps of 4
-    const int bhx = c_refineH[bestI][0], bhy = c_refineH[bestI][1];
-    unsigned qBest = best;  // candidate 0 of the quarter stage is the half-pel winner itself (same block, same bits)
-    int qBestI = 0;
-    const int qrows = h;
-    const int qRegionBytes = qrows * RW;
-    const int qPerPu = 4 * qRegionBytes;
-    const int qWordsPerRegion = qrows * wordsPerRow;
-#pragma unroll 1
-    for (int step = 0; step < 2; ++step) {
-      // publish each PU's half-pel winner for the cooperative staging loop
-      if (laneActive && tile0 == 0) s_win[myPu] = (bhx & 0xff) | ((bhy & 0xff) << 8);
-      __syncwarp();
-      const int totalQ = count * 4 * qWordsPerRegion;
-      for (int i = lane; i < totalQ; i += 32) {
-        int j = i / (4 * qWordsPerRegion);
-        int rem = i - j * 4 * qWordsPerRegion;
-        int k = rem / qWordsPerRegion;
-        rem -= k * qWordsPerRegion;
-        int row = rem / wordsPerRow, wd = rem - row * wordsPerRow;
-        int wv = s_win[j];
-        int jhx = (int)(int8_t)(wv & 0xff), jhy = (int)(int8_t)((wv >> 8) & 0xff);
-        int ci9 = 1 + step * 4 + k;  // candidate index in s_acMvRefineQ
-        int qx = 2 * jhx + c_refineQ[ci9][0], qy = 2 * jhy + c_refineQ[ci9][1];
-        int plane = (qy & 3) * 4 + (qx & 3);
-        int x0 = s_X[j] + (qx >> 2), y0 = s_Y[j] + (qy >> 2);
-        const uint8_t* src = planes + s_slotOff[j] + (size_t)plane * g.planeBytes +
-                             (size_t)(y0 + g.M + row) * g.pitch + ((x0 + g.M) & ~3) + wd * 4;
-        cp_async4(smem + j * qPerPu + k * qRegionBytes + row * RW + wd * 4, src);
-      }
-      cp_async_wait_all();
-      __syncwarp();
-#pragma unroll 1
-      for (int k = 0; k < 4; ++k) {
-        int ci9 = 1 + step * 4 + k;
-        int qx = 2 * bhx + c_refineQ[ci9][0], qy = 2 * bhy + c_refineQ[ci9][1];
-        unsigned dist = 0;
-        if (laneActive) {
-          int al = (s_X[myPu] + (qx >> 2) + g.M) & 3;
+        dist += costLut[golomb_bits(vx - predX) + golomb_bits(vy - predY)];
+        if (s < 4) {
 #pragma unroll
-          for (int rd = 0; rd < 2; ++rd) {
-            int t = tile0 + 32 * rd;
-            if (rd < rounds && t < T) {
-              int tx = t % ci.tilesX, ty = t / ci.tilesX;
-              const uint8_t* c = smem + myPu * qPerPu + k * qRegionBytes + (ty * TS) * RW + al + tx * TS;
-              dist += tile_dist<TS>(o[rd], c, RW, had);
-            }
-          }
-          dist = __reduce_add_sync(groupMask, dist);
-          // cost scale 0 (TEncSearch.cpp:5260): (((int<<1)+half)<<1) + q - pred
-          int vx = (((mvIntX << 1) + bhx) << 1) + c_refineQ[ci9][0];
-          int vy = (((mvIntY << 1) + bhy) << 1) + c_refineQ[ci9][1];
-          dist += costLut[golomb_bits(vx - predX) + golomb_bits(vy - predY)];
-          if (dist < qBest) { qBest = dist; qBestI = ci9; }
+          for (int q = 0; q < 9; ++q)
+            if (q == i) cost[q] = dist;
+        } else if (dist < qBest) {  // ascending i == table order, strict <
+          qBest = dist;
+          qBestI = i;
         }
       }
+    }
+    __syncwarp();  // all lanes are done with this buffer before step s+2 overwrites it
+    if (s == 3) {
+      unsigned best = cost[0];
+      int bestI = 0;
+#pragma unroll
+      for (int i = 1; i < 9; ++i)
+        if (cost[i] < best) { best = cost[i]; bestI = i; }  // strict <: first minimum (TEncSearch.cpp:1634)
+      bhx = c_refineH[bestI][0];
+      bhy = c_refineH[bestI][1];
+      qBest = best;  // candidate 0 of the quarter stage is the half-pel winner itself (same block, same bits)
+      qBestI = 0;
+      if (laneActive && unit0 == 0) s_win[myPu] = (bhx & 0xff) | ((bhy & 0xff) << 8);
       __syncwarp();
+      stage(4);
     }
+  }
 
-    if (laneActive && tile0 == 0) {
-      fme_result* r = &res[puIdx];
-      r->halfX = (int8_t)bhx; r->halfY = (int8_t)bhy;
-      r->qterX = c_refineQ[qBestI][0]; r->qterY = c_refineQ[qBestI][1];
-      r->cost = qBest;
-    }
+  if (laneActive && unit0 == 0) {
+    fme_result* r = &res[puIdx];
+    r->halfX = (int8_t)bhx; r->halfY = (int8_t)bhy;
+    r->qterX = c_refineQ[qBestI][0]; r->qterY = c_refineQ[qBestI][1];
+    r->cost = qBest;
   }
   __syncwarp();
 }
@@ -480,6 +553,7 @@ k2_refine(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, const ui
   __shared__ int s_Y[K2_WARPS][K2_MAX_PACK];
   __shared__ long long s_slot[K2_WARPS][K2_MAX_PACK];
   __shared__ int s_win[K2_WARPS][K2_MAX_PACK];
+  __shared__ unsigned long long s_base[K2_WARPS][K2_MAX_PACK];
 
   for (int i = threadIdx.x; i < FME_COST_LUT_SIZE; i += blockDim.x) s_lut[i] = costLutG[i];
   for (int i = threadIdx.x; i <= FME_MAX_CLASSES; i += blockDim.x) {
@@ -497,21 +571,26 @@ k2_refine(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, const ui
     if (lane == 0) pack = atomicAdd(workCounter, 1);
     pack = __shfl_sync(0xffffffffu, pack, 0);
     if (pack >= totalPacks) break;
-    // class of this pack: last c with packOff[c] <= pack (skipping empty classes)
-    int cls = 0;
-    for (int c = 0; c < FME_MAX_CLASSES; ++c)
-      if (s_packOff[c] <= pack && s_packOff[c + 1] > pack) { cls = c; break; }
+    // class of this pack: the c with packOff[c] <= pack < packOff[c+1]; two lanes cover the 64 classes
+    unsigned hit = __ballot_sync(0xffffffffu, s_packOff[lane] <= pack && s_packOff[lane + 1] > pack);
+    unsigned hit2 = __ballot_sync(0xffffffffu, s_packOff[lane + 32] <= pack && s_packOff[lane + 33] > pack);
+    int cls = hit ? (__ffs(hit) - 1) : (32 + __ffs(hit2) - 1);
     ClassInfo ci = class_info(cls);
     int inClass = s_classOff[cls + 1] - s_classOff[cls];
     int first = (pack - s_packOff[cls]) * ci.P;
     int count = min(ci.P, inClass - first);
     first += s_classOff[cls];
-    if (ci.ts == 8)
-      k2_pack<8>(ci, order, first, count, pus, res, planes, org, g, s_lut, useHad, smem, s_pu[warp], s_X[warp],
-                 s_Y[warp], s_slot[warp], s_win[warp]);
-    else
-      k2_pack<4>(ci, order, first, count, pus, res, planes, org, g, s_lut, useHad, smem, s_pu[warp], s_X[warp],
-                 s_Y[warp], s_slot[warp], s_win[warp]);
+#define K2_ARGS ci, order, first, count, pus, res, planes, org, g, s_lut, useHad, smem, s_pu[warp], s_X[warp], s_Y[warp], \
+                s_slot[warp], s_win[warp], s_base[warp]
+    if (ci.ts == 8) {
+      if (ci.w >= 16) k2_pack<8, 16>(K2_ARGS);
+      else k2_pack<8, 8>(K2_ARGS);
+    } else {
+      if (ci.w >= 16) k2_pack<4, 16>(K2_ARGS);
+      else if (ci.w >= 8) k2_pack<4, 8>(K2_ARGS);
+      else k2_pack<4, 4>(K2_ARGS);
+    }
+#undef K2_ARGS
   }
 }
 
