@@ -58,6 +58,7 @@ struct fme_ctx {
   fme_result* d_res = nullptr;
   float* d_nn = nullptr;
   size_t nnBytes = 0;
+  FmeNnHeader nnHeader{};
   uint32_t* d_costLut = nullptr;
   uint32_t* d_scratchU32 = nullptr;
   size_t scratchU32Capacity = 0;
@@ -159,7 +160,7 @@ int run_search(fme_ctx* c, fme_pu* d_pus, int n, fme_result* d_out, int mode) {
   }
   if (mode & FME_MODE_NN) {
     StageTimer t(c, 2);
-    CU_CHECK(fme_launch_k3(d_pus, n, d_out, c->d_nn, c->nnBytes, c->stream, &c->launches));
+    CU_CHECK(fme_launch_k3(d_pus, n, d_out, c->d_nn, c->nnBytes, c->nnHeader, c->stream, &c->launches));
   }
   return FME_OK;
 }
@@ -327,6 +328,7 @@ int fme_set_nn_weights(fme_ctx* c, const void* blob, size_t bytes) {
   CU_CHECK(cudaMalloc(&c->d_nn, need));
   CU_CHECK(cudaMemcpy(c->d_nn, blob, need, cudaMemcpyHostToDevice));
   c->nnBytes = need;
+  c->nnHeader = h;
   c->nnValid = true;
   return FME_OK;
 }

@@ -41,6 +41,7 @@ struct ClassInfo {
   int tilesX;    // tiles per PU row
   int tiles;     // tiles per PU
   int units;     // lane work units per PU: one 8x8 tile, or a pair of 4x4 tiles
+  int lanes;     // lanes per PU: units rounded up to a power of two (<= 32) so that per-PU sums are xor-shuffles
   int P;         // PUs per pack
 };
 
@@ -52,7 +53,9 @@ __host__ __device__ inline ClassInfo class_info(int cls) {
   c.tilesX = c.w / c.ts;
   c.tiles = c.tilesX * (c.h / c.ts);
   c.units = c.ts == 8 ? c.tiles : c.tiles / 2;  // 4x4-tiled PUs always have an even tile count
-  c.P = c.units >= 32 ? 1 : 32 / c.units;
+  c.lanes = 1;
+  while (c.lanes < c.units && c.lanes < 32) c.lanes <<= 1;
+  c.P = 32 / c.lanes;
   return c;
 }
 
@@ -349,12 +352,10 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   const int w = ci.w, h = ci.h;
   const int U = ci.units;                      // lane units per PU
   const int rounds = (U + 31) >> 5;            // 2 only when a single PU has more than 32 units (then P == 1)
-  const int lanesPerPu = U >= 32 ? 32 : U;
-  const int myPu = U >= 32 ? 0 : lane / lanesPerPu;   // PU slot in the pack served by this lane
-  const bool laneActive = myPu < count && myPu < ci.P;
-  const int unit0 = lane - myPu * lanesPerPu;  // unit index in round 0
-  const unsigned groupMask =
-      lanesPerPu == 32 ? 0xffffffffu : (((1u << lanesPerPu) - 1u) << (myPu * lanesPerPu));
+  const int lanesPerPu = ci.lanes;             // power of two
+  const int myPu = lane / lanesPerPu;          // PU slot in the pack served by this lane
+  const bool laneActive = myPu < count;
+  const int unit0 = lane - myPu * lanesPerPu;  // unit index in round 0 (may be >= U: idle lane of a padded group)
 
   // ---- pack table ----
   if (lane < ci.P) {
@@ -456,11 +457,10 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   if (rounds == 1) loadUnit(unit0);
 
   // ---- 12 steps: prefetch step s+1 while evaluating the candidates served by step s ----
-  unsigned cost[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) cost[i] = 0xffffffffu;
-  unsigned qBest = 0xffffffffu;
-  int qBestI = 0, bhx = 0, bhy = 0;
+  // running first-minimum: candidates of the half-pel stage are evaluated plane by plane, i.e. out of table
+  // order, so ties are broken by the table index explicitly (strict < in table order, TEncSearch.cpp:1634)
+  unsigned hBest = 0xffffffffu, qBest = 0xffffffffu;
+  int hBestI = 9, qBestI = 0, bhx = 0, bhy = 0;
 #pragma unroll 1
   for (int s = 0; s < 12; ++s) {
     const bool prefetch = (s != 3) && (s != 11);  // step 4 depends on the half-pel winner found after step 3
@@ -500,13 +500,11 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
         if (rounds > 1) loadUnit(unit0 + 32 * rd);  // PUs with more than 32 units: source tile re-fetched per round
         if (uOn) dist += unit_dist<TS>(o, region + uOff + candOff, sg.RW, u1Off, had);
       }
+      for (int d = lanesPerPu >> 1; d > 0; d >>= 1) dist += __shfl_xor_sync(0xffffffffu, dist, d);  // per-PU sum
       if (laneActive) {
-        dist = __reduce_add_sync(groupMask, dist);
         dist += costLut[golomb_bits(vx - predX) + golomb_bits(vy - predY)];
         if (s < 4) {
-#pragma unroll
-          for (int q = 0; q < 9; ++q)
-            if (q == i) cost[q] = dist;
+          if (dist < hBest || (dist == hBest && i < hBestI)) { hBest = dist; hBestI = i; }
         } else if (dist < qBest) {  // ascending i == table order, strict <
           qBest = dist;
           qBestI = i;
@@ -515,14 +513,10 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
     }
     __syncwarp();  // all lanes are done with this buffer before step s+2 overwrites it
     if (s == 3) {
-      unsigned best = cost[0];
-      int bestI = 0;
-#pragma unroll
-      for (int i = 1; i < 9; ++i)
-        if (cost[i] < best) { best = cost[i]; bestI = i; }  // strict <: first minimum (TEncSearch.cpp:1634)
+      const int bestI = hBestI < 9 ? hBestI : 0;
       bhx = c_refineH[bestI][0];
       bhy = c_refineH[bestI][1];
-      qBest = best;  // candidate 0 of the quarter stage is the half-pel winner itself (same block, same bits)
+      qBest = hBest;  // candidate 0 of the quarter stage is the half-pel winner itself (same block, same bits)
       qBestI = 0;
       if (laneActive && unit0 == 0) s_win[myPu] = (bhx & 0xff) | ((bhy & 0xff) << 8);
       __syncwarp();

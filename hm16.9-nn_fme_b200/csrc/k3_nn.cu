@@ -7,11 +7,16 @@
 //   X_l = relu(W_l X_{l-1} + b_l) * gamma_l + beta_l                                   (:120-127)
 //   OUT = W_o X + b_o ; class = first argmax ; class -> (half, quarter) per axis        (:130-193)
 //
-// One thread per PU, weights staged once per CTA in shared memory (8.3 KB for the shipped 17-22-20-49
-// nets; every lane reads the same weight -> broadcast, no bank conflicts).  The arithmetic is plain
-// fp32 with one rounding per operation and ascending-k dot products (__fmul_rn/__fadd_rn forbid FMA
-// contraction), i.e. the same operation order as the CPU restatement, so logits are bit-identical to
-// the oracle; against real Eigen the contract is 1e-5 relative (BASELINE.json).
+// The arithmetic is plain fp32 with one rounding per operation and ascending-k dot products
+// (__fmul_rn/__fadd_rn forbid FMA contraction), i.e. the operation order of the CPU restatement, so the
+// logits are bit-identical to the oracle; against real Eigen the contract is 1e-5 relative (BASELINE.json).
+//
+// Fast path (architectures known at compile time: the shipped 17-22-20-49 nets and the 9-40-40-40-49
+// "3-layer" shape): two PUs per thread, the layer input vector lives in registers (fully unrolled over k),
+// weights are re-laid out once per CTA into shared memory with rows padded to 4 floats and fetched as
+// broadcast LDS.128 (one wavefront for the whole warp), hidden activations go through a [unit][thread]
+// shared-memory transpose so that the output-unit loop can stay a runtime loop (small code, no local memory).
+// Generic path: any FMNN blob (up to 4 hidden layers of <= 64 units), one PU per thread, local-memory vectors.
 #include "fme_common.cuh"
 
 namespace {
@@ -32,6 +37,23 @@ __device__ __forceinline__ int emb_index(int v, bool isHeight) {
   }
 }
 
+// TEncSearch.cpp:136-193: class -> per-axis (half, quarter)
+__device__ __forceinline__ void store_class(fme_result* r, int best) {
+  int qx = best % 7, qy = best / 7;
+  const int kHalf = (0 << 0) | (0 << 2) | (1 << 4) | (1 << 6) | (1 << 8) | (2 << 10) | (2 << 12);  // +1 biased
+  const int kQter = (0 << 0) | (1 << 2) | (0 << 4) | (1 << 6) | (2 << 8) | (1 << 10) | (2 << 12);  // +1 biased
+  int8_t hx = 0, hy = 0, tx = 0, ty = 0;
+  if (best >= 0 && best <= 48) {
+    hx = (int8_t)(((kHalf >> (2 * qx)) & 3) - 1); tx = (int8_t)(((kQter >> (2 * qx)) & 3) - 1);
+    hy = (int8_t)(((kHalf >> (2 * qy)) & 3) - 1); ty = (int8_t)(((kQter >> (2 * qy)) & 3) - 1);
+  }
+  r->nnHalfX = hx; r->nnHalfY = hy; r->nnQterX = tx; r->nnQterY = ty;
+  r->nnClass = (uint8_t)best;
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic path
+// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(K3_THREADS) k3_nn_pred(const fme_pu* __restrict__ pus, int n,
                                                         fme_result* __restrict__ res,
                                                         const float* __restrict__ blob, int blobWords) {
@@ -89,26 +111,229 @@ __global__ void __launch_bounds__(K3_THREADS) k3_nn_pred(const fme_pu* __restric
       if (H->outSigmoid) acc = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-acc)));
       if (o == 0 || acc > bestV) { bestV = acc; best = o; }
     }
-    // TEncSearch.cpp:136-193: class -> per-axis (half, quarter)
-    int qx = best % 7, qy = best / 7;
-    const int kHalf = (0 << 0) | (0 << 2) | (1 << 4) | (1 << 6) | (1 << 8) | (2 << 10) | (2 << 12);   // +1 biased
-    const int kQter = (0 << 0) | (1 << 2) | (0 << 4) | (1 << 6) | (2 << 8) | (1 << 10) | (2 << 12);   // +1 biased
-    int8_t hx = 0, hy = 0, tx = 0, ty = 0;
-    if (best >= 0 && best <= 48) {
-      hx = (int8_t)(((kHalf >> (2 * qx)) & 3) - 1); tx = (int8_t)(((kQter >> (2 * qx)) & 3) - 1);
-      hy = (int8_t)(((kHalf >> (2 * qy)) & 3) - 1); ty = (int8_t)(((kQter >> (2 * qy)) & 3) - 1);
-    }
-    fme_result* r = &res[i];
-    r->nnHalfX = hx; r->nnHalfY = hy; r->nnQterX = tx; r->nnQterY = ty;
-    r->nnClass = (uint8_t)best;
+    store_class(&res[i], best);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast path: compile-time layer sizes
+// ------------------------------------------------------------------------------------------------
+constexpr int K3F_THREADS = 128;
+constexpr int K3F_NPU = 2;  // PUs per thread
+
+__host__ __device__ constexpr int pad4(int v) { return (v + 3) & ~3; }
+
+// One dense layer for NPU input vectors held in registers.  sW: rows padded to pad4(IN) floats, 16-byte aligned.
+// emit(o, acc[NPU]) receives the pre-activation W x + b of unit o (ascending-k, mul then add).
+template <int IN, int OUT, typename Emit>
+__device__ __forceinline__ void dense_rows(const float* __restrict__ sW, const float* __restrict__ sb,
+                                           const float (&x)[K3F_NPU][IN], Emit emit) {
+  constexpr int IN4 = pad4(IN);
+#pragma unroll 1
+  for (int o = 0; o < OUT; ++o) {
+    const float4* wr = reinterpret_cast<const float4*>(sW + o * IN4);
+    float acc[K3F_NPU];
+#pragma unroll
+    for (int q = 0; q < IN4 / 4; ++q) {
+      const float4 wv = wr[q];  // broadcast LDS.128
+      const float wk[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int k = 4 * q + t;
+        if (k < IN) {
+#pragma unroll
+          for (int u = 0; u < K3F_NPU; ++u) {
+            const float prod = __fmul_rn(wk[t], x[u][k]);
+            acc[u] = (k == 0) ? prod : __fadd_rn(acc[u], prod);
+          }
+        }
+      }
+    }
+    const float bo = sb[o];
+#pragma unroll
+    for (int u = 0; u < K3F_NPU; ++u) acc[u] = __fadd_rn(acc[u], bo);
+    emit(o, acc);
+  }
+}
+
+// shared-memory image of one layer
+template <int IN, int OUT>
+struct LayerSmem {
+  static constexpr int IN4 = pad4(IN);
+  static constexpr int WORDS = OUT * IN4 + 3 * pad4(OUT);
+  __device__ static const float* W(const float* s) { return s; }
+  __device__ static const float* b(const float* s) { return s + OUT * IN4; }
+  __device__ static const float* g(const float* s) { return s + OUT * IN4 + pad4(OUT); }
+  __device__ static const float* be(const float* s) { return s + OUT * IN4 + 2 * pad4(OUT); }
+  // blob layout: W[OUT][IN] b[OUT] gamma[OUT] beta[OUT] (gamma/beta absent for the output layer)
+  __device__ static void load(float* s, const float* __restrict__ blob, bool hasBn) {
+    for (int i = threadIdx.x; i < OUT * IN4; i += blockDim.x) {
+      int o = i / IN4, k = i - o * IN4;
+      s[i] = k < IN ? blob[o * IN + k] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < OUT; i += blockDim.x) {
+      s[OUT * IN4 + i] = blob[OUT * IN + i];
+      if (hasBn) {
+        s[OUT * IN4 + pad4(OUT) + i] = blob[OUT * IN + OUT + i];
+        s[OUT * IN4 + 2 * pad4(OUT) + i] = blob[OUT * IN + 2 * OUT + i];
+      }
+    }
+  }
+  static constexpr int BLOB_WORDS_BN = OUT * IN + 3 * OUT;
+  static constexpr int BLOB_WORDS_OUT = OUT * IN + OUT;
+};
+
+// NH hidden layers of sizes H1,H2,(H3); NEMB = 0 or 2 embedding tables of 8 x 4.
+template <int NEMB, int H1, int H2, int H3, int NOUT>
+__global__ void __launch_bounds__(K3F_THREADS) k3_nn_fixed(const fme_pu* __restrict__ pus, int n,
+                                                          fme_result* __restrict__ res,
+                                                          const float* __restrict__ blob) {
+  constexpr int IN0 = 9 + 4 * NEMB;
+  constexpr int HLAST = H3 > 0 ? H3 : H2;
+  constexpr int HMAX = (H1 > H2 ? (H1 > H3 ? H1 : H3) : (H2 > H3 ? H2 : H3));
+  using L1 = LayerSmem<IN0, H1>;
+  using L2 = LayerSmem<H1, H2>;
+  using L3 = LayerSmem<H2, (H3 > 0 ? H3 : 1)>;
+  using LO = LayerSmem<HLAST, NOUT>;
+  extern __shared__ __align__(16) float s_mem[];
+  float* s_in = s_mem;                                  // mean[9] stdev[9] gammaIn[9] emb[NEMB][8][4], padded to 4
+  constexpr int IN_WORDS = pad4(27 + NEMB * 32);
+  float* s_l1 = s_in + IN_WORDS;
+  float* s_l2 = s_l1 + L1::WORDS;
+  float* s_l3 = s_l2 + L2::WORDS;
+  float* s_lo = s_l3 + (H3 > 0 ? L3::WORDS : 0);
+  float* s_act = s_lo + LO::WORDS;                      // [HMAX][K3F_NPU * K3F_THREADS] activation transpose
+
+  {  // stage + re-layout the weights once per CTA
+    const float* p = blob + 16;
+    for (int i = threadIdx.x; i < 27 + NEMB * 32; i += blockDim.x) s_in[i] = p[i];
+    p += 27 + NEMB * 32;
+    L1::load(s_l1, p, true); p += L1::BLOB_WORDS_BN;
+    L2::load(s_l2, p, true); p += L2::BLOB_WORDS_BN;
+    if (H3 > 0) { L3::load(s_l3, p, true); p += L3::BLOB_WORDS_BN; }
+    LO::load(s_lo, p, false);
+  }
+  __syncthreads();
+
+  const int tid = threadIdx.x;
+  constexpr int ACT_STRIDE = K3F_NPU * K3F_THREADS;
+  for (int base = blockIdx.x * ACT_STRIDE; base < n; base += gridDim.x * ACT_STRIDE) {
+    int idx[K3F_NPU];
+    float x0[K3F_NPU][IN0];
+#pragma unroll
+    for (int u = 0; u < K3F_NPU; ++u) {
+      idx[u] = base + u * K3F_THREADS + tid;
+      const int ii = min(idx[u], n - 1);  // out-of-range lanes compute a valid PU and drop the result
+      const fme_pu p = pus[ii];
+      int c = 0;
+      if (NEMB == 2) {
+        const float* e0 = s_in + 27 + emb_index(p.h, true) * 4;
+        const float* e1 = s_in + 27 + 32 + emb_index(p.w, false) * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x0[u][c++] = e0[k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x0[u][c++] = e1[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        float e = __uint2float_rn(p.err[k]);
+        e = __fdiv_rn(__fsub_rn(e, s_in[k]), s_in[9 + k]);
+        x0[u][c++] = __fmul_rn(e, s_in[18 + k]);
+      }
+    }
+    // hidden layer 1
+    dense_rows<IN0, H1>(L1::W(s_l1), L1::b(s_l1), x0, [&](int o, const float (&acc)[K3F_NPU]) {
+      const float g = L1::g(s_l1)[o], be = L1::be(s_l1)[o];
+#pragma unroll
+      for (int u = 0; u < K3F_NPU; ++u) {
+        float a = acc[u] < 0.0f ? 0.0f : acc[u];
+        s_act[o * ACT_STRIDE + u * K3F_THREADS + tid] = __fadd_rn(__fmul_rn(a, g), be);
+      }
+    });
+    float x1[K3F_NPU][H1];
+#pragma unroll
+    for (int u = 0; u < K3F_NPU; ++u)
+#pragma unroll
+      for (int k = 0; k < H1; ++k) x1[u][k] = s_act[k * ACT_STRIDE + u * K3F_THREADS + tid];
+    // hidden layer 2 (each thread only touches its own column of s_act: no barrier needed)
+    dense_rows<H1, H2>(L2::W(s_l2), L2::b(s_l2), x1, [&](int o, const float (&acc)[K3F_NPU]) {
+      const float g = L2::g(s_l2)[o], be = L2::be(s_l2)[o];
+#pragma unroll
+      for (int u = 0; u < K3F_NPU; ++u) {
+        float a = acc[u] < 0.0f ? 0.0f : acc[u];
+        s_act[o * ACT_STRIDE + u * K3F_THREADS + tid] = __fadd_rn(__fmul_rn(a, g), be);
+      }
+    });
+    float x2[K3F_NPU][H2];
+#pragma unroll
+    for (int u = 0; u < K3F_NPU; ++u)
+#pragma unroll
+      for (int k = 0; k < H2; ++k) x2[u][k] = s_act[k * ACT_STRIDE + u * K3F_THREADS + tid];
+
+    int best[K3F_NPU];
+    float bestV[K3F_NPU];
+    auto argmax = [&](int o, const float (&acc)[K3F_NPU]) {
+#pragma unroll
+      for (int u = 0; u < K3F_NPU; ++u)
+        if (o == 0 || acc[u] > bestV[u]) { bestV[u] = acc[u]; best[u] = o; }  // first maximum (TEncSearch.cpp:134)
+    };
+    if constexpr (H3 > 0) {
+      dense_rows<H2, H3>(L3::W(s_l3), L3::b(s_l3), x2, [&](int o, const float (&acc)[K3F_NPU]) {
+        const float g = L3::g(s_l3)[o], be = L3::be(s_l3)[o];
+#pragma unroll
+        for (int u = 0; u < K3F_NPU; ++u) {
+          float a = acc[u] < 0.0f ? 0.0f : acc[u];
+          s_act[o * ACT_STRIDE + u * K3F_THREADS + tid] = __fadd_rn(__fmul_rn(a, g), be);
+        }
+      });
+      float x3[K3F_NPU][H3 > 0 ? H3 : 1];
+#pragma unroll
+      for (int u = 0; u < K3F_NPU; ++u)
+#pragma unroll
+        for (int k = 0; k < H3; ++k) x3[u][k] = s_act[k * ACT_STRIDE + u * K3F_THREADS + tid];
+      dense_rows<(H3 > 0 ? H3 : 1), NOUT>(LO::W(s_lo), LO::b(s_lo), x3, argmax);
+    } else {
+      dense_rows<H2, NOUT>(LO::W(s_lo), LO::b(s_lo), x2, argmax);
+    }
+#pragma unroll
+    for (int u = 0; u < K3F_NPU; ++u)
+      if (idx[u] < n) store_class(&res[idx[u]], best[u]);
+  }
+}
+
+template <int NEMB, int H1, int H2, int H3, int NOUT>
+cudaError_t launch_fixed(const fme_pu* d_pus, int n, fme_result* d_res, const float* d_nn, cudaStream_t s) {
+  constexpr int IN0 = 9 + 4 * NEMB;
+  constexpr int HLAST = H3 > 0 ? H3 : H2;
+  constexpr int HMAX = (H1 > H2 ? (H1 > H3 ? H1 : H3) : (H2 > H3 ? H2 : H3));
+  constexpr int words = pad4(27 + NEMB * 32) + LayerSmem<IN0, H1>::WORDS + LayerSmem<H1, H2>::WORDS +
+                        (H3 > 0 ? LayerSmem<H2, (H3 > 0 ? H3 : 1)>::WORDS : 0) + LayerSmem<HLAST, NOUT>::WORDS +
+                        HMAX * K3F_NPU * K3F_THREADS;
+  const int smem = words * 4;
+  static bool attr = false;
+  if (!attr && smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k3_nn_fixed<NEMB, H1, H2, H3, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  int blocks = (n + K3F_NPU * K3F_THREADS - 1) / (K3F_NPU * K3F_THREADS);
+  if (blocks > 148 * 6) blocks = 148 * 6;
+  k3_nn_fixed<NEMB, H1, H2, H3, NOUT><<<blocks, K3F_THREADS, smem, s>>>(d_pus, n, d_res, d_nn);
+  return cudaGetLastError();
 }
 
 }  // namespace
 
 cudaError_t fme_launch_k3(const fme_pu* d_pus, int n, fme_result* d_res, const float* d_nn, size_t nnBytes,
-                          cudaStream_t s, int64_t* launches) {
+                          const FmeNnHeader& h, cudaStream_t s, int64_t* launches) {
   if (n <= 0) return cudaSuccess;
+  ++*launches;
+  if (!h.outSigmoid && h.nOut == 49) {
+    if (h.nEmb == 2 && h.embDim == 4 && h.nHidden == 2 && h.hidden[0] == 22 && h.hidden[1] == 20)
+      return launch_fixed<2, 22, 20, 0, 49>(d_pus, n, d_res, d_nn, s);  // shipped per-QP nets (master)
+    if (h.nEmb == 0 && h.nHidden == 3 && h.hidden[0] == 40 && h.hidden[1] == 40 && h.hidden[2] == 40)
+      return launch_fixed<0, 40, 40, 40, 49>(d_pus, n, d_res, d_nn, s);  // "3-layer" 9-40-40-40-49 shape
+  }
   int blocks = (n + K3_THREADS - 1) / K3_THREADS;
   if (blocks > 148 * 16) blocks = 148 * 16;
   static size_t attrSet = 0;
@@ -118,6 +343,5 @@ cudaError_t fme_launch_k3(const fme_pu* d_pus, int n, fme_result* d_res, const f
     attrSet = nnBytes;
   }
   k3_nn_pred<<<blocks, K3_THREADS, nnBytes, s>>>(d_pus, n, d_res, d_nn, (int)(nnBytes / 4));
-  ++*launches;
   return cudaGetLastError();
 }
