@@ -26,7 +26,7 @@ PU_LOSSLESS, PU_ERR_ON_GPU = 0x01, 0x02
 EXPORTS = [
     "fme_create", "fme_destroy", "fme_last_error", "fme_version", "fme_set_stream", "fme_synchronize",
     "fme_set_nn_weights", "fme_load_nn_csv_dir", "fme_set_slice", "fme_upload_ref", "fme_upload_ref_u8",
-    "fme_upload_org", "fme_upload_org_u8", "fme_submit", "fme_submit_async", "fme_submit_device", "fme_interp_slot",
+    "fme_upload_org", "fme_upload_org_u8", "fme_submit", "fme_submit_async", "fme_wait_oldest", "fme_submit_device", "fme_interp_slot",
     "fme_upload_ref_device_u8", "fme_upload_org_device_u8", "fme_int_surface_device", "fme_filter_hor",
     "fme_filter_ver", "fme_dist", "fme_mv_cost", "fme_upload_ref_chroma", "fme_mc", "fme_download_plane",
     "fme_last_kernel_ms", "fme_launch_count", "fme_set_profiling",
@@ -75,6 +75,7 @@ def load_library():
     lib.fme_submit.argtypes = [vp, vp, i32, vp, i32]
     lib.fme_submit_async.argtypes = [vp, vp, i32, vp, i32]
     lib.fme_submit_device.argtypes = [vp, vp, i32, vp, i32]
+    lib.fme_wait_oldest.argtypes = [vp]
     lib.fme_interp_slot.argtypes = [vp, i32]
     lib.fme_upload_ref_device_u8.argtypes = [vp, i32, vp, i32]
     lib.fme_upload_org_device_u8.argtypes = [vp, vp, i32]
@@ -197,6 +198,9 @@ class Fme:
 
     def submit_async(self, pus_ptr, n, out_ptr, mode=MODE_BOTH):
         self._check(self.lib.fme_submit_async(self.h, C.c_void_p(pus_ptr), n, C.c_void_p(out_ptr), mode))
+
+    def wait_oldest(self):
+        self._check(self.lib.fme_wait_oldest(self.h))
 
     def submit_device(self, d_pus_ptr, n, d_out_ptr, mode=MODE_BOTH):
         self._check(self.lib.fme_submit_device(self.h, C.c_void_p(d_pus_ptr), n, C.c_void_p(d_out_ptr), mode))

@@ -40,21 +40,33 @@ struct fme_ctx {
   fme_config cfg;
   FmeGeom g;
   int numSMs = 0;
+  // `stream` carries every kernel.  With the ctx's own stream, host<->device copies of the async entry points run
+  // on two extra streams (sIn, sOut) and are ordered against the kernels with events, so that the copies of one
+  // frame overlap the kernels of its neighbours; with a caller-provided stream everything is issued on that stream.
   cudaStream_t ownStream = nullptr, stream = nullptr;
+  cudaStream_t ownIn = nullptr, ownOut = nullptr, sIn = nullptr, sOut = nullptr;
+  cudaEvent_t evIn[2] = {}, evDone[2] = {}, evOut[2] = {};      // per record/result buffer
+  cudaEvent_t evPicIn[2] = {}, evPicFree[2] = {};               // per picture staging buffer
+  cudaEvent_t evOrgFree[2] = {};                                // per source-picture buffer
+  uint64_t submitSeq = 0, picSeq = 0, orgSeq = 0;
+  int fifo[2] = {0, 0}, fifoCount = 0;                          // outstanding async submits (buffer ids), oldest first
   // device memory
   uint8_t* d_planes = nullptr;   // [slots][16][Hp][pitch]
-  uint8_t* d_org = nullptr;      // [H + 1][orgPitch]
-  uint8_t* d_pic = nullptr;      // raw u8 picture staging [H][picPitch]
+  uint8_t* d_orgBuf[2] = {nullptr, nullptr};  // double-buffered source picture, [H + 2][orgPitch] each
+  uint8_t* d_org = nullptr;      // the buffer the next submit reads
+  uint8_t* d_picBuf[2] = {nullptr, nullptr};  // double-buffered raw u8 picture staging [H][picPitch]
+  uint8_t* d_pic = nullptr;      // staging buffer K1 reads for the most recent upload
   int picPitch = 0;
   int16_t* d_pel = nullptr;      // Pel staging for uploads / block-level calls
   size_t pelCapacity = 0;        // in samples
   int16_t* d_pel2 = nullptr;
   size_t pel2Capacity = 0;
-  int16_t* d_pelPic = nullptr;   // Pel picture staging for fme_upload_ref / fme_upload_org
-  size_t pelPicCapacity = 0;
+  int16_t* d_pelPic[2] = {nullptr, nullptr};  // Pel picture staging for fme_upload_ref / fme_upload_org
   uint8_t* d_cb = nullptr;       // [slots][Hcp][cPitch]
   uint8_t* d_cr = nullptr;
-  fme_pu* d_pus = nullptr;
+  fme_pu* d_pusBuf[2] = {nullptr, nullptr};
+  fme_result* d_resBuf[2] = {nullptr, nullptr};
+  fme_pu* d_pus = nullptr;       // = d_pusBuf[0], used by the synchronous helpers (fme_mc)
   fme_result* d_res = nullptr;
   float* d_nn = nullptr;
   size_t nnBytes = 0;
@@ -98,20 +110,23 @@ int ensure_u32(fme_ctx* c, size_t n) {
 }
 
 // Copy a host picture (w x h, stride in samples) into a device u8 picture.  No CPU pass over the samples:
-// u8 input is DMA'd straight into place; Pel (int16) input is DMA'd into a device staging plane and narrowed
-// by a kernel.  With pinned caller memory both copies are fully asynchronous.
-int stage_picture(fme_ctx* c, const uint8_t* src, int stride, int w, int h, uint8_t* d_dst, int dstPitch) {
+// u8 input is DMA'd straight into place; Pel (int16) input is DMA'd into a device staging plane and narrowed by a
+// kernel.  The DMA runs on the copy-in stream; `stagingIdx` selects the Pel staging plane and the events that
+// keep a staging buffer from being overwritten while an earlier convert/K1 still reads it.
+int stage_picture(fme_ctx* c, const uint8_t* src, int stride, int w, int h, uint8_t* d_dst, int dstPitch, int stagingIdx) {
   if (!src || stride < w) return fail(FME_ERR_INVALID, "picture pointer/stride invalid");
-  CU_CHECK(cudaMemcpy2DAsync(d_dst, dstPitch, src, stride, w, h, cudaMemcpyHostToDevice, c->stream));
+  (void)stagingIdx;
+  CU_CHECK(cudaMemcpy2DAsync(d_dst, dstPitch, src, stride, w, h, cudaMemcpyHostToDevice, c->sIn));
   return FME_OK;
 }
-int stage_picture(fme_ctx* c, const int16_t* src, int stride, int w, int h, uint8_t* d_dst, int dstPitch) {
+int stage_picture(fme_ctx* c, const int16_t* src, int stride, int w, int h, uint8_t* d_dst, int dstPitch, int stagingIdx) {
   if (!src || stride < w) return fail(FME_ERR_INVALID, "picture pointer/stride invalid");
-  int rc = ensure_pel(&c->d_pelPic, &c->pelPicCapacity, (size_t)w * h);
-  if (rc) return rc;
-  CU_CHECK(cudaMemcpy2DAsync(c->d_pelPic, (size_t)w * 2, src, (size_t)stride * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice,
-                             c->stream));
-  CU_CHECK(fme_launch_pel_to_u8(c->d_pelPic, w, d_dst, dstPitch, w, h, c->stream, &c->launches));
+  CU_CHECK(cudaMemcpy2DAsync(c->d_pelPic[stagingIdx], (size_t)w * 2, src, (size_t)stride * 2, (size_t)w * 2, h,
+                             cudaMemcpyHostToDevice, c->sIn));
+  // the narrowing kernel runs on the kernel stream once the DMA has landed
+  CU_CHECK(cudaEventRecord(c->evPicIn[stagingIdx], c->sIn));
+  CU_CHECK(cudaStreamWaitEvent(c->stream, c->evPicIn[stagingIdx], 0));
+  CU_CHECK(fme_launch_pel_to_u8(c->d_pelPic[stagingIdx], w, d_dst, dstPitch, w, h, c->stream, &c->launches));
   return FME_OK;
 }
 
@@ -147,6 +162,27 @@ int run_k1(fme_ctx* c, int slot) {
   return FME_OK;
 }
 
+// Pick the next picture staging buffer: its previous reader (convert / K1 on the kernel stream) must be done
+// before the copy-in stream overwrites it.
+int begin_picture_upload(fme_ctx* c, int* idx) {
+  *idx = (int)(c->picSeq++ & 1);
+  CU_CHECK(cudaStreamWaitEvent(c->sIn, c->evPicFree[*idx], 0));
+  c->d_pic = c->d_picBuf[*idx];
+  return FME_OK;
+}
+// After the copy (and narrowing) have been issued: kernels wait for the DMA, and the buffer is released once the
+// kernel stream has consumed it.
+int end_picture_upload(fme_ctx* c, int idx, bool kernelsFollow) {
+  CU_CHECK(cudaEventRecord(c->evPicIn[idx], c->sIn));
+  CU_CHECK(cudaStreamWaitEvent(c->stream, c->evPicIn[idx], 0));
+  (void)kernelsFollow;
+  return FME_OK;
+}
+int release_picture(fme_ctx* c, int idx) {
+  CU_CHECK(cudaEventRecord(c->evPicFree[idx], c->stream));
+  return FME_OK;
+}
+
 int run_search(fme_ctx* c, fme_pu* d_pus, int n, fme_result* d_out, int mode) {
   if (mode < 1 || mode > 3) return fail(FME_ERR_INVALID, "mode must be FME_MODE_STD|NN|BOTH");
   if ((mode & FME_MODE_STD) && (!c->orgValid || !c->sliceValid))
@@ -162,6 +198,14 @@ int run_search(fme_ctx* c, fme_pu* d_pus, int n, fme_result* d_out, int mode) {
     StageTimer t(c, 2);
     CU_CHECK(fme_launch_k3(d_pus, n, d_out, c->d_nn, c->nnBytes, c->nnHeader, c->stream, &c->launches));
   }
+  return FME_OK;
+}
+
+int sync_all(fme_ctx* c) {
+  CU_CHECK(cudaStreamSynchronize(c->sIn));
+  CU_CHECK(cudaStreamSynchronize(c->stream));
+  CU_CHECK(cudaStreamSynchronize(c->sOut));
+  c->fifoCount = 0;
   return FME_OK;
 }
 
@@ -232,16 +276,26 @@ int fme_create(const fme_config* cfg, fme_ctx** out) {
     }                                                                                         \
   } while (0)
   CREATE_CHECK(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
-  c->stream = c->ownStream;
+  CREATE_CHECK(cudaStreamCreateWithFlags(&c->ownIn, cudaStreamNonBlocking));
+  CREATE_CHECK(cudaStreamCreateWithFlags(&c->ownOut, cudaStreamNonBlocking));
+  c->stream = c->ownStream; c->sIn = c->ownIn; c->sOut = c->ownOut;
   for (auto& e : c->ev) CREATE_CHECK(cudaEventCreate(&e));
+  for (int b = 0; b < 2; ++b) {
+    for (cudaEvent_t* e : {&c->evIn[b], &c->evDone[b], &c->evOut[b], &c->evPicIn[b], &c->evPicFree[b], &c->evOrgFree[b]})
+      CREATE_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
   // +1 plane of slack so that word-granular staging reads past the last row stay inside the allocation
   CREATE_CHECK(cudaMalloc(&c->d_planes, g.slotBytes * cfg->numRefSlots + g.pitch * 2));
   CREATE_CHECK(cudaMemsetAsync(c->d_planes, 0, g.slotBytes * cfg->numRefSlots + g.pitch * 2, c->stream));
-  CREATE_CHECK(cudaMalloc(&c->d_org, (size_t)(g.H + 2) * g.orgPitch));
-  CREATE_CHECK(cudaMemsetAsync(c->d_org, 0, (size_t)(g.H + 2) * g.orgPitch, c->stream));
-  CREATE_CHECK(cudaMalloc(&c->d_pic, (size_t)g.H * c->picPitch));
-  CREATE_CHECK(cudaMalloc(&c->d_pus, sizeof(fme_pu) * (size_t)cfg->maxPUs));
-  CREATE_CHECK(cudaMalloc(&c->d_res, sizeof(fme_result) * (size_t)cfg->maxPUs));
+  for (int b = 0; b < 2; ++b) {
+    CREATE_CHECK(cudaMalloc(&c->d_orgBuf[b], (size_t)(g.H + 2) * g.orgPitch));
+    CREATE_CHECK(cudaMemsetAsync(c->d_orgBuf[b], 0, (size_t)(g.H + 2) * g.orgPitch, c->stream));
+    CREATE_CHECK(cudaMalloc(&c->d_picBuf[b], (size_t)g.H * c->picPitch));
+    CREATE_CHECK(cudaMalloc(&c->d_pelPic[b], (size_t)g.W * g.H * sizeof(int16_t)));
+    CREATE_CHECK(cudaMalloc(&c->d_pusBuf[b], sizeof(fme_pu) * (size_t)cfg->maxPUs));
+    CREATE_CHECK(cudaMalloc(&c->d_resBuf[b], sizeof(fme_result) * (size_t)cfg->maxPUs));
+  }
+  c->d_org = c->d_orgBuf[0]; c->d_pic = c->d_picBuf[0]; c->d_pus = c->d_pusBuf[0]; c->d_res = c->d_resBuf[0];
   CREATE_CHECK(cudaMalloc(&c->d_costLut, sizeof(uint32_t) * FME_COST_LUT_SIZE));
   CREATE_CHECK(cudaMalloc(&c->k2.classCount, sizeof(int) * (4 * FME_MAX_CLASSES + 16)));
   c->k2.classCursor = c->k2.classCount + FME_MAX_CLASSES;
@@ -258,27 +312,50 @@ int fme_create(const fme_config* cfg, fme_ctx** out) {
 void fme_destroy(fme_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device);
-  if (c->stream) cudaStreamSynchronize(c->stream);
-  cudaFree(c->d_planes); cudaFree(c->d_org); cudaFree(c->d_pic); cudaFree(c->d_pel); cudaFree(c->d_pel2); cudaFree(c->d_pelPic);
-  cudaFree(c->d_cb); cudaFree(c->d_cr); cudaFree(c->d_pus); cudaFree(c->d_res); cudaFree(c->d_nn);
+  cudaDeviceSynchronize();
+  cudaFree(c->d_planes); cudaFree(c->d_pel); cudaFree(c->d_pel2);
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(c->d_orgBuf[b]); cudaFree(c->d_picBuf[b]); cudaFree(c->d_pelPic[b]); cudaFree(c->d_pusBuf[b]); cudaFree(c->d_resBuf[b]);
+    for (cudaEvent_t e : {c->evIn[b], c->evDone[b], c->evOut[b], c->evPicIn[b], c->evPicFree[b], c->evOrgFree[b]})
+      if (e) cudaEventDestroy(e);
+  }
+  cudaFree(c->d_cb); cudaFree(c->d_cr); cudaFree(c->d_nn);
   cudaFree(c->d_costLut); cudaFree(c->d_scratchU32); cudaFree(c->k2.classCount); cudaFree(c->k2.order);
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
   if (c->ownStream) cudaStreamDestroy(c->ownStream);
+  if (c->ownIn) cudaStreamDestroy(c->ownIn);
+  if (c->ownOut) cudaStreamDestroy(c->ownOut);
   delete c;
 }
 
 int fme_set_stream(fme_ctx* c, void* s) {
   if (!c) return fail(FME_ERR_INVALID, "null ctx");
-  CU_CHECK(cudaStreamSynchronize(c->stream));
-  c->stream = s ? static_cast<cudaStream_t>(s) : c->ownStream;
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  int rc = sync_all(c);
+  if (rc) return rc;
+  if (s) {  // caller-provided stream: everything, copies included, is issued on it
+    c->stream = c->sIn = c->sOut = static_cast<cudaStream_t>(s);
+  } else {
+    c->stream = c->ownStream; c->sIn = c->ownIn; c->sOut = c->ownOut;
+  }
   return FME_OK;
 }
 
 int fme_synchronize(fme_ctx* c) {
   if (!c) return fail(FME_ERR_INVALID, "null ctx");
-  CU_CHECK(cudaStreamSynchronize(c->stream));
+  int rc = sync_all(c);
+  if (rc) return rc;
   collect_ms(c);
+  return FME_OK;
+}
+
+int fme_wait_oldest(fme_ctx* c) {
+  if (!c) return fail(FME_ERR_INVALID, "null ctx");
+  if (c->fifoCount == 0) return FME_OK;
+  CU_CHECK(cudaEventSynchronize(c->evOut[c->fifo[0]]));
+  c->fifo[0] = c->fifo[1];
+  --c->fifoCount;
   return FME_OK;
 }
 
@@ -322,7 +399,10 @@ int fme_set_nn_weights(fme_ctx* c, const void* blob, size_t bytes) {
   if (bytes != need) return fail(FME_ERR_INVALID, "weight blob: size %zu, expected %zu", bytes, need);
   if (need > 200 * 1024) return fail(FME_ERR_INVALID, "weight blob too large for shared memory");
   CU_CHECK(cudaSetDevice(c->cfg.device));
-  CU_CHECK(cudaStreamSynchronize(c->stream));
+  {
+    int rc = sync_all(c);
+    if (rc) return rc;
+  }
   if (c->d_nn) cudaFree(c->d_nn);
   c->d_nn = nullptr;
   CU_CHECK(cudaMalloc(&c->d_nn, need));
@@ -411,7 +491,10 @@ int fme_set_slice(fme_ctx* c, double lambda) {
   // TComRdCost.h:165-169 Distortion((m_motionLambda * bits) / 65536.0)
   const double motionLambda = 65536.0 * sqrt(lambda);
   for (unsigned b = 0; b < FME_COST_LUT_SIZE; ++b) c->costLut[b] = (uint32_t)((motionLambda * b) / 65536.0);
-  CU_CHECK(cudaStreamSynchronize(c->stream));
+  {
+    int rc = sync_all(c);  // in-flight submits still read the previous table
+    if (rc) return rc;
+  }
   CU_CHECK(cudaMemcpyAsync(c->d_costLut, c->costLut, sizeof(c->costLut), cudaMemcpyHostToDevice, c->stream));
   CU_CHECK(cudaStreamSynchronize(c->stream));
   c->sliceValid = true;
@@ -433,31 +516,35 @@ int fme_mv_cost(fme_ctx* c, int x, int y, int scale, int predX, int predY, uint3
 }
 
 // ---- frame data ----------------------------------------------------------------------------
-int fme_upload_ref(fme_ctx* c, int slot, const int16_t* y, int stride) {
+extern "C++" {
+template <typename T>
+static int upload_ref_host(fme_ctx* c, int slot, const T* y, int stride) {
   int rc = check_slot(c, slot);
   if (rc) return rc;
   CU_CHECK(cudaSetDevice(c->cfg.device));
-  rc = stage_picture(c, y, stride, c->g.W, c->g.H, c->d_pic, c->picPitch);
-  if (rc) return rc;
-  return run_k1(c, slot);
+  int idx;
+  if ((rc = begin_picture_upload(c, &idx))) return rc;
+  if ((rc = stage_picture(c, y, stride, c->g.W, c->g.H, c->d_pic, c->picPitch, idx))) return rc;
+  if ((rc = end_picture_upload(c, idx, true))) return rc;
+  if ((rc = run_k1(c, slot))) return rc;
+  return release_picture(c, idx);
 }
-
-int fme_upload_ref_u8(fme_ctx* c, int slot, const uint8_t* y, int stride) {
-  int rc = check_slot(c, slot);
-  if (rc) return rc;
-  CU_CHECK(cudaSetDevice(c->cfg.device));
-  rc = stage_picture(c, y, stride, c->g.W, c->g.H, c->d_pic, c->picPitch);
-  if (rc) return rc;
-  return run_k1(c, slot);
-}
+}  // extern "C++"
+int fme_upload_ref(fme_ctx* c, int slot, const int16_t* y, int stride) { return upload_ref_host(c, slot, y, stride); }
+int fme_upload_ref_u8(fme_ctx* c, int slot, const uint8_t* y, int stride) { return upload_ref_host(c, slot, y, stride); }
 
 int fme_upload_ref_device_u8(fme_ctx* c, int slot, const uint8_t* d_y, int pitch) {
   int rc = check_slot(c, slot);
   if (rc) return rc;
   if (!d_y || pitch < c->g.W) return fail(FME_ERR_INVALID, "bad device picture");
   CU_CHECK(cudaSetDevice(c->cfg.device));
+  // device-resident input: ordered on the kernel stream, no copy-in stream involved
+  int idx = (int)(c->picSeq++ & 1);
+  CU_CHECK(cudaStreamWaitEvent(c->stream, c->evPicFree[idx], 0));
+  c->d_pic = c->d_picBuf[idx];
   CU_CHECK(cudaMemcpy2DAsync(c->d_pic, c->picPitch, d_y, pitch, c->g.W, c->g.H, cudaMemcpyDeviceToDevice, c->stream));
-  return run_k1(c, slot);
+  if ((rc = run_k1(c, slot))) return rc;
+  return release_picture(c, idx);
 }
 
 int fme_interp_slot(fme_ctx* c, int slot) {
@@ -467,27 +554,40 @@ int fme_interp_slot(fme_ctx* c, int slot) {
   return run_k1(c, slot);
 }
 
-int fme_upload_org(fme_ctx* c, const int16_t* y, int stride) {
+// The source picture is double-buffered: a new upload goes to the buffer the in-flight submit does NOT read.
+static int begin_org_upload(fme_ctx* c, cudaStream_t copyStream, int* idx) {
+  *idx = (int)(c->orgSeq++ & 1);
+  CU_CHECK(cudaStreamWaitEvent(copyStream, c->evOrgFree[*idx], 0));  // last submit that read this buffer is done
+  c->d_org = c->d_orgBuf[*idx];
+  return FME_OK;
+}
+extern "C++" {
+template <typename T>
+static int upload_org_host(fme_ctx* c, const T* y, int stride) {
   if (!c) return fail(FME_ERR_INVALID, "null ctx");
   CU_CHECK(cudaSetDevice(c->cfg.device));
-  int rc = stage_picture(c, y, stride, c->g.W, c->g.H, c->d_org, c->g.orgPitch);
-  if (rc) return rc;
+  int idx, rc;
+  if ((rc = begin_org_upload(c, c->sIn, &idx))) return rc;
+  // the narrowing kernel (Pel input) also writes d_org on the kernel stream: make that stream respect the same hazard
+  CU_CHECK(cudaStreamWaitEvent(c->stream, c->evOrgFree[idx], 0));
+  int pidx = (int)(c->picSeq++ & 1);
+  CU_CHECK(cudaStreamWaitEvent(c->sIn, c->evPicFree[pidx], 0));
+  if ((rc = stage_picture(c, y, stride, c->g.W, c->g.H, c->d_org, c->g.orgPitch, pidx))) return rc;
+  CU_CHECK(cudaEventRecord(c->evPicIn[pidx], c->sIn));
+  CU_CHECK(cudaStreamWaitEvent(c->stream, c->evPicIn[pidx], 0));
+  CU_CHECK(cudaEventRecord(c->evPicFree[pidx], c->stream));
   c->orgValid = true;
   return FME_OK;
 }
-
-int fme_upload_org_u8(fme_ctx* c, const uint8_t* y, int stride) {
-  if (!c) return fail(FME_ERR_INVALID, "null ctx");
-  CU_CHECK(cudaSetDevice(c->cfg.device));
-  int rc = stage_picture(c, y, stride, c->g.W, c->g.H, c->d_org, c->g.orgPitch);
-  if (rc) return rc;
-  c->orgValid = true;
-  return FME_OK;
-}
+}  // extern "C++"
+int fme_upload_org(fme_ctx* c, const int16_t* y, int stride) { return upload_org_host(c, y, stride); }
+int fme_upload_org_u8(fme_ctx* c, const uint8_t* y, int stride) { return upload_org_host(c, y, stride); }
 
 int fme_upload_org_device_u8(fme_ctx* c, const uint8_t* d_y, int pitch) {
   if (!c || !d_y || pitch < c->g.W) return fail(FME_ERR_INVALID, "bad device picture");
   CU_CHECK(cudaSetDevice(c->cfg.device));
+  int idx, rc;
+  if ((rc = begin_org_upload(c, c->stream, &idx))) return rc;
   CU_CHECK(cudaMemcpy2DAsync(c->d_org, c->g.orgPitch, d_y, pitch, c->g.W, c->g.H, cudaMemcpyDeviceToDevice, c->stream));
   c->orgValid = true;
   return FME_OK;
@@ -504,10 +604,13 @@ int fme_upload_ref_chroma(fme_ctx* c, int slot, const int16_t* cb, const int16_t
     CU_CHECK(cudaMalloc(&c->d_cr, g.cPlaneBytes * c->cfg.numRefSlots + g.cPitch));
   }
   for (int k = 0; k < 2; ++k) {
-    rc = stage_picture(c, k ? cr : cb, stride, g.Wc, g.Hc, c->d_pic, c->picPitch);
-    if (rc) return rc;
+    int idx;
+    if ((rc = begin_picture_upload(c, &idx))) return rc;
+    if ((rc = stage_picture(c, k ? cr : cb, stride, g.Wc, g.Hc, c->d_pic, c->picPitch, idx))) return rc;
+    if ((rc = end_picture_upload(c, idx, true))) return rc;
     CU_CHECK(fme_launch_pad_chroma(g, c->d_pic, c->picPitch, (k ? c->d_cr : c->d_cb) + (size_t)slot * g.cPlaneBytes,
                                    c->stream, &c->launches));
+    if ((rc = release_picture(c, idx))) return rc;
   }
   return FME_OK;
 }
@@ -518,7 +621,6 @@ static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, 
   if (n < 0 || n > c->cfg.maxPUs) return fail(FME_ERR_INVALID, "n=%d exceeds maxPUs=%d", n, c->cfg.maxPUs);
   if (n == 0) return FME_OK;
   CU_CHECK(cudaSetDevice(c->cfg.device));
-  CU_CHECK(cudaMemcpyAsync(c->d_pus, pus, sizeof(fme_pu) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   bool needK0 = false;
   if (sync) {  // full validation on the synchronous path
     for (int i = 0; i < n; ++i) {
@@ -533,16 +635,37 @@ static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, 
   } else {
     needK0 = (pus[0].flags & FME_PU_ERR_ON_GPU) != 0;
   }
-  if (needK0) {
-    if (!c->orgValid) return fail(FME_ERR_STATE, "FME_PU_ERR_ON_GPU needs fme_upload_org first");
-    StageTimer t(c, 3);
-    CU_CHECK(fme_launch_k0(c->g, c->d_planes, c->d_org, c->d_pus, n, c->cfg.fen, c->stream, &c->launches));
+  if (needK0 && !c->orgValid) return fail(FME_ERR_STATE, "FME_PU_ERR_ON_GPU needs fme_upload_org first");
+  if (c->fifoCount == 2) {  // at most two submits in flight: retire the oldest before reusing its buffers
+    int rc = fme_wait_oldest(c);
+    if (rc) return rc;
   }
-  int rc = run_search(c, c->d_pus, n, c->d_res, mode);
+  const int b = (int)(c->submitSeq++ & 1);
+  fme_pu* d_pus = c->d_pusBuf[b];
+  fme_result* d_res = c->d_resBuf[b];
+  // records in: the kernels that read d_pus[b] two submits ago must be done
+  CU_CHECK(cudaStreamWaitEvent(c->sIn, c->evDone[b], 0));
+  CU_CHECK(cudaMemcpyAsync(d_pus, pus, sizeof(fme_pu) * (size_t)n, cudaMemcpyHostToDevice, c->sIn));
+  CU_CHECK(cudaEventRecord(c->evIn[b], c->sIn));
+  // kernels: need the records, and the previous read-out of d_res[b] must be done
+  CU_CHECK(cudaStreamWaitEvent(c->stream, c->evIn[b], 0));
+  CU_CHECK(cudaStreamWaitEvent(c->stream, c->evOut[b], 0));
+  if (needK0) {
+    StageTimer t(c, 3);
+    CU_CHECK(fme_launch_k0(c->g, c->d_planes, c->d_org, d_pus, n, c->cfg.fen, c->stream, &c->launches));
+  }
+  int rc = run_search(c, d_pus, n, d_res, mode);
   if (rc) return rc;
-  CU_CHECK(cudaMemcpyAsync(out, c->d_res, sizeof(fme_result) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(cudaEventRecord(c->evDone[b], c->stream));
+  CU_CHECK(cudaEventRecord(c->evOrgFree[(c->orgSeq + 1) & 1], c->stream));  // the source buffer this submit read
+  // results out
+  CU_CHECK(cudaStreamWaitEvent(c->sOut, c->evDone[b], 0));
+  CU_CHECK(cudaMemcpyAsync(out, d_res, sizeof(fme_result) * (size_t)n, cudaMemcpyDeviceToHost, c->sOut));
+  CU_CHECK(cudaEventRecord(c->evOut[b], c->sOut));
+  c->fifo[c->fifoCount++] = b;
   if (sync) {
-    CU_CHECK(cudaStreamSynchronize(c->stream));
+    rc = sync_all(c);
+    if (rc) return rc;
     collect_ms(c);
   }
   return FME_OK;
@@ -560,7 +683,10 @@ int fme_submit_device(fme_ctx* c, const fme_pu* d_pus, int n, fme_result* d_out,
   if (n < 0 || n > c->cfg.maxPUs) return fail(FME_ERR_INVALID, "n=%d exceeds maxPUs=%d", n, c->cfg.maxPUs);
   if (n == 0) return FME_OK;
   CU_CHECK(cudaSetDevice(c->cfg.device));
-  return run_search(c, const_cast<fme_pu*>(d_pus), n, d_out, mode);
+  int rc = run_search(c, const_cast<fme_pu*>(d_pus), n, d_out, mode);
+  if (rc) return rc;
+  CU_CHECK(cudaEventRecord(c->evOrgFree[(c->orgSeq + 1) & 1], c->stream));
+  return FME_OK;
 }
 
 int fme_int_surface_device(fme_ctx* c, fme_pu* d_pus, int n) {
@@ -568,8 +694,11 @@ int fme_int_surface_device(fme_ctx* c, fme_pu* d_pus, int n) {
   if (!c->orgValid) return fail(FME_ERR_STATE, "fme_int_surface_device needs fme_upload_org first");
   if (n <= 0) return FME_OK;
   CU_CHECK(cudaSetDevice(c->cfg.device));
-  StageTimer t(c, 3);
-  CU_CHECK(fme_launch_k0(c->g, c->d_planes, c->d_org, d_pus, n, c->cfg.fen, c->stream, &c->launches));
+  {
+    StageTimer t(c, 3);
+    CU_CHECK(fme_launch_k0(c->g, c->d_planes, c->d_org, d_pus, n, c->cfg.fen, c->stream, &c->launches));
+  }
+  CU_CHECK(cudaEventRecord(c->evOrgFree[(c->orgSeq + 1) & 1], c->stream));
   return FME_OK;
 }
 
@@ -646,6 +775,10 @@ int fme_mc(fme_ctx* c, const fme_mc_pu* pus, int n, int16_t* dstY, int16_t* dstC
     if (pus[i].w > 64 || pus[i].h > 64 || pus[i].w < 4 || pus[i].h < 4) return fail(FME_ERR_INVALID, "PU %d: bad size", i);
   }
   CU_CHECK(cudaSetDevice(c->cfg.device));
+  {
+    int rc0 = sync_all(c);  // the record staging buffer is shared with the async submit path
+    if (rc0) return rc0;
+  }
   size_t ySamples = (size_t)n * 64 * 64, cSamples = (size_t)n * 32 * 32;
   int rc = ensure_pel(&c->d_pel, &c->pelCapacity, ySamples);
   if (rc) return rc;

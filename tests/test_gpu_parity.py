@@ -354,3 +354,47 @@ def test_1080p_properties(orc):
     # checksum of the result fields, printed for the record
     print("1080p checksum cost=%d classes=%d" % (int(full["cost"].astype(np.uint64).sum()), int(full["nnClass"].astype(np.uint64).sum())))
     eng.close()
+
+
+def test_pipelined_async_matches_synchronous():
+    """fme_submit_async / fme_wait_oldest with pinned buffers: copies of frame i+1 overlap the kernels of frame i
+    (double-buffered staging inside the ctx); results must equal the synchronous call frame by frame."""
+    import torch
+    W, H, F = 416, 240, 7
+    frames = []
+    for f in range(F):
+        org, refs, motions = fme.pu_list.synth_frames(W, H, n_refs=2, seed=500 + f)
+        recs = fme.pu_list.make_records(W, H, motions, seed=f, amp=(f % 2 == 0), err_on_gpu=True)
+        frames.append((org, refs, recs))
+    nmax = max(len(fr[2]) for fr in frames)
+    eng = fme.Fme(W, H, num_ref_slots=2, max_pus=nmax)
+    eng.set_nn_weights(fme.nn_weights.load_blob(27))
+    eng.set_slice(fme.pu_list.slice_lambda(27))
+    # synchronous reference run
+    want = []
+    for org, refs, recs in frames:
+        eng.upload_org(org)
+        for s in range(2):
+            eng.upload_ref(s, refs[s])
+        want.append(eng.submit(recs, fme.MODE_BOTH))
+    # pipelined run from pinned host memory (Pel planes, as an encoder holds them)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_org = [pin(fr[0].astype(np.int16)) for fr in frames]
+    h_ref = [[pin(r.astype(np.int16)) for r in fr[1]] for fr in frames]
+    h_pus = [pin(fr[2].view(np.uint8).reshape(len(fr[2]), -1)) for fr in frames]
+    h_out = [torch.zeros((nmax, 16), dtype=torch.uint8).pin_memory() for _ in range(F)]
+    import ctypes
+    for rep in range(3):
+        for f in range(F):
+            eng._check(eng.lib.fme_upload_org(eng.h, ctypes.c_void_p(h_org[f].data_ptr()), W))
+            for s in range(2):
+                eng._check(eng.lib.fme_upload_ref(eng.h, s, ctypes.c_void_p(h_ref[f][s].data_ptr()), W))
+            eng.submit_async(h_pus[f].data_ptr(), len(frames[f][2]), h_out[f].data_ptr(), fme.MODE_BOTH)
+            if f >= 1:
+                eng.wait_oldest()
+                got = h_out[f - 1].numpy()[:len(frames[f - 1][2])].copy().view(fme.RESULT_DTYPE).reshape(-1)
+                assert np.array_equal(got.view(np.uint8), want[f - 1].view(np.uint8)), (rep, f - 1)
+        eng.synchronize()
+        got = h_out[F - 1].numpy()[:len(frames[F - 1][2])].copy().view(fme.RESULT_DTYPE).reshape(-1)
+        assert np.array_equal(got.view(np.uint8), want[F - 1].view(np.uint8))
+    eng.close()
