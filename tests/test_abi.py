@@ -73,3 +73,15 @@ def test_product_never_references_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dp, f), errors="ignore").read()
                 assert "libfme_oracle" not in text and "libhmref" not in text and "oracle_bindings" not in text, f
+
+
+def test_hm_adaptor_compiles_against_reference_headers():
+    """The header-only C++ adaptor (reference signatures over the C ABI) must compile inside the reference tree."""
+    ref = "/root/reference/source/Lib"
+    if not os.path.isdir(ref):
+        pytest.skip("reference headers not available on this box")
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.cpp")
+        open(src, "w").write('#include "fme_hm_adaptor.h"\nint main() { FmeHmAdaptor a; (void)a; return 0; }\n')
+        subprocess.check_call(["g++", "-std=gnu++11", "-fsyntax-only", "-w", "-I", ref, "-I", os.path.join(ROOT, "include"),
+                               "-I", os.path.join(ROOT, "hm16.9-nn_fme_b200", "adaptor"), src])
