@@ -285,6 +285,17 @@ def run_gpu(args):
             kms["k2_refine"].append(ev[1].elapsed_time(ev[2]))
             kms["k3_nn"].append(ev[2].elapsed_time(ev[3]))
     kavg = {k: float(np.mean(v)) for k, v in kms.items()}
+    # K1 alone, back to back over the 4 slots (4 x 43 MB of output > L2), no picture copy in between
+    for s_ in range(N_REFS):
+        eng.interp_slot(s_)
+    k1e0, k1e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k1e0.record(stream)
+    K1_REPS = 16
+    for r_ in range(K1_REPS):
+        eng.interp_slot(r_ % N_REFS)
+    k1e1.record(stream)
+    torch.cuda.synchronize(dev)
+    kavg["k1_interp_alone"] = k1e0.elapsed_time(k1e1) / K1_REPS
 
     out = None
     if rank == 0:
@@ -297,9 +308,10 @@ def run_gpu(args):
         k3_flops = fme.nn_weights.flops_per_pu(blob) * len(rc)
         gbs = lambda b, ms: b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         kernels = {
-            "k1_interp": {"ms": kavg["k1_interp"], "bound": "hbm", "achieved": gbs(k1_bytes, kavg["k1_interp"]),
-                          "peak": peak, "unit": "GB/s", "frac": gbs(k1_bytes, kavg["k1_interp"]) / peak,
-                          "alg_bytes": k1_bytes, "note": "incl. the D2D picture copy that precedes the kernel"},
+            "k1_interp": {"ms": kavg["k1_interp_alone"], "bound": "hbm", "achieved": gbs(k1_bytes, kavg["k1_interp_alone"]),
+                          "peak": peak, "unit": "GB/s", "frac": gbs(k1_bytes, kavg["k1_interp_alone"]) / peak,
+                          "alg_bytes": k1_bytes, "ms_in_step_with_picture_copy": kavg["k1_interp"],
+                          "note": "16 back-to-back launches cycling 4 slots (172 MB of planes, larger than L2)"},
             "k2_refine": {"ms": kavg["k2_refine"], "bound": "hbm", "achieved": gbs(k2_bytes, kavg["k2_refine"]),
                           "peak": peak, "unit": "GB/s", "frac": gbs(k2_bytes, kavg["k2_refine"]) / peak,
                           "alg_bytes": k2_bytes, "int_ops_per_s": 144.0 * pu_px / (kavg["k2_refine"] * 1e-3) if kavg["k2_refine"] > 0 else 0,

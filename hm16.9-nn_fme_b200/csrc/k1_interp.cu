@@ -12,7 +12,8 @@
 // One CTA produces a 128 x 32 tile of all 16 planes:
 //   stage A  (136 x 39) u8 input tile -> shared memory, coordinates clamped to the picture
 //   stage B  horizontal 8-tap for fx = 0..3 with dp4a (u8 samples x s8 taps) -> int16 in shared memory
-//   stage C  vertical 8-tap for fy = 1..3 with dp2a (s16 x s8 tap pairs), fy = 0 by shift; u8x4 stores
+//   stage C  vertical 8-tap for fy = 1..3 with dp2a (s16 x s8 tap pairs) on 4-row register blocks, fy = 0 by
+//            shift; cvt.pack.sat (I2IP) narrowing, u8x4 stores
 // Algorithmic HBM bytes: 1 B read + 16 B written per padded sample (plane 0 is the padded copy).
 #include "fme_common.cuh"
 
@@ -47,6 +48,18 @@ __constant__ int c_lumaLo[4] = {PACK4(0, 0, 0, 64), PACK4(-1, 4, -10, 58), PACK4
 __constant__ int c_lumaHi[4] = {PACK4(0, 0, 0, 0), PACK4(17, -5, 1, 0), PACK4(40, -11, 4, -1), PACK4(58, -10, 4, -1)};
 
 __device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
+// cvt.pack.sat.u8.s32: d = (c << 16) | (sat_u8(a) << 8) | sat_u8(b)   (SASS: I2IP.U8.S32.SAT)
+__device__ __forceinline__ unsigned pack_sat_u8x2(int lo, int hi, unsigned upper) {
+  unsigned d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(upper));
+  return d;
+}
+__device__ __forceinline__ unsigned pack_sat_u8x4(int p0, int p1, int p2, int p3) {
+  unsigned hi16, d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi16) : "r"(p3), "r"(p2), "r"(0));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(p1), "r"(p0), "r"(hi16));
+  return d;
+}
 
 __global__ void __launch_bounds__(K1_THREADS) k1_interp_planes(const uint8_t* __restrict__ pic, int picPitch, int W,
                                                                int H, int M, int Wp, int Hp, int pitch,
@@ -115,49 +128,61 @@ __global__ void __launch_bounds__(K1_THREADS) k1_interp_planes(const uint8_t* __
   __syncthreads();
 
   // ---- stage C: vertical filters, 16 planes, u8x4 stores -------------------------------------
-  for (int i = tid; i < TH * (TW / 4); i += K1_THREADS) {
-    int r = i / (TW / 4), q = i - r * (TW / 4);
-    int gy = y0 + r, gx = x0 + q * 4;
-    if (gy >= Hp || gx >= Wp) continue;  // Wp is a multiple of 4
-    uint8_t* outBase = planes + (size_t)gy * pitch + gx;
-#pragma unroll
+  // item = (quad of 4 columns, group of 4 output rows); the 11 intermediate rows a group needs are loaded once
+  // and shared by its 4 rows x 3 vertical phases (register blocking), results are shifted, saturated and packed
+  // with cvt.pack.sat (I2IP) and stored as one 32-bit word per plane row.
+  for (int i = tid; i < (TH / 4) * (TW / 4); i += K1_THREADS) {
+    const int rg = i / (TW / 4), q = i - rg * (TW / 4);
+    const int r0 = rg * 4;
+    const int gy0 = y0 + r0, gx = x0 + q * 4;
+    if (gx >= Wp || gy0 >= Hp) continue;  // Wp is a multiple of 4
+    uint8_t* outBase = planes + (size_t)gy0 * pitch + gx;
+#pragma unroll 1
     for (int fx = 0; fx < 4; ++fx) {
-      // rows r .. r+7 of T_fx (output row r is centred on input row r+3)
-      int2 v[8];
+      int2 v[11];  // rows r0 .. r0+10 of T_fx (output row r is centred on input row r+3)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = *reinterpret_cast<const int2*>(&s_t[fx][r + k][q * 4]);
-      // fy = 0: (T + 8192 + 32) >> 6 on the centre row
-      {
-        int2 c = v[3];
-        int a0 = (int)(short)(c.x & 0xffff), a1 = c.x >> 16, a2 = (int)(short)(c.y & 0xffff), a3 = c.y >> 16;
-        unsigned o = clip255((a0 + 8224) >> 6) | (clip255((a1 + 8224) >> 6) << 8) |
-                     (clip255((a2 + 8224) >> 6) << 16) | (clip255((a3 + 8224) >> 6) << 24);
-        *reinterpret_cast<unsigned*>(outBase + (size_t)(0 * 4 + fx) * planeBytes) = o;
-      }
-      // vertical pairs (T(x,k), T(x,k+1)) for the four columns
-      int p[4][4];
+      for (int k = 0; k < 11; ++k) v[k] = *reinterpret_cast<const int2*>(&s_t[fx][r0 + k][q * 4]);
+      // fy = 0: (T + 8192 + 32) >> 6 on the centre rows; dp2a with taps (1,0) / (0,1) extracts a sign-extended half
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        p[0][k] = __byte_perm(v[2 * k].x, v[2 * k + 1].x, 0x5410);
-        p[1][k] = __byte_perm(v[2 * k].x, v[2 * k + 1].x, 0x7632);
-        p[2][k] = __byte_perm(v[2 * k].y, v[2 * k + 1].y, 0x5410);
-        p[3][k] = __byte_perm(v[2 * k].y, v[2 * k + 1].y, 0x7632);
-      }
-#pragma unroll
-      for (int fy = 1; fy < 4; ++fy) {
-        int tl = c_lumaLo[fy], th = c_lumaHi[fy];
-        int o[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          int acc = 2048 + (8192 << 6);
-          acc = dp2a_lo(p[c][0], tl, acc);
-          acc = dp2a_hi(p[c][1], tl, acc);
-          acc = dp2a_lo(p[c][2], th, acc);
-          acc = dp2a_hi(p[c][3], th, acc);
-          o[c] = clip255(acc >> 12);
+      for (int r = 0; r < 4; ++r) {
+        if (gy0 + r < Hp) {
+          const int2 c = v[r + 3];
+          int a0 = dp2a_lo(c.x, 0x0001, 8224) >> 6, a1 = dp2a_lo(c.x, 0x0100, 8224) >> 6;
+          int a2 = dp2a_lo(c.y, 0x0001, 8224) >> 6, a3 = dp2a_lo(c.y, 0x0100, 8224) >> 6;
+          *reinterpret_cast<unsigned*>(outBase + (size_t)(0 * 4 + fx) * planeBytes + (size_t)r * pitch) =
+              pack_sat_u8x4(a0, a1, a2, a3);
         }
-        unsigned ov = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
-        *reinterpret_cast<unsigned*>(outBase + (size_t)(fy * 4 + fx) * planeBytes) = ov;
+      }
+      // columns two at a time (3,2 first, then 1,0 so that the second cvt.pack completes the 32-bit word):
+      // vertical pairs (T(x,k), T(x,k+1)), k = 0..9
+      unsigned hi16[3][4];
+#pragma unroll
+      for (int half = 1; half >= 0; --half) {
+        int pa[10], pb[10];  // column 2*half and 2*half+1
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+          const int lo = half ? v[k].y : v[k].x, hi = half ? v[k + 1].y : v[k + 1].x;
+          pa[k] = __byte_perm(lo, hi, 0x5410);
+          pb[k] = __byte_perm(lo, hi, 0x7632);
+        }
+#pragma unroll
+        for (int fy = 1; fy < 4; ++fy) {
+          const int tl = c_lumaLo[fy], th = c_lumaHi[fy];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            int acc0 = 2048 + (8192 << 6), acc1 = acc0;
+            acc0 = dp2a_lo(pa[r + 0], tl, acc0); acc1 = dp2a_lo(pb[r + 0], tl, acc1);
+            acc0 = dp2a_hi(pa[r + 2], tl, acc0); acc1 = dp2a_hi(pb[r + 2], tl, acc1);
+            acc0 = dp2a_lo(pa[r + 4], th, acc0); acc1 = dp2a_lo(pb[r + 4], th, acc1);
+            acc0 = dp2a_hi(pa[r + 6], th, acc0); acc1 = dp2a_hi(pb[r + 6], th, acc1);
+            if (half) {
+              hi16[fy - 1][r] = pack_sat_u8x2(acc0 >> 12, acc1 >> 12, 0);
+            } else if (gy0 + r < Hp) {
+              *reinterpret_cast<unsigned*>(outBase + (size_t)(fy * 4 + fx) * planeBytes + (size_t)r * pitch) =
+                  pack_sat_u8x2(acc0 >> 12, acc1 >> 12, hi16[fy - 1][r]);
+            }
+          }
+        }
       }
     }
   }
