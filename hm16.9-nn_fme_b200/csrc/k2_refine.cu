@@ -314,15 +314,21 @@ __device__ __forceinline__ ItemPos item_pos(int lane, int rows, int G) {
 // One staging step: copy `rows` rows of RW bytes of every PU's region (source base pointers in s_base) into
 // buf + j*RB.  The pack's regions form one flat item space (count * rows * G granules) walked by all 32 lanes;
 // rows keep the source's alignment modulo A (readers funnel-shift).  No divisions in the loop.
+// An item is a granule column of TWO consecutive rows (p.row counts row pairs): the index stepping and the address
+// arithmetic are paid once per two copies.
 template <int A>
 __device__ __forceinline__ void stage_regions(uint8_t* buf, const StageGeom sg, int rows, int count, int pitch,
                                               const unsigned long long* s_base, ItemPos p) {
+  const int rowPairs = (rows + 1) >> 1;
   while (p.j < count) {
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(s_base[p.j]) + (size_t)(p.row * pitch + p.gi * A);
-    cp_async_g<A>(buf + p.j * sg.RB + p.row * sg.RW + p.gi * A, src);
+    const int row = 2 * p.row;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(s_base[p.j]) + (size_t)(row * pitch + p.gi * A);
+    uint8_t* dst = buf + p.j * sg.RB + row * sg.RW + p.gi * A;
+    cp_async_g<A>(dst, src);
+    if (row + 1 < rows) cp_async_g<A>(dst + sg.RW, src + pitch);
     p.gi += p.dG; p.row += p.dRow; p.j += p.dJ;
     if (p.gi >= sg.G) { p.gi -= sg.G; ++p.row; }
-    if (p.row >= rows) { p.row -= rows; ++p.j; }
+    if (p.row >= rowPairs) { p.row -= rowPairs; ++p.j; }
   }
 }
 
@@ -377,8 +383,9 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   sg.RW = ((w + A + A - 1) / A) * A;  // covers [x0 & ~(A-1), x0 + w + 1)
   sg.G = sg.RW / A;
   sg.RB = (h + 1) * sg.RW;
-  const ItemPos posHalf = item_pos(lane, h + 1, sg.G);  // a handful of divisions per pack, none per item
-  const ItemPos posQter = item_pos(lane, h, sg.G);
+  if (((sg.RB / A) & 1) == 0) sg.RB += A;  // odd region stride in granules: lanes of different PUs spread over the banks
+  const ItemPos posHalf = item_pos(lane, (h + 2) >> 1, sg.G);  // in row pairs; a handful of divisions per pack
+  const ItemPos posQter = item_pos(lane, (h + 1) >> 1, sg.G);
   const int bufBytes = (ci.P * sg.RB + 16 + 15) & ~15;
   uint8_t* const bufA = smem;
   uint8_t* const bufB = smem + bufBytes;
