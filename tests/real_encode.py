@@ -1,0 +1,41 @@
+"""Loader for tests/golden/real_encode_416x240.npz: the reference encoder's own FME calls captured on a real
+416x240 lowdelay_P QP22 encode (oracle/capture/make_capture.py)."""
+import os
+
+import numpy as np
+
+from common import HERE, PU_DTYPE
+
+COLS = ["poc", "x", "y", "w", "h", "refPoc", "list", "mvIntX", "mvIntY", "predX", "predY", "esize",
+        "e0", "e1", "e2", "e3", "e4", "e5", "e6", "e7", "C", "bBi", "lossless",
+        "halfX", "halfY", "qterX", "qterY", "cost", "nnHx", "nnHy", "nnQx", "nnQy", "nnOut"]
+
+
+def load():
+    g = dict(np.load(os.path.join(HERE, "golden", "real_encode_416x240.npz")))
+    recs = g["recs"]
+    col = {n: recs[:, i] for i, n in enumerate(COLS)}
+    pictures = []
+    for poc in sorted(set(col["poc"].tolist())):
+        sel = np.nonzero(col["poc"] == poc)[0]
+        ref_pocs = sorted(set(col["refPoc"][sel].tolist()))
+        slot_of = {rp: s for s, rp in enumerate(ref_pocs)}
+        pus = np.zeros(len(sel), PU_DTYPE)
+        pus["x"], pus["y"], pus["w"], pus["h"] = col["x"][sel], col["y"][sel], col["w"][sel], col["h"][sel]
+        pus["refSlot"] = [slot_of[rp] for rp in col["refPoc"][sel]]
+        pus["flags"] = col["lossless"][sel] & 1
+        pus["mvIntX"], pus["mvIntY"] = col["mvIntX"][sel], col["mvIntY"][sel]
+        pus["mvPredX"], pus["mvPredY"] = col["predX"][sel], col["predY"][sel]
+        e = np.stack([col["e%d" % i][sel] for i in range(8)], 1).astype(np.uint32)
+        # IN_errors << array_e[0..3], C, array_e[4..7]  (TEncSearch.cpp:88)
+        pus["err"][:, 0:4] = e[:, 0:4]
+        pus["err"][:, 4] = col["C"][sel].astype(np.uint32)
+        pus["err"][:, 5:9] = e[:, 4:8]
+        lam = g["lambda"][sel]
+        assert (lam == lam[0]).all()
+        pictures.append(dict(poc=poc, org=g["org_%d" % poc], refs=[g["ref_%d_%d" % (poc, rp)] for rp in ref_pocs],
+                             pus=pus, lam=float(lam[0]),
+                             uni=(col["bBi"][sel] == 0), nn_ok=(col["esize"][sel] == 8),
+                             want_std=np.stack([col[k][sel] for k in ("halfX", "halfY", "qterX", "qterY", "cost")], 1),
+                             want_nn=np.stack([col[k][sel] for k in ("nnHx", "nnHy", "nnQx", "nnQy", "nnOut")], 1)))
+    return pictures

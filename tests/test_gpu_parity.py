@@ -398,3 +398,25 @@ def test_pipelined_async_matches_synchronous():
         got = h_out[F - 1].numpy()[:len(frames[F - 1][2])].copy().view(fme.RESULT_DTYPE).reshape(-1)
         assert np.array_equal(got.view(np.uint8), want[F - 1].view(np.uint8))
     eng.close()
+
+
+def test_real_encode_capture_matches_engine():
+    """Config C1: every fractional-ME call the reference encoder made while encoding 416x240 lowdelay_P QP22
+    (31 017 calls, captured at TEncSearch.cpp:4534-4541) -- half/quarter MV and cost bit-exact, NN class and MV
+    identical wherever the reference had its 8 neighbour errors."""
+    import real_encode
+    pics = real_encode.load()
+    for p in pics:
+        eng = fme.Fme(416, 240, num_ref_slots=len(p["refs"]), max_pus=len(p["pus"]))
+        eng.set_nn_weights(fme.nn_weights.load_blob(22))
+        eng.set_slice(p["lam"])
+        eng.upload_org(p["org"])
+        for s, r in enumerate(p["refs"]):
+            eng.upload_ref(s, r)
+        got = eng.submit(p["pus"], fme.MODE_BOTH)
+        std = np.stack([got["halfX"], got["halfY"], got["qterX"], got["qterY"], got["cost"]], 1).astype(np.int64)
+        nn = np.stack([got["nnHalfX"], got["nnHalfY"], got["nnQterX"], got["nnQterY"], got["nnClass"]], 1).astype(np.int64)
+        assert np.array_equal(std, p["want_std"]), p["poc"]
+        k = p["nn_ok"]
+        assert np.array_equal(nn[k], p["want_nn"][k]), p["poc"]
+        eng.close()

@@ -1,0 +1,26 @@
+"""CPU: the oracle reproduces every fractional-ME decision the REFERENCE ENCODER ITSELF made on a real encode
+(416x240, encoder_lowdelay_P_main.cfg, QP22 -- BASELINE.json configs[0]); fixture captured by
+oracle/capture/make_capture.py at the call site TEncSearch.cpp:4534-4541."""
+import numpy as np
+
+import oracle_bindings as ob
+import real_encode
+from common import fme
+
+
+def test_oracle_reproduces_the_reference_encoders_fme_decisions():
+    pics = real_encode.load()
+    total = 0
+    blob = fme.nn_weights.load_blob(22)
+    for p in pics:
+        frame = ob.CpuFrame(p["org"], p["refs"])
+        got = frame.oracle_run(p["pus"], 3, p["lam"], 1, blob)
+        std = np.stack([got["halfX"], got["halfY"], got["qterX"], got["qterY"], got["cost"]], 1).astype(np.int64)
+        nn = np.stack([got["nnHalfX"], got["nnHalfY"], got["nnQterX"], got["nnQterY"], got["nnClass"]], 1).astype(np.int64)
+        u, k = p["uni"], p["nn_ok"]
+        assert u.all()  # lowdelay_P: no bi-prediction refinement calls
+        bad = np.nonzero((std[u] != p["want_std"][u]).any(1))[0]
+        assert len(bad) == 0, (p["poc"], len(bad), p["pus"][u][bad[:3]], std[u][bad[:3]], p["want_std"][u][bad[:3]])
+        assert np.array_equal(nn[k], p["want_nn"][k]), p["poc"]
+        total += int(u.sum())
+    assert total == 31017
