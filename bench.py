@@ -320,8 +320,14 @@ def run_gpu(args):
                       "unit": "TFLOP/s"},
         }
         dom = max(("k1_interp", "k2_refine"), key=lambda k: kavg[k])
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
+        # (1080p workload only; the plane set of 4 references, 173 MB, does not fit the 126 MB L2)
+        ncu_traffic = {"k2_refine": 1.612242e9 + 88.116e6, "k1_interp": 2.09e6 + 111.36e6} if not banded else {}
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved"], "peak": peak, "unit": "GB/s",
-                    "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src}
+                    "frac": kernels[dom]["frac"], "traffic": ncu_traffic.get(dom), "peak_source": peak_src,
+                    "traffic_source": "profiles/r1_k2_metrics_v3.txt (ncu --set full, one launch)",
+                    "note": "K2 is INT-issue bound (issue_active 69 %, 613 SASS instructions per 8x8 tile-candidate); "
+                            "the HBM fraction is reported because the contract asks for bound in {hbm, tensor}"}
         out = {
             "metric": "FME PUs/sec at 1080p QP22 (xPatternSearchFracDIF + NN_pred per PU)" if not banded else
                       "FME PUs/sec at 2160p QP22, CTU-row bands",
