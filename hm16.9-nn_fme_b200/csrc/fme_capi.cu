@@ -800,6 +800,28 @@ int fme_mc(fme_ctx* c, const fme_mc_pu* pus, int n, int16_t* dstY, int16_t* dstC
   return FME_OK;
 }
 
+int fme_pred_error(fme_ctx* c, const fme_mc_pu* pus, int n, uint32_t* out) {
+  if (!c || !pus || !out) return fail(FME_ERR_INVALID, "null argument");
+  if (n < 0 || n > c->cfg.maxPUs) return fail(FME_ERR_INVALID, "n out of range");
+  if (n == 0) return FME_OK;
+  if (!c->orgValid) return fail(FME_ERR_STATE, "fme_pred_error needs fme_upload_org first");
+  for (int i = 0; i < n; ++i) {
+    if (pus[i].refSlot >= c->cfg.numRefSlots || !c->refValid[pus[i].refSlot])
+      return fail(FME_ERR_STATE, "PU %d references slot %d which holds no picture", i, pus[i].refSlot);
+    if (fme_dim_index(pus[i].w) < 0 || fme_dim_index(pus[i].h) < 0) return fail(FME_ERR_INVALID, "PU %d: bad size", i);
+  }
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  int rc = sync_all(c);  // the record staging buffer is shared with the async submit path
+  if (rc) return rc;
+  if ((rc = ensure_u32(c, n))) return rc;
+  CU_CHECK(cudaMemcpyAsync(c->d_pus, pus, sizeof(fme_mc_pu) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CU_CHECK(fme_launch_pred_error(c->g, c->d_planes, c->d_org, reinterpret_cast<const fme_mc_pu*>(c->d_pus), n,
+                                 c->cfg.useHadME, c->d_scratchU32, c->stream, &c->launches));
+  CU_CHECK(cudaMemcpyAsync(out, c->d_scratchU32, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(cudaStreamSynchronize(c->stream));
+  return FME_OK;
+}
+
 // ---- introspection -----------------------------------------------------------------------------------
 int fme_download_plane(fme_ctx* c, int slot, int fy, int fx, uint8_t* dst, int dstStride) {
   int rc = check_slot(c, slot);

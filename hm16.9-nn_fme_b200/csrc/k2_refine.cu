@@ -154,15 +154,42 @@ __device__ __forceinline__ unsigned lds_row4(const uint8_t* base) {
   return __funnelshift_r(p[0], p[1], sh);
 }
 
+// A candidate tile in shared memory: rows are `pitchWords` 32-bit words apart (the staged row pitch is a multiple of
+// 4 bytes), so the byte misalignment of the tile is the same in every row and is resolved once.
+struct CandTile {
+  const unsigned* base;  // word containing the first byte of row 0
+  unsigned shift;        // 8 * (byte address & 3)
+  int pitchWords;
+};
+__device__ __forceinline__ CandTile cand_tile(const uint8_t* cand, int candPitch) {
+  CandTile t;
+  unsigned addr = (unsigned)(size_t)cand;
+  t.base = reinterpret_cast<const unsigned*>(cand - (addr & 3u));
+  t.shift = (addr & 3u) * 8u;
+  t.pitchWords = candPitch >> 2;
+  return t;
+}
+__device__ __forceinline__ void cand_row8(const CandTile& t, int r, unsigned& lo, unsigned& hi) {
+  const unsigned* p = t.base + r * t.pitchWords;
+  unsigned w0 = p[0], w1 = p[1], w2 = p[2];
+  lo = __funnelshift_r(w0, w1, t.shift);
+  hi = __funnelshift_r(w1, w2, t.shift);
+}
+__device__ __forceinline__ unsigned cand_row4(const CandTile& t, int r) {
+  const unsigned* p = t.base + r * t.pitchWords;
+  return __funnelshift_r(p[0], p[1], t.shift);
+}
+
 // SATD of one 8x8 tile: xCalcHADs8x8 (TComRdCost.cpp:1330-1425).  o[] holds the source tile as
 // 16 words of u8x4 (row r -> o[2r], o[2r+1]); cand points at the candidate tile's row 0 in smem.
 template <typename OrgRow>
 __device__ __forceinline__ unsigned satd8x8(OrgRow orgRow, const uint8_t* cand, int candPitch) {
   unsigned d[32];  // d[4r + j] = (res(r,2j), res(r,2j+1)) packed lo/hi
+  const CandTile ct = cand_tile(cand, candPitch);
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     unsigned c0, c1, o0, o1;
-    lds_row8(cand + r * candPitch, c0, c1);
+    cand_row8(ct, r, c0, c1);
     orgRow(r, o0, o1);
     d[4 * r + 0] = __byte_perm(o0, 0, 0x4140) - __byte_perm(c0, 0, 0x4140);
     d[4 * r + 1] = __byte_perm(o0, 0, 0x4342) - __byte_perm(c0, 0, 0x4342);
@@ -206,9 +233,10 @@ __device__ __forceinline__ unsigned satd8x8(OrgRow orgRow, const uint8_t* cand, 
 // SATD of one 4x4 tile: xCalcHADs4x4 (TComRdCost.cpp:1234-1328).  o[r] = source row r (u8x4).
 __device__ __forceinline__ unsigned satd4x4(const unsigned (&o)[4], const uint8_t* cand, int candPitch) {
   unsigned d[8];
+  const CandTile ct = cand_tile(cand, candPitch);
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    unsigned c = lds_row4(cand + r * candPitch);
+    unsigned c = cand_row4(ct, r);
     d[2 * r + 0] = __byte_perm(o[r], 0, 0x4140) - __byte_perm(c, 0, 0x4140);
     d[2 * r + 1] = __byte_perm(o[r], 0, 0x4342) - __byte_perm(c, 0, 0x4342);
   }
@@ -233,10 +261,11 @@ __device__ __forceinline__ unsigned satd4x4(const unsigned (&o)[4], const uint8_
 template <typename OrgRow>
 __device__ __forceinline__ unsigned sad8x8(OrgRow orgRow, const uint8_t* cand, int candPitch) {
   unsigned s = 0;
+  const CandTile ct = cand_tile(cand, candPitch);
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     unsigned c0, c1, o0, o1;
-    lds_row8(cand + r * candPitch, c0, c1);
+    cand_row8(ct, r, c0, c1);
     orgRow(r, o0, o1);
     s = __vsadu4(o0, c0) + s;
     s = __vsadu4(o1, c1) + s;
@@ -245,8 +274,9 @@ __device__ __forceinline__ unsigned sad8x8(OrgRow orgRow, const uint8_t* cand, i
 }
 __device__ __forceinline__ unsigned sad4x4(const unsigned (&o)[4], const uint8_t* cand, int candPitch) {
   unsigned s = 0;
+  const CandTile ct = cand_tile(cand, candPitch);
 #pragma unroll
-  for (int r = 0; r < 4; ++r) s += __vsadu4(o[r], lds_row4(cand + r * candPitch));
+  for (int r = 0; r < 4; ++r) s += __vsadu4(o[r], cand_row4(ct, r));
   return s;
 }
 
@@ -595,6 +625,67 @@ k2_refine(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, const ui
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Prediction error of a uni-predicted PU at a given quarter-pel MV: luma motion compensation + HADs/SAD against
+// the source block, i.e. TEncSearch::xGetInterPredictionError (TEncSearch.cpp:3576-3596, used by merge estimation)
+// and the distortion part of xGetTemplateCost (TEncSearch.cpp:4397-4436, AMVP candidate cost, SAD).
+// The MC block at MV (mx,my) is plane P[my&3][mx&3] at integer offset (mx>>2, my>>2)  (SURVEY.md A.1).
+// One warp per item: the candidate block is staged into shared memory, lanes take tiles.
+// ------------------------------------------------------------------------------------------------
+constexpr int PE_WARPS = 4;
+constexpr int PE_SMEM_PER_WARP = 64 * 68 + 16;
+
+__global__ void __launch_bounds__(PE_WARPS * 32) k_pred_error(const fme_mc_pu* __restrict__ pus, int n,
+                                                              const uint8_t* __restrict__ planes,
+                                                              const uint8_t* __restrict__ org, const FmeGeom g,
+                                                              int useHad, uint32_t* __restrict__ out) {
+  __shared__ __align__(16) uint8_t s_buf[PE_WARPS][PE_SMEM_PER_WARP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* buf = s_buf[warp];
+  for (int i = blockIdx.x * PE_WARPS + warp; i < n; i += gridDim.x * PE_WARPS) {
+    const fme_mc_pu p = pus[i];
+    const int w = p.w, h = p.h;
+    if (fme_dim_index(w) < 0 || fme_dim_index(h) < 0) {
+      if (lane == 0) out[i] = 0xffffffffu;
+      continue;
+    }
+    const int fx = p.mvX & 3, fy = p.mvY & 3;
+    const int X = min(max(p.x + (p.mvX >> 2), -(g.M - 8)), g.W + g.M - 8 - w);
+    const int Y = min(max(p.y + (p.mvY >> 2), -(g.M - 8)), g.H + g.M - 8 - h);
+    const int ox = min(max((int)p.x, 0), g.W - w), oy = min(max((int)p.y, 0), g.H - h);
+    const uint8_t* src = planes + (size_t)min((int)p.refSlot, g.numSlots - 1) * g.slotBytes +
+                         (size_t)(fy * 4 + fx) * g.planeBytes + (size_t)(Y + g.M) * g.pitch + ((X + g.M) & ~3);
+    const int al = (X + g.M) & 3;
+    const int RW = w + 4, wpr = RW >> 2;
+    __syncwarp();
+    for (int t = lane; t < h * wpr; t += 32) {
+      int r = t / wpr, c = t - r * wpr;
+      reinterpret_cast<unsigned*>(buf + r * RW)[c] = __ldg(reinterpret_cast<const unsigned*>(src + (size_t)r * g.pitch) + c);
+    }
+    __syncwarp();
+    const bool had = useHad && !(p.flags & FME_PU_LOSSLESS);
+    const int ts = ((w & 7) == 0 && (h & 7) == 0) ? 8 : 4;
+    const int tilesX = w / ts, tiles = tilesX * (h / ts);
+    unsigned dist = 0;
+    for (int t = lane; t < tiles; t += 32) {
+      const int ty = t / tilesX, tx = t - ty * tilesX;
+      const uint8_t* o = org + (size_t)(oy + ty * ts) * g.orgPitch + ox + tx * ts;
+      const uint8_t* c = buf + ty * ts * RW + al + tx * ts;
+      if (ts == 8) {
+        auto row = [&](int r, unsigned& lo, unsigned& hi) { ldg_row8(o + (size_t)r * g.orgPitch, lo, hi); };
+        dist += had ? satd8x8(row, c, RW) : sad8x8(row, c, RW);
+      } else {
+        unsigned oo[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) oo[r] = ldg_row4(o + (size_t)r * g.orgPitch);
+        dist += had ? satd4x4(oo, c, RW) : sad4x4(oo, c, RW);
+      }
+    }
+    dist = __reduce_add_sync(0xffffffffu, dist);
+    if (lane == 0) out[i] = dist;
+  }
+}
+
 __global__ void k_clear_results(fme_result* res, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
@@ -632,6 +723,16 @@ cudaError_t fme_launch_k2(const FmeGeom& g, const uint8_t* d_planes, const uint8
   }
   k2_refine<<<numSMs, K2_THREADS, smemBytes, s>>>(d_pus, d_res, d_planes, d_org, g, d_costLut, useHad, sc.order,
                                                   sc.classOffset, sc.packOffset, sc.workCounter);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t fme_launch_pred_error(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_mc_pu* d_pus,
+                                  int n, int useHad, uint32_t* d_out, cudaStream_t s, int64_t* launches) {
+  if (n <= 0) return cudaSuccess;
+  int blocks = (n + PE_WARPS - 1) / PE_WARPS;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_pred_error<<<blocks, PE_WARPS * 32, 0, s>>>(d_pus, n, d_planes, d_org, g, useHad, d_out);
   ++*launches;
   return cudaGetLastError();
 }

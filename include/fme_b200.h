@@ -167,6 +167,12 @@ typedef struct fme_mc_pu {
 } fme_mc_pu; /* 12 bytes */
 int fme_mc(fme_ctx* ctx, const fme_mc_pu* pus, int n, int16_t* dstY, int16_t* dstCb, int16_t* dstCr);
 
+/* Prediction error of n uni-predicted PUs at quarter-pel MVs: luma MC + HADs (SAD when HadamardME is off or the PU is
+ * lossless) against the source block -- TEncSearch::xGetInterPredictionError (TEncSearch.cpp:3576-3596, merge
+ * estimation) and the distortion of xGetTemplateCost (TEncSearch.cpp:4397-4436; there the ctx is created with
+ * useHadME = 0).  SURVEY.md "next" row f3. */
+int fme_pred_error(fme_ctx* ctx, const fme_mc_pu* pus, int n, uint32_t* out);
+
 /* ---- introspection (parity tests, profiling) ------------------------------------------------ */
 /* Copy padded sub-pel plane P[fy][fx] of `slot` to host: (height+2*margin) rows of (width+2*margin) bytes. */
 int fme_download_plane(fme_ctx* ctx, int slot, int fy, int fx, uint8_t* dst, int dstStride);

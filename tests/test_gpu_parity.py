@@ -420,3 +420,36 @@ def test_real_encode_capture_matches_engine():
         k = p["nn_ok"]
         assert np.array_equal(nn[k], p["want_nn"][k]), p["poc"]
         eng.close()
+
+
+@pytest.mark.parametrize("use_had", [True, False])
+def test_pred_error_vs_oracle(use_had, orc):
+    """f3: MC + HADs/SAD at arbitrary quarter-pel MVs (xGetInterPredictionError / xGetTemplateCost distortion)."""
+    g = golden()
+    recs = golden_recs(g)
+    eng = fme.Fme(128, 96, num_ref_slots=2, max_pus=4096, use_had=use_had)
+    eng.upload_org(g["small_org"])
+    for s in range(2):
+        eng.upload_ref(s, g["small_refs"][s])
+    rng = np.random.default_rng(8)
+    n = 600
+    sel = rng.integers(0, len(recs), n)
+    pus = np.zeros(n, fme.MC_PU_DTYPE)
+    pus["x"], pus["y"], pus["w"], pus["h"] = recs["x"][sel], recs["y"][sel], recs["w"][sel], recs["h"][sel]
+    pus["refSlot"] = rng.integers(0, 2, n)
+    pus["mvX"] = rng.integers(-48, 49, n)
+    pus["mvY"] = rng.integers(-48, 49, n)
+    got = eng.pred_error(pus)
+    M = 80
+    org = g["small_org"].astype(np.int16)
+    padded = [ob.pad_plane(g["small_refs"][s], M) for s in range(2)]
+    S = padded[0].shape[1]
+    for i in range(n):
+        p = pus[i]
+        w, h, mvx, mvy = int(p["w"]), int(p["h"]), int(p["mvX"]), int(p["mvY"])
+        x0, y0 = int(p["x"]) + (mvx >> 2), int(p["y"]) + (mvy >> 2)
+        pred = orc.subpel_plane(padded[p["refSlot"]], M * S + M, S, x0, y0, w, h, mvy & 3, mvx & 3)
+        o = np.ascontiguousarray(org[int(p["y"]):int(p["y"]) + h, int(p["x"]):int(p["x"]) + w])
+        want = orc.dist(1 if use_had else 2, o, 0, w, pred, 0, w, w, h)
+        assert int(got[i]) == want, (i, p, int(got[i]), want)
+    eng.close()

@@ -75,3 +75,35 @@ def test_two_rank_gloo_band_merge():
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "BAND_MERGE_OK" in out.stdout
+
+
+def test_yuv420_round_trip(tmp_path):
+    rng = np.random.default_rng(0)
+    frames = [(rng.integers(0, 256, (48, 64)).astype(np.uint8), rng.integers(0, 256, (24, 32)).astype(np.uint8),
+               rng.integers(0, 256, (24, 32)).astype(np.uint8)) for _ in range(3)]
+    p = tmp_path / "t.yuv"
+    with open(p, "wb") as f:
+        for y, cb, cr in frames:
+            fme.formats.write_yuv420_frame(f, y, cb, cr)
+    assert os.path.getsize(p) == 3 * fme.formats.yuv420_frame_bytes(64, 48)
+    for i, (y, cb, cr) in enumerate(frames):
+        gy, gcb, gcr = fme.formats.read_yuv420_frame(str(p), 64, 48, i)
+        assert np.array_equal(gy, y) and np.array_equal(gcb, cb) and np.array_equal(gcr, cr)
+    import pytest
+    with pytest.raises(EOFError):
+        fme.formats.read_yuv420_frame(str(p), 64, 48, 3)
+
+
+def test_h5_models_equal_csv_weights():
+    """The reference ships the same weights three times; the .h5 state_dicts must pack to the same
+    blob as the CSV directory up to float32 rounding of the stored values."""
+    import glob
+    import pytest
+    models = sorted(glob.glob("/root/reference/DL/models/QP22_*.h5"))
+    if not models:
+        pytest.skip("reference models not available on this box")
+    a = fme.formats.blob_from_state_dict(models[0], "/root/reference/DL/blowing/22/14.mapper_22.csv")
+    b = fme.nn_weights.load_blob(22)
+    assert a[:64] == b[:64]
+    fa, fb = np.frombuffer(a[64:], "<f4"), np.frombuffer(b[64:], "<f4")
+    assert np.allclose(fa, fb, rtol=2e-6, atol=1e-7)
