@@ -24,7 +24,7 @@
 namespace {
 
 #ifndef FME_K2_WARPS
-#define FME_K2_WARPS 16
+#define FME_K2_WARPS 12
 #endif
 constexpr int K2_WARPS = FME_K2_WARPS;
 constexpr int K2_THREADS = K2_WARPS * 32;
@@ -327,17 +327,25 @@ struct ItemPos {
   int j, row, gi;
   int dJ, dRow, dG;
 };
+// n / G for G in {2,3,4,5} and small n (exact for n < 2^13): multiply by ceil(2^16 / G) and shift.
+__device__ __forceinline__ int div_small(int n, int G) {
+  const int inv = G == 2 ? 32768 : G == 3 ? 21846 : G == 4 ? 16384 : 13108;
+  return (n * inv) >> 16;
+}
 __device__ __forceinline__ ItemPos item_pos(int lane, int rows, int G) {
   ItemPos p;
   const int items = rows * G;
-  p.j = lane / items;
-  int r = lane - p.j * items;
-  p.row = r / G;
+  // lane < 32 and items >= 4: a few subtractions instead of an integer division
+  int j = 0, r = lane;
+  while (r >= items) { r -= items; ++j; }
+  p.j = j;
+  p.row = div_small(r, G);
   p.gi = r - p.row * G;
-  p.dJ = 32 / items;
-  r = 32 - p.dJ * items;
-  p.dRow = r / G;
-  p.dG = r - p.dRow * G;
+  int dJ = 0, rem = 32;
+  while (rem >= items) { rem -= items; ++dJ; }
+  p.dJ = dJ;
+  p.dRow = div_small(rem, G);
+  p.dG = rem - p.dRow * G;
   return p;
 }
 
@@ -403,7 +411,9 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
       // X in [-71, W+7]); the clamp below only guards device memory against out-of-contract records.
       s_X[lane] = min(max(p.x + p.mvIntX, -(g.M - 8)), g.W + g.M - 8 - w);
       s_Y[lane] = min(max(p.y + p.mvIntY, -(g.M - 8)), g.H + g.M - 8 - h);
-      s_slotOff[lane] = (long long)min((int)p.refSlot, g.numSlots - 1) * (long long)g.slotBytes;
+      // byte offset of sample (X, Y) of the slot's plane 0; steps add plane * planeBytes and small (dx, dy)
+      s_slotOff[lane] = (long long)min((int)p.refSlot, g.numSlots - 1) * (long long)g.slotBytes +
+                        (long long)(s_Y[lane] + g.M) * g.pitch + (s_X[lane] + g.M);
     }
   }
   __syncwarp();
@@ -424,21 +434,22 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   // h+1 rows.  Steps 4..11: quarter-pel candidate s-3 of s_acMvRefineQ around the PU's half-pel winner, h rows.
   auto publishBases = [&](int s) {
     if (lane < count) {
-      int plane, x0, y0;
+      int plane, dx, dy;
       if (s < 4) {
         plane = (s & 1) * 2 + (s >> 1) * 8;
-        x0 = s_X[lane] - 1;
-        y0 = s_Y[lane] - 1;
+        dx = -1;
+        dy = -1;
       } else {
         int wv = s_win[lane];
         int jhx = (int)(int8_t)(wv & 0xff), jhy = (int)(int8_t)((wv >> 8) & 0xff);
         int qx = 2 * jhx + c_refineQ[s - 3][0], qy = 2 * jhy + c_refineQ[s - 3][1];
         plane = (qy & 3) * 4 + (qx & 3);
-        x0 = s_X[lane] + (qx >> 2);
-        y0 = s_Y[lane] + (qy >> 2);
+        dx = qx >> 2;
+        dy = qy >> 2;
       }
-      s_base[lane] = (unsigned long long)(planes + s_slotOff[lane] + (size_t)plane * g.planeBytes +
-                                          (size_t)(y0 + g.M) * g.pitch + ((x0 + g.M) & ~(A - 1)));
+      // planes is 128-byte aligned and pitch / planeBytes are multiples of 128: aligning the offset aligns the address
+      long long off = s_slotOff[lane] + (long long)plane * (long long)g.planeBytes + dy * g.pitch + dx;
+      s_base[lane] = (unsigned long long)(planes + (off & ~(long long)(A - 1)));
     }
     __syncwarp();
   };
@@ -498,6 +509,13 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   // order, so ties are broken by the table index explicitly (strict < in table order, TEncSearch.cpp:1634)
   unsigned hBest = 0xffffffffu, qBest = 0xffffffffu;
   int hBestI = 9, qBestI = 0, bhx = 0, bhy = 0;
+  // MV bits per axis for offsets -1, 0, +1.  Half stage, cost scale 1 (TEncSearch.cpp:4531): ((int<<1)+h)<<1 - pred
+  int bitsX[3], bitsY[3];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    bitsX[t] = golomb_bits((((mvIntX << 1) + (t - 1)) << 1) - predX);
+    bitsY[t] = golomb_bits((((mvIntY << 1) + (t - 1)) << 1) - predY);
+  }
 #pragma unroll 1
   for (int s = 0; s < 12; ++s) {
     const bool prefetch = (s != 3) && (s != 11);  // step 4 depends on the half-pel winner found after step 3
@@ -516,21 +534,19 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
 #pragma unroll 1
     for (int c = 0; c < iCount; ++c) {
       const int i = iFirst + c;
-      int candOff, vx, vy;
+      int candOff, ox3, oy3;  // ox3/oy3: candidate offset -1/0/1 per axis in units of the current stage
       if (s < 4) {
-        const int hx = c_refineH[i][0], hy = c_refineH[i][1];
+        ox3 = c_refineH[i][0]; oy3 = c_refineH[i][1];
         // inside the region (origin X-1, Y-1): x offset 1 + ((2hx)>>2), y offset 1 + ((2hy)>>2)
-        candOff = (1 + ((2 * hy) >> 2)) * sg.RW + ((alignX - 1) & (A - 1)) + 1 + ((2 * hx) >> 2);
-        // cost scale 1 (TEncSearch.cpp:4531): ((int<<1)+h) << 1 - pred
-        vx = ((mvIntX << 1) + hx) << 1;
-        vy = ((mvIntY << 1) + hy) << 1;
+        candOff = (1 + ((2 * oy3) >> 2)) * sg.RW + ((alignX - 1) & (A - 1)) + 1 + ((2 * ox3) >> 2);
       } else {
-        const int qx = 2 * bhx + c_refineQ[i][0];
+        ox3 = c_refineQ[i][0]; oy3 = c_refineQ[i][1];
+        const int qx = 2 * bhx + ox3;
         candOff = (alignX + (qx >> 2)) & (A - 1);
-        // cost scale 0 (TEncSearch.cpp:5260): (((int<<1)+half)<<1) + q - pred
-        vx = (((mvIntX << 1) + bhx) << 1) + c_refineQ[i][0];
-        vy = (((mvIntY << 1) + bhy) << 1) + c_refineQ[i][1];
       }
+      // exp-Golomb bit counts of the three possible vector components per axis were computed once per stage
+      const int bits = (ox3 < 0 ? bitsX[0] : ox3 == 0 ? bitsX[1] : bitsX[2]) +
+                       (oy3 < 0 ? bitsY[0] : oy3 == 0 ? bitsY[1] : bitsY[2]);
       unsigned dist = 0;
 #pragma unroll 1
       for (int rd = 0; rd < rounds; ++rd) {
@@ -539,7 +555,7 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
       }
       for (int d = lanesPerPu >> 1; d > 0; d >>= 1) dist += __shfl_xor_sync(0xffffffffu, dist, d);  // per-PU sum
       if (laneActive) {
-        dist += costLut[golomb_bits(vx - predX) + golomb_bits(vy - predY)];
+        dist += costLut[bits];
         if (s < 4) {
           if (dist < hBest || (dist == hBest && i < hBestI)) { hBest = dist; hBestI = i; }
         } else if (dist < qBest) {  // ascending i == table order, strict <
@@ -558,6 +574,12 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
       if (laneActive && unit0 == 0) s_win[myPu] = (bhx & 0xff) | ((bhy & 0xff) << 8);
       __syncwarp();
       stage(4);
+      // quarter stage, cost scale 0 (TEncSearch.cpp:5260): (((int<<1)+half)<<1) + q - pred
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        bitsX[t] = golomb_bits((((mvIntX << 1) + bhx) << 1) + (t - 1) - predX);
+        bitsY[t] = golomb_bits((((mvIntY << 1) + bhy) << 1) + (t - 1) - predY);
+      }
     }
   }
 
