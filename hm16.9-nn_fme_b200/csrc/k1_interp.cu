@@ -9,7 +9,7 @@
 // which is bit-identical to what the reference's per-PU two-stage filtering produces at every
 // position.  Layout in HBM: planes[p = fy*4+fx][Hp][pitch] u8, picture sample (0,0) at [M][M].
 //
-// One CTA produces a 128 x 32 tile of all 16 planes:
+// Persistent CTAs walk 128 x 16 output tiles (all 16 planes per tile), prefetching the next tile's input:
 //   stage A  (136 x 39) u8 input tile -> shared memory, coordinates clamped to the picture
 //   stage B  horizontal 8-tap for fx = 0..3 with dp4a (u8 samples x s8 taps) -> int16 in shared memory
 //   stage C  vertical 8-tap for fy = 1..3 with dp2a (s16 x s8 tap pairs) on 4-row register blocks, fy = 0 by
@@ -20,7 +20,7 @@
 namespace {
 
 constexpr int TW = 128;           // output tile width  (one 128-byte line per plane row)
-constexpr int TH = 32;            // output tile height
+constexpr int TH = 16;            // output tile height
 constexpr int IN_W = TW + 8;      // input columns x0-4 .. x0+TW+3 (word aligned)
 constexpr int IN_H = TH + 7;      // input rows    y0-3 .. y0+TH+3
 constexpr int K1_THREADS = 256;
@@ -61,37 +61,58 @@ __device__ __forceinline__ unsigned pack_sat_u8x4(int p0, int p1, int p2, int p3
   return d;
 }
 
-__global__ void __launch_bounds__(K1_THREADS) k1_interp_planes(const uint8_t* __restrict__ pic, int picPitch, int W,
-                                                               int H, int M, int Wp, int Hp, int pitch,
-                                                               size_t planeBytes, uint8_t* __restrict__ planes) {
+// Input-tile word `i` (row-major over IN_H x IN_W/4) of the tile at (x0, y0), coordinates clamped to the picture.
+__device__ __forceinline__ unsigned k1_load_word(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int pxBase,
+                                                 int pyBase, int i) {
+  const int r = i / (IN_W / 4), wq = i - r * (IN_W / 4);
+  const int py = min(max(pyBase + r, 0), H - 1);
+  const int px = pxBase + wq * 4;
+  const uint8_t* row = pic + (size_t)py * picPitch;
+  if (px >= 0 && px + 3 <= W - 1) return *reinterpret_cast<const unsigned*>(row + px);
+  unsigned b0 = row[min(max(px + 0, 0), W - 1)], b1 = row[min(max(px + 1, 0), W - 1)];
+  unsigned b2 = row[min(max(px + 2, 0), W - 1)], b3 = row[min(max(px + 3, 0), W - 1)];
+  return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+}
+
+constexpr int K1_IN_WORDS = IN_H * (IN_W / 4);
+constexpr int K1_PREF = (K1_IN_WORDS + K1_THREADS - 1) / K1_THREADS;  // input words per thread
+
+// Persistent: gridDim.x CTAs walk the tile list; the next tile's input words are fetched into registers before the
+// current tile's filtering starts and parked in shared memory after it, so global latency hides behind stages B/C.
+__global__ void __launch_bounds__(K1_THREADS, 2)
+k1_interp_planes(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int M, int Wp, int Hp, int pitch,
+                 size_t planeBytes, uint8_t* __restrict__ planes, int tilesX, int nTiles) {
   __shared__ __align__(16) uint8_t s_in[IN_H][IN_W];
   __shared__ __align__(16) int16_t s_t[4][IN_H][TW];
 
   const int tid = threadIdx.x;
-  const int x0 = blockIdx.x * TW;  // padded-plane coordinates of the tile
-  const int y0 = blockIdx.y * TH;
-
-  // ---- stage A: input tile, clamped to the picture --------------------------------------------
-  {
-    const int pxBase = x0 - M - 4;  // picture x of input column 0 (multiple of 4)
-    const int pyBase = y0 - M - 3;
-    for (int i = tid; i < IN_H * (IN_W / 4); i += K1_THREADS) {
-      int r = i / (IN_W / 4), wq = i - r * (IN_W / 4);
-      int py = min(max(pyBase + r, 0), H - 1);
-      int px = pxBase + wq * 4;
-      const uint8_t* row = pic + (size_t)py * picPitch;
-      unsigned v;
-      if (px >= 0 && px + 3 <= W - 1) {
-        v = *reinterpret_cast<const unsigned*>(row + px);
-      } else {
-        unsigned b0 = row[min(max(px + 0, 0), W - 1)], b1 = row[min(max(px + 1, 0), W - 1)];
-        unsigned b2 = row[min(max(px + 2, 0), W - 1)], b3 = row[min(max(px + 3, 0), W - 1)];
-        v = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
-      }
-      *reinterpret_cast<unsigned*>(&s_in[r][wq * 4]) = v;
+  unsigned pref[K1_PREF];
+  auto fetch = [&](int tile) {
+    const int ty = tile / tilesX, tx = tile - ty * tilesX;
+    const int pxBase = tx * TW - M - 4, pyBase = ty * TH - M - 3;  // picture coords of input (0,0); pxBase % 4 == 0
+#pragma unroll
+    for (int k = 0; k < K1_PREF; ++k) {
+      const int i = tid + k * K1_THREADS;
+      pref[k] = i < K1_IN_WORDS ? k1_load_word(pic, picPitch, W, H, pxBase, pyBase, i) : 0u;
     }
-  }
-  __syncthreads();
+  };
+  auto park = [&]() {
+#pragma unroll
+    for (int k = 0; k < K1_PREF; ++k) {
+      const int i = tid + k * K1_THREADS;
+      if (i < K1_IN_WORDS) reinterpret_cast<unsigned*>(&s_in[0][0])[i] = pref[k];
+    }
+  };
+
+  int tile = blockIdx.x;
+  if (tile < nTiles) fetch(tile);
+  for (; tile < nTiles; tile += gridDim.x) {
+    const int tyI = tile / tilesX, txI = tile - tyI * tilesX;
+    const int x0 = txI * TW, y0 = tyI * TH;  // padded-plane coordinates of the tile
+    __syncthreads();  // every thread is done with s_in / s_t of the previous tile
+    park();
+    __syncthreads();
+    if (tile + (int)gridDim.x < nTiles) fetch(tile + gridDim.x);  // in flight during stages B and C
 
   // ---- stage B: horizontal filters -> int16 T_fx ---------------------------------------------
   // item = (row, quad of 4 output columns).  Output column x uses input columns x+1 .. x+8
@@ -131,14 +152,17 @@ __global__ void __launch_bounds__(K1_THREADS) k1_interp_planes(const uint8_t* __
   // item = (quad of 4 columns, group of 4 output rows); the 11 intermediate rows a group needs are loaded once
   // and shared by its 4 rows x 3 vertical phases (register blocking), results are shifted, saturated and packed
   // with cvt.pack.sat (I2IP) and stored as one 32-bit word per plane row.
-  for (int i = tid; i < (TH / 4) * (TW / 4); i += K1_THREADS) {
+  // A 128 x 16 tile has 128 (quad, row group) items: the two halves of the CTA take different horizontal phases.
+  static_assert((TH / 4) * (TW / 4) * 2 == K1_THREADS, "stage C mapping assumes 2 x 128 items");
+  {
+    const int i = tid & 127, fxHalf = tid >> 7;
     const int rg = i / (TW / 4), q = i - rg * (TW / 4);
     const int r0 = rg * 4;
     const int gy0 = y0 + r0, gx = x0 + q * 4;
-    if (gx >= Wp || gy0 >= Hp) continue;  // Wp is a multiple of 4
+    const bool inside = gx < Wp && gy0 < Hp;  // Wp is a multiple of 4
     uint8_t* outBase = planes + (size_t)gy0 * pitch + gx;
 #pragma unroll 1
-    for (int fx = 0; fx < 4; ++fx) {
+    for (int fx = fxHalf; fx < 4 && inside; fx += 2) {
       int2 v[11];  // rows r0 .. r0+10 of T_fx (output row r is centred on input row r+3)
 #pragma unroll
       for (int k = 0; k < 11; ++k) v[k] = *reinterpret_cast<const int2*>(&s_t[fx][r0 + k][q * 4]);
@@ -178,6 +202,9 @@ __global__ void __launch_bounds__(K1_THREADS) k1_interp_planes(const uint8_t* __
             if (half) {
               hi16[fy - 1][r] = pack_sat_u8x2(acc0 >> 12, acc1 >> 12, 0);
             } else if (gy0 + r < Hp) {
+#ifdef K1_PROBE_NOSTORE
+              if (planeBytes == 1)
+#endif
               *reinterpret_cast<unsigned*>(outBase + (size_t)(fy * 4 + fx) * planeBytes + (size_t)r * pitch) =
                   pack_sat_u8x2(acc0 >> 12, acc1 >> 12, hi16[fy - 1][r]);
             }
@@ -186,6 +213,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_interp_planes(const uint8_t* __
       }
     }
   }
+  }  // tile loop
 }
 
 // Edge-replicating copy of a chroma picture into its padded plane (used by MC only).
@@ -217,9 +245,17 @@ __global__ void k_pel_to_u8(const int16_t* __restrict__ src, int srcStride, uint
 
 cudaError_t fme_launch_k1(const FmeGeom& g, const uint8_t* d_pic, int picPitch, uint8_t* d_planes, cudaStream_t s,
                           int64_t* launches) {
-  dim3 grid((g.Wp + TW - 1) / TW, (g.Hp + TH - 1) / TH);
+  const int tilesX = (g.Wp + TW - 1) / TW, tilesY = (g.Hp + TH - 1) / TH;
+  const int nTiles = tilesX * tilesY;
+  static int numSMs = 0;
+  if (!numSMs) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int grid = nTiles < numSMs * 2 ? nTiles : numSMs * 2;
   k1_interp_planes<<<grid, K1_THREADS, 0, s>>>(d_pic, picPitch, g.W, g.H, g.M, g.Wp, g.Hp, g.pitch, g.planeBytes,
-                                                d_planes);
+                                                d_planes, tilesX, nTiles);
   ++*launches;
   return cudaGetLastError();
 }
