@@ -129,7 +129,7 @@ def run_gpu(args):
     n_full = len(sets[0][2])
     if banded:
         sets = [(o, r, np.ascontiguousarray(fme.pu_list.band_of_pus(rc, rank, world, height))) for (o, r, rc) in sets]
-    n_pus = max(len(s[2]) for s in sets)
+    n_pus = max(1, max(len(s[2]) for s in sets))
     lam = fme.pu_list.slice_lambda(QP)
     blob = fme.nn_weights.load_blob(QP)
 

@@ -126,8 +126,13 @@ def make_records(width, height, motions, seed=0, amp=False, err_on_gpu=False):
 
 
 def band_of_pus(recs, band, n_bands, height, ctu=64):
-    """CTU-row band sharding: band b owns CTU rows [b*R, (b+1)*R), R = ceil(rows/n_bands)."""
-    rows = (height + ctu - 1) // ctu
-    per = (rows + n_bands - 1) // n_bands
+    """CTU-row band sharding (SURVEY.md 8e): band b owns CTU rows [b*rows//n, (b+1)*rows//n) -- balanced to within
+    one CTU row, never empty while there are at least n_bands CTU rows."""
+    lo, hi = band_rows(band, n_bands, height, ctu)
     ctu_row = recs["y"] // ctu
-    return recs[(ctu_row >= band * per) & (ctu_row < (band + 1) * per)]
+    return recs[(ctu_row >= lo) & (ctu_row < hi)]
+
+
+def band_rows(band, n_bands, height, ctu=64):
+    rows = (height + ctu - 1) // ctu
+    return band * rows // n_bands, (band + 1) * rows // n_bands

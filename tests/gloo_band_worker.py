@@ -32,8 +32,8 @@ dist.all_gather_object(gathered, res.tobytes())
 if rank == 0:
     full = frame.oracle_run(recs, 3, lam, 1, fme.nn_weights.load_blob(22))
     merged = np.concatenate([np.frombuffer(b, fme.RESULT_DTYPE) for b in gathered])
-    order = np.concatenate([np.nonzero((recs["y"] // 64 >= b * ((3 + world - 1) // world)) &
-                                       (recs["y"] // 64 < (b + 1) * ((3 + world - 1) // world)))[0] for b in range(world)])
+    bands = [fme.pu_list.band_rows(b, world, H) for b in range(world)]
+    order = np.concatenate([np.nonzero((recs["y"] // 64 >= lo) & (recs["y"] // 64 < hi))[0] for lo, hi in bands])
     assert np.array_equal(merged.view(np.uint8), full[order].view(np.uint8))
     print("BAND_MERGE_OK", len(merged))
 dist.barrier()

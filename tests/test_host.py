@@ -60,9 +60,11 @@ def test_band_sharding_partitions_the_list():
         parts = [fme.pu_list.band_of_pus(recs, b, nb, 192) for b in range(nb)]
         assert sum(len(p) for p in parts) == len(recs)
         for b, p in enumerate(parts):
+            lo, hi = fme.pu_list.band_rows(b, nb, 192)
             if len(p):
-                per = (3 + nb - 1) // nb
-                assert (p["y"] // 64 >= b * per).all() and (p["y"] // 64 < (b + 1) * per).all()
+                assert (p["y"] // 64 >= lo).all() and (p["y"] // 64 < hi).all()
+    # 2160p over 8 bands: 34 CTU rows -> every band non-empty
+    assert all(hi > lo for lo, hi in (fme.pu_list.band_rows(b, 8, 2160) for b in range(8)))
 
 
 def test_two_rank_gloo_band_merge():
