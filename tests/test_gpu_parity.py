@@ -453,3 +453,86 @@ def test_pred_error_vs_oracle(use_had, orc):
         want = orc.dist(1 if use_had else 2, o, 0, w, pred, 0, w, w, h)
         assert int(got[i]) == want, (i, p, int(got[i]), want)
     eng.close()
+
+
+# ---------------------------------------------------------------- BASELINE.json configs 3-5 as parity cases
+def _sample_check(eng, frame, recs, lam, blob, n_sample, seed, fields):
+    rng = np.random.default_rng(seed)
+    idx = np.sort(rng.choice(len(recs), n_sample, replace=False))
+    sample = np.ascontiguousarray(recs[idx])
+    frame.oracle_fill_surface(sample)
+    want = frame.oracle_run(sample, 3, lam, 1, blob)
+    return idx, want
+
+
+def test_c3_qp_sweep_1080p():
+    """configs[2]: 1080p, QP sweep 22/27/32/37 with the per-QP NN weights and the per-QP slice lambda."""
+    W, H = 1920, 1080
+    org, refs, motions = fme.pu_list.synth_frames(W, H, n_refs=2, seed=2027)
+    recs = fme.pu_list.make_records(W, H, motions, seed=3, err_on_gpu=True)
+    frame = ob.CpuFrame(org, refs)
+    eng = fme.Fme(W, H, num_ref_slots=2, max_pus=len(recs))
+    eng.upload_org(org)
+    for s in range(2):
+        eng.upload_ref(s, refs[s])
+    for qp in (22, 27, 32, 37):
+        lam = fme.pu_list.slice_lambda(qp)
+        blob = fme.nn_weights.load_blob(qp)
+        eng.set_slice(lam)
+        eng.set_nn_weights(blob)
+        got = eng.submit(recs, fme.MODE_BOTH)
+        idx, want = _sample_check(eng, frame, recs, lam, blob, 1500, qp, None)
+        for f in ("halfX", "halfY", "qterX", "qterY", "cost", "nnHalfX", "nnHalfY", "nnQterX", "nnQterY", "nnClass"):
+            assert np.array_equal(got[f][idx], want[f]), (qp, f)
+    eng.close()
+
+
+def test_c4_three_layer_1080p():
+    """configs[3]: 3-layer ANN (9-40-40-40-49) batched over a whole 1080p frame; every PU compared with the oracle."""
+    W, H = 1920, 1080
+    org, refs, motions = fme.pu_list.synth_frames(W, H, n_refs=1, seed=2040)
+    recs = fme.pu_list.make_records(W, H, motions, seed=4, err_on_gpu=True)
+    frame = ob.CpuFrame(org, refs)
+    blob = fme.nn_weights.synthetic_blob((40, 40, 40), n_emb=0, seed=40)
+    eng = fme.Fme(W, H, num_ref_slots=1, max_pus=len(recs))
+    eng.set_nn_weights(blob)
+    eng.upload_org(org)
+    eng.upload_ref(0, refs[0])
+    got = eng.submit(recs, fme.MODE_NN)  # errors come from the device (K0), classes from the 3-layer fast path
+    cpu = recs.copy()
+    frame.oracle_fill_surface(cpu)
+    want = frame.oracle_run(cpu, 2, 1.0, 1, blob)
+    mism = int((nn_fields(got) != nn_fields(want)).any(1).sum())
+    assert mism == 0, "%d of %d PUs differ (%.4f%%)" % (mism, len(recs), 100.0 * mism / len(recs))
+    eng.close()
+
+
+def test_c5_2160p_ctu_row_bands():
+    """configs[4]: 3840x2160, CTU-row band sharding: the union of 8 band submissions equals the whole-frame
+    submission, and a sample of it equals the oracle."""
+    W, H = 3840, 2160
+    org, refs, motions = fme.pu_list.synth_frames(W, H, n_refs=1, seed=3000)
+    recs = fme.pu_list.make_records(W, H, motions, seed=5, err_on_gpu=True)
+    assert len(recs) == 860100
+    lam = fme.pu_list.slice_lambda(22)
+    blob = fme.nn_weights.load_blob(22)
+    eng = fme.Fme(W, H, num_ref_slots=1, max_pus=len(recs))
+    eng.set_nn_weights(blob)
+    eng.set_slice(lam)
+    eng.upload_org(org)
+    eng.upload_ref(0, refs[0])
+    full = eng.submit(recs, fme.MODE_BOTH)
+    merged = np.zeros_like(full)
+    seen = np.zeros(len(recs), bool)
+    for b in range(8):
+        lo, hi = fme.pu_list.band_rows(b, 8, H)
+        sel = np.nonzero((recs["y"] // 64 >= lo) & (recs["y"] // 64 < hi))[0]
+        assert len(sel) > 0
+        merged[sel] = eng.submit(np.ascontiguousarray(recs[sel]), fme.MODE_BOTH)
+        seen[sel] = True
+    assert seen.all() and np.array_equal(merged.view(np.uint8), full.view(np.uint8))
+    frame = ob.CpuFrame(org, refs)
+    idx, want = _sample_check(eng, frame, recs, lam, blob, 1500, 5, None)
+    for f in ("halfX", "halfY", "qterX", "qterY", "cost", "nnClass"):
+        assert np.array_equal(full[f][idx], want[f]), f
+    eng.close()
