@@ -315,6 +315,7 @@ def run_gpu(args):
             "k2_refine": {"ms": kavg["k2_refine"], "bound": "hbm", "achieved": gbs(k2_bytes, kavg["k2_refine"]),
                           "peak": peak, "unit": "GB/s", "frac": gbs(k2_bytes, kavg["k2_refine"]) / peak,
                           "alg_bytes": k2_bytes, "int_ops_per_s": 144.0 * pu_px / (kavg["k2_refine"] * 1e-3) if kavg["k2_refine"] > 0 else 0,
+                          "int_lane_rate_frac": (144.0 * pu_px / (kavg["k2_refine"] * 1e-3)) / (148 * 128 * 1.965e9) if kavg["k2_refine"] > 0 else 0,
                           "note": "issue-bound integer SATD; HBM fraction reported because the contract asks for it"},
             "k3_nn": {"ms": kavg["k3_nn"], "bound": "fp32", "achieved": k3_flops / (kavg["k3_nn"] * 1e-3) / 1e12 if kavg["k3_nn"] > 0 else 0,
                       "unit": "TFLOP/s"},
@@ -322,12 +323,13 @@ def run_gpu(args):
         dom = max(("k1_interp", "k2_refine"), key=lambda k: kavg[k])
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
         # (1080p workload only; the plane set of 4 references, 173 MB, does not fit the 126 MB L2)
-        ncu_traffic = {"k2_refine": 1.612242e9 + 88.116e6, "k1_interp": 2.09e6 + 111.36e6} if not banded else {}
+        ncu_traffic = {"k2_refine": 1.515457e9 + 45.597e6, "k1_interp": 2.09e6 + 111.36e6} if not banded else {}
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved"], "peak": peak, "unit": "GB/s",
                     "frac": kernels[dom]["frac"], "traffic": ncu_traffic.get(dom), "peak_source": peak_src,
-                    "traffic_source": "profiles/r1_k2_metrics_v3.txt (ncu --set full, one launch)",
-                    "note": "K2 is INT-issue bound (issue_active 69 %, 613 SASS instructions per 8x8 tile-candidate); "
-                            "the HBM fraction is reported because the contract asks for bound in {hbm, tensor}"}
+                    "traffic_source": "profiles/r1_k2_metrics_v4.txt (ncu --set full, one launch)",
+                    "note": "K2 is INT-issue/pipe bound (ncu: issue_active 70 %, 612 SASS instructions per 8x8 tile-candidate, "
+                            "DRAM 18 % busy); the HBM fraction is reported because the contract asks for bound in {hbm, tensor}; "
+                            "kernels.k2_refine.int_lane_rate_frac is the fraction of the 148x128-lane integer rate"}
         out = {
             "metric": "FME PUs/sec at 1080p QP22 (xPatternSearchFracDIF + NN_pred per PU)" if not banded else
                       "FME PUs/sec at 2160p QP22, CTU-row bands",
