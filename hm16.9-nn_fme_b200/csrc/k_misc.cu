@@ -9,63 +9,88 @@ namespace {
 // TComRdCost::setDistParam(pattern, ref, stride, dp) (TComRdCost.cpp:200-229): SSE for widths
 // 4/8/16/32/64, SAD12/24/48 otherwise, the SADs on every second row (<< 1) when FEN is on and rows > 8.
 // Raster order [TL,T,TR,L,C,R,BL,B,BR] = array_e[0..3], C, array_e[4..7] (TEncSearch.cpp:88, 1341-1376).
-// One warp per PU; lanes stride over the PU's 4-sample groups; plane 0 is the padded integer-pel copy.
+// Plane 0 is the padded integer-pel copy.
 // ------------------------------------------------------------------------------------------------
+// 8 lanes per PU (4 PUs per warp); a lane's item is one 4-sample group of one source row against the 3x3
+// neighbourhood: three reference rows, each read as three aligned words and funnel-shifted to the three horizontal
+// offsets; SSE per word = VABSDIFF4 + dp4a(d, d), SAD per word = VABSDIFF4.ACC.
+__device__ __forceinline__ unsigned k0_word_at(unsigned w0, unsigned w1, unsigned w2, int byteShift) {
+  // 4 bytes starting `byteShift` (0..6) bytes into the 12-byte window w0:w1:w2
+  return byteShift < 4 ? __funnelshift_r(w0, w1, 8 * byteShift) : __funnelshift_r(w1, w2, 8 * (byteShift - 4));
+}
+
 __global__ void __launch_bounds__(256) k0_int_surface(fme_pu* __restrict__ pus, int n, const uint8_t* __restrict__ planes,
                                                       const uint8_t* __restrict__ org, const FmeGeom g, int fen) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  int nWarps = (gridDim.x * blockDim.x) >> 5;
-  for (int i = warp; i < n; i += nWarps) {
-    fme_pu p = pus[i];
-    if (!(p.flags & FME_PU_ERR_ON_GPU)) continue;
-    int w = p.w, h = p.h;
-    bool useSad = (w == 12 || w == 24 || w == 48);
-    int step = (useSad && fen && h > 8) ? 2 : 1;
-    int X = min(max(p.x + p.mvIntX, -(g.M - 8)), g.W + g.M - 8 - w);
-    int Y = min(max(p.y + p.mvIntY, -(g.M - 8)), g.H + g.M - 8 - h);
-    int ox = min(max((int)p.x, 0), g.W - w), oy = min(max((int)p.y, 0), g.H - h);
-    const uint8_t* ref = planes + (size_t)min((int)p.refSlot, g.numSlots - 1) * g.slotBytes + (size_t)(Y + g.M) * g.pitch + (X + g.M);
-    const uint8_t* src = org + (size_t)oy * g.orgPitch + ox;
+  const int sub = threadIdx.x & 7;                                      // lane within the PU's 8-lane group
+  const int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;        // PU group index
+  const int nGrp = (gridDim.x * blockDim.x) >> 3;
+  for (int i0 = grp; i0 < ((n + 3) & ~3); i0 += nGrp) {               // all 4 groups of a warp iterate together
+    const int i = i0;
+    const bool valid = i < n;
+    fme_pu p;
+    if (valid) p = pus[i];
+    const bool doit = valid && (p.flags & FME_PU_ERR_ON_GPU) && fme_dim_index(p.w) >= 0 && fme_dim_index(p.h) >= 0;
     unsigned acc[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[k] = 0;
-    int groups = w >> 2;  // 4-sample groups per row
-    int rows = h / step;
-    for (int t = lane; t < groups * rows; t += 32) {
-      int r = (t / groups) * step, c = (t % groups) * 4;
-      int o[4];
+    int step = 1;
+    if (doit) {
+      const int w = p.w, h = p.h;
+      const bool useSad = (w == 12 || w == 24 || w == 48);
+      step = (useSad && fen && h > 8) ? 2 : 1;
+      const int X = min(max(p.x + p.mvIntX, -(g.M - 8)), g.W + g.M - 8 - w);
+      const int Y = min(max(p.y + p.mvIntY, -(g.M - 8)), g.H + g.M - 8 - h);
+      const int ox = min(max((int)p.x, 0), g.W - w), oy = min(max((int)p.y, 0), g.H - h);
+      const uint8_t* ref = planes + (size_t)min((int)p.refSlot, g.numSlots - 1) * g.slotBytes +
+                           (size_t)(Y + g.M) * g.pitch + (X + g.M);
+      const uint8_t* src = org + (size_t)oy * g.orgPitch + ox;
+      const int groups = w >> 2, rows = h / step;
+      for (int t = sub; t < groups * rows; t += 8) {
+        const int rr = t / groups, c = (t - rr * groups) * 4;
+        const int r = rr * step;
+        // source word (may be unaligned for out-of-contract x)
+        const uint8_t* sp = src + (size_t)r * g.orgPitch + c;
+        const unsigned* spw = reinterpret_cast<const unsigned*>((size_t)sp & ~(size_t)3);
+        const unsigned so = (unsigned)((size_t)sp & 3) * 8u;
+        const unsigned o = __funnelshift_r(__ldg(spw), __ldg(spw + 1), so);
+        // reference window: bytes (c - 1) .. (c + 4) of rows r-1, r, r+1
+        const uint8_t* rp = ref + (ptrdiff_t)(r - 1) * g.pitch + c - 1;
+        const unsigned* rpw = reinterpret_cast<const unsigned*>((size_t)rp & ~(size_t)3);
+        const int a = (int)((size_t)rp & 3);
+        const int pitchW = g.pitch >> 2;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) o[k] = src[(size_t)r * g.orgPitch + c + k];
+        for (int dy = 0; dy < 3; ++dy) {
+          const unsigned w0 = __ldg(rpw + dy * pitchW), w1 = __ldg(rpw + dy * pitchW + 1), w2 = __ldg(rpw + dy * pitchW + 2);
 #pragma unroll
-      for (int dy = -1; dy <= 1; ++dy) {
-        const uint8_t* rr = ref + (ptrdiff_t)(r + dy) * g.pitch + c;
-        int v[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) v[k] = rr[k - 1];
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-          unsigned s = 0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            int d = o[k] - v[k + 1 + dx];
-            s += useSad ? (unsigned)abs(d) : (unsigned)(d * d);
+          for (int dx = 0; dx < 3; ++dx) {
+            const unsigned v = k0_word_at(w0, w1, w2, a + dx);
+            if (useSad) {
+              acc[dy * 3 + dx] = __vsadu4(o, v) + acc[dy * 3 + dx];
+            } else {
+              const unsigned d = __vabsdiffu4(o, v);
+              acc[dy * 3 + dx] = __dp4a(d, d, acc[dy * 3 + dx]);
+            }
           }
-          acc[(dy + 1) * 3 + dx + 1] += s;
         }
       }
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      unsigned v = __reduce_add_sync(0xffffffffu, acc[k]);
+      unsigned v = acc[k];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
       if (step == 2) v <<= 1;  // uiSum <<= iSubShift (TComRdCost.cpp, xGetSAD12/24/48)
       acc[k] = v;
     }
-    if (lane < 9) {
+    if (doit) {
+      // every lane of the group holds all nine totals: lane k stores err[k], lane 0 also err[8]
       unsigned v = acc[0];
 #pragma unroll
-      for (int k = 1; k < 9; ++k)
-        if (lane == k) v = acc[k];
-      pus[i].err[lane] = v;
+      for (int k = 1; k < 8; ++k)
+        if (sub == k) v = acc[k];
+      pus[i].err[sub] = v;
+      if (sub == 0) pus[i].err[8] = acc[8];
     }
   }
 }
@@ -283,7 +308,7 @@ __global__ void __launch_bounds__(256) k_mc(const fme_mc_pu* __restrict__ pus, i
 cudaError_t fme_launch_k0(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, fme_pu* d_pus, int n,
                           int fen, cudaStream_t s, int64_t* launches) {
   if (n <= 0) return cudaSuccess;
-  int blocks = (n + 7) / 8;
+  int blocks = (n + 31) / 32;  // 32 PUs per 256-thread CTA
   if (blocks > 148 * 16) blocks = 148 * 16;
   k0_int_surface<<<blocks, 256, 0, s>>>(d_pus, n, d_planes, d_org, g, fen);
   ++*launches;
