@@ -247,12 +247,11 @@ cudaError_t fme_launch_k1(const FmeGeom& g, const uint8_t* d_pic, int picPitch, 
                           int64_t* launches) {
   const int tilesX = (g.Wp + TW - 1) / TW, tilesY = (g.Hp + TH - 1) / TH;
   const int nTiles = tilesX * tilesY;
-  static int numSMs = 0;
-  if (!numSMs) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev);
-  }
+  static int smCount[64] = {};  // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!smCount[dev & 63]) cudaDeviceGetAttribute(&smCount[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+  const int numSMs = smCount[dev & 63];
   const int grid = nTiles < numSMs * 2 ? nTiles : numSMs * 2;
   k1_interp_planes<<<grid, K1_THREADS, 0, s>>>(d_pic, picPitch, g.W, g.H, g.M, g.Wp, g.Hp, g.pitch, g.planeBytes,
                                                 d_planes, tilesX, nTiles);

@@ -736,12 +736,14 @@ cudaError_t fme_launch_k2(const FmeGeom& g, const uint8_t* d_planes, const uint8
   k2_scan<<<1, 32, 0, s>>>(sc.classCount, sc.classOffset, sc.packOffset, sc.classCursor, sc.workCounter);
   k2_scatter<<<blocks, 256, 0, s>>>(d_pus, n, sc.classOffset, sc.classCursor, sc.order);
   *launches += 3;
-  static bool attrSet = false;
+  static bool attrSet[64] = {};  // per device: the opt-in to > 48 KB dynamic shared memory is a per-device attribute
   const int smemBytes = K2_WARPS * K2_SMEM_PER_WARP;
-  if (!attrSet) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attrSet[dev & 63]) {
     e = cudaFuncSetAttribute(k2_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
     if (e != cudaSuccess) return e;
-    attrSet = true;
+    attrSet[dev & 63] = true;
   }
   k2_refine<<<numSMs, K2_THREADS, smemBytes, s>>>(d_pus, d_res, d_planes, d_org, g, d_costLut, useHad, sc.order,
                                                   sc.classOffset, sc.packOffset, sc.workCounter);

@@ -310,11 +310,13 @@ cudaError_t launch_fixed(const fme_pu* d_pus, int n, fme_result* d_res, const fl
                         (H3 > 0 ? LayerSmem<H2, (H3 > 0 ? H3 : 1)>::WORDS : 0) + LayerSmem<HLAST, NOUT>::WORDS +
                         HMAX * K3F_NPU * K3F_THREADS;
   const int smem = words * 4;
-  static bool attr = false;
-  if (!attr && smem > 48 * 1024) {
+  static bool attr[64] = {};  // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr[dev & 63] && smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k3_nn_fixed<NEMB, H1, H2, H3, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr[dev & 63] = true;
   }
   int blocks = (n + K3F_NPU * K3F_THREADS - 1) / (K3F_NPU * K3F_THREADS);
   if (blocks > 148 * 6) blocks = 148 * 6;
@@ -336,11 +338,9 @@ cudaError_t fme_launch_k3(const fme_pu* d_pus, int n, fme_result* d_res, const f
   }
   int blocks = (n + K3_THREADS - 1) / K3_THREADS;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  static size_t attrSet = 0;
-  if (nnBytes > 48 * 1024 && attrSet < nnBytes) {
+  if (nnBytes > 48 * 1024) {  // rare (generic path with a large blob): set on every launch, it is cheap
     cudaError_t e = cudaFuncSetAttribute(k3_nn_pred, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nnBytes);
     if (e != cudaSuccess) return e;
-    attrSet = nnBytes;
   }
   k3_nn_pred<<<blocks, K3_THREADS, nnBytes, s>>>(d_pus, n, d_res, d_nn, (int)(nnBytes / 4));
   return cudaGetLastError();
