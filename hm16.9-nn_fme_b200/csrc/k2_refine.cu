@@ -127,7 +127,9 @@ __global__ void k2_scatter(const fme_pu* __restrict__ pus, int n, const int* __r
 // x264-style packed |.| on two 16-bit lanes held carry-tolerantly in one 32-bit word
 // (value = hi*65536 + lo with signed lo); returns true unsigned fields (|hi| , |lo|).
 __device__ __forceinline__ unsigned abs2(unsigned a) {
-  unsigned s = ((a >> 15) & 0x10001u) * 0xffffu;
+  // s = 0xffff in every 16-bit field whose raw sign bit is set: one PRMT in sign-replicate mode (selector nibbles
+  // 9 / b replicate the msb of byte 1 / byte 3) instead of shift + mask + multiply
+  unsigned s = __byte_perm(a, 0, 0xbb99);
   return (a + s) ^ s;
 }
 // acc + max of the two 16-bit fields of m: swap halves, packed max, then one dp2a picks the low field
@@ -152,6 +154,13 @@ __device__ __forceinline__ unsigned lds_row4(const uint8_t* base) {
   const unsigned* p = reinterpret_cast<const unsigned*>(base - (addr & 3u));
   unsigned sh = (addr & 3u) * 8u;
   return __funnelshift_r(p[0], p[1], sh);
+}
+
+// In-place 4-point Hadamard of (a, b, c, d) on SWAR words: two 2-input and four 3-input adds.
+__device__ __forceinline__ void had4(unsigned& a, unsigned& b, unsigned& c, unsigned& d) {
+  const unsigned t = a + b, u = a - b;
+  const unsigned y0 = t + c + d, y2 = t - c - d, y1 = u + c - d, y3 = u - c + d;
+  a = y0; b = y1; c = y2; d = y3;
 }
 
 // A candidate tile in shared memory: rows are `pitchWords` 32-bit words apart (the staged row pitch is a multiple of
@@ -197,29 +206,23 @@ __device__ __forceinline__ unsigned satd8x8(OrgRow orgRow, const uint8_t* cand, 
     d[4 * r + 3] = __byte_perm(o1, 0, 0x4342) - __byte_perm(c1, 0, 0x4342);
   }
   // horizontal: column-index bits 1 and 2 (bit 0 lives inside a word and is folded into the final max)
+  // (radix-4: 6 three-input adds per 4 points instead of 8 two-input ones; IADD3 takes negated operands)
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    unsigned a0 = d[4 * r] + d[4 * r + 1], a1 = d[4 * r] - d[4 * r + 1];
-    unsigned a2 = d[4 * r + 2] + d[4 * r + 3], a3 = d[4 * r + 2] - d[4 * r + 3];
-    d[4 * r] = a0 + a2; d[4 * r + 2] = a0 - a2;
-    d[4 * r + 1] = a1 + a3; d[4 * r + 3] = a1 - a3;
-  }
+  for (int r = 0; r < 8; ++r) had4(d[4 * r], d[4 * r + 1], d[4 * r + 2], d[4 * r + 3]);
   // vertical: three stages over the row index
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     unsigned v[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) v[r] = d[4 * r + j];
+    had4(v[0], v[1], v[2], v[3]);
+    had4(v[4], v[5], v[6], v[7]);
 #pragma unroll
-    for (int len = 1; len < 8; len <<= 1)
-#pragma unroll
-      for (int i = 0; i < 8; i += 2 * len)
-#pragma unroll
-        for (int k = i; k < i + len; ++k) {
-          unsigned a = v[k], b = v[k + len];
-          v[k] = a + b;
-          v[k + len] = a - b;
-        }
+    for (int k = 0; k < 4; ++k) {
+      unsigned a = v[k], b = v[k + 4];
+      v[k] = a + b;
+      v[k + 4] = a - b;
+    }
 #pragma unroll
     for (int r = 0; r < 8; ++r) d[4 * r + j] = v[r];
   }
@@ -247,11 +250,7 @@ __device__ __forceinline__ unsigned satd4x4(const unsigned (&o)[4], const uint8_
     d[2 * r + 1] = a - b;
   }
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    unsigned v0 = d[j], v1 = d[2 + j], v2 = d[4 + j], v3 = d[6 + j];
-    unsigned a0 = v0 + v1, a1 = v0 - v1, a2 = v2 + v3, a3 = v2 - v3;
-    d[j] = a0 + a2; d[4 + j] = a0 - a2; d[2 + j] = a1 + a3; d[6 + j] = a1 - a3;
-  }
+  for (int j = 0; j < 2; ++j) had4(d[j], d[2 + j], d[4 + j], d[6 + j]);
   unsigned sum = 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) sum = acc_hmax2(abs2(d[i]), sum);
