@@ -129,7 +129,9 @@ __global__ void k2_scatter(const fme_pu* __restrict__ pus, int n, const int* __r
 __device__ __forceinline__ unsigned abs2(unsigned a) {
   // s = 0xffff in every 16-bit field whose raw sign bit is set: one PRMT in sign-replicate mode (selector nibbles
   // 9 / b replicate the msb of byte 1 / byte 3) instead of shift + mask + multiply
-  unsigned s = __byte_perm(a, 0, 0xbb99);
+  // (inline PTX: the __byte_perm intrinsic drops bit 3 of each selector nibble, i.e. the sign-replicate mode)
+  unsigned s;
+  asm("prmt.b32 %0, %1, %2, 0xbb99;" : "=r"(s) : "r"(a), "r"(0u));
   return (a + s) ^ s;
 }
 // acc + max of the two 16-bit fields of m: swap halves, packed max, then one dp2a picks the low field
