@@ -134,11 +134,12 @@ __device__ __forceinline__ unsigned abs2(unsigned a) {
   asm("prmt.b32 %0, %1, %2, 0xbb99;" : "=r"(s) : "r"(a), "r"(0u));
   return (a + s) ^ s;
 }
-// acc + max of the two 16-bit fields of m: swap halves, packed max, then one dp2a picks the low field
-__device__ __forceinline__ unsigned acc_hmax2(unsigned m, unsigned acc) {
-  unsigned mx = __vmaxu2(m, __byte_perm(m, 0, 0x1032));
+// acc + max(A.lo, A.hi) + max(B.lo, B.hi) for two words of unsigned 16-bit fields: regroup (A.hi, B.hi) and
+// (A.lo, B.lo) with two PRMTs, one packed max, one dp2a with multipliers (1, 1) sums both fields into 32 bits
+__device__ __forceinline__ unsigned acc_hmax2x2(unsigned A, unsigned B, unsigned acc) {
+  unsigned mx = __vmaxu2(__byte_perm(A, B, 0x7632), __byte_perm(A, B, 0x5410));
   unsigned d;
-  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(mx), "r"(1u), "r"(acc));
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(mx), "r"(0x0101u), "r"(acc));
   return d;
 }
 
@@ -231,7 +232,7 @@ __device__ __forceinline__ unsigned satd8x8(OrgRow orgRow, const uint8_t* cand, 
   // last horizontal stage + abs: |lo+hi| + |lo-hi| = 2 max(|lo|,|hi|)
   unsigned sum = 0;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) sum = acc_hmax2(abs2(d[i]), sum);
+  for (int i = 0; i < 32; i += 2) sum = acc_hmax2x2(abs2(d[i]), abs2(d[i + 1]), sum);
   return (2 * sum + 2) >> 2;  // TComRdCost.cpp:1421
 }
 
@@ -255,7 +256,7 @@ __device__ __forceinline__ unsigned satd4x4(const unsigned (&o)[4], const uint8_
   for (int j = 0; j < 2; ++j) had4(d[j], d[2 + j], d[4 + j], d[6 + j]);
   unsigned sum = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) sum = acc_hmax2(abs2(d[i]), sum);
+  for (int i = 0; i < 8; i += 2) sum = acc_hmax2x2(abs2(d[i]), abs2(d[i + 1]), sum);
   return (2 * sum + 1) >> 1;  // TComRdCost.cpp:1325
 }
 
