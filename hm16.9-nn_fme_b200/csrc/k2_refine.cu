@@ -29,7 +29,6 @@ namespace {
 constexpr int K2_WARPS = FME_K2_WARPS;
 constexpr int K2_THREADS = K2_WARPS * 32;
 constexpr int K2_SMEM_PER_WARP = 10496;  // two staging buffers of max P*(h+1)*RW + 16 bytes (64x64: 65*80 = 5200)
-constexpr int K2_MAX_PACK = 32;
 
 // TEncSearch.cpp:212-236
 __constant__ int8_t c_refineH[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {1, -1}, {-1, 1}, {1, 1}};
@@ -314,6 +313,12 @@ __device__ __forceinline__ void cp_async_g(void* smemDst, const void* gsrc) {
   else if constexpr (A == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
   else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
 }
+template <int A>
+__device__ __forceinline__ void cp_async_s(unsigned sa, const void* gsrc) {
+  if constexpr (A == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+  else if constexpr (A == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -324,51 +329,22 @@ struct StageGeom {
   int G;    // granules per row
   int RB;   // bytes per staged region = (h + 1) * RW
 };
-// Mixed-radix position of a lane's current copy item (PU j, row, granule) and its +32 step.
-struct ItemPos {
-  int j, row, gi;
-  int dJ, dRow, dG;
-};
-// n / G for G in {2,3,4,5} and small n (exact for n < 2^13): multiply by ceil(2^16 / G) and shift.
-__device__ __forceinline__ int div_small(int n, int G) {
-  const int inv = G == 2 ? 32768 : G == 3 ? 21846 : G == 4 ? 16384 : 13108;
-  return (n * inv) >> 16;
-}
-__device__ __forceinline__ ItemPos item_pos(int lane, int rows, int G) {
-  ItemPos p;
-  const int items = rows * G;
-  // lane < 32 and items >= 4: a few subtractions instead of an integer division
-  int j = 0, r = lane;
-  while (r >= items) { r -= items; ++j; }
-  p.j = j;
-  p.row = div_small(r, G);
-  p.gi = r - p.row * G;
-  int dJ = 0, rem = 32;
-  while (rem >= items) { rem -= items; ++dJ; }
-  p.dJ = dJ;
-  p.dRow = div_small(rem, G);
-  p.dG = rem - p.dRow * G;
-  return p;
-}
-
-// One staging step: copy `rows` rows of RW bytes of every PU's region (source base pointers in s_base) into
-// buf + j*RB.  The pack's regions form one flat item space (count * rows * G granules) walked by all 32 lanes;
-// rows keep the source's alignment modulo A (readers funnel-shift).  No divisions in the loop.
-// An item is a granule column of TWO consecutive rows (p.row counts row pairs): the index stepping and the address
-// arithmetic are paid once per two copies.
+// One staging step for one lane.  A PU's region is copied by the lanes that serve that PU (ci.lanes, a power of two):
+// lane `sub` of the group owns granule column gi = sub % Gp of the rows rowSub, rowSub + rowStep, ... where
+// Gp = min(pow2ceil(G), lanes) and rowStep = lanes / Gp.  Lanes of one PU read neighbouring granules of the same rows
+// (sector-coalesced); the walk is one pointer bump per row, no index arithmetic.  Single-lane groups (8x8, 8x4, 4x8)
+// have G == 2 and copy both granules of every row themselves (second = true); elsewhere Gp >= G.
 template <int A>
-__device__ __forceinline__ void stage_regions(uint8_t* buf, const StageGeom sg, int rows, int count, int pitch,
-                                              const unsigned long long* s_base, ItemPos p) {
-  const int rowPairs = (rows + 1) >> 1;
-  while (p.j < count) {
-    const int row = 2 * p.row;
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(s_base[p.j]) + (size_t)(row * pitch + p.gi * A);
-    uint8_t* dst = buf + p.j * sg.RB + row * sg.RW + p.gi * A;
-    cp_async_g<A>(dst, src);
-    if (row + 1 < rows) cp_async_g<A>(dst + sg.RW, src + pitch);
-    p.gi += p.dG; p.row += p.dRow; p.j += p.dJ;
-    if (p.gi >= sg.G) { p.gi -= sg.G; ++p.row; }
-    if (p.row >= rowPairs) { p.row -= rowPairs; ++p.j; }
+__device__ __forceinline__ void stage_rows(unsigned dst, const uint8_t* src, int rowSub, int rowStep, int rows, int RW,
+                                           int pitch, bool second) {
+  const long long srcStep = (long long)rowStep * pitch;
+  const int dstStep = rowStep * RW;
+#pragma unroll 4
+  for (int r = rowSub; r < rows; r += rowStep) {
+    cp_async_s<A>(dst, src);
+    if (second) cp_async_s<A>(dst + A, src + A);
+    src += srcStep;
+    dst += dstStep;
   }
 }
 
@@ -392,8 +368,7 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
                                      const fme_pu* __restrict__ pus, fme_result* __restrict__ res,
                                      const uint8_t* __restrict__ planes, const uint8_t* __restrict__ org,
                                      const FmeGeom& g, const uint32_t* __restrict__ costLut, int useHad,
-                                     uint8_t* smem, int* s_pu, int* s_X, int* s_Y, long long* s_slotOff, int* s_win,
-                                     unsigned long long* s_base) {
+                                     uint8_t* smem) {
   const int lane = threadIdx.x & 31;
   const int w = ci.w, h = ci.h;
   const int U = ci.units;                      // lane units per PU
@@ -403,22 +378,25 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   const bool laneActive = myPu < count;
   const int unit0 = lane - myPu * lanesPerPu;  // unit index in round 0 (may be >= U: idle lane of a padded group)
 
-  // ---- pack table ----
-  if (lane < ci.P) {
-    int idx = lane < count ? order[first + lane] : -1;
-    s_pu[lane] = idx;
-    if (idx >= 0) {
-      fme_pu p = pus[idx];
-      // The reference clips MVs so that reads stay inside its padded planes (TComDataCU.cpp:2773-2786:
-      // X in [-71, W+7]); the clamp below only guards device memory against out-of-contract records.
-      s_X[lane] = min(max(p.x + p.mvIntX, -(g.M - 8)), g.W + g.M - 8 - w);
-      s_Y[lane] = min(max(p.y + p.mvIntY, -(g.M - 8)), g.H + g.M - 8 - h);
-      // byte offset of sample (X, Y) of the slot's plane 0; steps add plane * planeBytes and small (dx, dy)
-      s_slotOff[lane] = (long long)min((int)p.refSlot, g.numSlots - 1) * (long long)g.slotBytes +
-                        (long long)(s_Y[lane] + g.M) * g.pitch + (s_X[lane] + g.M);
-    }
+  // ---- this lane's PU ----
+  int predX = 0, predY = 0, mvIntX = 0, mvIntY = 0, lossless = 0, puIdx = -1, alignX = 0;
+  int ox = 0, oy = 0;
+  long long slotOff = 0;  // byte offset of sample (X, Y) of the slot's plane 0; steps add plane * planeBytes and (dx, dy)
+  if (laneActive) {
+    puIdx = order[first + myPu];
+    const fme_pu p = pus[puIdx];
+    predX = p.mvPredX; predY = p.mvPredY; mvIntX = p.mvIntX; mvIntY = p.mvIntY;
+    lossless = p.flags & FME_PU_LOSSLESS;
+    // The reference clips MVs so that reads stay inside its padded planes (TComDataCU.cpp:2773-2786:
+    // X in [-71, W+7]); the clamp below only guards device memory against out-of-contract records.
+    const int X = min(max(p.x + p.mvIntX, -(g.M - 8)), g.W + g.M - 8 - w);
+    const int Y = min(max(p.y + p.mvIntY, -(g.M - 8)), g.H + g.M - 8 - h);
+    alignX = X + g.M;
+    slotOff = (long long)min((int)p.refSlot, g.numSlots - 1) * (long long)g.slotBytes +
+              (long long)(Y + g.M) * g.pitch + alignX;
+    ox = min(max((int)p.x, 0), g.W - w);
+    oy = min(max((int)p.y, 0), g.H - h);
   }
-  __syncwarp();
 
   // ---- staging geometry ----
   StageGeom sg;
@@ -426,38 +404,41 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   sg.G = sg.RW / A;
   sg.RB = (h + 1) * sg.RW;
   if (((sg.RB / A) & 1) == 0) sg.RB += A;  // odd region stride in granules: lanes of different PUs spread over the banks
-  const ItemPos posHalf = item_pos(lane, (h + 2) >> 1, sg.G);  // in row pairs; a handful of divisions per pack
-  const ItemPos posQter = item_pos(lane, (h + 1) >> 1, sg.G);
   const int bufBytes = (ci.P * sg.RB + 16 + 15) & ~15;
   uint8_t* const bufA = smem;
   uint8_t* const bufB = smem + bufBytes;
+  // lane -> (granule column, first row, row step) inside its PU's region
+  int gpShift = 0;
+  while ((1 << gpShift) < sg.G && (1 << gpShift) < lanesPerPu) ++gpShift;
+  const int Gp = 1 << gpShift;
+  const int stGi = unit0 & (Gp - 1), stRowSub = unit0 >> gpShift, stRowStep = lanesPerPu >> gpShift;
+  const bool stSecond = Gp < sg.G;                   // only single-lane groups: G == 2
+  const bool stOn = laneActive && stGi < sg.G;
+  const unsigned stDst = (unsigned)__cvta_generic_to_shared(smem) + myPu * sg.RB + stRowSub * sg.RW + stGi * A;
+  const int stSrcOff = stRowSub * g.pitch + stGi * A;
 
-  // Region of step s for PU j.  Steps 0..3: half-pel planes (0,0) (0,2) (2,0) (2,2), origin (X-1, Y-1),
-  // h+1 rows.  Steps 4..11: quarter-pel candidate s-3 of s_acMvRefineQ around the PU's half-pel winner, h rows.
-  auto publishBases = [&](int s) {
-    if (lane < count) {
+  // half-pel winner of this lane's PU (identical in all lanes of the PU after the per-PU sums)
+  int bhx = 0, bhy = 0;
+  // Region of step s.  Steps 0..3: half-pel planes (0,0) (0,2) (2,0) (2,2), origin (X-1, Y-1), h+1 rows.
+  // Steps 4..11: quarter-pel candidate s-3 of s_acMvRefineQ around the PU's half-pel winner, h rows.
+  auto stage = [&](int s) {
+    if (stOn) {
       int plane, dx, dy;
       if (s < 4) {
         plane = (s & 1) * 2 + (s >> 1) * 8;
         dx = -1;
         dy = -1;
       } else {
-        int wv = s_win[lane];
-        int jhx = (int)(int8_t)(wv & 0xff), jhy = (int)(int8_t)((wv >> 8) & 0xff);
-        int qx = 2 * jhx + c_refineQ[s - 3][0], qy = 2 * jhy + c_refineQ[s - 3][1];
+        int qx = 2 * bhx + c_refineQ[s - 3][0], qy = 2 * bhy + c_refineQ[s - 3][1];
         plane = (qy & 3) * 4 + (qx & 3);
         dx = qx >> 2;
         dy = qy >> 2;
       }
       // planes is 128-byte aligned and pitch / planeBytes are multiples of 128: aligning the offset aligns the address
-      long long off = s_slotOff[lane] + (long long)plane * (long long)g.planeBytes + dy * g.pitch + dx;
-      s_base[lane] = (unsigned long long)(planes + (off & ~(long long)(A - 1)));
+      const long long off = slotOff + (long long)plane * (long long)g.planeBytes + dy * g.pitch + dx;
+      stage_rows<A>(stDst + ((s & 1) ? bufBytes : 0), planes + (off & ~(long long)(A - 1)) + stSrcOff, stRowSub, stRowStep,
+                    s < 4 ? h + 1 : h, sg.RW, g.pitch, stSecond);
     }
-    __syncwarp();
-  };
-  auto stage = [&](int s) {
-    publishBases(s);
-    stage_regions<A>((s & 1) ? bufB : bufA, sg, s < 4 ? h + 1 : h, count, g.pitch, s_base, s < 4 ? posHalf : posQter);
     cp_async_commit();
   };
   stage(0);  // in flight while the source tiles are fetched
@@ -465,17 +446,6 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   // ---- source tile(s) of this lane into registers ----
   constexpr int OW = 16 / 2 * 2 / (TS == 8 ? 1 : 2);  // 16 words (one 8x8 tile) or 8 words (two 4x4 tiles)
   unsigned o[OW];
-  int predX = 0, predY = 0, mvIntX = 0, mvIntY = 0, lossless = 0, puIdx = -1, alignX = 0;
-  int ox = 0, oy = 0;
-  if (laneActive) {
-    puIdx = s_pu[myPu];
-    fme_pu p = pus[puIdx];
-    predX = p.mvPredX; predY = p.mvPredY; mvIntX = p.mvIntX; mvIntY = p.mvIntY;
-    lossless = p.flags & FME_PU_LOSSLESS;
-    alignX = s_X[myPu] + g.M;
-    ox = min(max((int)p.x, 0), g.W - w);
-    oy = min(max((int)p.y, 0), g.H - h);
-  }
   const bool had = useHad && !lossless;
   // unit -> byte offset of its (first) tile inside a staged region, offset of the second 4x4 tile, source load
   int uOff = 0, u1Off = 0;
@@ -510,7 +480,7 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   // running first-minimum: candidates of the half-pel stage are evaluated plane by plane, i.e. out of table
   // order, so ties are broken by the table index explicitly (strict < in table order, TEncSearch.cpp:1634)
   unsigned hBest = 0xffffffffu, qBest = 0xffffffffu;
-  int hBestI = 9, qBestI = 0, bhx = 0, bhy = 0;
+  int hBestI = 9, qBestI = 0;
   // MV bits per axis for offsets -1, 0, +1.  Half stage, cost scale 1 (TEncSearch.cpp:4531): ((int<<1)+h)<<1 - pred
   int bitsX[3], bitsY[3];
 #pragma unroll
@@ -573,8 +543,6 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
       bhy = c_refineH[bestI][1];
       qBest = hBest;  // candidate 0 of the quarter stage is the half-pel winner itself (same block, same bits)
       qBestI = 0;
-      if (laneActive && unit0 == 0) s_win[myPu] = (bhx & 0xff) | ((bhy & 0xff) << 8);
-      __syncwarp();
       stage(4);
       // quarter stage, cost scale 0 (TEncSearch.cpp:5260): (((int<<1)+half)<<1) + q - pred
 #pragma unroll
@@ -603,12 +571,6 @@ k2_refine(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, const ui
   __shared__ uint32_t s_lut[FME_COST_LUT_SIZE];
   __shared__ int s_packOff[FME_MAX_CLASSES + 1];
   __shared__ int s_classOff[FME_MAX_CLASSES + 1];
-  __shared__ int s_pu[K2_WARPS][K2_MAX_PACK];
-  __shared__ int s_X[K2_WARPS][K2_MAX_PACK];
-  __shared__ int s_Y[K2_WARPS][K2_MAX_PACK];
-  __shared__ long long s_slot[K2_WARPS][K2_MAX_PACK];
-  __shared__ int s_win[K2_WARPS][K2_MAX_PACK];
-  __shared__ unsigned long long s_base[K2_WARPS][K2_MAX_PACK];
 
   for (int i = threadIdx.x; i < FME_COST_LUT_SIZE; i += blockDim.x) s_lut[i] = costLutG[i];
   for (int i = threadIdx.x; i <= FME_MAX_CLASSES; i += blockDim.x) {
@@ -635,8 +597,7 @@ k2_refine(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, const ui
     int first = (pack - s_packOff[cls]) * ci.P;
     int count = min(ci.P, inClass - first);
     first += s_classOff[cls];
-#define K2_ARGS ci, order, first, count, pus, res, planes, org, g, s_lut, useHad, smem, s_pu[warp], s_X[warp], s_Y[warp], \
-                s_slot[warp], s_win[warp], s_base[warp]
+#define K2_ARGS ci, order, first, count, pus, res, planes, org, g, s_lut, useHad, smem
     if (ci.ts == 8) {
       if (ci.w >= 16) k2_pack<8, 16>(K2_ARGS);
       else k2_pack<8, 8>(K2_ARGS);
