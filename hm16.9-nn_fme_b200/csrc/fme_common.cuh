@@ -45,8 +45,9 @@ __host__ __device__ inline int fme_dim_index(int v) {
   }
 }
 __host__ __device__ inline int fme_index_dim(int i) {
-  const int t[8] = {4, 8, 12, 16, 24, 32, 48, 64};
-  return t[i & 7];
+  // {4, 8, 12, 16, 24, 32, 48, 64} without a (local-memory) table
+  i &= 7;
+  return i < 4 ? 4 * (i + 1) : ((i & 1) ? 32 : 24) << ((i - 4) >> 1);
 }
 
 // ---- launchers implemented in the kernel translation units ----------------------------------
