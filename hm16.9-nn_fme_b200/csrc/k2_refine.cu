@@ -28,10 +28,19 @@ namespace {
 #endif
 constexpr int K2_WARPS = FME_K2_WARPS;
 constexpr int K2_THREADS = K2_WARPS * 32;
-constexpr int K2_SMEM_PER_WARP = 10496;  // two staging buffers of max P*(h+1)*RW + 16 bytes (64x64: 65*80 = 5200)
+#ifdef FME_K2_ORG_SMEM
+constexpr int K2_ORG_BYTES = 2048;  // the source tile of every lane lives in shared memory: 8 rows x 32 lanes x 8 B
+#else
+constexpr int K2_ORG_BYTES = 0;     // ... or in 16 registers
+#endif
+constexpr int K2_STAGE_BYTES = 10496;  // two staging buffers of max P*(h+1)*RW + 16 bytes (64x64: 65*80 = 5200)
+constexpr int K2_SMEM_PER_WARP = K2_STAGE_BYTES + K2_ORG_BYTES;
 
 // TEncSearch.cpp:212-236
 __constant__ int8_t c_refineH[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {1, -1}, {-1, 1}, {1, 1}};
+// candidates served by staging step s, in table order: first index and count (see the step list in k2_pack)
+__constant__ int8_t c_stepFirst[12] = {0, 3, 1, 5, 1, 2, 3, 4, 5, 6, 7, 8};
+__constant__ int8_t c_stepCount[12] = {1, 2, 2, 4, 1, 1, 1, 1, 1, 1, 1, 1};
 __constant__ int8_t c_refineQ[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {1, 1}};
 
 struct ClassInfo {
@@ -352,6 +361,20 @@ __device__ __forceinline__ void stage_rows(unsigned dst, const uint8_t* src, int
 template <int TS>
 __device__ __forceinline__ unsigned unit_dist(const unsigned* o, const uint8_t* cand, int candPitch, int tile1Off,
                                               bool had) {
+#ifdef FME_K2_ORG_SMEM
+  // o -> this lane's column of the warp's [8 rows][32 lanes] uint2 table
+  const uint2* so = reinterpret_cast<const uint2*>(o);
+  if constexpr (TS == 8) {
+    auto row = [&](int r, unsigned& lo, unsigned& hi) { const uint2 v = so[r * 32]; lo = v.x; hi = v.y; };
+    return had ? satd8x8(row, cand, candPitch) : sad8x8(row, cand, candPitch);
+  } else {
+    unsigned oa[4], ob[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { const uint2 v = so[r * 32]; oa[r] = v.x; ob[r] = v.y; }
+    return had ? satd4x4(oa, cand, candPitch) + satd4x4(ob, cand + tile1Off, candPitch)
+               : sad4x4(oa, cand, candPitch) + sad4x4(ob, cand + tile1Off, candPitch);
+  }
+#else
   if constexpr (TS == 8) {
     auto row = [&](int r, unsigned& lo, unsigned& hi) { lo = o[2 * r]; hi = o[2 * r + 1]; };
     return had ? satd8x8(row, cand, candPitch) : sad8x8(row, cand, candPitch);
@@ -361,6 +384,7 @@ __device__ __forceinline__ unsigned unit_dist(const unsigned* o, const uint8_t* 
     return had ? satd4x4(oa, cand, candPitch) + satd4x4(ob, cand + tile1Off, candPitch)
                : sad4x4(oa, cand, candPitch) + sad4x4(ob, cand + tile1Off, candPitch);
   }
+#endif
 }
 
 template <int TS, int A>
@@ -372,7 +396,10 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   const int lane = threadIdx.x & 31;
   const int w = ci.w, h = ci.h;
   const int U = ci.units;                      // lane units per PU
-  const int rounds = (U + 31) >> 5;            // 2 only when a single PU has more than 32 units (then P == 1)
+  // 2 only when a single PU has more than 32 units (64x64, 64x48, 48x64; then P == 1); never for 4x4-tiled shapes
+  const int rounds = TS == 8 ? (U + 31) >> 5 : 1;
+  const int gPitch = g.pitch, gOrgPitch = g.orgPitch;
+  const int gPlaneBytes = (int)g.planeBytes;   // < 2^31 (padded 8K plane: 4480 * 7936)
   const int lanesPerPu = ci.lanes;             // power of two
   const int myPu = lane / lanesPerPu;          // PU slot in the pack served by this lane
   const bool laneActive = myPu < count;
@@ -393,7 +420,7 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
     const int Y = min(max(p.y + p.mvIntY, -(g.M - 8)), g.H + g.M - 8 - h);
     alignX = X + g.M;
     slotOff = (long long)min((int)p.refSlot, g.numSlots - 1) * (long long)g.slotBytes +
-              (long long)(Y + g.M) * g.pitch + alignX;
+              (long long)((Y + g.M) * gPitch + alignX);
     ox = min(max((int)p.x, 0), g.W - w);
     oy = min(max((int)p.y, 0), g.H - h);
   }
@@ -415,7 +442,7 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   const bool stSecond = Gp < sg.G;                   // only single-lane groups: G == 2
   const bool stOn = laneActive && stGi < sg.G;
   const unsigned stDst = (unsigned)__cvta_generic_to_shared(smem) + myPu * sg.RB + stRowSub * sg.RW + stGi * A;
-  const int stSrcOff = stRowSub * g.pitch + stGi * A;
+  const int stSrcOff = stRowSub * gPitch + stGi * A;
 
   // half-pel winner of this lane's PU (identical in all lanes of the PU after the per-PU sums)
   int bhx = 0, bhy = 0;
@@ -435,9 +462,9 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
         dy = qy >> 2;
       }
       // planes is 128-byte aligned and pitch / planeBytes are multiples of 128: aligning the offset aligns the address
-      const long long off = slotOff + (long long)plane * (long long)g.planeBytes + dy * g.pitch + dx;
+      const long long off = slotOff + (long long)(plane * gPlaneBytes + dy * gPitch + dx);  // 16 planes < 2^31 bytes
       stage_rows<A>(stDst + ((s & 1) ? bufBytes : 0), planes + (off & ~(long long)(A - 1)) + stSrcOff, stRowSub, stRowStep,
-                    s < 4 ? h + 1 : h, sg.RW, g.pitch, stSecond);
+                    s < 4 ? h + 1 : h, sg.RW, gPitch, stSecond);
     }
     cp_async_commit();
   };
@@ -445,7 +472,12 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
 
   // ---- source tile(s) of this lane into registers ----
   constexpr int OW = 16 / 2 * 2 / (TS == 8 ? 1 : 2);  // 16 words (one 8x8 tile) or 8 words (two 4x4 tiles)
+#ifdef FME_K2_ORG_SMEM
+  uint2* const so = reinterpret_cast<uint2*>(smem + K2_STAGE_BYTES) + lane;
+  const unsigned* const o = reinterpret_cast<const unsigned*>(so);
+#else
   unsigned o[OW];
+#endif
   const bool had = useHad && !lossless;
   // unit -> byte offset of its (first) tile inside a staged region, offset of the second 4x4 tile, source load
   int uOff = 0, u1Off = 0;
@@ -456,21 +488,33 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
     if constexpr (TS == 8) {
       int ty = u / ci.tilesX, tx = u - ty * ci.tilesX;
       uOff = ty * 8 * sg.RW + tx * 8;
-      const uint8_t* src = org + (size_t)(oy + ty * 8) * g.orgPitch + ox + tx * 8;
+      const uint8_t* src = org + (size_t)(oy + ty * 8) * gOrgPitch + ox + tx * 8;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) ldg_row8(src + (size_t)r * g.orgPitch, o[2 * r], o[2 * r + 1]);
+#ifdef FME_K2_ORG_SMEM
+      for (int r = 0; r < 8; ++r) {
+        unsigned lo, hi;
+        ldg_row8(src + (size_t)r * gOrgPitch, lo, hi);
+        so[r * 32] = make_uint2(lo, hi);
+      }
+#else
+      for (int r = 0; r < 8; ++r) ldg_row8(src + (size_t)r * gOrgPitch, o[2 * r], o[2 * r + 1]);
+#endif
     } else {
       int t0 = 2 * u, t1 = 2 * u + 1;
       int ty0 = t0 / ci.tilesX, tx0 = t0 - ty0 * ci.tilesX;
       int ty1 = t1 / ci.tilesX, tx1 = t1 - ty1 * ci.tilesX;
       uOff = ty0 * 4 * sg.RW + tx0 * 4;
       u1Off = (ty1 * 4 * sg.RW + tx1 * 4) - uOff;
-      const uint8_t* s0 = org + (size_t)(oy + ty0 * 4) * g.orgPitch + ox + tx0 * 4;
-      const uint8_t* s1 = org + (size_t)(oy + ty1 * 4) * g.orgPitch + ox + tx1 * 4;
+      const uint8_t* s0 = org + (size_t)(oy + ty0 * 4) * gOrgPitch + ox + tx0 * 4;
+      const uint8_t* s1 = org + (size_t)(oy + ty1 * 4) * gOrgPitch + ox + tx1 * 4;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        o[r] = ldg_row4(s0 + (size_t)r * g.orgPitch);
-        o[4 + r] = ldg_row4(s1 + (size_t)r * g.orgPitch);
+#ifdef FME_K2_ORG_SMEM
+        so[r * 32] = make_uint2(ldg_row4(s0 + (size_t)r * gOrgPitch), ldg_row4(s1 + (size_t)r * gOrgPitch));
+#else
+        o[r] = ldg_row4(s0 + (size_t)r * gOrgPitch);
+        o[4 + r] = ldg_row4(s1 + (size_t)r * gOrgPitch);
+#endif
       }
     }
   };
@@ -501,8 +545,7 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
     const uint8_t* region = ((s & 1) ? bufB : bufA) + myPu * sg.RB;
     // candidates served by this step, in table order (TEncSearch.cpp:212-236):
     // s=0: H0 | s=1 (fx=2): H3 (-1,0), H4 (1,0) | s=2 (fy=2): H1 (0,-1), H2 (0,1) | s=3: H5..H8 | s>=4: Q(s-3)
-    const int iFirst = (s == 0) ? 0 : (s == 1) ? 3 : (s == 2) ? 1 : (s == 3) ? 5 : s - 3;
-    const int iCount = (s == 0 || s >= 4) ? 1 : (s == 3) ? 4 : 2;
+    const int iFirst = c_stepFirst[s], iCount = c_stepCount[s];
 #pragma unroll 1
     for (int c = 0; c < iCount; ++c) {
       const int i = iFirst + c;
@@ -520,10 +563,14 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
       const int bits = (ox3 < 0 ? bitsX[0] : ox3 == 0 ? bitsX[1] : bitsX[2]) +
                        (oy3 < 0 ? bitsY[0] : oy3 == 0 ? bitsY[1] : bitsY[2]);
       unsigned dist = 0;
+      if (rounds == 1) {
+        if (uOn) dist = unit_dist<TS>(o, region + uOff + candOff, sg.RW, u1Off, had);
+      } else {
 #pragma unroll 1
-      for (int rd = 0; rd < rounds; ++rd) {
-        if (rounds > 1) loadUnit(unit0 + 32 * rd);  // PUs with more than 32 units: source tile re-fetched per round
-        if (uOn) dist += unit_dist<TS>(o, region + uOff + candOff, sg.RW, u1Off, had);
+        for (int rd = 0; rd < rounds; ++rd) {
+          loadUnit(unit0 + 32 * rd);  // PUs with more than 32 units: source tile re-fetched per round
+          if (uOn) dist += unit_dist<TS>(o, region + uOff + candOff, sg.RW, u1Off, had);
+        }
       }
       for (int d = lanesPerPu >> 1; d > 0; d >>= 1) dist += __shfl_xor_sync(0xffffffffu, dist, d);  // per-PU sum
       if (laneActive) {
@@ -562,7 +609,11 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   __syncwarp();
 }
 
+#ifdef FME_K2_MAXREG
+__global__ void __maxnreg__(FME_K2_MAXREG)
+#else
 __global__ void __launch_bounds__(K2_THREADS, 1)
+#endif
 k2_refine(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, const uint8_t* __restrict__ planes,
           const uint8_t* __restrict__ org, const FmeGeom g, const uint32_t* __restrict__ costLutG, int useHad,
           const int* __restrict__ order, const int* __restrict__ classOffset, const int* __restrict__ packOffset,
@@ -583,11 +634,13 @@ k2_refine(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, const ui
   uint8_t* smem = dynSmem + warp * K2_SMEM_PER_WARP;
   const int totalPacks = s_packOff[FME_MAX_CLASSES];
 
+  // dynamic pack scheduler; the next pack index is requested while the current pack is processed
+  int nextPack = 0;
+  if (lane == 0) nextPack = atomicAdd(workCounter, 1);
   while (true) {
-    int pack = 0;
-    if (lane == 0) pack = atomicAdd(workCounter, 1);
-    pack = __shfl_sync(0xffffffffu, pack, 0);
+    const int pack = __shfl_sync(0xffffffffu, nextPack, 0);
     if (pack >= totalPacks) break;
+    if (lane == 0) nextPack = atomicAdd(workCounter, 1);
     // class of this pack: the c with packOff[c] <= pack < packOff[c+1]; two lanes cover the 64 classes
     unsigned hit = __ballot_sync(0xffffffffu, s_packOff[lane] <= pack && s_packOff[lane + 1] > pack);
     unsigned hit2 = __ballot_sync(0xffffffffu, s_packOff[lane + 32] <= pack && s_packOff[lane + 33] > pack);
