@@ -28,13 +28,7 @@ namespace {
 #endif
 constexpr int K2_WARPS = FME_K2_WARPS;
 constexpr int K2_THREADS = K2_WARPS * 32;
-#ifdef FME_K2_ORG_SMEM
-constexpr int K2_ORG_BYTES = 2048;  // the source tile of every lane lives in shared memory: 8 rows x 32 lanes x 8 B
-#else
-constexpr int K2_ORG_BYTES = 0;     // ... or in 16 registers
-#endif
-constexpr int K2_STAGE_BYTES = 10496;  // two staging buffers of max P*(h+1)*RW + 16 bytes (64x64: 65*80 = 5200)
-constexpr int K2_SMEM_PER_WARP = K2_STAGE_BYTES + K2_ORG_BYTES;
+constexpr int K2_SMEM_PER_WARP = 10496;  // two staging buffers of max P*(h+1)*RW + 16 bytes (64x64: 65*80 = 5200)
 
 // TEncSearch.cpp:212-236
 __constant__ int8_t c_refineH[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {1, -1}, {-1, 1}, {1, 1}};
@@ -149,22 +143,6 @@ __device__ __forceinline__ unsigned acc_hmax2x2(unsigned A, unsigned B, unsigned
   unsigned d;
   asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(mx), "r"(0x0101u), "r"(acc));
   return d;
-}
-
-// Read 8 bytes at arbitrary byte address from shared memory (3 aligned words + 2 funnel shifts).
-__device__ __forceinline__ void lds_row8(const uint8_t* base, unsigned& lo, unsigned& hi) {
-  unsigned addr = (unsigned)(size_t)base;  // only the low bits matter for alignment
-  const unsigned* p = reinterpret_cast<const unsigned*>(base - (addr & 3u));
-  unsigned sh = (addr & 3u) * 8u;
-  unsigned w0 = p[0], w1 = p[1], w2 = p[2];
-  lo = __funnelshift_r(w0, w1, sh);
-  hi = __funnelshift_r(w1, w2, sh);
-}
-__device__ __forceinline__ unsigned lds_row4(const uint8_t* base) {
-  unsigned addr = (unsigned)(size_t)base;
-  const unsigned* p = reinterpret_cast<const unsigned*>(base - (addr & 3u));
-  unsigned sh = (addr & 3u) * 8u;
-  return __funnelshift_r(p[0], p[1], sh);
 }
 
 // In-place 4-point Hadamard of (a, b, c, d) on SWAR words: two 2-input and four 3-input adds.
@@ -361,20 +339,6 @@ __device__ __forceinline__ void stage_rows(unsigned dst, const uint8_t* src, int
 template <int TS>
 __device__ __forceinline__ unsigned unit_dist(const unsigned* o, const uint8_t* cand, int candPitch, int tile1Off,
                                               bool had) {
-#ifdef FME_K2_ORG_SMEM
-  // o -> this lane's column of the warp's [8 rows][32 lanes] uint2 table
-  const uint2* so = reinterpret_cast<const uint2*>(o);
-  if constexpr (TS == 8) {
-    auto row = [&](int r, unsigned& lo, unsigned& hi) { const uint2 v = so[r * 32]; lo = v.x; hi = v.y; };
-    return had ? satd8x8(row, cand, candPitch) : sad8x8(row, cand, candPitch);
-  } else {
-    unsigned oa[4], ob[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) { const uint2 v = so[r * 32]; oa[r] = v.x; ob[r] = v.y; }
-    return had ? satd4x4(oa, cand, candPitch) + satd4x4(ob, cand + tile1Off, candPitch)
-               : sad4x4(oa, cand, candPitch) + sad4x4(ob, cand + tile1Off, candPitch);
-  }
-#else
   if constexpr (TS == 8) {
     auto row = [&](int r, unsigned& lo, unsigned& hi) { lo = o[2 * r]; hi = o[2 * r + 1]; };
     return had ? satd8x8(row, cand, candPitch) : sad8x8(row, cand, candPitch);
@@ -384,7 +348,6 @@ __device__ __forceinline__ unsigned unit_dist(const unsigned* o, const uint8_t* 
     return had ? satd4x4(oa, cand, candPitch) + satd4x4(ob, cand + tile1Off, candPitch)
                : sad4x4(oa, cand, candPitch) + sad4x4(ob, cand + tile1Off, candPitch);
   }
-#endif
 }
 
 template <int TS, int A>
@@ -472,12 +435,7 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
 
   // ---- source tile(s) of this lane into registers ----
   constexpr int OW = 16 / 2 * 2 / (TS == 8 ? 1 : 2);  // 16 words (one 8x8 tile) or 8 words (two 4x4 tiles)
-#ifdef FME_K2_ORG_SMEM
-  uint2* const so = reinterpret_cast<uint2*>(smem + K2_STAGE_BYTES) + lane;
-  const unsigned* const o = reinterpret_cast<const unsigned*>(so);
-#else
   unsigned o[OW];
-#endif
   const bool had = useHad && !lossless;
   // unit -> byte offset of its (first) tile inside a staged region, offset of the second 4x4 tile, source load
   int uOff = 0, u1Off = 0;
@@ -490,15 +448,7 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
       uOff = ty * 8 * sg.RW + tx * 8;
       const uint8_t* src = org + (size_t)(oy + ty * 8) * gOrgPitch + ox + tx * 8;
 #pragma unroll
-#ifdef FME_K2_ORG_SMEM
-      for (int r = 0; r < 8; ++r) {
-        unsigned lo, hi;
-        ldg_row8(src + (size_t)r * gOrgPitch, lo, hi);
-        so[r * 32] = make_uint2(lo, hi);
-      }
-#else
       for (int r = 0; r < 8; ++r) ldg_row8(src + (size_t)r * gOrgPitch, o[2 * r], o[2 * r + 1]);
-#endif
     } else {
       int t0 = 2 * u, t1 = 2 * u + 1;
       int ty0 = t0 / ci.tilesX, tx0 = t0 - ty0 * ci.tilesX;
@@ -509,12 +459,8 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
       const uint8_t* s1 = org + (size_t)(oy + ty1 * 4) * gOrgPitch + ox + tx1 * 4;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-#ifdef FME_K2_ORG_SMEM
-        so[r * 32] = make_uint2(ldg_row4(s0 + (size_t)r * gOrgPitch), ldg_row4(s1 + (size_t)r * gOrgPitch));
-#else
         o[r] = ldg_row4(s0 + (size_t)r * gOrgPitch);
         o[4 + r] = ldg_row4(s1 + (size_t)r * gOrgPitch);
-#endif
       }
     }
   };
