@@ -299,9 +299,9 @@ int fme_create(const fme_config* cfg, fme_ctx** out) {
   CREATE_CHECK(cudaMalloc(&c->d_costLut, sizeof(uint32_t) * FME_COST_LUT_SIZE));
   CREATE_CHECK(cudaMalloc(&c->k2.classCount, sizeof(int) * (4 * FME_MAX_CLASSES + 16)));
   c->k2.classCursor = c->k2.classCount + FME_MAX_CLASSES;
-  c->k2.classOffset = c->k2.classCursor + FME_MAX_CLASSES;
+  c->k2.workCounter = c->k2.classCursor + FME_MAX_CLASSES;  // counts, cursors and the work counter are cleared together
+  c->k2.classOffset = c->k2.workCounter + 4;
   c->k2.packOffset = c->k2.classOffset + FME_MAX_CLASSES + 1;
-  c->k2.workCounter = c->k2.packOffset + FME_MAX_CLASSES + 1;
   CREATE_CHECK(cudaMalloc(&c->k2.order, sizeof(int) * (size_t)cfg->maxPUs));
   CREATE_CHECK(cudaStreamSynchronize(c->stream));
 #undef CREATE_CHECK

@@ -77,28 +77,35 @@ __global__ void k2_count(const fme_pu* __restrict__ pus, int n, int* __restrict_
     if (s_cnt[i]) atomicAdd(&classCount[i], s_cnt[i]);
 }
 
-__global__ void k2_scan(const int* __restrict__ classCount, int* __restrict__ classOffset, int* __restrict__ packOffset,
-                        int* __restrict__ classCursor, int* __restrict__ workCounter) {
-  if (threadIdx.x == 0) {
-    int off = 0, packs = 0;
-    for (int c = 0; c < FME_MAX_CLASSES; ++c) {
-      classOffset[c] = off;
-      packOffset[c] = packs;
-      classCursor[c] = 0;
-      int cnt = classCount[c];
-      off += cnt;
-      if (cnt) packs += (cnt + class_info(c).P - 1) / class_info(c).P;
-    }
-    classOffset[FME_MAX_CLASSES] = off;
-    packOffset[FME_MAX_CLASSES] = packs;
-    *workCounter = 0;
-  }
-}
-
-__global__ void k2_scatter(const fme_pu* __restrict__ pus, int n, const int* __restrict__ classOffset,
+// Scatter PU indices into class-major order.  Every block derives the class and pack offsets itself from the 64
+// class counts (a warp scan, cheaper than a separate launch); block 0 also publishes them for k2_refine.
+__global__ void k2_scatter(const fme_pu* __restrict__ pus, int n, const int* __restrict__ classCount,
+                           int* __restrict__ classOffset, int* __restrict__ packOffset,
                            int* __restrict__ classCursor, int* __restrict__ order) {
   __shared__ int s_cnt[FME_MAX_CLASSES];
   __shared__ int s_base[FME_MAX_CLASSES];
+  __shared__ int s_classOff[FME_MAX_CLASSES];
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;  // two classes per lane
+    const int c0 = classCount[2 * lane], c1 = classCount[2 * lane + 1];
+    const int p0 = c0 ? (c0 + class_info(2 * lane).P - 1) / class_info(2 * lane).P : 0;
+    const int p1 = c1 ? (c1 + class_info(2 * lane + 1).P - 1) / class_info(2 * lane + 1).P : 0;
+    int sc = c0 + c1, sp = p0 + p1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int tc = __shfl_up_sync(0xffffffffu, sc, d), tp = __shfl_up_sync(0xffffffffu, sp, d);
+      if (lane >= d) { sc += tc; sp += tp; }
+    }
+    s_classOff[2 * lane] = sc - c0 - c1;
+    s_classOff[2 * lane + 1] = sc - c1;
+    if (blockIdx.x == 0) {
+      classOffset[2 * lane] = sc - c0 - c1;
+      classOffset[2 * lane + 1] = sc - c1;
+      packOffset[2 * lane] = sp - p0 - p1;
+      packOffset[2 * lane + 1] = sp - p1;
+      if (lane == 31) { classOffset[FME_MAX_CLASSES] = sc; packOffset[FME_MAX_CLASSES] = sp; }
+    }
+  }
   // one contiguous chunk per block so that local ranks are well defined
   int chunk = (n + gridDim.x - 1) / gridDim.x;
   int lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
@@ -110,7 +117,7 @@ __global__ void k2_scatter(const fme_pu* __restrict__ pus, int n, const int* __r
   }
   __syncthreads();
   for (int i = threadIdx.x; i < FME_MAX_CLASSES; i += blockDim.x) {
-    s_base[i] = s_cnt[i] ? classOffset[i] + atomicAdd(&classCursor[i], s_cnt[i]) : 0;
+    s_base[i] = s_cnt[i] ? s_classOff[i] + atomicAdd(&classCursor[i], s_cnt[i]) : 0;
     s_cnt[i] = 0;
   }
   __syncthreads();
@@ -691,13 +698,13 @@ cudaError_t fme_launch_k2(const FmeGeom& g, const uint8_t* d_planes, const uint8
                           fme_result* d_res, const uint32_t* d_costLut, int useHad, const FmeK2Scratch& sc,
                           int numSMs, cudaStream_t s, int64_t* launches) {
   if (n <= 0) return cudaSuccess;
-  cudaError_t e = cudaMemsetAsync(sc.classCount, 0, sizeof(int) * FME_MAX_CLASSES, s);
+  // classCount[64], classCursor[64] and the work counter are adjacent (fme_create)
+  cudaError_t e = cudaMemsetAsync(sc.classCount, 0, sizeof(int) * (2 * FME_MAX_CLASSES + 1), s);
   if (e != cudaSuccess) return e;
   int blocks = min(numSMs * 4, (n + 255) / 256);
   k2_count<<<blocks, 256, 0, s>>>(d_pus, n, sc.classCount);
-  k2_scan<<<1, 32, 0, s>>>(sc.classCount, sc.classOffset, sc.packOffset, sc.classCursor, sc.workCounter);
-  k2_scatter<<<blocks, 256, 0, s>>>(d_pus, n, sc.classOffset, sc.classCursor, sc.order);
-  *launches += 3;
+  k2_scatter<<<blocks, 256, 0, s>>>(d_pus, n, sc.classCount, sc.classOffset, sc.packOffset, sc.classCursor, sc.order);
+  *launches += 2;
   static bool attrSet[64] = {};  // per device: the opt-in to > 48 KB dynamic shared memory is a per-device attribute
   const int smemBytes = K2_WARPS * K2_SMEM_PER_WARP;
   int dev = 0;
