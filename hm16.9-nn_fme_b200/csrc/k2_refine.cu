@@ -28,7 +28,9 @@ namespace {
 #endif
 constexpr int K2_WARPS = FME_K2_WARPS;
 constexpr int K2_THREADS = K2_WARPS * 32;
-constexpr int K2_SMEM_PER_WARP = 10496;  // two staging buffers of max P*(h+1)*RW + 16 bytes (64x64: 65*80 = 5200)
+constexpr int K2_STAGE_BYTES = 10496;  // two staging buffers of max P*(h+1)*RW + 16 bytes (64x64: 65*80 = 5200)
+constexpr int K2_ORG2_BYTES = 2048;    // second source tile of every lane for PUs with more than 32 tiles (8 rows x 32 lanes x 8 B)
+constexpr int K2_SMEM_PER_WARP = K2_STAGE_BYTES + K2_ORG2_BYTES;
 
 // TEncSearch.cpp:212-236
 __constant__ int8_t c_refineH[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {1, -1}, {-1, 1}, {1, 1}};
@@ -366,8 +368,9 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   const int lane = threadIdx.x & 31;
   const int w = ci.w, h = ci.h;
   const int U = ci.units;                      // lane units per PU
-  // 2 only when a single PU has more than 32 units (64x64, 64x48, 48x64; then P == 1); never for 4x4-tiled shapes
-  const int rounds = TS == 8 ? (U + 31) >> 5 : 1;
+  // PUs with more than 32 units (64x64, 64x48, 48x64: one PU per pack, 8x8 tiles, 16-byte granules): every lane
+  // also serves unit lane + 32, whose source tile is parked in shared memory
+  const bool twoUnits = TS == 8 && A == 16 && U > 32;
   const int gPitch = g.pitch, gOrgPitch = g.orgPitch;
   const int gPlaneBytes = (int)g.planeBytes;   // < 2^31 (padded 8K plane: 4480 * 7936)
   const int lanesPerPu = ci.lanes;             // power of two
@@ -471,7 +474,27 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
       }
     }
   };
-  if (rounds == 1) loadUnit(unit0);
+  loadUnit(unit0);
+  [[maybe_unused]] uint2* const so2 = reinterpret_cast<uint2*>(smem + K2_STAGE_BYTES) + lane;  // [row][lane]
+  [[maybe_unused]] int uOff2 = 0;
+  [[maybe_unused]] bool uOn2 = false;
+  if constexpr (TS == 8 && A == 16) {
+    if (twoUnits) {
+      const int u = unit0 + 32;
+      uOn2 = laneActive && u < U;
+      if (uOn2) {
+        const int ty = u / ci.tilesX, tx = u - ty * ci.tilesX;
+        uOff2 = ty * 8 * sg.RW + tx * 8;
+        const uint8_t* src = org + (size_t)(oy + ty * 8) * gOrgPitch + ox + tx * 8;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          unsigned lo, hi;
+          ldg_row8(src + (size_t)r * gOrgPitch, lo, hi);
+          so2[r * 32] = make_uint2(lo, hi);
+        }
+      }
+    }
+  }
 
   // ---- 12 steps: prefetch step s+1 while evaluating the candidates served by step s ----
   // running first-minimum: candidates of the half-pel stage are evaluated plane by plane, i.e. out of table
@@ -516,13 +539,11 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
       const int bits = (ox3 < 0 ? bitsX[0] : ox3 == 0 ? bitsX[1] : bitsX[2]) +
                        (oy3 < 0 ? bitsY[0] : oy3 == 0 ? bitsY[1] : bitsY[2]);
       unsigned dist = 0;
-      if (rounds == 1) {
-        if (uOn) dist = unit_dist<TS>(o, region + uOff + candOff, sg.RW, u1Off, had);
-      } else {
-#pragma unroll 1
-        for (int rd = 0; rd < rounds; ++rd) {
-          loadUnit(unit0 + 32 * rd);  // PUs with more than 32 units: source tile re-fetched per round
-          if (uOn) dist += unit_dist<TS>(o, region + uOff + candOff, sg.RW, u1Off, had);
+      if (uOn) dist = unit_dist<TS>(o, region + uOff + candOff, sg.RW, u1Off, had);
+      if constexpr (TS == 8 && A == 16) {
+        if (uOn2) {
+          auto row2 = [&](int r, unsigned& lo, unsigned& hi) { const uint2 v = so2[r * 32]; lo = v.x; hi = v.y; };
+          dist += had ? satd8x8(row2, region + uOff2 + candOff, sg.RW) : sad8x8(row2, region + uOff2 + candOff, sg.RW);
         }
       }
       for (int d = lanesPerPu >> 1; d > 0; d >>= 1) dist += __shfl_xor_sync(0xffffffffu, dist, d);  // per-PU sum
