@@ -15,7 +15,7 @@ import numpy as np
 
 from . import nn_weights  # noqa: F401  (re-export)
 from . import formats  # noqa: F401
-from .pu_list import PU_DTYPE, RESULT_DTYPE, MC_PU_DTYPE  # noqa: F401
+from .pu_list import PU_DTYPE, RESULT_DTYPE, MC_PU_DTYPE, MC_BI_PU_DTYPE  # noqa: F401
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libfme_b200.so")
@@ -29,7 +29,7 @@ EXPORTS = [
     "fme_set_nn_weights", "fme_load_nn_csv_dir", "fme_set_slice", "fme_upload_ref", "fme_upload_ref_u8",
     "fme_upload_org", "fme_upload_org_u8", "fme_submit", "fme_submit_async", "fme_wait_oldest", "fme_submit_device", "fme_interp_slot",
     "fme_upload_ref_device_u8", "fme_upload_org_device_u8", "fme_int_surface_device", "fme_filter_hor",
-    "fme_filter_ver", "fme_dist", "fme_mv_cost", "fme_upload_ref_chroma", "fme_mc", "fme_pred_error", "fme_download_plane",
+    "fme_filter_ver", "fme_dist", "fme_mv_cost", "fme_upload_ref_chroma", "fme_mc", "fme_mc_bi", "fme_pred_error", "fme_download_plane",
     "fme_last_kernel_ms", "fme_launch_count", "fme_set_profiling",
 ]
 
@@ -87,6 +87,7 @@ def load_library():
     lib.fme_mv_cost.argtypes = [vp, i32, i32, i32, i32, i32, C.POINTER(C.c_uint32)]
     lib.fme_upload_ref_chroma.argtypes = [vp, i32, vp, vp, i32]
     lib.fme_mc.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.fme_mc_bi.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.fme_pred_error.argtypes = [vp, vp, i32, vp]
     lib.fme_download_plane.argtypes = [vp, i32, i32, i32, vp, i32]
     lib.fme_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
@@ -246,6 +247,17 @@ class Fme:
         cr = np.zeros((n, 32, 32), np.int16)
         self._check(self.lib.fme_mc(self.h, _addr(pus), n, _addr(y), _addr(cb) if chroma else None,
                                     _addr(cr) if chroma else None))
+        return y, cb, cr
+
+    def mc_bi(self, pus, chroma=True):
+        """xPredInterBi with both lists valid: two 14-bit uni predictions averaged by addAvg."""
+        pus = np.ascontiguousarray(pus, dtype=MC_BI_PU_DTYPE)
+        n = len(pus)
+        y = np.zeros((n, 64, 64), np.int16)
+        cb = np.zeros((n, 32, 32), np.int16)
+        cr = np.zeros((n, 32, 32), np.int16)
+        self._check(self.lib.fme_mc_bi(self.h, _addr(pus), n, _addr(y), _addr(cb) if chroma else None,
+                                       _addr(cr) if chroma else None))
         return y, cb, cr
 
     def pred_error(self, pus):

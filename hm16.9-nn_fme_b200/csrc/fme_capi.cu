@@ -800,6 +800,45 @@ int fme_mc(fme_ctx* c, const fme_mc_pu* pus, int n, int16_t* dstY, int16_t* dstC
   return FME_OK;
 }
 
+int fme_mc_bi(fme_ctx* c, const fme_mc_bi_pu* pus, int n, int16_t* dstY, int16_t* dstCb, int16_t* dstCr) {
+  if (!c || !pus || !dstY) return fail(FME_ERR_INVALID, "null argument");
+  if (n < 0 || n > c->cfg.maxPUs) return fail(FME_ERR_INVALID, "n out of range");
+  if (n == 0) return FME_OK;
+  bool chroma = dstCb && dstCr;
+  if (chroma && !c->d_cb) return fail(FME_ERR_STATE, "fme_mc_bi with chroma needs fme_upload_ref_chroma first");
+  for (int i = 0; i < n; ++i) {
+    const int sl[2] = {pus[i].refSlot0, pus[i].refSlot1};
+    for (int l = 0; l < 2; ++l)
+      if (sl[l] >= c->cfg.numRefSlots || !c->refValid[sl[l]])
+        return fail(FME_ERR_STATE, "PU %d references slot %d which holds no picture", i, sl[l]);
+    if (pus[i].w > 64 || pus[i].h > 64 || pus[i].w < 4 || pus[i].h < 4) return fail(FME_ERR_INVALID, "PU %d: bad size", i);
+  }
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  {
+    int rc0 = sync_all(c);  // the record staging buffer is shared with the async submit path
+    if (rc0) return rc0;
+  }
+  size_t ySamples = (size_t)n * 64 * 64, cSamples = (size_t)n * 32 * 32;
+  int rc = ensure_pel(&c->d_pel, &c->pelCapacity, ySamples);
+  if (rc) return rc;
+  if (chroma) {
+    rc = ensure_pel(&c->d_pel2, &c->pel2Capacity, 2 * cSamples);
+    if (rc) return rc;
+  }
+  static_assert(sizeof(fme_mc_bi_pu) <= sizeof(fme_pu), "record staging reuses d_pus");
+  CU_CHECK(cudaMemcpyAsync(c->d_pus, pus, sizeof(fme_mc_bi_pu) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CU_CHECK(fme_launch_mc_bi(c->g, c->d_planes, chroma ? c->d_cb : nullptr, chroma ? c->d_cr : nullptr,
+                            reinterpret_cast<const fme_mc_bi_pu*>(c->d_pus), n, c->d_pel, chroma ? c->d_pel2 : nullptr,
+                            chroma ? c->d_pel2 + cSamples : nullptr, c->stream, &c->launches));
+  CU_CHECK(cudaMemcpyAsync(dstY, c->d_pel, ySamples * 2, cudaMemcpyDeviceToHost, c->stream));
+  if (chroma) {
+    CU_CHECK(cudaMemcpyAsync(dstCb, c->d_pel2, cSamples * 2, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(cudaMemcpyAsync(dstCr, c->d_pel2 + cSamples, cSamples * 2, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU_CHECK(cudaStreamSynchronize(c->stream));
+  return FME_OK;
+}
+
 int fme_pred_error(fme_ctx* c, const fme_mc_pu* pus, int n, uint32_t* out) {
   if (!c || !pus || !out) return fail(FME_ERR_INVALID, "null argument");
   if (n < 0 || n > c->cfg.maxPUs) return fail(FME_ERR_INVALID, "n out of range");

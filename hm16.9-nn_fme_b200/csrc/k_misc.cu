@@ -303,6 +303,98 @@ __global__ void __launch_bounds__(256) k_mc(const fme_mc_pu* __restrict__ pus, i
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Motion compensation, bi-prediction: xPredInterBi with both lists valid (TComPrediction.cpp:575-621) =
+// two xPredInterUni(bi = true) blocks of 14-bit intermediates (xPredInterBlk with isLast = !bi = false,
+// TComPrediction.cpp:661-680) averaged by TComYuv::addAvg (TComYuv.cpp:354-409).  The intermediates are not
+// recoverable from the clipped 8-bit planes, so they are filtered here from the integer plane P[0][0]:
+//   yFrac == 0: sum c_x * s - 8192 (copy: (s << 6) - 8192) | xFrac == 0: same vertically |
+//   else      : (sum_j c_y[j] * (sum_k c_x[k] * s - 8192)) >> 6      (first stage shift 0 at 8 bit, IF.cpp:94-257)
+// ------------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ int bi_sample(const uint8_t* plane, int pitch, int x, int y, const int8_t* cx, const int8_t* cy,
+                                         bool fracX, bool fracY) {
+  const uint8_t* p = plane + (ptrdiff_t)y * pitch + x;
+  constexpr int L = N / 2 - 1;  // taps to the left / above
+  if (!fracY) {
+    if (!fracX) return ((int)p[0] << 6) - 8192;
+    int s = -8192;
+#pragma unroll
+    for (int k = 0; k < N; ++k) s += cx[k] * (int)p[k - L];
+    return s;
+  }
+  if (!fracX) {
+    int s = -8192;
+#pragma unroll
+    for (int k = 0; k < N; ++k) s += cy[k] * (int)p[(ptrdiff_t)(k - L) * pitch];
+    return s;
+  }
+  int acc = 0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const uint8_t* q = p + (ptrdiff_t)(j - L) * pitch;
+    int t = -8192;
+#pragma unroll
+    for (int k = 0; k < N; ++k) t += cx[k] * (int)q[k - L];
+    acc += cy[j] * t;
+  }
+  return acc >> 6;
+}
+__device__ __forceinline__ int add_avg8(int a, int b) { return min(max((a + b + 64 + 2 * 8192) >> 7, 0), 255); }
+
+__global__ void __launch_bounds__(256) k_mc_bi(const fme_mc_bi_pu* __restrict__ pus, int n, const uint8_t* __restrict__ planes,
+                                               const uint8_t* __restrict__ cb, const uint8_t* __restrict__ cr,
+                                               const FmeGeom g, int16_t* __restrict__ dstY, int16_t* __restrict__ dstCb,
+                                               int16_t* __restrict__ dstCr) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const fme_mc_bi_pu p = pus[i];
+  const int w = p.w, h = p.h;
+  const int slot[2] = {min((int)p.refSlot0, g.numSlots - 1), min((int)p.refSlot1, g.numSlots - 1)};
+  const int mvx[2] = {p.mv0X, p.mv1X}, mvy[2] = {p.mv0Y, p.mv1Y};
+  {  // luma: 8-tap at quarter pel from plane P[0][0] of each slot
+    const uint8_t* src[2];
+    int X[2], Y[2];
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+      X[l] = min(max(p.x + (mvx[l] >> 2), -(g.M - 8)), g.W + g.M - 8 - w) + g.M;
+      Y[l] = min(max(p.y + (mvy[l] >> 2), -(g.M - 8)), g.H + g.M - 8 - h) + g.M;
+      src[l] = planes + (size_t)slot[l] * g.slotBytes;
+    }
+    int16_t* d = dstY + (size_t)i * 64 * 64;
+    for (int t = threadIdx.x; t < w * h; t += blockDim.x) {
+      const int r = t / w, c = t % w;
+      const int a = bi_sample<8>(src[0], g.pitch, X[0] + c, Y[0] + r, c_luma[mvx[0] & 3], c_luma[mvy[0] & 3], mvx[0] & 3, mvy[0] & 3);
+      const int b = bi_sample<8>(src[1], g.pitch, X[1] + c, Y[1] + r, c_luma[mvx[1] & 3], c_luma[mvy[1] & 3], mvx[1] & 3, mvy[1] & 3);
+      d[r * 64 + c] = (int16_t)add_avg8(a, b);
+    }
+  }
+  if (cb && cr && dstCb && dstCr) {  // chroma 4:2:0: 4-tap at 1/8 pel
+    const int cw = w >> 1, ch = h >> 1;
+    int X[2], Y[2];
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+      X[l] = min(max((p.x >> 1) + (mvx[l] >> 3), -(g.Mc - 4)), g.Wc + g.Mc - 4 - cw) + g.Mc;
+      Y[l] = min(max((p.y >> 1) + (mvy[l] >> 3), -(g.Mc - 4)), g.Hc + g.Mc - 4 - ch) + g.Mc;
+    }
+    int16_t* dcb = dstCb + (size_t)i * 32 * 32;
+    int16_t* dcr = dstCr + (size_t)i * 32 * 32;
+    for (int t = threadIdx.x; t < cw * ch; t += blockDim.x) {
+      const int r = t / cw, c = t % cw;
+      int v[2][2];
+#pragma unroll
+      for (int l = 0; l < 2; ++l) {
+        const int8_t* cx = c_chroma[mvx[l] & 7];
+        const int8_t* cy = c_chroma[mvy[l] & 7];
+        v[l][0] = bi_sample<4>(cb + (size_t)slot[l] * g.cPlaneBytes, g.cPitch, X[l] + c, Y[l] + r, cx, cy, mvx[l] & 7, mvy[l] & 7);
+        v[l][1] = bi_sample<4>(cr + (size_t)slot[l] * g.cPlaneBytes, g.cPitch, X[l] + c, Y[l] + r, cx, cy, mvx[l] & 7, mvy[l] & 7);
+      }
+      dcb[r * 32 + c] = (int16_t)add_avg8(v[0][0], v[1][0]);
+      dcr[r * 32 + c] = (int16_t)add_avg8(v[0][1], v[1][1]);
+    }
+  }
+}
+
 }  // namespace
 
 cudaError_t fme_launch_k0(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, fme_pu* d_pus, int n,
@@ -331,6 +423,15 @@ cudaError_t fme_launch_dist(int kind, const int16_t* d_org, int orgStride, const
   int blocks = (nBlocks + 3) / 4;
   k_dist_blocks<<<blocks, 128, 0, s>>>(kind, d_org, orgStride, d_cur, curStride, w, h, bitDepth, subShift, nBlocks,
                                        d_out);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t fme_launch_mc_bi(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_cb, const uint8_t* d_cr,
+                             const fme_mc_bi_pu* d_pus, int n, int16_t* d_y, int16_t* d_cbOut, int16_t* d_crOut,
+                             cudaStream_t s, int64_t* launches) {
+  if (n <= 0) return cudaSuccess;
+  k_mc_bi<<<n, 256, 0, s>>>(d_pus, n, d_planes, d_cb, d_cr, g, d_y, d_cbOut, d_crOut);
   ++*launches;
   return cudaGetLastError();
 }

@@ -167,6 +167,17 @@ typedef struct fme_mc_pu {
 } fme_mc_pu; /* 12 bytes */
 int fme_mc(fme_ctx* ctx, const fme_mc_pu* pus, int n, int16_t* dstY, int16_t* dstCb, int16_t* dstCr);
 
+/* xPredInterBi with both lists valid (TComPrediction.cpp:575-621): two xPredInterUni(bi = true) blocks of 14-bit
+ * intermediates (xPredInterBlk with isLast = false, TComPrediction.cpp:661-680) averaged by TComYuv::addAvg
+ * (TComYuv.cpp:354-409).  Default weights only (weighted prediction is off in the reference configs).
+ * Output layout as fme_mc.  Chroma needs fme_upload_ref_chroma for both slots. */
+typedef struct fme_mc_bi_pu {
+  int16_t x, y;
+  uint8_t w, h, refSlot0, refSlot1;
+  int16_t mv0X, mv0Y, mv1X, mv1Y; /* quarter-pel luma MVs of list 0 / list 1 */
+} fme_mc_bi_pu; /* 16 bytes */
+int fme_mc_bi(fme_ctx* ctx, const fme_mc_bi_pu* pus, int n, int16_t* dstY, int16_t* dstCb, int16_t* dstCr);
+
 /* Prediction error of n uni-predicted PUs at quarter-pel MVs: luma MC + HADs (SAD when HadamardME is off or the PU is
  * lossless) against the source block -- TEncSearch::xGetInterPredictionError (TEncSearch.cpp:3576-3596, merge
  * estimation) and the distortion of xGetTemplateCost (TEncSearch.cpp:4397-4436; there the ctx is created with

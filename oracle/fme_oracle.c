@@ -94,6 +94,21 @@ void orc_filter_ver(int isLuma, const orc_pel* src, int ss, orc_pel* dst, int ds
   else filter_fir(4, 1, isFirst, isLast, bitDepth, src, ss, dst, ds, w, h, kChroma[frac]);
 }
 
+/* TComYuv::addAvg, one component (TComYuv.cpp:354-409).  The reference unrolls by 2 or 4 columns; the per-sample
+ * expression is the same in every branch.  rightShift(x, s) is an arithmetic >> for s >= 0 (CommonDef.h). */
+void orc_add_avg(const orc_pel* src0, int st0, const orc_pel* src1, int st1, orc_pel* dst, int ds, int w, int h,
+                 int bitDepth) {
+  const int headRoom = 14 - bitDepth;
+  const int shiftNum = (headRoom > 2 ? headRoom : 2) + 1;
+  const int offset = (1 << (shiftNum - 1)) + 2 * 8192;
+  const int maxv = (1 << bitDepth) - 1;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      int v = ((int)src0[y * st0 + x] + (int)src1[y * st1 + x] + offset) >> shiftNum;
+      dst[y * ds + x] = (orc_pel)(v < 0 ? 0 : v > maxv ? maxv : v);
+    }
+}
+
 /* ---------------------------------------------------------------- distortion */
 
 /* RD:359-855.  Widths 4..64 (and 12/24/48): rows subsampled by 1<<subShift, sum <<= subShift.

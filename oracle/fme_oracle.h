@@ -30,6 +30,11 @@ void orc_filter_hor(int isLuma, const orc_pel* src, int srcStride, orc_pel* dst,
 void orc_filter_ver(int isLuma, const orc_pel* src, int srcStride, orc_pel* dst, int dstStride, int w, int h,
                     int frac, int isFirst, int isLast, int bitDepth);
 
+/* TComYuv::addAvg for one component (TComYuv.cpp:354-409): bi-prediction average of two 14-bit intermediate blocks,
+ * dst = ClipBD((s0 + s1 + (1 << (shift-1)) + 2*IF_INTERNAL_OFFS) >> shift), shift = max(2, 14 - bitDepth) + 1. */
+void orc_add_avg(const orc_pel* src0, int stride0, const orc_pel* src1, int stride1, orc_pel* dst, int dstStride, int w,
+                 int h, int bitDepth);
+
 /* TComRdCost distortion functions (TComRdCost.cpp:359-855, 861-1206, 1212-1495) */
 uint32_t orc_sad(const orc_pel* org, int orgStride, const orc_pel* cur, int curStride, int w, int h, int bitDepth,
                  int subShift);

@@ -23,6 +23,7 @@
 #include "TLibCommon/CommonDef.h"
 #include "TLibCommon/TComRom.h"
 #include "TLibCommon/TComPattern.h"
+#include "TLibCommon/TComYuv.h"
 #include "TLibCommon/TComRdCost.h"
 #include "TLibCommon/TComInterpolationFilter.h"
 #include "TLibEncoder/TEncCfg.h"
@@ -91,6 +92,24 @@ void hmref_filter_ver(int comp, short* src, int srcStride, short* dst, int dstSt
   TComInterpolationFilter f;
   f.filterVer(ComponentID(comp), src, srcStride, dst, dstStride, w, h, frac, isFirst != 0, isLast != 0, CHROMA_420,
               bitDepth);
+}
+
+// TComYuv::addAvg (TComYuv.cpp:354-409) on luma-only TComYuv buffers (CHROMA_400), partition 0: the bi-prediction
+// average TComPrediction::xWeightedAverage applies to the two xPredInterUni(bi = true) outputs.
+void hmref_add_avg(const short* src0, int stride0, const short* src1, int stride1, short* dst, int dstStride, int w,
+                   int h) {
+  TComYuv a, b, d;
+  a.create(64, 64, CHROMA_400); b.create(64, 64, CHROMA_400); d.create(64, 64, CHROMA_400);
+  Pel* pa = a.getAddr(COMPONENT_Y); Pel* pb = b.getAddr(COMPONENT_Y);
+  const int sa = a.getStride(COMPONENT_Y), sb = b.getStride(COMPONENT_Y);
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) { pa[y * sa + x] = src0[y * stride0 + x]; pb[y * sb + x] = src1[y * stride1 + x]; }
+  d.addAvg(&a, &b, 0, w, h, g.bd);
+  const Pel* pd = d.getAddr(COMPONENT_Y);
+  const int sd = d.getStride(COMPONENT_Y);
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) dst[y * dstStride + x] = pd[y * sd + x];
+  a.destroy(); b.destroy(); d.destroy();
 }
 
 // kind 0: integer-ME metric chosen by setDistParam(pattern, ref, stride, dp) (TComRdCost.cpp:200-229)

@@ -130,6 +130,18 @@ for qp in (22, 27, 32, 37):
         res.append((cls, hxy[0], hxy[1], qxy[0], qxy[1]))
     out["nn_out%d" % qp] = np.array(res, np.int32)
 
+# ---- bi-prediction average: TComYuv::addAvg on 14-bit intermediates (own RNG stream: added later) ----
+rng2 = np.random.default_rng(20261019)
+R.init(22, 1, 1)
+avg_a = rng2.integers(-14312, 14249, (64, 64)).astype(np.int16)
+avg_b = rng2.integers(-14312, 14249, (64, 64)).astype(np.int16)
+avg_a[0, :8] = [-14312, 14248, -8192, 8128, 0, -1, 1, 14248]
+avg_b[0, :8] = [-14312, 14248, -8192, 8128, 0, -1, -64, -14312]
+out["avg_a"], out["avg_b"] = avg_a, avg_b
+avg_shapes = [(64, 64), (32, 16), (16, 32), (8, 8), (4, 8), (8, 4), (12, 16), (2, 4), (6, 8)]  # incl. chroma-sized
+out["avg_shapes"] = np.array(avg_shapes, np.int32)
+out["avg_out"] = np.concatenate([R.add_avg(avg_a, 0, 64, avg_b, 0, 64, w, h).ravel() for (w, h) in avg_shapes]).astype(np.int16)
+
 path = os.path.join(HERE, "fme_golden.npz")
 np.savez_compressed(path, **out)
 print("wrote", path, os.path.getsize(path), "bytes;", len(fcases), "filter cases,", len(dval), "dist cases,",

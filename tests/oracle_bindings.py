@@ -91,6 +91,11 @@ class Oracle:
                               int(is_last), bit_depth)
         return dst
 
+    def add_avg(self, a, a_off, astride, b, b_off, bstride, w, h, bit_depth=8):
+        dst = np.zeros((h, w), np.int16)
+        self.L.orc_add_avg(_ptr(a, a_off), astride, _ptr(b, b_off), bstride, _ptr(dst), w, w, h, bit_depth)
+        return dst
+
     def dist(self, kind, org, org_off, ostride, cur, cur_off, cstride, w, h, bit_depth=8, sub_shift=0):
         return int(self.L.orc_dist(kind, _ptr(org, org_off), ostride, _ptr(cur, cur_off), cstride, w, h, bit_depth,
                                    sub_shift))
@@ -179,6 +184,12 @@ class Reference:
         dst = np.zeros((h, w), np.int16)
         self.L.hmref_filter_ver(0 if is_luma else 1, _ptr(src, src_off), sstride, _ptr(dst), w, w, h, frac,
                                 int(is_first), int(is_last), bit_depth)
+        return dst
+
+    def add_avg(self, a, a_off, astride, b, b_off, bstride, w, h):
+        """TComYuv::addAvg at the bit depth of the last init() (8)."""
+        dst = np.zeros((h, w), np.int16)
+        self.L.hmref_add_avg(_ptr(a, a_off), astride, _ptr(b, b_off), bstride, _ptr(dst), w, w, h)
         return dst
 
     def dist(self, kind, org, org_off, ostride, cur, cur_off, cstride, w, h, bit_depth=8, sub_shift=0):

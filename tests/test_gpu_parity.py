@@ -320,6 +320,64 @@ def test_mc_luma_and_chroma_vs_oracle(small, orc):
             assert np.array_equal(got[i, :ch, :cw], want), ("chroma", i, p)
 
 
+def test_mc_bi_luma_and_chroma_vs_oracle(small, orc):
+    """xPredInterBi, both lists valid: two xPredInterBlk(bi = true) blocks of 14-bit intermediates (three cases of
+    TComPrediction.cpp:661-680 with isLast = false) averaged by TComYuv::addAvg (TComYuv.cpp:354-409)."""
+    eng, g, recs = small
+    rng = np.random.default_rng(16)
+    H, W = 96, 128
+    chroma = {}
+    for slot in (0, 1):
+        cb = rng.integers(0, 256, (H // 2, W // 2)).astype(np.int16)
+        cr = rng.integers(0, 256, (H // 2, W // 2)).astype(np.int16)
+        eng.upload_ref_chroma(slot, cb, cr)
+        chroma[slot] = (cb, cr)
+    n = 240
+    pus = np.zeros(n, fme.MC_BI_PU_DTYPE)
+    sel = rng.integers(0, len(recs), n)
+    pus["x"], pus["y"], pus["w"], pus["h"] = recs["x"][sel], recs["y"][sel], recs["w"][sel], recs["h"][sel]
+    pus["refSlot0"] = rng.integers(0, 2, n)
+    pus["refSlot1"] = rng.integers(0, 2, n)
+    for f in ("mv0X", "mv0Y", "mv1X", "mv1Y"):
+        pus[f] = rng.integers(-40, 41, n)
+    pus["mv0X"][:12] &= ~3   # full-pel / one-dimensional cases on purpose
+    pus["mv1Y"][6:18] &= ~3
+    pus["mv0Y"][:6] &= ~3
+    y, ocb, ocr = eng.mc_bi(pus)
+    M = 80
+
+    def inter(plane, S, off, w, h, fx, fy, luma):
+        taps = 8 if luma else 4
+        if fy == 0:
+            return orc.filter_hor(luma, plane, off, S, w, h, fx, 0)
+        if fx == 0:
+            return orc.filter_ver(luma, plane, off, S, w, h, fy, 1, 0)
+        half = taps // 2 - 1
+        tmp = orc.filter_hor(luma, plane, off - half * S, S, w, h + taps - 1, fx, 0)
+        return orc.filter_ver(luma, tmp, half * w, w, w, h, fy, 0, 0)
+
+    lumas = {s: ob.pad_plane(g["small_refs"][s], M) for s in (0, 1)}
+    cpad = {s: (ob.pad_plane(chroma[s][0], M // 2), ob.pad_plane(chroma[s][1], M // 2)) for s in (0, 1)}
+    for i in range(n):
+        p = pus[i]
+        w, h = int(p["w"]), int(p["h"])
+        pl, pcb, pcr = [], [], []
+        for l in (0, 1):
+            slot, mvx, mvy = int(p["refSlot%d" % l]), int(p["mv%dX" % l]), int(p["mv%dY" % l])
+            luma = lumas[slot]
+            S = luma.shape[1]
+            off = (M + int(p["y"]) + (mvy >> 2)) * S + M + int(p["x"]) + (mvx >> 2)
+            pl.append(inter(luma, S, off, w, h, mvx & 3, mvy & 3, 1))
+            Sc = cpad[slot][0].shape[1]
+            offc = (M // 2 + (int(p["y"]) >> 1) + (mvy >> 3)) * Sc + M // 2 + (int(p["x"]) >> 1) + (mvx >> 3)
+            pcb.append(inter(cpad[slot][0], Sc, offc, w // 2, h // 2, mvx & 7, mvy & 7, 0))
+            pcr.append(inter(cpad[slot][1], Sc, offc, w // 2, h // 2, mvx & 7, mvy & 7, 0))
+        assert np.array_equal(y[i, :h, :w], orc.add_avg(pl[0], 0, w, pl[1], 0, w, w, h)), ("luma", i, p)
+        cw, ch = w // 2, h // 2
+        assert np.array_equal(ocb[i, :ch, :cw], orc.add_avg(pcb[0], 0, cw, pcb[1], 0, cw, cw, ch)), ("cb", i, p)
+        assert np.array_equal(ocr[i, :ch, :cw], orc.add_avg(pcr[0], 0, cw, pcr[1], 0, cw, cw, ch)), ("cr", i, p)
+
+
 # ---------------------------------------------------------------- full-size properties (config C3 shape)
 def test_1080p_properties(orc):
     """1920x1080, 4 references, 858 000 PUs: (1) a 3 000-PU random sample agrees with the oracle bit for bit,

@@ -29,6 +29,16 @@ def test_distortions_match_reference_fixture(orc):
         assert got == int(want), (w, h, kind, ss, pair)
 
 
+def test_add_avg_matches_reference_fixture(orc):
+    """TComYuv::addAvg (bi-prediction average of 14-bit intermediates), outputs of the compiled reference."""
+    g = golden()
+    a, b, pos = g["avg_a"], g["avg_b"], 0
+    for (w, h) in g["avg_shapes"]:
+        want = g["avg_out"][pos:pos + w * h].reshape(h, w)
+        pos += w * h
+        assert np.array_equal(orc.add_avg(a, 0, 64, b, 0, 64, int(w), int(h)), want), (w, h)
+
+
 def test_mv_cost_matches_reference_fixture(orc):
     g = golden()
     for (lam, x, y, sc, px, py), want in zip(g["mv_meta"], g["mv_val"]):

@@ -35,6 +35,15 @@ def test_filters_random(orc, refl):
                                                   refl.filter_ver(luma, s, off, 48, w, h, frac, first, last, bd))
 
 
+def test_add_avg_random(orc, refl):
+    rng = np.random.default_rng(12)
+    refl.init(22, 1, 1)
+    for (w, h) in SHAPES + [(2, 4), (4, 2), (6, 8), (32, 32)]:
+        a = rng.integers(-14312, 14249, (64, 72)).astype(np.int16)
+        b = rng.integers(-14312, 14249, (64, 80)).astype(np.int16)
+        assert np.array_equal(orc.add_avg(a, 3, 72, b, 5, 80, w, h), refl.add_avg(a, 3, 72, b, 5, 80, w, h)), (w, h)
+
+
 def test_dist_random(orc, refl):
     rng = np.random.default_rng(2)
     refl.init(22, 1, 1)
