@@ -16,6 +16,8 @@ __device__ __forceinline__ void one(int& x, int b, int b0) {
   if (OP == 8) asm volatile("{.reg .f32 t; mov.b32 t, %0; fma.rn.f32 t, t, 1.0001, 0.5; mov.b32 %0, t;}" : "+r"(x));
   if (OP == 9) asm volatile("cvt.pack.sat.u8.s32.b32 %0, %0, %1, %2;" : "+r"(x) : "r"(b), "r"(b0));
   if (OP == 10) asm volatile("{.reg .b32 t; mov.b32 t, %0; add.f16x2 t, t, t; mov.b32 %0, t;}" : "+r"(x));
+  if (OP == 11) asm volatile("{.reg .f32 t; mov.b32 t, %0; mul.rn.f32 t, t, 1.0001; mov.b32 %0, t;}" : "+r"(x));
+  if (OP == 12) asm volatile("{.reg .f32 t; mov.b32 t, %0; add.rn.f32 t, t, 0.5; mov.b32 %0, t;}" : "+r"(x));
 }
 // two instruction kinds interleaved 1:1 on independent registers: 2x the single-kind rate means different pipes
 template <int A, int B>
@@ -65,6 +67,8 @@ __global__ void k(int* out, int a0, int b0) {
       if (OP == 8) asm volatile("{.reg .f32 t; mov.b32 t, %0; fma.rn.f32 t, t, 1.0001, 0.5; mov.b32 %0, t;}" : "+r"(a[i]));
       if (OP == 9) asm volatile("cvt.pack.sat.u8.s32.b32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(b0));
       if (OP == 10) asm volatile("{.reg .b32 t; mov.b32 t, %0; add.f16x2 t, t, t; mov.b32 %0, t;}" : "+r"(a[i]));
+      if (OP == 11) asm volatile("{.reg .f32 t; mov.b32 t, %0; mul.rn.f32 t, t, 1.0001; mov.b32 %0, t;}" : "+r"(a[i]));
+      if (OP == 12) asm volatile("{.reg .f32 t; mov.b32 t, %0; add.rn.f32 t, t, 0.5; mov.b32 %0, t;}" : "+r"(a[i]));
     }
   }
   int s = 0;
@@ -88,7 +92,8 @@ void run(const char* name) {
 }
 int main() {
   run<0>("dp4a"); run<1>("dp2a"); run<2>("imad"); run<3>("iadd"); run<4>("prmt"); run<5>("shf"); run<6>("lop3");
-  run<7>("vimnmx16x2"); run<8>("ffma"); run<9>("i2ip"); run<10>("hadd2");
+  run<7>("vimnmx16x2"); run<8>("ffma"); run<9>("i2ip"); run<10>("hadd2"); run<11>("fmul"); run<12>("fadd");
+  runp<11, 12>("fmul+fadd"); runp<11, 2>("fmul+imad"); runp<12, 3>("fadd+iadd");
   runp<0, 2>("dp4a+imad"); runp<0, 4>("dp4a+prmt"); runp<2, 4>("imad+prmt"); runp<2, 8>("imad+ffma"); runp<4, 8>("prmt+ffma");
   runp<1, 8>("dp2a+ffma"); runp<5, 4>("shf+prmt"); runp<9, 2>("i2ip+imad"); runp<9, 4>("i2ip+prmt"); runp<10, 4>("hadd2+prmt");
   runp<10, 2>("hadd2+imad"); runp<6, 2>("lop3+imad"); runp<6, 4>("lop3+prmt"); runp<0, 6>("dp4a+lop3"); runp<3, 4>("iadd+prmt");
