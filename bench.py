@@ -220,12 +220,13 @@ def run_gpu(args):
     h_out = torch.zeros((n_pus, 16), dtype=torch.uint8).pin_memory()
     lib, hnd = eng.lib, eng.h
 
-    h_outs = [h_out, torch.zeros((n_pus, 16), dtype=torch.uint8).pin_memory()]
+    LAG = 2                                # frames in flight behind the one being submitted (the engine rings hold 3)
+    h_outs = [h_out] + [torch.zeros((n_pus, 16), dtype=torch.uint8).pin_memory() for _ in range(LAG)]
 
     def run_e2e(first, count):
         """`count` frames through the host-buffer calls a reference adaptor makes.  The engine overlaps the copies
-        of frame i+1 with the kernels of frame i (its own copy streams, two submits in flight); the host reads
-        frame i's results after fme_wait_oldest, i.e. every step includes its H2D and its D2H."""
+        of frames i+1, i+2 with the kernels of frame i (its own copy streams, three submits in flight); the host
+        reads frame i's results after fme_wait_oldest, i.e. every step includes its H2D and its D2H."""
         acc = 0
         for j in range(count):
             i = first + j
@@ -238,12 +239,13 @@ def run_gpu(args):
             else:
                 eng._check(lib.fme_upload_ref(hnd, slot, ctypes.c_void_p(h_ref16[k][slot].data_ptr()), width))
             eng._check(lib.fme_upload_org(hnd, ctypes.c_void_p(h_org16[k].data_ptr()), width))
-            eng.submit_async(h_pus[k].data_ptr(), len(sets[k][2]), h_outs[i & 1].data_ptr(), fme.MODE_BOTH)
-            if j >= 1:
+            eng.submit_async(h_pus[k].data_ptr(), len(sets[k][2]), h_outs[i % (LAG + 1)].data_ptr(), fme.MODE_BOTH)
+            if j >= LAG:
                 eng.wait_oldest()
-                acc += int(h_outs[(i - 1) & 1][0, 4])   # the caller consumes frame i-1's results here
-        eng.wait_oldest()
-        acc += int(h_outs[(first + count - 1) & 1][0, 4])
+                acc += int(h_outs[(i - LAG) % (LAG + 1)][0, 4])   # the caller consumes frame i-LAG's results here
+        for t in range(min(LAG, count)):
+            eng.wait_oldest()
+            acc += int(h_outs[(first + count - min(LAG, count) + t) % (LAG + 1)][0, 4])
         return acc
 
     eng.set_stream(0)                      # the engine's own kernel + copy streams

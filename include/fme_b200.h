@@ -124,7 +124,7 @@ int fme_submit(fme_ctx* ctx, const fme_pu* pus, int n, fme_result* out, int mode
  * fme_submit_async enqueues H2D + kernels + D2H on the ctx stream; fme_synchronize completes it. */
 int fme_submit_async(fme_ctx* ctx, const fme_pu* pus, int n, fme_result* out, int mode);
 /* With the ctx's own streams the copies of fme_upload_* / fme_submit_async run on dedicated copy streams and
- * overlap the kernels of neighbouring frames (double-buffered staging, at most two submits in flight).
+ * overlap the kernels of neighbouring frames (staging rings of three, at most three submits in flight).
  * fme_wait_oldest blocks until the results of the oldest outstanding fme_submit_async are in `out`. */
 int fme_wait_oldest(fme_ctx* ctx);
 /* Device-resident variant: d_pus / d_out are device pointers; nothing is copied. */
