@@ -416,7 +416,7 @@ def test_1080p_properties(orc):
 
 def test_pipelined_async_matches_synchronous():
     """fme_submit_async / fme_wait_oldest with pinned buffers: copies of frame i+1 overlap the kernels of frame i
-    (double-buffered staging inside the ctx); results must equal the synchronous call frame by frame."""
+    (and i+2: staging rings of three inside the ctx); results must equal the synchronous call frame by frame."""
     import torch
     W, H, F = 416, 240, 7
     frames = []
@@ -442,19 +442,23 @@ def test_pipelined_async_matches_synchronous():
     h_pus = [pin(fr[2].view(np.uint8).reshape(len(fr[2]), -1)) for fr in frames]
     h_out = [torch.zeros((nmax, 16), dtype=torch.uint8).pin_memory() for _ in range(F)]
     import ctypes
-    for rep in range(3):
+    check = lambda f, tag: np.testing.assert_array_equal(
+        h_out[f].numpy()[:len(frames[f][2])].copy().view(np.uint8), want[f].view(np.uint8).reshape(len(want[f]), -1),
+        err_msg=str(tag))
+    for rep, lag in enumerate((1, 2, 2)):  # the caller consumes results one or two frames behind (rings hold three)
+        for b in h_out:
+            b.zero_()
         for f in range(F):
             eng._check(eng.lib.fme_upload_org(eng.h, ctypes.c_void_p(h_org[f].data_ptr()), W))
             for s in range(2):
                 eng._check(eng.lib.fme_upload_ref(eng.h, s, ctypes.c_void_p(h_ref[f][s].data_ptr()), W))
             eng.submit_async(h_pus[f].data_ptr(), len(frames[f][2]), h_out[f].data_ptr(), fme.MODE_BOTH)
-            if f >= 1:
+            if f >= lag:
                 eng.wait_oldest()
-                got = h_out[f - 1].numpy()[:len(frames[f - 1][2])].copy().view(fme.RESULT_DTYPE).reshape(-1)
-                assert np.array_equal(got.view(np.uint8), want[f - 1].view(np.uint8)), (rep, f - 1)
+                check(f - lag, (rep, lag, f - lag))
         eng.synchronize()
-        got = h_out[F - 1].numpy()[:len(frames[F - 1][2])].copy().view(fme.RESULT_DTYPE).reshape(-1)
-        assert np.array_equal(got.view(np.uint8), want[F - 1].view(np.uint8))
+        for f in range(max(0, F - lag), F):
+            check(f, (rep, lag, f))
     eng.close()
 
 
