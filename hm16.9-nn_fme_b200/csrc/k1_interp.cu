@@ -47,7 +47,6 @@ __device__ __forceinline__ int dp2a_hi(int a, int b, int c) {
 __constant__ int c_lumaLo[4] = {PACK4(0, 0, 0, 64), PACK4(-1, 4, -10, 58), PACK4(-1, 4, -11, 40), PACK4(0, 1, -5, 17)};
 __constant__ int c_lumaHi[4] = {PACK4(0, 0, 0, 0), PACK4(17, -5, 1, 0), PACK4(40, -11, 4, -1), PACK4(58, -10, 4, -1)};
 
-__device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
 // cvt.pack.sat.u8.s32: d = (c << 16) | (sat_u8(a) << 8) | sat_u8(b)   (SASS: I2IP.U8.S32.SAT)
 __device__ __forceinline__ unsigned pack_sat_u8x2(int lo, int hi, unsigned upper) {
   unsigned d;

@@ -179,8 +179,7 @@ struct LayerSmem {
       }
     }
   }
-  static constexpr int BLOB_WORDS_BN = OUT * IN + 3 * OUT;
-  static constexpr int BLOB_WORDS_OUT = OUT * IN + OUT;
+  __host__ __device__ static constexpr int blob_words_bn() { return OUT * IN + 3 * OUT; }
 };
 
 // NH hidden layers of sizes H1,H2,(H3); NEMB = 0 or 2 embedding tables of 8 x 4.
@@ -190,7 +189,6 @@ __global__ void __launch_bounds__(K3F_THREADS) k3_nn_fixed(const fme_pu* __restr
                                                           const float* __restrict__ blob) {
   constexpr int IN0 = 9 + 4 * NEMB;
   constexpr int HLAST = H3 > 0 ? H3 : H2;
-  constexpr int HMAX = (H1 > H2 ? (H1 > H3 ? H1 : H3) : (H2 > H3 ? H2 : H3));
   using L1 = LayerSmem<IN0, H1>;
   using L2 = LayerSmem<H1, H2>;
   using L3 = LayerSmem<H2, (H3 > 0 ? H3 : 1)>;
@@ -208,9 +206,9 @@ __global__ void __launch_bounds__(K3F_THREADS) k3_nn_fixed(const fme_pu* __restr
     const float* p = blob + 16;
     for (int i = threadIdx.x; i < 27 + NEMB * 32; i += blockDim.x) s_in[i] = p[i];
     p += 27 + NEMB * 32;
-    L1::load(s_l1, p, true); p += L1::BLOB_WORDS_BN;
-    L2::load(s_l2, p, true); p += L2::BLOB_WORDS_BN;
-    if (H3 > 0) { L3::load(s_l3, p, true); p += L3::BLOB_WORDS_BN; }
+    L1::load(s_l1, p, true); p += L1::blob_words_bn();
+    L2::load(s_l2, p, true); p += L2::blob_words_bn();
+    if (H3 > 0) { L3::load(s_l3, p, true); p += L3::blob_words_bn(); }
     LO::load(s_lo, p, false);
   }
   __syncthreads();
