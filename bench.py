@@ -223,7 +223,9 @@ def run_gpu(args):
     LAG = 2                                # frames in flight behind the one being submitted (the engine rings hold 3)
     h_outs = [h_out] + [torch.zeros((n_pus, 16), dtype=torch.uint8).pin_memory() for _ in range(LAG)]
 
-    def run_e2e(first, count):
+    h_heads = [pin(fme.pu_list.heads_of(r).view(np.uint8).reshape(len(r), -1)) for r in h_recs]
+
+    def run_e2e(first, count, heads=False):
         """`count` frames through the host-buffer calls a reference adaptor makes.  The engine overlaps the copies
         of frames i+1, i+2 with the kernels of frame i (its own copy streams, three submits in flight); the host
         reads frame i's results after fme_wait_oldest, i.e. every step includes its H2D and its D2H."""
@@ -239,7 +241,10 @@ def run_gpu(args):
             else:
                 eng._check(lib.fme_upload_ref(hnd, slot, ctypes.c_void_p(h_ref16[k][slot].data_ptr()), width))
             eng._check(lib.fme_upload_org(hnd, ctypes.c_void_p(h_org16[k].data_ptr()), width))
-            eng.submit_async(h_pus[k].data_ptr(), len(sets[k][2]), h_outs[i % (LAG + 1)].data_ptr(), fme.MODE_BOTH)
+            if heads:   # 16-byte records: the engine computes the 3x3 integer error surface itself (K0)
+                eng.submit_heads_async(h_heads[k].data_ptr(), len(sets[k][2]), h_outs[i % (LAG + 1)].data_ptr(), fme.MODE_BOTH)
+            else:
+                eng.submit_async(h_pus[k].data_ptr(), len(sets[k][2]), h_outs[i % (LAG + 1)].data_ptr(), fme.MODE_BOTH)
             if j >= LAG:
                 eng.wait_oldest()
                 acc += int(h_outs[(i - LAG) % (LAG + 1)][0, 4])   # the caller consumes frame i-LAG's results here
@@ -260,6 +265,18 @@ def run_gpu(args):
         t = torch.tensor([ms_e2e], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
+    # the same loop with 16-byte records (no error grid on PCIe, K0 on the device instead); informational
+    run_e2e(0, args.warmup, heads=True)
+    eng.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    run_e2e(args.warmup, args.steps, heads=True)
+    eng.synchronize()
+    ms_e2e_heads = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([ms_e2e_heads], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e_heads = float(t.item())
     eng.set_stream(stream.cuda_stream)
     e2e_value = pus_per_step_all * args.steps / (ms_e2e / 1e3)
     h2d = width * height * 2 * (1 if banded and world > 1 else 2) + int(pus_per_step) * 52
@@ -351,6 +368,11 @@ def run_gpu(args):
             "interp_gb_s": kernels["k1_interp"]["achieved"],
             "e2e": {"value": e2e_value, "unit": "PU/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "frames_per_sec": frames_per_step * args.steps / (ms_e2e / 1e3)},
+            "e2e_heads": {"value": pus_per_step_all * args.steps / (ms_e2e_heads / 1e3), "unit": "PU/s",
+                          "h2d_bytes_per_step": h2d - int(pus_per_step) * 36, "d2h_bytes_per_step": d2h,
+                          "ms_per_step": ms_e2e_heads / args.steps,
+                          "note": "same loop through fme_submit_heads_async: 16-byte records, the 3x3 integer error "
+                                  "surface is computed on the device (K0) instead of being uploaded"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,

@@ -15,7 +15,7 @@ import numpy as np
 
 from . import nn_weights  # noqa: F401  (re-export)
 from . import formats  # noqa: F401
-from .pu_list import PU_DTYPE, RESULT_DTYPE, MC_PU_DTYPE, MC_BI_PU_DTYPE  # noqa: F401
+from .pu_list import PU_DTYPE, HEAD_DTYPE, RESULT_DTYPE, MC_PU_DTYPE, MC_BI_PU_DTYPE  # noqa: F401
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libfme_b200.so")
@@ -27,7 +27,7 @@ PU_LOSSLESS, PU_ERR_ON_GPU = 0x01, 0x02
 EXPORTS = [
     "fme_create", "fme_destroy", "fme_last_error", "fme_version", "fme_set_stream", "fme_synchronize",
     "fme_set_nn_weights", "fme_load_nn_csv_dir", "fme_set_slice", "fme_upload_ref", "fme_upload_ref_u8",
-    "fme_upload_org", "fme_upload_org_u8", "fme_submit", "fme_submit_async", "fme_wait_oldest", "fme_submit_device", "fme_interp_slot",
+    "fme_upload_org", "fme_upload_org_u8", "fme_submit", "fme_submit_async", "fme_submit_heads", "fme_submit_heads_async", "fme_wait_oldest", "fme_submit_device", "fme_interp_slot",
     "fme_upload_ref_device_u8", "fme_upload_org_device_u8", "fme_int_surface_device", "fme_filter_hor",
     "fme_filter_ver", "fme_dist", "fme_mv_cost", "fme_upload_ref_chroma", "fme_mc", "fme_mc_bi", "fme_pred_error", "fme_download_plane",
     "fme_last_kernel_ms", "fme_launch_count", "fme_set_profiling",
@@ -75,6 +75,8 @@ def load_library():
     lib.fme_upload_org_u8.argtypes = [vp, vp, i32]
     lib.fme_submit.argtypes = [vp, vp, i32, vp, i32]
     lib.fme_submit_async.argtypes = [vp, vp, i32, vp, i32]
+    lib.fme_submit_heads.argtypes = [vp, vp, i32, vp, i32]
+    lib.fme_submit_heads_async.argtypes = [vp, vp, i32, vp, i32]
     lib.fme_submit_device.argtypes = [vp, vp, i32, vp, i32]
     lib.fme_wait_oldest.argtypes = [vp]
     lib.fme_interp_slot.argtypes = [vp, i32]
@@ -198,6 +200,16 @@ class Fme:
         out = np.zeros(len(pus), RESULT_DTYPE)
         self._check(self.lib.fme_submit(self.h, _addr(pus), len(pus), _addr(out), mode))
         return out
+
+    def submit_heads(self, heads, mode=MODE_BOTH):
+        """Records without err[]: the engine computes the 3x3 integer error surface itself (K0)."""
+        heads = np.ascontiguousarray(heads, dtype=HEAD_DTYPE)
+        out = np.zeros(len(heads), RESULT_DTYPE)
+        self._check(self.lib.fme_submit_heads(self.h, _addr(heads), len(heads), _addr(out), mode))
+        return out
+
+    def submit_heads_async(self, heads_ptr, n, out_ptr, mode=MODE_BOTH):
+        self._check(self.lib.fme_submit_heads_async(self.h, C.c_void_p(heads_ptr), n, C.c_void_p(out_ptr), mode))
 
     def submit_async(self, pus_ptr, n, out_ptr, mode=MODE_BOTH):
         self._check(self.lib.fme_submit_async(self.h, C.c_void_p(pus_ptr), n, C.c_void_p(out_ptr), mode))

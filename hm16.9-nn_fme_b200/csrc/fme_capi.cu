@@ -70,6 +70,7 @@ struct fme_ctx {
   uint8_t* d_cb = nullptr;       // [slots][Hcp][cPitch]
   uint8_t* d_cr = nullptr;
   fme_pu* d_pusBuf[FME_NBUF] = {};
+  fme_pu_head* d_headBuf[FME_NBUF] = {};  // allocated on the first fme_submit_heads*
   fme_result* d_resBuf[FME_NBUF] = {};
   fme_pu* d_pus = nullptr;       // = d_pusBuf[0], used by the synchronous helpers (fme_mc)
   fme_result* d_res = nullptr;
@@ -321,6 +322,7 @@ void fme_destroy(fme_ctx* c) {
   cudaFree(c->d_planes); cudaFree(c->d_pel); cudaFree(c->d_pel2);
   for (int b = 0; b < FME_NBUF; ++b) {
     cudaFree(c->d_orgBuf[b]); cudaFree(c->d_picBuf[b]); cudaFree(c->d_pelPic[b]); cudaFree(c->d_pusBuf[b]); cudaFree(c->d_resBuf[b]);
+    cudaFree(c->d_headBuf[b]);
     for (cudaEvent_t e : {c->evIn[b], c->evDone[b], c->evOut[b], c->evPicIn[b], c->evPicFree[b], c->evOrgFree[b]})
       if (e) cudaEventDestroy(e);
   }
@@ -621,13 +623,26 @@ int fme_upload_ref_chroma(fme_ctx* c, int slot, const int16_t* cb, const int16_t
 }
 
 // ---- the batched search ------------------------------------------------------------------------
-static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, int mode, bool sync) {
-  if (!c || !pus || !out) return fail(FME_ERR_INVALID, "null argument");
+static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, int mode, bool sync,
+                         const fme_pu_head* heads = nullptr) {
+  if (!c || (!pus && !heads) || !out) return fail(FME_ERR_INVALID, "null argument");
   if (n < 0 || n > c->cfg.maxPUs) return fail(FME_ERR_INVALID, "n=%d exceeds maxPUs=%d", n, c->cfg.maxPUs);
   if (n == 0) return FME_OK;
   CU_CHECK(cudaSetDevice(c->cfg.device));
   bool needK0 = false;
-  if (sync) {  // full validation on the synchronous path
+  if (heads) {
+    needK0 = true;
+    if (sync) {
+      for (int i = 0; i < n; ++i) {
+        if (heads[i].refSlot >= c->cfg.numRefSlots || !c->refValid[heads[i].refSlot])
+          return fail(FME_ERR_STATE, "PU %d references slot %d which holds no picture", i, heads[i].refSlot);
+        if (fme_dim_index(heads[i].w) < 0 || fme_dim_index(heads[i].h) < 0)
+          return fail(FME_ERR_INVALID, "PU %d: %dx%d is not an HEVC PU size", i, heads[i].w, heads[i].h);
+      }
+    }
+    for (int b = 0; b < FME_NBUF; ++b)
+      if (!c->d_headBuf[b]) CU_CHECK(cudaMalloc(&c->d_headBuf[b], sizeof(fme_pu_head) * (size_t)c->cfg.maxPUs));
+  } else if (sync) {  // full validation on the synchronous path
     for (int i = 0; i < n; ++i) {
       if (pus[i].flags & FME_PU_ERR_ON_GPU) needK0 = true;
       if ((mode & FME_MODE_STD) || (pus[i].flags & FME_PU_ERR_ON_GPU)) {
@@ -650,11 +665,13 @@ static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, 
   fme_result* d_res = c->d_resBuf[b];
   // records in: the kernels that read d_pus[b] FME_NBUF submits ago must be done
   CU_CHECK(cudaStreamWaitEvent(c->sIn, c->evDone[b], 0));
-  CU_CHECK(cudaMemcpyAsync(d_pus, pus, sizeof(fme_pu) * (size_t)n, cudaMemcpyHostToDevice, c->sIn));
+  if (heads) CU_CHECK(cudaMemcpyAsync(c->d_headBuf[b], heads, sizeof(fme_pu_head) * (size_t)n, cudaMemcpyHostToDevice, c->sIn));
+  else CU_CHECK(cudaMemcpyAsync(d_pus, pus, sizeof(fme_pu) * (size_t)n, cudaMemcpyHostToDevice, c->sIn));
   CU_CHECK(cudaEventRecord(c->evIn[b], c->sIn));
   // kernels: need the records, and the previous read-out of d_res[b] must be done
   CU_CHECK(cudaStreamWaitEvent(c->stream, c->evIn[b], 0));
   CU_CHECK(cudaStreamWaitEvent(c->stream, c->evOut[b], 0));
+  if (heads) CU_CHECK(fme_launch_expand_heads(c->d_headBuf[b], n, d_pus, c->stream, &c->launches));
   if (needK0) {
     StageTimer t(c, 3);
     CU_CHECK(fme_launch_k0(c->g, c->d_planes, c->d_org, d_pus, n, c->cfg.fen, c->stream, &c->launches));
@@ -681,6 +698,13 @@ int fme_submit(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, int mode) 
 }
 int fme_submit_async(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, int mode) {
   return submit_common(c, pus, n, out, mode, false);
+}
+
+int fme_submit_heads(fme_ctx* c, const fme_pu_head* heads, int n, fme_result* out, int mode) {
+  return submit_common(c, nullptr, n, out, mode, true, heads);
+}
+int fme_submit_heads_async(fme_ctx* c, const fme_pu_head* heads, int n, fme_result* out, int mode) {
+  return submit_common(c, nullptr, n, out, mode, false, heads);
 }
 
 int fme_submit_device(fme_ctx* c, const fme_pu* d_pus, int n, fme_result* d_out, int mode) {

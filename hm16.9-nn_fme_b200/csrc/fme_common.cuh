@@ -81,6 +81,7 @@ cudaError_t fme_launch_dist(int kind, const int16_t* d_org, int orgStride, const
                             int64_t* launches);
 cudaError_t fme_launch_pel_to_u8(const int16_t* d_src, int srcStride, uint8_t* d_dst, int dstPitch, int w, int h,
                                  cudaStream_t s, int64_t* launches);
+cudaError_t fme_launch_expand_heads(const fme_pu_head* d_heads, int n, fme_pu* d_pus, cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_mc_bi(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_cb, const uint8_t* d_cr,
                              const fme_mc_bi_pu* d_pus, int n, int16_t* d_y, int16_t* d_cbOut, int16_t* d_crOut,
                              cudaStream_t s, int64_t* launches);

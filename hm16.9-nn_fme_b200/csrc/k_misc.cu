@@ -303,6 +303,17 @@ __global__ void __launch_bounds__(256) k_mc(const fme_mc_pu* __restrict__ pus, i
   }
 }
 
+// Records without the error grid -> full records flagged for the K0 pass (which fills err[]).
+static_assert(sizeof(fme_pu_head) == 16 && sizeof(fme_pu) == 52, "record layouts");
+__global__ void k_expand_heads(const fme_pu_head* __restrict__ heads, int n, fme_pu* __restrict__ pus) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint4 v = reinterpret_cast<const uint4*>(heads)[i];
+  v.y |= (unsigned)FME_PU_ERR_ON_GPU << 24;  // flags is byte 7 of the record
+  unsigned* d = reinterpret_cast<unsigned*>(&pus[i]);  // 52-byte records are 4-byte aligned
+  d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Motion compensation, bi-prediction: xPredInterBi with both lists valid (TComPrediction.cpp:575-621) =
 // two xPredInterUni(bi = true) blocks of 14-bit intermediates (xPredInterBlk with isLast = !bi = false,
@@ -423,6 +434,13 @@ cudaError_t fme_launch_dist(int kind, const int16_t* d_org, int orgStride, const
   int blocks = (nBlocks + 3) / 4;
   k_dist_blocks<<<blocks, 128, 0, s>>>(kind, d_org, orgStride, d_cur, curStride, w, h, bitDepth, subShift, nBlocks,
                                        d_out);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t fme_launch_expand_heads(const fme_pu_head* d_heads, int n, fme_pu* d_pus, cudaStream_t s, int64_t* launches) {
+  if (n <= 0) return cudaSuccess;
+  k_expand_heads<<<(n + 255) / 256, 256, 0, s>>>(d_heads, n, d_pus);
   ++*launches;
   return cudaGetLastError();
 }

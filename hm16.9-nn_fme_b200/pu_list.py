@@ -11,6 +11,20 @@ PU_DTYPE = np.dtype(
     [("x", "<i2"), ("y", "<i2"), ("w", "u1"), ("h", "u1"), ("refSlot", "u1"), ("flags", "u1"),
      ("mvIntX", "<i2"), ("mvIntY", "<i2"), ("mvPredX", "<i2"), ("mvPredY", "<i2"), ("err", "<u4", (9,))],
     align=True)
+HEAD_DTYPE = np.dtype(   # fme_pu_head: the record without the error grid (computed on the device)
+    [("x", "<i2"), ("y", "<i2"), ("w", "u1"), ("h", "u1"), ("refSlot", "u1"), ("flags", "u1"),
+     ("mvIntX", "<i2"), ("mvIntY", "<i2"), ("mvPredX", "<i2"), ("mvPredY", "<i2")])
+assert HEAD_DTYPE.itemsize == 16
+
+
+def heads_of(recs):
+    """fme_pu records -> fme_pu_head records (drops err[])."""
+    h = np.zeros(len(recs), HEAD_DTYPE)
+    for f in HEAD_DTYPE.names:
+        h[f] = recs[f]
+    return h
+
+
 RESULT_DTYPE = np.dtype(
     [("halfX", "i1"), ("halfY", "i1"), ("qterX", "i1"), ("qterY", "i1"), ("cost", "<u4"),
      ("nnHalfX", "i1"), ("nnHalfY", "i1"), ("nnQterX", "i1"), ("nnQterY", "i1"), ("nnClass", "u1"),

@@ -76,6 +76,17 @@ typedef struct fme_pu {
   uint32_t err[9];
 } fme_pu; /* 52 bytes */
 
+/* The same hand-off without the error grid: the engine computes err[] itself with the integer-ME metric (K0 pass,
+ * SURVEY.md "next" row f1), which removes 36 of the 52 bytes per PU from the host->device traffic. */
+typedef struct fme_pu_head {
+  int16_t x, y;
+  uint8_t w, h;
+  uint8_t refSlot;
+  uint8_t flags;
+  int16_t mvIntX, mvIntY;
+  int16_t mvPredX, mvPredY;
+} fme_pu_head; /* 16 bytes = the first 16 bytes of fme_pu */
+
 typedef struct fme_result {
   int8_t halfX, halfY, qterX, qterY;         /* rcMvHalf, rcMvQter in {-1,0,1} (TEncSearch.h:423-432) */
   uint32_t cost;                             /* ruiCost: best quarter-stage cost incl. MV bits         */
@@ -123,6 +134,10 @@ int fme_submit(fme_ctx* ctx, const fme_pu* pus, int n, fme_result* out, int mode
 /* Asynchronous halves for pipelining: records/results in pinned host memory owned by the caller.
  * fme_submit_async enqueues H2D + kernels + D2H on the ctx stream; fme_synchronize completes it. */
 int fme_submit_async(fme_ctx* ctx, const fme_pu* pus, int n, fme_result* out, int mode);
+/* fme_submit / fme_submit_async for records without the error grid: equivalent to full records carrying
+ * FME_PU_ERR_ON_GPU (the 3x3 surface of TEncSearch.cpp:5037-5050 is computed on the device before K2 / K3). */
+int fme_submit_heads(fme_ctx* ctx, const fme_pu_head* heads, int n, fme_result* out, int mode);
+int fme_submit_heads_async(fme_ctx* ctx, const fme_pu_head* heads, int n, fme_result* out, int mode);
 /* With the ctx's own streams the copies of fme_upload_* / fme_submit_async run on dedicated copy streams and
  * overlap the kernels of neighbouring frames (staging rings of three, at most three submits in flight).
  * fme_wait_oldest blocks until the results of the oldest outstanding fme_submit_async are in `out`. */

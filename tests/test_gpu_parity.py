@@ -414,6 +414,30 @@ def test_1080p_properties(orc):
     eng.close()
 
 
+def test_submit_heads_equals_records_with_device_surface(small):
+    """fme_submit_heads (16-byte records, error grid computed by K0) == fme_submit of full records flagged
+    FME_PU_ERR_ON_GPU, which the K0 tests pin against the reference; also through the async entry point."""
+    import torch
+    eng, g, recs = small
+    full = recs.copy()
+    full["flags"] |= fme.PU_ERR_ON_GPU
+    full["err"] = 0
+    want = eng.submit(full, fme.MODE_BOTH)
+    heads = fme.pu_list.heads_of(recs)
+    got = eng.submit_heads(heads, fme.MODE_BOTH)
+    assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+    h_in = torch.from_numpy(heads.view(np.uint8).reshape(len(heads), -1).copy()).pin_memory()
+    h_out = torch.zeros((len(heads), 16), dtype=torch.uint8).pin_memory()
+    for _ in range(4):
+        eng.submit_heads_async(h_in.data_ptr(), len(heads), h_out.data_ptr(), fme.MODE_BOTH)
+    eng.synchronize()
+    assert np.array_equal(h_out.numpy().reshape(-1), want.view(np.uint8).reshape(-1))
+    bad = heads[:3].copy()
+    bad["w"] = 20
+    with pytest.raises(fme.FmeError):
+        eng.submit_heads(bad, fme.MODE_STD)
+
+
 def test_pipelined_async_matches_synchronous():
     """fme_submit_async / fme_wait_oldest with pinned buffers: copies of frame i+1 overlap the kernels of frame i
     (and i+2: staging rings of three inside the ctx); results must equal the synchronous call frame by frame."""
