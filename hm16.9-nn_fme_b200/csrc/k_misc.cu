@@ -11,12 +11,50 @@ namespace {
 // Raster order [TL,T,TR,L,C,R,BL,B,BR] = array_e[0..3], C, array_e[4..7] (TEncSearch.cpp:88, 1341-1376).
 // Plane 0 is the padded integer-pel copy.
 // ------------------------------------------------------------------------------------------------
-// 8 lanes per PU (4 PUs per warp); a lane's item is one 4-sample group of one source row against the 3x3
-// neighbourhood: three reference rows, each read as three aligned words and funnel-shifted to the three horizontal
-// offsets; SSE per word = VABSDIFF4 + dp4a(d, d), SAD per word = VABSDIFF4.ACC.
-__device__ __forceinline__ unsigned k0_word_at(unsigned w0, unsigned w1, unsigned w2, int byteShift) {
-  // 4 bytes starting `byteShift` (0..6) bytes into the 12-byte window w0:w1:w2
-  return byteShift < 4 ? __funnelshift_r(w0, w1, 8 * byteShift) : __funnelshift_r(w1, w2, 8 * (byteShift - 4));
+// 8 lanes per PU (4 PUs per warp), arranged as lanesX x lanesY over (4-sample column groups, rows) with lanesX the
+// power-of-two factor of w/4 (no divisions).  A lane's item is one 4-sample group of one source row against the 3x3
+// neighbourhood: three reference rows, each read as three aligned words, aligned once (2 funnel shifts) and then
+// shifted to the three horizontal offsets; SSE per word = VABSDIFF4 + dp4a(d, d), SAD per word = VABSDIFF4.ACC.
+template <bool SAD>
+__device__ __forceinline__ void k0_accumulate(unsigned (&acc)[9], const uint8_t* __restrict__ src, int orgPitch,
+                                              const uint8_t* __restrict__ ref, int pitch, int w, int rows, int step,
+                                              int sub) {
+  const int groups = w >> 2;
+  const int lanesX = min(groups & -groups, 8);  // 1,2,1,4,2,8,4,8 for w/4 = 1,2,3,4,6,8,12,16
+  const int lxShift = 31 - __clz(lanesX);
+  const int lanesY = 8 >> lxShift;
+  const int cg0 = sub & (lanesX - 1), r0 = sub >> lxShift;
+  // source words: aligned in contract (PU x is a multiple of 4, the picture base and pitch are 128-byte aligned)
+  const unsigned so = (unsigned)((size_t)src & 3) * 8u;
+  // reference window of column group 0, row -1: bytes -1 .. 6; the alignment is the same for every item of the PU
+  const uint8_t* rp0 = ref - pitch - 1;
+  const unsigned a8 = (unsigned)((size_t)rp0 & 3) * 8u;
+  const unsigned* rw0 = reinterpret_cast<const unsigned*>((size_t)rp0 & ~(size_t)3);
+  const int pitchW = pitch >> 2, orgPitchW = orgPitch >> 2;
+  const unsigned* sw0 = reinterpret_cast<const unsigned*>((size_t)src & ~(size_t)3);
+  for (int rr = r0; rr < rows; rr += lanesY) {
+    const int r = rr * step;
+    for (int cg = cg0; cg < groups; cg += lanesX) {
+      const unsigned* spw = sw0 + r * orgPitchW + cg;
+      const unsigned o = so ? __funnelshift_r(__ldg(spw), __ldg(spw + 1), so) : __ldg(spw);
+      const unsigned* rpw = rw0 + r * pitchW + cg;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const unsigned w0 = __ldg(rpw + dy * pitchW), w1 = __ldg(rpw + dy * pitchW + 1), w2 = __ldg(rpw + dy * pitchW + 2);
+        const unsigned x0 = __funnelshift_r(w0, w1, a8), x1 = __funnelshift_r(w1, w2, a8);  // bytes -1..2, 3..6
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const unsigned v = dx == 0 ? x0 : __funnelshift_r(x0, x1, 8 * dx);
+          if (SAD) {
+            acc[dy * 3 + dx] = __vsadu4(o, v) + acc[dy * 3 + dx];
+          } else {
+            const unsigned d = __vabsdiffu4(o, v);
+            acc[dy * 3 + dx] = __dp4a(d, d, acc[dy * 3 + dx]);
+          }
+        }
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) k0_int_surface(fme_pu* __restrict__ pus, int n, const uint8_t* __restrict__ planes,
@@ -27,52 +65,31 @@ __global__ void __launch_bounds__(256) k0_int_surface(fme_pu* __restrict__ pus, 
   for (int i0 = grp; i0 < ((n + 3) & ~3); i0 += nGrp) {               // all 4 groups of a warp iterate together
     const int i = i0;
     const bool valid = i < n;
-    fme_pu p;
-    if (valid) p = pus[i];
-    const bool doit = valid && (p.flags & FME_PU_ERR_ON_GPU) && fme_dim_index(p.w) >= 0 && fme_dim_index(p.h) >= 0;
+    // the first 12 bytes of the record (position, size, slot, flags, integer MV); records are 4-byte aligned
+    int px = 0, py = 0, w = 0, h = 0, slot = 0, flags = 0, mvx = 0, mvy = 0;
+    if (valid) {
+      const unsigned* rec = reinterpret_cast<const unsigned*>(&pus[i]);
+      const unsigned r0 = rec[0], r1 = rec[1], r2 = rec[2];
+      px = (int)(short)(r0 & 0xffff); py = (int)(short)(r0 >> 16);
+      w = r1 & 0xff; h = (r1 >> 8) & 0xff; slot = (r1 >> 16) & 0xff; flags = r1 >> 24;
+      mvx = (int)(short)(r2 & 0xffff); mvy = (int)(short)(r2 >> 16);
+    }
+    const bool doit = valid && (flags & FME_PU_ERR_ON_GPU) && fme_dim_index(w) >= 0 && fme_dim_index(h) >= 0;
     unsigned acc[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[k] = 0;
     int step = 1;
     if (doit) {
-      const int w = p.w, h = p.h;
       const bool useSad = (w == 12 || w == 24 || w == 48);
       step = (useSad && fen && h > 8) ? 2 : 1;
-      const int X = min(max(p.x + p.mvIntX, -(g.M - 8)), g.W + g.M - 8 - w);
-      const int Y = min(max(p.y + p.mvIntY, -(g.M - 8)), g.H + g.M - 8 - h);
-      const int ox = min(max((int)p.x, 0), g.W - w), oy = min(max((int)p.y, 0), g.H - h);
-      const uint8_t* ref = planes + (size_t)min((int)p.refSlot, g.numSlots - 1) * g.slotBytes +
-                           (size_t)(Y + g.M) * g.pitch + (X + g.M);
-      const uint8_t* src = org + (size_t)oy * g.orgPitch + ox;
-      const int groups = w >> 2, rows = h / step;
-      for (int t = sub; t < groups * rows; t += 8) {
-        const int rr = t / groups, c = (t - rr * groups) * 4;
-        const int r = rr * step;
-        // source word (may be unaligned for out-of-contract x)
-        const uint8_t* sp = src + (size_t)r * g.orgPitch + c;
-        const unsigned* spw = reinterpret_cast<const unsigned*>((size_t)sp & ~(size_t)3);
-        const unsigned so = (unsigned)((size_t)sp & 3) * 8u;
-        const unsigned o = __funnelshift_r(__ldg(spw), __ldg(spw + 1), so);
-        // reference window: bytes (c - 1) .. (c + 4) of rows r-1, r, r+1
-        const uint8_t* rp = ref + (ptrdiff_t)(r - 1) * g.pitch + c - 1;
-        const unsigned* rpw = reinterpret_cast<const unsigned*>((size_t)rp & ~(size_t)3);
-        const int a = (int)((size_t)rp & 3);
-        const int pitchW = g.pitch >> 2;
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-          const unsigned w0 = __ldg(rpw + dy * pitchW), w1 = __ldg(rpw + dy * pitchW + 1), w2 = __ldg(rpw + dy * pitchW + 2);
-#pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            const unsigned v = k0_word_at(w0, w1, w2, a + dx);
-            if (useSad) {
-              acc[dy * 3 + dx] = __vsadu4(o, v) + acc[dy * 3 + dx];
-            } else {
-              const unsigned d = __vabsdiffu4(o, v);
-              acc[dy * 3 + dx] = __dp4a(d, d, acc[dy * 3 + dx]);
-            }
-          }
-        }
-      }
+      const int X = min(max(px + mvx, -(g.M - 8)), g.W + g.M - 8 - w);
+      const int Y = min(max(py + mvy, -(g.M - 8)), g.H + g.M - 8 - h);
+      const int ox = min(max(px, 0), g.W - w), oy = min(max(py, 0), g.H - h);
+      const uint8_t* ref = planes + (size_t)min(slot, g.numSlots - 1) * g.slotBytes +
+                           (size_t)((Y + g.M) * g.pitch + (X + g.M));
+      const uint8_t* src = org + (size_t)(oy * g.orgPitch + ox);
+      if (useSad) k0_accumulate<true>(acc, src, g.orgPitch, ref, g.pitch, w, step == 2 ? h >> 1 : h, step, sub);
+      else k0_accumulate<false>(acc, src, g.orgPitch, ref, g.pitch, w, h, 1, sub);
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
