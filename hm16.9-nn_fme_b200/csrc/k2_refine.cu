@@ -7,17 +7,19 @@
 // (X,Y) = PU origin + integer MV and total quarter-pel offset (qx,qy) in [-3,3]^2 the candidate block is
 // plane P[qy&3][qx&3] at integer origin (X + (qx>>2), Y + (qy>>2)).
 //
-// Work decomposition (v1):
-//   * a prepass groups PU indices by shape class (w,h) so that a warp always works on same-shape PUs;
+// Work decomposition:
+//   * a prepass groups PU indices by shape class (w,h) so that a warp always works on same-shape PUs and all warps
+//     of an SM run the same k2_pack instantiation (class-major pack order: mixing classes thrashes the i-cache);
 //   * one warp = one "pack" of P PUs whose tiles (8x8, or 4x4 when w or h is not a multiple of 8,
 //     TComRdCost.cpp:1446-1492) fill the 32 lanes: lane = (PU in pack, tile in PU);
 //   * the warp walks 12 staging steps per pack (4 half-pel planes, then one plane per quarter-pel candidate):
 //     the candidate regions of all its PUs are copied from the HBM/L2-resident planes into shared memory
 //     with 4/8/16-byte cp.async into one of two buffers while the previous step's candidates are evaluated
-//     from the other (rows stay source-aligned, readers funnel-shift); every lane
+//     from the other (rows stay source-aligned, readers funnel-shift; each PU's region is copied by the lanes that
+//     serve that PU, one pointer bump per row); every lane
 //     computes the SATD of its own tile in registers: two 16-bit residuals per 32-bit register (SWAR),
 //     butterflies as plain 32-bit adds, |a+b|+|a-b| = 2 max(|a|,|b|) for the intra-register stage;
-//   * per-PU sums by __reduce_add_sync over the PU's lane group, MV cost from an exact host-built LUT,
+//   * per-PU sums by xor-shuffles over the PU's power-of-two lane group, MV cost from an exact host-built LUT,
 //     first-minimum argmin in the reference's table order (TEncSearch.cpp:212-236, strict < at :1634).
 #include "fme_common.cuh"
 
