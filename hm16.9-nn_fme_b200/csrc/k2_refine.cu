@@ -89,11 +89,14 @@ __global__ void k2_scatter(const fme_pu* __restrict__ pus, int n, const int* __r
   __shared__ int s_cnt[FME_MAX_CLASSES];
   __shared__ int s_base[FME_MAX_CLASSES];
   __shared__ int s_classOff[FME_MAX_CLASSES];
+  // Offsets are laid out in SCHEDULE order v = 63 - class: large shapes (one 64x64 PU is a whole, double-length pack)
+  // come first and the cheap 4x8 / 8x4 packs last, so the tail of the persistent kernel is short.
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;  // two classes per lane
-    const int c0 = classCount[2 * lane], c1 = classCount[2 * lane + 1];
-    const int p0 = c0 ? (c0 + class_info(2 * lane).P - 1) / class_info(2 * lane).P : 0;
-    const int p1 = c1 ? (c1 + class_info(2 * lane + 1).P - 1) / class_info(2 * lane + 1).P : 0;
+    const int k0 = FME_MAX_CLASSES - 1 - 2 * lane, k1 = k0 - 1;
+    const int c0 = classCount[k0], c1 = classCount[k1];
+    const int p0 = c0 ? (c0 + class_info(k0).P - 1) / class_info(k0).P : 0;
+    const int p1 = c1 ? (c1 + class_info(k1).P - 1) / class_info(k1).P : 0;
     int sc = c0 + c1, sp = p0 + p1;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -121,7 +124,7 @@ __global__ void k2_scatter(const fme_pu* __restrict__ pus, int n, const int* __r
   }
   __syncthreads();
   for (int i = threadIdx.x; i < FME_MAX_CLASSES; i += blockDim.x) {
-    s_base[i] = s_cnt[i] ? s_classOff[i] + atomicAdd(&classCursor[i], s_cnt[i]) : 0;
+    s_base[i] = s_cnt[i] ? s_classOff[FME_MAX_CLASSES - 1 - i] + atomicAdd(&classCursor[i], s_cnt[i]) : 0;
     s_cnt[i] = 0;
   }
   __syncthreads();
@@ -617,15 +620,16 @@ k2_refine(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, const ui
     const int pack = __shfl_sync(0xffffffffu, nextPack, 0);
     if (pack >= totalPacks) break;
     if (lane == 0) nextPack = atomicAdd(workCounter, 1);
-    // class of this pack: the c with packOff[c] <= pack < packOff[c+1]; two lanes cover the 64 classes
+    // schedule slot of this pack: the v with packOff[v] <= pack < packOff[v+1] (two lanes cover the 64 slots);
+    // slot v holds class 63 - v (k2_scatter)
     unsigned hit = __ballot_sync(0xffffffffu, s_packOff[lane] <= pack && s_packOff[lane + 1] > pack);
     unsigned hit2 = __ballot_sync(0xffffffffu, s_packOff[lane + 32] <= pack && s_packOff[lane + 33] > pack);
-    int cls = hit ? (__ffs(hit) - 1) : (32 + __ffs(hit2) - 1);
-    ClassInfo ci = class_info(cls);
-    int inClass = s_classOff[cls + 1] - s_classOff[cls];
-    int first = (pack - s_packOff[cls]) * ci.P;
+    const int v = hit ? (__ffs(hit) - 1) : (32 + __ffs(hit2) - 1);
+    ClassInfo ci = class_info(FME_MAX_CLASSES - 1 - v);
+    int inClass = s_classOff[v + 1] - s_classOff[v];
+    int first = (pack - s_packOff[v]) * ci.P;
     int count = min(ci.P, inClass - first);
-    first += s_classOff[cls];
+    first += s_classOff[v];
 #define K2_ARGS ci, order, first, count, pus, res, planes, org, g, s_lut, useHad, smem
     if (ci.ts == 8) {
       if (ci.w >= 16) k2_pack<8, 16>(K2_ARGS);
