@@ -622,6 +622,10 @@ int fme_upload_ref_chroma(fme_ctx* c, int slot, const int16_t* cb, const int16_t
   return FME_OK;
 }
 
+// Inter PU shapes of HEVC: both sides in {4,8,12,16,24,32,48,64}; 4x4 does not exist (8x4 / 4x8 are the smallest)
+// and K2's lane units are 8x8 tiles or PAIRS of 4x4 tiles.
+static bool valid_pu_size(int w, int h) { return fme_dim_index(w) >= 0 && fme_dim_index(h) >= 0 && w * h >= 32; }
+
 // ---- the batched search ------------------------------------------------------------------------
 static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, int mode, bool sync,
                          const fme_pu_head* heads = nullptr) {
@@ -636,7 +640,7 @@ static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, 
       for (int i = 0; i < n; ++i) {
         if (heads[i].refSlot >= c->cfg.numRefSlots || !c->refValid[heads[i].refSlot])
           return fail(FME_ERR_STATE, "PU %d references slot %d which holds no picture", i, heads[i].refSlot);
-        if (fme_dim_index(heads[i].w) < 0 || fme_dim_index(heads[i].h) < 0)
+        if (!valid_pu_size(heads[i].w, heads[i].h))
           return fail(FME_ERR_INVALID, "PU %d: %dx%d is not an HEVC PU size", i, heads[i].w, heads[i].h);
       }
     }
@@ -648,7 +652,7 @@ static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, 
       if ((mode & FME_MODE_STD) || (pus[i].flags & FME_PU_ERR_ON_GPU)) {
         if (pus[i].refSlot >= c->cfg.numRefSlots || !c->refValid[pus[i].refSlot])
           return fail(FME_ERR_STATE, "PU %d references slot %d which holds no picture", i, pus[i].refSlot);
-        if (fme_dim_index(pus[i].w) < 0 || fme_dim_index(pus[i].h) < 0)
+        if (!valid_pu_size(pus[i].w, pus[i].h))
           return fail(FME_ERR_INVALID, "PU %d: %dx%d is not an HEVC PU size", i, pus[i].w, pus[i].h);
       }
     }

@@ -256,6 +256,9 @@ def test_edge_cases(small):
     bad["w"] = 20
     with pytest.raises(fme.FmeError):
         eng.submit(bad, fme.MODE_STD)                                     # not an HEVC PU size
+    bad["w"], bad["h"] = 4, 4
+    with pytest.raises(fme.FmeError):
+        eng.submit(bad, fme.MODE_STD)                                     # 4x4 inter PUs do not exist
 
 
 def test_state_errors():
