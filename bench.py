@@ -315,6 +315,23 @@ def run_gpu(args):
     k1e1.record(stream)
     torch.cuda.synchronize(dev)
     kavg["k1_interp_alone"] = k1e0.elapsed_time(k1e1) / K1_REPS
+    # informational: K3 in the opt-in fused-multiply-add mode (fme_config.nnFma; within BASELINE's NN tolerance, not
+    # bit-exact).  The headline numbers above always use the exact mode.
+    k3_fma_ms = None
+    if rank == 0 and world == 1:
+        fast = fme.Fme(width, height, num_ref_slots=1, max_pus=n_pus, device=local, nn_fma=True)
+        fast.set_stream(stream.cuda_stream)
+        fast.set_nn_weights(blob)
+        for _ in range(2):
+            fast.submit_device(d_recs[0].data_ptr(), len(sets[0][2]), d_res.data_ptr(), fme.MODE_NN)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(8):
+            fast.submit_device(d_recs[0].data_ptr(), len(sets[0][2]), d_res.data_ptr(), fme.MODE_NN)
+        f1.record(stream)
+        torch.cuda.synchronize(dev)
+        k3_fma_ms = f0.elapsed_time(f1) / 8
+        fast.close()
 
     out = None
     if rank == 0:
@@ -337,7 +354,7 @@ def run_gpu(args):
                           "int_lane_rate_frac": (144.0 * pu_px / (kavg["k2_refine"] * 1e-3)) / (148 * 128 * 1.965e9) if kavg["k2_refine"] > 0 else 0,
                           "note": "issue-bound integer SATD; HBM fraction reported because the contract asks for it"},
             "k3_nn": {"ms": kavg["k3_nn"], "bound": "fp32", "achieved": k3_flops / (kavg["k3_nn"] * 1e-3) / 1e12 if kavg["k3_nn"] > 0 else 0,
-                      "unit": "TFLOP/s"},
+                      "unit": "TFLOP/s", "ms_opt_in_fma_mode": k3_fma_ms},
         }
         dom = max(("k1_interp", "k2_refine"), key=lambda k: kavg[k])
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/

@@ -37,7 +37,7 @@ EXPORTS = [
 class FmeConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("margin", C.c_int32),
                 ("bitDepth", C.c_int32), ("numRefSlots", C.c_int32), ("maxPUs", C.c_int32), ("useHadME", C.c_int32),
-                ("fen", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("fen", C.c_int32), ("nnFma", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
 class FmeError(RuntimeError):
@@ -105,10 +105,12 @@ def _addr(a, off_elems=0):
 class Fme:
     """One engine context (= one encoder instance's TEncSearch for the fractional-ME path)."""
 
-    def __init__(self, width, height, num_ref_slots=4, max_pus=1 << 20, margin=80, use_had=True, fen=True, device=0):
+    def __init__(self, width, height, num_ref_slots=4, max_pus=1 << 20, margin=80, use_had=True, fen=True, device=0,
+                 nn_fma=False):
         self.lib = load_library()
         self.cfg = FmeConfig(device=device, width=width, height=height, margin=margin, bitDepth=8,
-                             numRefSlots=num_ref_slots, maxPUs=max_pus, useHadME=int(use_had), fen=int(fen))
+                             numRefSlots=num_ref_slots, maxPUs=max_pus, useHadME=int(use_had), fen=int(fen),
+                             nnFma=int(nn_fma))
         self.h = C.c_void_p()
         self._check(self.lib.fme_create(C.byref(self.cfg), C.byref(self.h)))
         self.width, self.height, self.margin = width, height, margin

@@ -202,7 +202,7 @@ int run_search(fme_ctx* c, fme_pu* d_pus, int n, fme_result* d_out, int mode) {
   }
   if (mode & FME_MODE_NN) {
     StageTimer t(c, 2);
-    CU_CHECK(fme_launch_k3(d_pus, n, d_out, c->d_nn, c->nnBytes, c->nnHeader, c->stream, &c->launches));
+    CU_CHECK(fme_launch_k3(d_pus, n, d_out, c->d_nn, c->nnBytes, c->nnHeader, c->cfg.nnFma, c->stream, &c->launches));
   }
   return FME_OK;
 }

@@ -125,7 +125,7 @@ __host__ __device__ constexpr int pad4(int v) { return (v + 3) & ~3; }
 
 // One dense layer for NPU input vectors held in registers.  sW: rows padded to pad4(IN) floats, 16-byte aligned.
 // emit(o, acc[NPU]) receives the pre-activation W x + b of unit o (ascending-k, mul then add).
-template <int IN, int OUT, typename Emit>
+template <bool FMA, int IN, int OUT, typename Emit>
 __device__ __forceinline__ void dense_rows(const float* __restrict__ sW, const float* __restrict__ sb,
                                            const float (&x)[K3F_NPU][IN], Emit emit) {
   constexpr int IN4 = pad4(IN);
@@ -143,8 +143,12 @@ __device__ __forceinline__ void dense_rows(const float* __restrict__ sW, const f
         if (k < IN) {
 #pragma unroll
           for (int u = 0; u < K3F_NPU; ++u) {
-            const float prod = __fmul_rn(wk[t], x[u][k]);
-            acc[u] = (k == 0) ? prod : __fadd_rn(acc[u], prod);
+            if (FMA) {  // opt-in relaxed mode (fme_config.nnFma): one rounding per tap
+              acc[u] = (k == 0) ? __fmul_rn(wk[t], x[u][k]) : __fmaf_rn(wk[t], x[u][k], acc[u]);
+            } else {
+              const float prod = __fmul_rn(wk[t], x[u][k]);
+              acc[u] = (k == 0) ? prod : __fadd_rn(acc[u], prod);
+            }
           }
         }
       }
@@ -183,7 +187,7 @@ struct LayerSmem {
 };
 
 // NH hidden layers of sizes H1,H2,(H3); NEMB = 0 or 2 embedding tables of 8 x 4.
-template <int NEMB, int H1, int H2, int H3, int NOUT>
+template <int NEMB, int H1, int H2, int H3, int NOUT, bool FMA>
 __global__ void __launch_bounds__(K3F_THREADS) k3_nn_fixed(const fme_pu* __restrict__ pus, int n,
                                                           fme_result* __restrict__ res,
                                                           const float* __restrict__ blob) {
@@ -240,7 +244,7 @@ __global__ void __launch_bounds__(K3F_THREADS) k3_nn_fixed(const fme_pu* __restr
       }
     }
     // hidden layer 1
-    dense_rows<IN0, H1>(L1::W(s_l1), L1::b(s_l1), x0, [&](int o, const float (&acc)[K3F_NPU]) {
+    dense_rows<FMA, IN0, H1>(L1::W(s_l1), L1::b(s_l1), x0, [&](int o, const float (&acc)[K3F_NPU]) {
       const float g = L1::g(s_l1)[o], be = L1::be(s_l1)[o];
 #pragma unroll
       for (int u = 0; u < K3F_NPU; ++u) {
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(K3F_THREADS) k3_nn_fixed(const fme_pu* __restr
 #pragma unroll
       for (int k = 0; k < H1; ++k) x1[u][k] = s_act[k * ACT_STRIDE + u * K3F_THREADS + tid];
     // hidden layer 2 (each thread only touches its own column of s_act: no barrier needed)
-    dense_rows<H1, H2>(L2::W(s_l2), L2::b(s_l2), x1, [&](int o, const float (&acc)[K3F_NPU]) {
+    dense_rows<FMA, H1, H2>(L2::W(s_l2), L2::b(s_l2), x1, [&](int o, const float (&acc)[K3F_NPU]) {
       const float g = L2::g(s_l2)[o], be = L2::be(s_l2)[o];
 #pragma unroll
       for (int u = 0; u < K3F_NPU; ++u) {
@@ -276,7 +280,7 @@ __global__ void __launch_bounds__(K3F_THREADS) k3_nn_fixed(const fme_pu* __restr
         if (o == 0 || acc[u] > bestV[u]) { bestV[u] = acc[u]; best[u] = o; }  // first maximum (TEncSearch.cpp:134)
     };
     if constexpr (H3 > 0) {
-      dense_rows<H2, H3>(L3::W(s_l3), L3::b(s_l3), x2, [&](int o, const float (&acc)[K3F_NPU]) {
+      dense_rows<FMA, H2, H3>(L3::W(s_l3), L3::b(s_l3), x2, [&](int o, const float (&acc)[K3F_NPU]) {
         const float g = L3::g(s_l3)[o], be = L3::be(s_l3)[o];
 #pragma unroll
         for (int u = 0; u < K3F_NPU; ++u) {
@@ -289,9 +293,9 @@ __global__ void __launch_bounds__(K3F_THREADS) k3_nn_fixed(const fme_pu* __restr
       for (int u = 0; u < K3F_NPU; ++u)
 #pragma unroll
         for (int k = 0; k < H3; ++k) x3[u][k] = s_act[k * ACT_STRIDE + u * K3F_THREADS + tid];
-      dense_rows<(H3 > 0 ? H3 : 1), NOUT>(LO::W(s_lo), LO::b(s_lo), x3, argmax);
+      dense_rows<FMA, (H3 > 0 ? H3 : 1), NOUT>(LO::W(s_lo), LO::b(s_lo), x3, argmax);
     } else {
-      dense_rows<H2, NOUT>(LO::W(s_lo), LO::b(s_lo), x2, argmax);
+      dense_rows<FMA, H2, NOUT>(LO::W(s_lo), LO::b(s_lo), x2, argmax);
     }
 #pragma unroll
     for (int u = 0; u < K3F_NPU; ++u)
@@ -299,7 +303,7 @@ __global__ void __launch_bounds__(K3F_THREADS) k3_nn_fixed(const fme_pu* __restr
   }
 }
 
-template <int NEMB, int H1, int H2, int H3, int NOUT>
+template <int NEMB, int H1, int H2, int H3, int NOUT, bool FMA>
 cudaError_t launch_fixed(const fme_pu* d_pus, int n, fme_result* d_res, const float* d_nn, cudaStream_t s) {
   constexpr int IN0 = 9 + 4 * NEMB;
   constexpr int HLAST = H3 > 0 ? H3 : H2;
@@ -312,27 +316,29 @@ cudaError_t launch_fixed(const fme_pu* d_pus, int n, fme_result* d_res, const fl
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr[dev & 63] && smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k3_nn_fixed<NEMB, H1, H2, H3, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k3_nn_fixed<NEMB, H1, H2, H3, NOUT, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr[dev & 63] = true;
   }
   int blocks = (n + K3F_NPU * K3F_THREADS - 1) / (K3F_NPU * K3F_THREADS);
   if (blocks > 148 * 6) blocks = 148 * 6;
-  k3_nn_fixed<NEMB, H1, H2, H3, NOUT><<<blocks, K3F_THREADS, smem, s>>>(d_pus, n, d_res, d_nn);
+  k3_nn_fixed<NEMB, H1, H2, H3, NOUT, FMA><<<blocks, K3F_THREADS, smem, s>>>(d_pus, n, d_res, d_nn);
   return cudaGetLastError();
 }
 
 }  // namespace
 
 cudaError_t fme_launch_k3(const fme_pu* d_pus, int n, fme_result* d_res, const float* d_nn, size_t nnBytes,
-                          const FmeNnHeader& h, cudaStream_t s, int64_t* launches) {
+                          const FmeNnHeader& h, int fma, cudaStream_t s, int64_t* launches) {
   if (n <= 0) return cudaSuccess;
   ++*launches;
   if (!h.outSigmoid && h.nOut == 49) {
     if (h.nEmb == 2 && h.embDim == 4 && h.nHidden == 2 && h.hidden[0] == 22 && h.hidden[1] == 20)
-      return launch_fixed<2, 22, 20, 0, 49>(d_pus, n, d_res, d_nn, s);  // shipped per-QP nets (master)
+      return fma ? launch_fixed<2, 22, 20, 0, 49, true>(d_pus, n, d_res, d_nn, s)
+                 : launch_fixed<2, 22, 20, 0, 49, false>(d_pus, n, d_res, d_nn, s);  // shipped per-QP nets (master)
     if (h.nEmb == 0 && h.nHidden == 3 && h.hidden[0] == 40 && h.hidden[1] == 40 && h.hidden[2] == 40)
-      return launch_fixed<0, 40, 40, 40, 49>(d_pus, n, d_res, d_nn, s);  // "3-layer" 9-40-40-40-49 shape
+      return fma ? launch_fixed<0, 40, 40, 40, 49, true>(d_pus, n, d_res, d_nn, s)
+                 : launch_fixed<0, 40, 40, 40, 49, false>(d_pus, n, d_res, d_nn, s);  // "3-layer" 9-40-40-40-49 shape
   }
   int blocks = (n + K3_THREADS - 1) / K3_THREADS;
   if (blocks > 148 * 16) blocks = 148 * 16;

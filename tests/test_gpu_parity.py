@@ -169,6 +169,36 @@ def test_k3_matches_reference_fixture_all_qps(small):
         assert np.array_equal(nn_fields(got), want[:, [1, 2, 3, 4, 0]])
 
 
+def test_k3_fma_mode_within_tolerance(small):
+    """fme_config.nnFma = 1 (opt-in): fused multiply-add in the dense layers.  BASELINE.json's contract for the
+    floating-point path is 1e-5 relative on the logits and >= 99.9 % identical classes; the engine reports classes,
+    so the test holds it to the class agreement against the reference fixture -- on the 3 532-PU frame for every QP
+    and on a 1080p list -- and requires identical MV fields wherever the class agrees."""
+    eng, g, recs = small
+    fast = fme.Fme(128, 96, num_ref_slots=2, max_pus=len(recs), nn_fma=True)
+    for qp in (22, 27, 32, 37):
+        fast.set_nn_weights(fme.nn_weights.load_blob(qp))
+        got = nn_fields(fast.submit(recs, fme.MODE_NN))
+        want = nn_fields(golden_res(g, "small_res_nn%d" % qp))
+        same = (got[:, 4] == want[:, 4])
+        assert same.mean() >= 0.999, "QP%d: class agreement %.5f" % (qp, same.mean())
+        assert np.array_equal(got[same], want[same])
+    fast.close()
+    W, H = 1920, 1080
+    _, _, motions = fme.pu_list.synth_frames(W, H, n_refs=4, seed=2022)
+    big = fme.pu_list.make_records(W, H, motions, seed=2)
+    rng = np.random.default_rng(9)
+    big["err"] = rng.integers(0, 1 << 22, big["err"].shape).astype(np.uint32)   # spread-out grids: many near-ties
+    exact = fme.Fme(W, H, num_ref_slots=1, max_pus=len(big))
+    fast = fme.Fme(W, H, num_ref_slots=1, max_pus=len(big), nn_fma=True)
+    blob = fme.nn_weights.load_blob(22)
+    exact.set_nn_weights(blob); fast.set_nn_weights(blob)
+    a, b = nn_fields(exact.submit(big, fme.MODE_NN)), nn_fields(fast.submit(big, fme.MODE_NN))
+    agree = (a[:, 4] == b[:, 4]).mean()
+    assert agree >= 0.999, "1080p list: class agreement %.6f" % agree
+    exact.close(); fast.close()
+
+
 def test_k3_three_layer_variant(small, orc):
     """Config C4: generic layer list (9 -> 40 -> 40 -> 40 -> 49, no embeddings); oracle = same generic forward."""
     eng, g, recs = small
