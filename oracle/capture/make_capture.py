@@ -136,7 +136,7 @@ def build_encoder():
     return exe
 
 
-def synth_yuv(path, w, h, frames, seed=7):
+def synth_yuv(path, w, h, frames, seed=7, scale=1.0):
     """Moving low-pass texture + noise, 4:2:0 planar 8-bit."""
     import fme_loader
     fme = fme_loader.load()
@@ -145,7 +145,7 @@ def synth_yuv(path, w, h, frames, seed=7):
     base = np.clip(base + rng.normal(0, 5.0, base.shape), 0, 255)
     with open(path, "wb") as f:
         for t in range(frames):
-            dx, dy = 1.3 * t, 0.7 * t
+            dx, dy = 1.3 * t * scale, 0.7 * t * scale
             ix, iy, fx, fy = int(dx), int(dy), dx - int(dx), dy - int(dy)
             a = base[16 + iy:16 + iy + h + 1, 16 + ix:16 + ix + w + 1]
             y = (a[:-1, :-1] * (1 - fx) + a[:-1, 1:] * fx) * (1 - fy) + (a[1:, :-1] * (1 - fx) + a[1:, 1:] * fx) * fy
@@ -182,10 +182,16 @@ def parse_capture(path):
 
 
 def main():
-    w, h, frames, qp = 416, 240, 3, 22
+    # usage: make_capture.py [qp [frames [seed [motion_scale]]]]   (defaults reproduce real_encode_416x240.npz)
+    a = sys.argv[1:]
+    w, h = 416, 240
+    qp = int(a[0]) if len(a) > 0 else 22
+    frames = int(a[1]) if len(a) > 1 else 3
+    seed = int(a[2]) if len(a) > 2 else 7
+    scale = float(a[3]) if len(a) > 3 else 1.0
     exe = build_encoder()
-    yuv = os.path.join(OUT, "syn_416x240.yuv")
-    synth_yuv(yuv, w, h, frames)
+    yuv = os.path.join(OUT, "syn_416x240_%d.yuv" % seed)
+    synth_yuv(yuv, w, h, frames, seed=seed, scale=scale)
     cap = os.path.join(OUT, "capture.bin")
     env = dict(os.environ, FME_CAPTURE_FILE=cap)
     cmd = [exe, "-c", REF + "/cfg/encoder_lowdelay_P_main.cfg", "-c", REF + "/cfg/per-sequence/BlowingBubbles.cfg",
@@ -195,12 +201,13 @@ def main():
     assert log.returncode == 0, log.stdout[-2000:] + log.stderr[-2000:]
     orgs, refs, recs, lams = parse_capture(cap)
     print("captured", len(recs), "FME calls;", len(orgs), "source pictures;", len(refs), "(cur,ref) reference pictures")
-    out = {"recs": recs.astype(np.int32), "lambda": lams}
+    out = {"recs": recs.astype(np.int32), "lambda": lams, "qp": np.array([qp], np.int32)}
     for poc, p in orgs.items():
         out["org_%d" % poc] = p
     for (cur, rp), p in refs.items():
         out["ref_%d_%d" % (cur, rp)] = p
-    path = os.path.join(ROOT, "tests", "golden", "real_encode_416x240.npz")
+    name = "real_encode_416x240.npz" if (qp, seed) == (22, 7) else "real_encode_416x240_qp%d.npz" % qp
+    path = os.path.join(ROOT, "tests", "golden", name)
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
 

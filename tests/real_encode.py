@@ -1,5 +1,5 @@
-"""Loader for tests/golden/real_encode_416x240.npz: the reference encoder's own FME calls captured on a real
-416x240 lowdelay_P QP22 encode (oracle/capture/make_capture.py)."""
+"""Loader for tests/golden/real_encode_416x240*.npz: the reference encoder's own FME calls captured on real
+416x240 lowdelay_P encodes (oracle/capture/make_capture.py): QP22 (3 frames) and QP37 (2 frames, faster motion)."""
 import os
 
 import numpy as np
@@ -11,8 +11,12 @@ COLS = ["poc", "x", "y", "w", "h", "refPoc", "list", "mvIntX", "mvIntY", "predX"
         "halfX", "halfY", "qterX", "qterY", "cost", "nnHx", "nnHy", "nnQx", "nnQy", "nnOut"]
 
 
-def load():
-    g = dict(np.load(os.path.join(HERE, "golden", "real_encode_416x240.npz")))
+CAPTURES = ["real_encode_416x240.npz", "real_encode_416x240_qp37.npz"]
+
+
+def load(name=CAPTURES[0]):
+    g = dict(np.load(os.path.join(HERE, "golden", name)))
+    qp = int(g["qp"][0]) if "qp" in g else 22
     recs = g["recs"]
     col = {n: recs[:, i] for i, n in enumerate(COLS)}
     pictures = []
@@ -33,7 +37,7 @@ def load():
         pus["err"][:, 5:9] = e[:, 4:8]
         lam = g["lambda"][sel]
         assert (lam == lam[0]).all()
-        pictures.append(dict(poc=poc, org=g["org_%d" % poc], refs=[g["ref_%d_%d" % (poc, rp)] for rp in ref_pocs],
+        pictures.append(dict(poc=poc, qp=qp, org=g["org_%d" % poc], refs=[g["ref_%d_%d" % (poc, rp)] for rp in ref_pocs],
                              pus=pus, lam=float(lam[0]),
                              uni=(col["bBi"][sel] == 0), nn_ok=(col["esize"][sel] == 8),
                              want_std=np.stack([col[k][sel] for k in ("halfX", "halfY", "qterX", "qterY", "cost")], 1),

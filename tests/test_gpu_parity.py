@@ -519,15 +519,16 @@ def test_pipelined_async_matches_synchronous():
     eng.close()
 
 
-def test_real_encode_capture_matches_engine():
-    """Config C1: every fractional-ME call the reference encoder made while encoding 416x240 lowdelay_P QP22
-    (31 017 calls, captured at TEncSearch.cpp:4534-4541) -- half/quarter MV and cost bit-exact, NN class and MV
-    identical wherever the reference had its 8 neighbour errors."""
+@pytest.mark.parametrize("capture", [0, 1])
+def test_real_encode_capture_matches_engine(capture):
+    """Config C1: every fractional-ME call the reference encoder made while encoding 416x240 lowdelay_P at QP22
+    (31 017 calls) and QP37 (faster motion), captured at TEncSearch.cpp:4534-4541 -- half/quarter MV and cost
+    bit-exact, NN class and MV identical wherever the reference had its 8 neighbour errors."""
     import real_encode
-    pics = real_encode.load()
+    pics = real_encode.load(real_encode.CAPTURES[capture])
     for p in pics:
         eng = fme.Fme(416, 240, num_ref_slots=len(p["refs"]), max_pus=len(p["pus"]))
-        eng.set_nn_weights(fme.nn_weights.load_blob(22))
+        eng.set_nn_weights(fme.nn_weights.load_blob(p["qp"]))
         eng.set_slice(p["lam"])
         eng.upload_org(p["org"])
         for s, r in enumerate(p["refs"]):
