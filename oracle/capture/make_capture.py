@@ -189,12 +189,13 @@ def main():
     frames = int(a[1]) if len(a) > 1 else 3
     seed = int(a[2]) if len(a) > 2 else 7
     scale = float(a[3]) if len(a) > 3 else 1.0
+    cfg = a[4] if len(a) > 4 else "encoder_lowdelay_P_main.cfg"   # e.g. encoder_randomaccess_main.cfg (B slices)
     exe = build_encoder()
     yuv = os.path.join(OUT, "syn_416x240_%d.yuv" % seed)
     synth_yuv(yuv, w, h, frames, seed=seed, scale=scale)
     cap = os.path.join(OUT, "capture.bin")
     env = dict(os.environ, FME_CAPTURE_FILE=cap)
-    cmd = [exe, "-c", REF + "/cfg/encoder_lowdelay_P_main.cfg", "-c", REF + "/cfg/per-sequence/BlowingBubbles.cfg",
+    cmd = [exe, "-c", REF + "/cfg/" + cfg, "-c", REF + "/cfg/per-sequence/BlowingBubbles.cfg",
            "-i", yuv, "-f", str(frames), "-q", str(qp), "-b", os.path.join(OUT, "str.bin"), "-o", os.path.join(OUT, "rec.yuv")]
     log = subprocess.run(cmd, env=env, capture_output=True, text=True)
     open(os.path.join(OUT, "encode.log"), "w").write(log.stdout + log.stderr)
@@ -206,7 +207,8 @@ def main():
         out["org_%d" % poc] = p
     for (cur, rp), p in refs.items():
         out["ref_%d_%d" % (cur, rp)] = p
-    name = "real_encode_416x240.npz" if (qp, seed) == (22, 7) else "real_encode_416x240_qp%d.npz" % qp
+    tag = "" if "lowdelay_P" in cfg else "_" + cfg.split("_")[1]
+    name = "real_encode_416x240.npz" if (qp, seed, tag) == (22, 7, "") else "real_encode_416x240%s_qp%d.npz" % (tag, qp)
     path = os.path.join(ROOT, "tests", "golden", name)
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -1,5 +1,7 @@
 """Loader for tests/golden/real_encode_416x240*.npz: the reference encoder's own FME calls captured on real
-416x240 lowdelay_P encodes (oracle/capture/make_capture.py): QP22 (3 frames) and QP37 (2 frames, faster motion)."""
+416x240 encodes (oracle/capture/make_capture.py): lowdelay_P QP22 (3 frames) and QP37 (2 frames, faster motion),
+and randomaccess QP32 (4 frames: B slices, two lists; the bi-prediction refinement calls are flagged `uni == False`
+and skipped -- that pattern is 2*org - pred, outside this path's scope)."""
 import os
 
 import numpy as np
@@ -11,7 +13,7 @@ COLS = ["poc", "x", "y", "w", "h", "refPoc", "list", "mvIntX", "mvIntY", "predX"
         "halfX", "halfY", "qterX", "qterY", "cost", "nnHx", "nnHy", "nnQx", "nnQy", "nnOut"]
 
 
-CAPTURES = ["real_encode_416x240.npz", "real_encode_416x240_qp37.npz"]
+CAPTURES = ["real_encode_416x240.npz", "real_encode_416x240_qp37.npz", "real_encode_416x240_randomaccess_qp32.npz"]
 
 
 def load(name=CAPTURES[0]):
