@@ -93,6 +93,28 @@ POST_NN = r'''
     fwrite(rec, sizeof(int), 32, fmecap::file());
     double lam = m_pcRdCost->getLambda();
     fwrite(&lam, sizeof(double), 1, fmecap::file());
+    if (bBi) {
+      // the other list's uni-prediction that removeHighFreq subtracted (TEncSearch.cpp:4462-4472): its picture and
+      // the MV xPredInterUni used (clipped), plus a checksum of the search pattern 2*org - pred
+      RefPicList eOther = RefPicList(1 - (Int)eRefPicList);
+      TComMv om = pcCU->getCUMvField(eOther)->getMv(uiPartAddr);
+      pcCU->clipMv(om);
+      TComPic* op = pcCU->getSlice()->getRefPic(eOther, pcCU->getCUMvField(eOther)->getRefIdx(uiPartAddr));
+      int cur = pcCU->getSlice()->getPOC();
+      long long key = ((long long)cur << 32) | (unsigned)(op->getPOC() & 0xffff) | 0x10000;
+      if (!fmecap::dumped.count(key)) { fmecap::dumped.insert(key);
+        fmecap::dumpPlane(2, (cur << 16) | (op->getPOC() & 0xffff), op->getPicYuvRec()->getAddr(COMPONENT_Y),
+                          op->getPicYuvRec()->getStride(COMPONENT_Y), op->getPicYuvRec()->getWidth(COMPONENT_Y),
+                          op->getPicYuvRec()->getHeight(COMPONENT_Y)); }
+      long long chk = 0;
+      const Pel* pat = pcPatternKey->getROIY();
+      for (int y = 0; y < iRoiHeight; y++)
+        for (int x = 0; x < iRoiWidth; x++) chk += (long long)pat[y * pcPatternKey->getPatternLStride() + x] * (y * iRoiWidth + x + 1);
+      int hdr4[5] = {4, cur, 0, 0, 0};
+      fwrite(hdr4, sizeof(int), 5, fmecap::file());
+      int r4[6] = {op->getPOC(), om.getHor(), om.getVer(), (int)eOther, (int)(chk & 0x7fffffff), (int)((chk >> 31) & 0x7fffffff)};
+      fwrite(r4, sizeof(int), 6, fmecap::file());
+    }
   }
 '''
 
@@ -158,7 +180,7 @@ def synth_yuv(path, w, h, frames, seed=7, scale=1.0):
 def parse_capture(path):
     data = open(path, "rb").read()
     pos = 0
-    orgs, refs, recs, lams = {}, {}, [], []
+    orgs, refs, recs, lams, others = {}, {}, [], [], []
     while pos < len(data):
         tag, a, w, h, _ = struct.unpack_from("<5i", data, pos)
         pos += 20
@@ -176,9 +198,13 @@ def parse_capture(path):
             pos += 8
             recs.append((a,) + rec)
             lams.append(lam)
+            others.append((-1, 0, 0, 0, 0, 0))
+        elif tag == 4:   # belongs to the tag-3 record just read
+            others[-1] = struct.unpack_from("<6i", data, pos)
+            pos += 24
         else:
             raise ValueError("bad tag %d at %d" % (tag, pos))
-    return orgs, refs, np.array(recs, np.int64), np.array(lams)
+    return orgs, refs, np.array(recs, np.int64), np.array(lams), np.array(others, np.int64)
 
 
 def main():
@@ -200,9 +226,12 @@ def main():
     log = subprocess.run(cmd, env=env, capture_output=True, text=True)
     open(os.path.join(OUT, "encode.log"), "w").write(log.stdout + log.stderr)
     assert log.returncode == 0, log.stdout[-2000:] + log.stderr[-2000:]
-    orgs, refs, recs, lams = parse_capture(cap)
+    orgs, refs, recs, lams, others = parse_capture(cap)
     print("captured", len(recs), "FME calls;", len(orgs), "source pictures;", len(refs), "(cur,ref) reference pictures")
     out = {"recs": recs.astype(np.int32), "lambda": lams, "qp": np.array([qp], np.int32)}
+    if (others[:, 0] >= 0).any():
+        # per call: POC / quarter-pel MV / list of the other list's prediction, pattern checksum (bi calls; -1 else)
+        out["other"] = others.astype(np.int32)
     for poc, p in orgs.items():
         out["org_%d" % poc] = p
     for (cur, rp), p in refs.items():

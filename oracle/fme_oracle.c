@@ -447,13 +447,46 @@ void orc_fill_surface(const orc_pel* org, int os, const orc_pel* const* refs, in
   }
 }
 
+/* TComPrediction::xPredInterBlk for luma with bi = false (TComPrediction.cpp:661-680): three cases. */
+void orc_mc_luma(const orc_pel* ref, int rs, orc_pel* dst, int ds, int w, int h, int xFrac, int yFrac) {
+  if (yFrac == 0) {
+    orc_filter_hor(1, ref, rs, dst, ds, w, h, xFrac, 1, 8);
+  } else if (xFrac == 0) {
+    orc_filter_ver(1, ref, rs, dst, ds, w, h, yFrac, 1, 1, 8);
+  } else {
+    orc_pel tmp[(64 + 7) * 64];
+    orc_filter_hor(1, ref - 3 * rs, rs, tmp, 64, w, h + 7, xFrac, 0, 8);
+    orc_filter_ver(1, tmp + 3 * 64, 64, dst, ds, w, h, yFrac, 0, 1, 8);
+  }
+}
+
+/* TComYuv::removeHighFreq, bClipToBitDepths = false (TComYuv.cpp:443-452) */
+void orc_bi_pattern(const orc_pel* org, int os, const orc_pel* pred, int ps, orc_pel* dst, int ds, int w, int h) {
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) dst[y * ds + x] = (orc_pel)(2 * org[y * os + x] - pred[y * ps + x]);
+}
+
 void orc_run_pu_list(const orc_pel* org, int os, const orc_pel* const* refs, int rs, const orc_pu* pus, int n, int mode,
                      double lambda, int useHad, const void* nnBlob, orc_result* out) {
   for (int i = 0; i < n; ++i) {
     const orc_pu* p = &pus[i];
     orc_result r;
     memset(&r, 0, sizeof(r));
-    if (mode & 1) {
+    if ((mode & 1) && (p->flags & ORC_PU_BI)) {
+      /* xMotionEstimation with bBi: the pattern is 2*org - (other list's prediction) (TEncSearch.cpp:4462-4472) */
+      const int oslot = (int)(p->err[0] & 0xff);
+      const int omx = (int16_t)(p->err[1] & 0xffff), omy = (int16_t)(p->err[1] >> 16);
+      orc_pel pred[64 * 64], pat[64 * 64];
+      int16_t hxy[2], qxy[2];
+      uint32_t c;
+      orc_mc_luma(refs[oslot] + (p->y + (omy >> 2)) * rs + p->x + (omx >> 2), rs, pred, 64, p->w, p->h, omx & 3, omy & 3);
+      orc_bi_pattern(org + p->y * os + p->x, os, pred, 64, pat, 64, p->w, p->h);
+      orc_frac_dif(pat, 64, p->w, p->h, refs[p->refSlot] + p->y * rs + p->x, rs, p->mvIntX, p->mvIntY, p->mvPredX,
+                   p->mvPredY, lambda, useHad, 0, hxy, qxy, &c);
+      r.halfX = (int8_t)hxy[0]; r.halfY = (int8_t)hxy[1];
+      r.qterX = (int8_t)qxy[0]; r.qterY = (int8_t)qxy[1];
+      r.cost = c;
+    } else if (mode & 1) {
       int16_t hxy[2], qxy[2];
       uint32_t c;
       orc_frac_dif(org + p->y * os + p->x, os, p->w, p->h, refs[p->refSlot] + p->y * rs + p->x, rs, p->mvIntX,

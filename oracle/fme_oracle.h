@@ -109,6 +109,17 @@ typedef struct {
   int8_t nnHalfX, nnHalfY, nnQterX, nnQterY;
   uint8_t nnClass, pad[3];
 } orc_result;
+/* Bi-predictive refinement (bBi, TEncSearch.cpp:4462-4472): flags & ORC_PU_BI marks a record whose search pattern is
+ * 2*org - P_other instead of org, P_other being the other list's uni-prediction (xPredInterBlk, bi = false) from
+ * reference slot err[0] & 0xff at the quarter-pel MV packed in err[1] (x = low, y = high int16).  err[] carries no
+ * error grid for such records: the reference's NN_pred runs on stale globals there (integer search is xPatternSearch,
+ * which never refreshes array_e). */
+#define ORC_PU_BI 0x04
+/* xPredInterBlk, luma, uni-prediction (TComPrediction.cpp:661-680): ref -> the sample the integer part of mv points at */
+void orc_mc_luma(const orc_pel* ref, int refStride, orc_pel* dst, int dstStride, int w, int h, int xFrac, int yFrac);
+/* TComYuv::removeHighFreq without clipping (TComYuv.cpp:411-455; ClipForBiPredMEEnabled = 0): dst = 2*org - pred */
+void orc_bi_pattern(const orc_pel* org, int orgStride, const orc_pel* pred, int predStride, orc_pel* dst, int dstStride,
+                    int w, int h);
 void orc_fill_surface(const orc_pel* org, int orgStride, const orc_pel* const* refs, int refStride, orc_pu* pus, int n,
                       int fen);
 /* mode bit0 = standard FME, bit1 = NN_pred.  refs[s] -> picture sample (0,0) of padded plane s. */

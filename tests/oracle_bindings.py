@@ -91,6 +91,15 @@ class Oracle:
                               int(is_last), bit_depth)
         return dst
 
+    def bi_pattern(self, org, org_off, ostride, ref, ref_off, rstride, w, h, mvx, mvy):
+        """2*org - xPredInterBlk(ref at quarter-pel mv): the search pattern of a bi-predictive refinement call."""
+        pred = np.zeros((h, w), np.int16)
+        self.L.orc_mc_luma(_ptr(ref, ref_off + (mvy >> 2) * rstride + (mvx >> 2)), rstride, _ptr(pred), w, w, h,
+                           mvx & 3, mvy & 3)
+        pat = np.zeros((h, w), np.int16)
+        self.L.orc_bi_pattern(_ptr(org, org_off), ostride, _ptr(pred), w, _ptr(pat), w, w, h)
+        return pat
+
     def add_avg(self, a, a_off, astride, b, b_off, bstride, w, h, bit_depth=8):
         dst = np.zeros((h, w), np.int16)
         self.L.orc_add_avg(_ptr(a, a_off), astride, _ptr(b, b_off), bstride, _ptr(dst), w, w, h, bit_depth)

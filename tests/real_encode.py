@@ -21,10 +21,14 @@ def load(name=CAPTURES[0]):
     qp = int(g["qp"][0]) if "qp" in g else 22
     recs = g["recs"]
     col = {n: recs[:, i] for i, n in enumerate(COLS)}
+    other = g["other"] if "other" in g else None   # per call: other list's POC, MV x/y, list, pattern checksum (bi calls)
     pictures = []
     for poc in sorted(set(col["poc"].tolist())):
         sel = np.nonzero(col["poc"] == poc)[0]
-        ref_pocs = sorted(set(col["refPoc"][sel].tolist()))
+        ref_pocs = set(col["refPoc"][sel].tolist())
+        if other is not None:
+            ref_pocs |= set(other[sel][other[sel][:, 0] >= 0][:, 0].tolist())
+        ref_pocs = sorted(ref_pocs)
         slot_of = {rp: s for s, rp in enumerate(ref_pocs)}
         pus = np.zeros(len(sel), PU_DTYPE)
         pus["x"], pus["y"], pus["w"], pus["h"] = col["x"][sel], col["y"][sel], col["w"][sel], col["h"][sel]
@@ -37,11 +41,21 @@ def load(name=CAPTURES[0]):
         pus["err"][:, 0:4] = e[:, 0:4]
         pus["err"][:, 4] = col["C"][sel].astype(np.uint32)
         pus["err"][:, 5:9] = e[:, 4:8]
+        bi = col["bBi"][sel] != 0
+        if other is not None and bi.any():
+            # bi-predictive refinement calls: the pattern is 2*org - (other list's prediction); see fme_pu / orc_pu
+            o = other[sel]
+            pus["flags"][bi] |= 0x04
+            pus["err"][bi] = 0
+            pus["err"][bi, 0] = [slot_of[int(rp)] for rp in o[bi, 0]]
+            pus["err"][bi, 1] = (o[bi, 1].astype(np.int64) & 0xffff) | ((o[bi, 2].astype(np.int64) & 0xffff) << 16)
         lam = g["lambda"][sel]
         assert (lam == lam[0]).all()
         pictures.append(dict(poc=poc, qp=qp, org=g["org_%d" % poc], refs=[g["ref_%d_%d" % (poc, rp)] for rp in ref_pocs],
                              pus=pus, lam=float(lam[0]),
-                             uni=(col["bBi"][sel] == 0), nn_ok=(col["esize"][sel] == 8),
+                             uni=(col["bBi"][sel] == 0), nn_ok=(col["esize"][sel] == 8) & (col["bBi"][sel] == 0),
+                             pat_chk=(other[sel][:, 4].astype(np.int64) | (other[sel][:, 5].astype(np.int64) << 31))
+                             if other is not None else None,
                              want_std=np.stack([col[k][sel] for k in ("halfX", "halfY", "qterX", "qterY", "cost")], 1),
                              want_nn=np.stack([col[k][sel] for k in ("nnHx", "nnHy", "nnQx", "nnQy", "nnOut")], 1)))
     return pictures

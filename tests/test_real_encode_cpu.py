@@ -10,7 +10,7 @@ from common import fme
 
 
 @pytest.mark.parametrize("capture,calls", [(real_encode.CAPTURES[0], 31017), (real_encode.CAPTURES[1], 10311),
-                                           (real_encode.CAPTURES[2], 51491)])
+                                           (real_encode.CAPTURES[2], 71782)])
 def test_oracle_reproduces_the_reference_encoders_fme_decisions(capture, calls):
     pics = real_encode.load(capture)
     total = 0
@@ -22,8 +22,32 @@ def test_oracle_reproduces_the_reference_encoders_fme_decisions(capture, calls):
         nn = np.stack([got["nnHalfX"], got["nnHalfY"], got["nnQterX"], got["nnQterY"], got["nnClass"]], 1).astype(np.int64)
         u, k = p["uni"], p["nn_ok"]
         assert u.all() or "randomaccess" in capture  # lowdelay_P: no bi-prediction refinement calls
-        bad = np.nonzero((std[u] != p["want_std"][u]).any(1))[0]
-        assert len(bad) == 0, (p["poc"], len(bad), p["pus"][u][bad[:3]], std[u][bad[:3]], p["want_std"][u][bad[:3]])
-        assert np.array_equal(nn[k & u], p["want_nn"][k & u]), p["poc"]
-        total += int(u.sum())
+        # uni-prediction calls and bi-predictive refinement calls (pattern 2*org - other list's prediction) alike
+        bad = np.nonzero((std != p["want_std"]).any(1))[0]
+        assert len(bad) == 0, (p["poc"], len(bad), p["pus"][bad[:3]], std[bad[:3]], p["want_std"][bad[:3]])
+        assert np.array_equal(nn[k], p["want_nn"][k]), p["poc"]
+        total += len(u)
     assert total > 5000 and (calls is None or total == calls)
+
+
+def test_bi_pattern_checksum_matches_the_reference_encoder(orc):
+    """The search pattern of bi-predictive refinement calls, rebuilt from the captured other-list MV, has the checksum
+    the reference encoder computed over its own TComYuv::removeHighFreq output (TEncSearch.cpp:4462-4472)."""
+    pics = real_encode.load(real_encode.CAPTURES[2])
+    M, checked = 80, 0
+    for p in pics:
+        org = p["org"].astype(np.int16)
+        refs = [ob.pad_plane(r, M) for r in p["refs"]]
+        S = refs[0].shape[1]
+        bi = np.nonzero(~p["uni"])[0][::37]
+        for i in bi:
+            r = p["pus"][i]
+            x, y, w, h = int(r["x"]), int(r["y"]), int(r["w"]), int(r["h"])
+            slot = int(r["err"][0]) & 0xff
+            s16 = lambda v: ((v & 0xffff) ^ 0x8000) - 0x8000
+            mvx, mvy = s16(int(r["err"][1])), s16(int(r["err"][1]) >> 16)
+            pat = orc.bi_pattern(org, y * org.shape[1] + x, org.shape[1], refs[slot], (M + y) * S + M + x, S, w, h, mvx, mvy)
+            chk = int((pat.astype(np.int64).ravel() * np.arange(1, w * h + 1)).sum()) & ((1 << 62) - 1)
+            assert chk == int(p["pat_chk"][i]), (p["poc"], i, r)
+            checked += 1
+    assert checked > 400
