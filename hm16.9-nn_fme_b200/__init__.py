@@ -21,7 +21,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libfme_b200.so")
 
 MODE_STD, MODE_NN, MODE_BOTH = 1, 2, 3
-PU_LOSSLESS, PU_ERR_ON_GPU = 0x01, 0x02
+PU_LOSSLESS, PU_ERR_ON_GPU, PU_BI = 0x01, 0x02, 0x04
 
 # every symbol include/fme_b200.h declares (checked by tests/test_abi.py against the header)
 EXPORTS = [
@@ -37,7 +37,7 @@ EXPORTS = [
 class FmeConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("margin", C.c_int32),
                 ("bitDepth", C.c_int32), ("numRefSlots", C.c_int32), ("maxPUs", C.c_int32), ("useHadME", C.c_int32),
-                ("fen", C.c_int32), ("nnFma", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("fen", C.c_int32), ("nnFma", C.c_int32), ("biPred", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class FmeError(RuntimeError):
@@ -106,11 +106,11 @@ class Fme:
     """One engine context (= one encoder instance's TEncSearch for the fractional-ME path)."""
 
     def __init__(self, width, height, num_ref_slots=4, max_pus=1 << 20, margin=80, use_had=True, fen=True, device=0,
-                 nn_fma=False):
+                 nn_fma=False, bi_pred=False):
         self.lib = load_library()
         self.cfg = FmeConfig(device=device, width=width, height=height, margin=margin, bitDepth=8,
                              numRefSlots=num_ref_slots, maxPUs=max_pus, useHadME=int(use_had), fen=int(fen),
-                             nnFma=int(nn_fma))
+                             nnFma=int(nn_fma), biPred=int(bi_pred))
         self.h = C.c_void_p()
         self._check(self.lib.fme_create(C.byref(self.cfg), C.byref(self.h)))
         self.width, self.height, self.margin = width, height, margin

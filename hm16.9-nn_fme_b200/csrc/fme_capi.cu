@@ -197,7 +197,7 @@ int run_search(fme_ctx* c, fme_pu* d_pus, int n, fme_result* d_out, int mode) {
   if (mode != FME_MODE_BOTH) CU_CHECK(fme_launch_clear_results(d_out, n, c->stream, &c->launches));
   if (mode & FME_MODE_STD) {
     StageTimer t(c, 1);
-    CU_CHECK(fme_launch_k2(c->g, c->d_planes, c->d_org, d_pus, n, d_out, c->d_costLut, c->cfg.useHadME, c->k2,
+    CU_CHECK(fme_launch_k2(c->g, c->d_planes, c->d_org, d_pus, n, d_out, c->d_costLut, c->cfg.useHadME, c->cfg.biPred, c->k2,
                            c->numSMs, c->stream, &c->launches));
   }
   if (mode & FME_MODE_NN) {
@@ -654,6 +654,14 @@ static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, 
           return fail(FME_ERR_STATE, "PU %d references slot %d which holds no picture", i, pus[i].refSlot);
         if (!valid_pu_size(pus[i].w, pus[i].h))
           return fail(FME_ERR_INVALID, "PU %d: %dx%d is not an HEVC PU size", i, pus[i].w, pus[i].h);
+        if (pus[i].flags & FME_PU_BI) {
+          if (!c->cfg.biPred) return fail(FME_ERR_INVALID, "PU %d carries FME_PU_BI but the ctx was created with biPred = 0", i);
+          if (pus[i].flags & FME_PU_ERR_ON_GPU)
+            return fail(FME_ERR_INVALID, "PU %d: FME_PU_BI records carry the other list's prediction in err[], not an error grid", i);
+          const int os = (int)(pus[i].err[0] & 0xff);
+          if (os >= c->cfg.numRefSlots || !c->refValid[os])
+            return fail(FME_ERR_STATE, "PU %d: other-list slot %d holds no picture", i, os);
+        }
       }
     }
   } else {

@@ -65,7 +65,7 @@ cudaError_t fme_launch_k1(const FmeGeom& g, const uint8_t* d_pic, int picPitch, 
 cudaError_t fme_launch_pad_chroma(const FmeGeom& g, const uint8_t* d_pic, int picPitch, uint8_t* d_plane,
                                   cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_k2(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_pu* d_pus, int n,
-                          fme_result* d_res, const uint32_t* d_costLut, int useHad, const FmeK2Scratch& sc,
+                          fme_result* d_res, const uint32_t* d_costLut, int useHad, int biPred, const FmeK2Scratch& sc,
                           int numSMs, cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_k3(const fme_pu* d_pus, int n, fme_result* d_res, const float* d_nn, size_t nnBytes,
                           const FmeNnHeader& h, int fma, cudaStream_t s, int64_t* launches);

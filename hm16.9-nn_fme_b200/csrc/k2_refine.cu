@@ -68,13 +68,21 @@ __host__ __device__ inline ClassInfo class_info(int cls) {
 // ------------------------------------------------------------------------------------------------
 // prepass: counting sort of PU indices by shape class
 // ------------------------------------------------------------------------------------------------
-__global__ void k2_count(const fme_pu* __restrict__ pus, int n, int* __restrict__ classCount) {
+// Records are binned in two passes: uni-prediction records (wantBi = 0) and, when the ctx enables it, bi-predictive
+// refinement records (FME_PU_BI, wantBi = 1) -- a pack never mixes the two kinds (different k2_pack instantiations).
+__device__ __forceinline__ int k2_class_of(const fme_pu& p, int wantBi) {
+  if (((p.flags & FME_PU_BI) != 0) != (wantBi != 0)) return -1;
+  const int wi = fme_dim_index(p.w), hi = fme_dim_index(p.h);
+  return (wi >= 0 && hi >= 0) ? wi * 8 + hi : -1;
+}
+
+__global__ void k2_count(const fme_pu* __restrict__ pus, int n, int* __restrict__ classCount, int wantBi) {
   __shared__ int s_cnt[FME_MAX_CLASSES];
   for (int i = threadIdx.x; i < FME_MAX_CLASSES; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    int wi = fme_dim_index(pus[i].w), hi = fme_dim_index(pus[i].h);
-    if (wi >= 0 && hi >= 0) atomicAdd(&s_cnt[wi * 8 + hi], 1);
+    const int c = k2_class_of(pus[i], wantBi);
+    if (c >= 0) atomicAdd(&s_cnt[c], 1);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < FME_MAX_CLASSES; i += blockDim.x)
@@ -85,7 +93,7 @@ __global__ void k2_count(const fme_pu* __restrict__ pus, int n, int* __restrict_
 // class counts (a warp scan, cheaper than a separate launch); block 0 also publishes them for k2_refine.
 __global__ void k2_scatter(const fme_pu* __restrict__ pus, int n, const int* __restrict__ classCount,
                            int* __restrict__ classOffset, int* __restrict__ packOffset,
-                           int* __restrict__ classCursor, int* __restrict__ order) {
+                           int* __restrict__ classCursor, int* __restrict__ order, int wantBi) {
   __shared__ int s_cnt[FME_MAX_CLASSES];
   __shared__ int s_base[FME_MAX_CLASSES];
   __shared__ int s_classOff[FME_MAX_CLASSES];
@@ -119,8 +127,8 @@ __global__ void k2_scatter(const fme_pu* __restrict__ pus, int n, const int* __r
   for (int i = threadIdx.x; i < FME_MAX_CLASSES; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
   for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    int wi = fme_dim_index(pus[i].w), hh = fme_dim_index(pus[i].h);
-    if (wi >= 0 && hh >= 0) atomicAdd(&s_cnt[wi * 8 + hh], 1);
+    const int c = k2_class_of(pus[i], wantBi);
+    if (c >= 0) atomicAdd(&s_cnt[c], 1);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < FME_MAX_CLASSES; i += blockDim.x) {
@@ -129,11 +137,8 @@ __global__ void k2_scatter(const fme_pu* __restrict__ pus, int n, const int* __r
   }
   __syncthreads();
   for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    int wi = fme_dim_index(pus[i].w), hh = fme_dim_index(pus[i].h);
-    if (wi >= 0 && hh >= 0) {
-      int c = wi * 8 + hh;
-      order[s_base[c] + atomicAdd(&s_cnt[c], 1)] = i;
-    }
+    const int c = k2_class_of(pus[i], wantBi);
+    if (c >= 0) order[s_base[c] + atomicAdd(&s_cnt[c], 1)] = i;
   }
 }
 
@@ -192,22 +197,8 @@ __device__ __forceinline__ unsigned cand_row4(const CandTile& t, int r) {
   return __funnelshift_r(p[0], p[1], t.shift);
 }
 
-// SATD of one 8x8 tile: xCalcHADs8x8 (TComRdCost.cpp:1330-1425).  o[] holds the source tile as
-// 16 words of u8x4 (row r -> o[2r], o[2r+1]); cand points at the candidate tile's row 0 in smem.
-template <typename OrgRow>
-__device__ __forceinline__ unsigned satd8x8(OrgRow orgRow, const uint8_t* cand, int candPitch) {
-  unsigned d[32];  // d[4r + j] = (res(r,2j), res(r,2j+1)) packed lo/hi
-  const CandTile ct = cand_tile(cand, candPitch);
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    unsigned c0, c1, o0, o1;
-    cand_row8(ct, r, c0, c1);
-    orgRow(r, o0, o1);
-    d[4 * r + 0] = __byte_perm(o0, 0, 0x4140) - __byte_perm(c0, 0, 0x4140);
-    d[4 * r + 1] = __byte_perm(o0, 0, 0x4342) - __byte_perm(c0, 0, 0x4342);
-    d[4 * r + 2] = __byte_perm(o1, 0, 0x4140) - __byte_perm(c1, 0, 0x4140);
-    d[4 * r + 3] = __byte_perm(o1, 0, 0x4342) - __byte_perm(c1, 0, 0x4342);
-  }
+// Transform + sum of an 8x8 residual held as d[4r + j] = (res(r,2j), res(r,2j+1)) packed lo/hi.
+__device__ __forceinline__ unsigned satd8x8_tail(unsigned (&d)[32]) {
   // horizontal: column-index bits 1 and 2 (bit 0 lives inside a word and is folded into the final max)
   // (radix-4: 6 three-input adds per 4 points instead of 8 two-input ones; IADD3 takes negated operands)
 #pragma unroll
@@ -236,16 +227,26 @@ __device__ __forceinline__ unsigned satd8x8(OrgRow orgRow, const uint8_t* cand, 
   return (2 * sum + 2) >> 2;  // TComRdCost.cpp:1421
 }
 
-// SATD of one 4x4 tile: xCalcHADs4x4 (TComRdCost.cpp:1234-1328).  o[r] = source row r (u8x4).
-__device__ __forceinline__ unsigned satd4x4(const unsigned (&o)[4], const uint8_t* cand, int candPitch) {
-  unsigned d[8];
+// SATD of one 8x8 tile: xCalcHADs8x8 (TComRdCost.cpp:1330-1425).  o[] holds the source tile as
+// 16 words of u8x4 (row r -> o[2r], o[2r+1]); cand points at the candidate tile's row 0 in smem.
+template <typename OrgRow>
+__device__ __forceinline__ unsigned satd8x8(OrgRow orgRow, const uint8_t* cand, int candPitch) {
+  unsigned d[32];  // d[4r + j] = (res(r,2j), res(r,2j+1)) packed lo/hi
   const CandTile ct = cand_tile(cand, candPitch);
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    unsigned c = cand_row4(ct, r);
-    d[2 * r + 0] = __byte_perm(o[r], 0, 0x4140) - __byte_perm(c, 0, 0x4140);
-    d[2 * r + 1] = __byte_perm(o[r], 0, 0x4342) - __byte_perm(c, 0, 0x4342);
+  for (int r = 0; r < 8; ++r) {
+    unsigned c0, c1, o0, o1;
+    cand_row8(ct, r, c0, c1);
+    orgRow(r, o0, o1);
+    d[4 * r + 0] = __byte_perm(o0, 0, 0x4140) - __byte_perm(c0, 0, 0x4140);
+    d[4 * r + 1] = __byte_perm(o0, 0, 0x4342) - __byte_perm(c0, 0, 0x4342);
+    d[4 * r + 2] = __byte_perm(o1, 0, 0x4140) - __byte_perm(c1, 0, 0x4140);
+    d[4 * r + 3] = __byte_perm(o1, 0, 0x4342) - __byte_perm(c1, 0, 0x4342);
   }
+  return satd8x8_tail(d);
+}
+
+__device__ __forceinline__ unsigned satd4x4_tail(unsigned (&d)[8]) {
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     unsigned a = d[2 * r], b = d[2 * r + 1];
@@ -258,6 +259,19 @@ __device__ __forceinline__ unsigned satd4x4(const unsigned (&o)[4], const uint8_
 #pragma unroll
   for (int i = 0; i < 8; i += 2) sum = acc_hmax2x2(abs2(d[i]), abs2(d[i + 1]), sum);
   return (2 * sum + 1) >> 1;  // TComRdCost.cpp:1325
+}
+
+// SATD of one 4x4 tile: xCalcHADs4x4 (TComRdCost.cpp:1234-1328).  o[r] = source row r (u8x4).
+__device__ __forceinline__ unsigned satd4x4(const unsigned (&o)[4], const uint8_t* cand, int candPitch) {
+  unsigned d[8];
+  const CandTile ct = cand_tile(cand, candPitch);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    unsigned c = cand_row4(ct, r);
+    d[2 * r + 0] = __byte_perm(o[r], 0, 0x4140) - __byte_perm(c, 0, 0x4140);
+    d[2 * r + 1] = __byte_perm(o[r], 0, 0x4342) - __byte_perm(c, 0, 0x4342);
+  }
+  return satd4x4_tail(d);
 }
 
 template <typename OrgRow>
@@ -349,11 +363,76 @@ __device__ __forceinline__ void stage_rows(unsigned dst, const uint8_t* src, int
   }
 }
 
+// The same transforms for a source block that is already held as carry-tolerant 16-bit pairs (the pattern
+// 2*org - pred of bi-predictive refinement, samples in [-255, 510]): ou[4r + j] = (pat(r,2j), pat(r,2j+1)) for an 8x8
+// tile, ou[2r + j] for a 4x4 tile.  Residuals stay within +-510, the 8x8 coefficients within +-32640: int16 fields.
+__device__ __forceinline__ unsigned satd8x8_p(const unsigned* ou, const uint8_t* cand, int candPitch) {
+  unsigned d[32];
+  const CandTile ct = cand_tile(cand, candPitch);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    unsigned c0, c1;
+    cand_row8(ct, r, c0, c1);
+    d[4 * r + 0] = ou[4 * r + 0] - __byte_perm(c0, 0, 0x4140);
+    d[4 * r + 1] = ou[4 * r + 1] - __byte_perm(c0, 0, 0x4342);
+    d[4 * r + 2] = ou[4 * r + 2] - __byte_perm(c1, 0, 0x4140);
+    d[4 * r + 3] = ou[4 * r + 3] - __byte_perm(c1, 0, 0x4342);
+  }
+  return satd8x8_tail(d);
+}
+__device__ __forceinline__ unsigned satd4x4_p(const unsigned* ou, const uint8_t* cand, int candPitch) {
+  unsigned d[8];
+  const CandTile ct = cand_tile(cand, candPitch);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const unsigned c = cand_row4(ct, r);
+    d[2 * r + 0] = ou[2 * r + 0] - __byte_perm(c, 0, 0x4140);
+    d[2 * r + 1] = ou[2 * r + 1] - __byte_perm(c, 0, 0x4342);
+  }
+  return satd4x4_tail(d);
+}
+// SAD on 16-bit pairs: packed |.| then a dp2a with multipliers (1, 1)
+__device__ __forceinline__ unsigned acc_abs2(unsigned d, unsigned acc) {
+  unsigned r;
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(abs2(d)), "r"(0x0101u), "r"(acc));
+  return r;
+}
+__device__ __forceinline__ unsigned sad8x8_p(const unsigned* ou, const uint8_t* cand, int candPitch) {
+  unsigned s = 0;
+  const CandTile ct = cand_tile(cand, candPitch);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    unsigned c0, c1;
+    cand_row8(ct, r, c0, c1);
+    s = acc_abs2(ou[4 * r + 0] - __byte_perm(c0, 0, 0x4140), s);
+    s = acc_abs2(ou[4 * r + 1] - __byte_perm(c0, 0, 0x4342), s);
+    s = acc_abs2(ou[4 * r + 2] - __byte_perm(c1, 0, 0x4140), s);
+    s = acc_abs2(ou[4 * r + 3] - __byte_perm(c1, 0, 0x4342), s);
+  }
+  return s;
+}
+__device__ __forceinline__ unsigned sad4x4_p(const unsigned* ou, const uint8_t* cand, int candPitch) {
+  unsigned s = 0;
+  const CandTile ct = cand_tile(cand, candPitch);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const unsigned c = cand_row4(ct, r);
+    s = acc_abs2(ou[2 * r + 0] - __byte_perm(c, 0, 0x4140), s);
+    s = acc_abs2(ou[2 * r + 1] - __byte_perm(c, 0, 0x4342), s);
+  }
+  return s;
+}
+
 // Distortion of one lane unit against the candidate at `cand` (row 0 of the unit's first tile).
-template <int TS>
+template <int TS, bool BI = false>
 __device__ __forceinline__ unsigned unit_dist(const unsigned* o, const uint8_t* cand, int candPitch, int tile1Off,
                                               bool had) {
-  if constexpr (TS == 8) {
+  if constexpr (BI && TS == 8) {
+    return had ? satd8x8_p(o, cand, candPitch) : sad8x8_p(o, cand, candPitch);
+  } else if constexpr (BI) {
+    return had ? satd4x4_p(o, cand, candPitch) + satd4x4_p(o + 8, cand + tile1Off, candPitch)
+               : sad4x4_p(o, cand, candPitch) + sad4x4_p(o + 8, cand + tile1Off, candPitch);
+  } else if constexpr (TS == 8) {
     auto row = [&](int r, unsigned& lo, unsigned& hi) { lo = o[2 * r]; hi = o[2 * r + 1]; };
     return had ? satd8x8(row, cand, candPitch) : sad8x8(row, cand, candPitch);
   } else {
@@ -364,7 +443,10 @@ __device__ __forceinline__ unsigned unit_dist(const unsigned* o, const uint8_t* 
   }
 }
 
-template <int TS, int A>
+// BI = bi-predictive refinement records (FME_PU_BI): the source block is the pattern 2*org - P_other, P_other being
+// the other list's uni-prediction = plane P[mvY&3][mvX&3] of slot err[0] at the integer part of the MV packed in err[1]
+// (TEncSearch.cpp:4462-4472, TComYuv::removeHighFreq without clipping).  Everything else is the same search.
+template <int TS, int A, bool BI>
 __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__ order, int first, int count,
                                      const fme_pu* __restrict__ pus, fme_result* __restrict__ res,
                                      const uint8_t* __restrict__ planes, const uint8_t* __restrict__ org,
@@ -376,6 +458,7 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   // PUs with more than 32 units (64x64, 64x48, 48x64: one PU per pack, 8x8 tiles, 16-byte granules): every lane
   // also serves unit lane + 32, whose source tile is parked in shared memory
   const bool twoUnits = TS == 8 && A == 16 && U > 32;
+  [[maybe_unused]] long long otherOff = 0;     // BI: byte offset of the other list's prediction block in the plane set
   const int gPitch = g.pitch, gOrgPitch = g.orgPitch;
   const int gPlaneBytes = (int)g.planeBytes;   // < 2^31 (padded 8K plane: 4480 * 7936)
   const int lanesPerPu = ci.lanes;             // power of two
@@ -401,6 +484,14 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
               (long long)((Y + g.M) * gPitch + alignX);
     ox = min(max((int)p.x, 0), g.W - w);
     oy = min(max((int)p.y, 0), g.H - h);
+    if constexpr (BI) {
+      const int oslot = min((int)(p.err[0] & 0xff), g.numSlots - 1);
+      const int omx = (int)(short)(p.err[1] & 0xffff), omy = (int)(short)(p.err[1] >> 16);
+      const int X2 = min(max(p.x + (omx >> 2), -(g.M - 8)), g.W + g.M - 8 - w);
+      const int Y2 = min(max(p.y + (omy >> 2), -(g.M - 8)), g.H + g.M - 8 - h);
+      otherOff = (long long)oslot * (long long)g.slotBytes +
+                 (long long)(((omy & 3) * 4 + (omx & 3)) * gPlaneBytes + (Y2 + g.M) * gPitch + X2 + g.M);
+    }
   }
 
   // ---- staging geometry ----
@@ -449,16 +540,53 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   stage(0);  // in flight while the source tiles are fetched
 
   // ---- source tile(s) of this lane into registers ----
-  constexpr int OW = 16 / 2 * 2 / (TS == 8 ? 1 : 2);  // 16 words (one 8x8 tile) or 8 words (two 4x4 tiles)
+  // packed u8: 16 words (one 8x8 tile) or 8 words (two 4x4 tiles); BI: 16-bit pattern pairs, 32 or 16 words
+  constexpr int OW = BI ? (TS == 8 ? 32 : 16) : (TS == 8 ? 16 : 8);
   unsigned o[OW];
   const bool had = useHad && !lossless;
   // unit -> byte offset of its (first) tile inside a staged region, offset of the second 4x4 tile, source load
   int uOff = 0, u1Off = 0;
   bool uOn = false;
+  // BI: pattern pair word = 2 * (source pair) - (other prediction pair); a plain 32-bit subtraction leaves the
+  // carry-tolerant form (value = hi * 65536 + lo with signed lo) that the transforms expect
+  auto patPair = [](unsigned srcWord, unsigned predWord, unsigned sel) {
+    return 2u * __byte_perm(srcWord, 0, sel) - __byte_perm(predWord, 0, sel);
+  };
   auto loadUnit = [&](int u) {
     uOn = laneActive && u < U;
     if (!uOn) return;
-    if constexpr (TS == 8) {
+    if constexpr (BI && TS == 8) {
+      int ty = u / ci.tilesX, tx = u - ty * ci.tilesX;
+      uOff = ty * 8 * sg.RW + tx * 8;
+      const uint8_t* src = org + (size_t)(oy + ty * 8) * gOrgPitch + ox + tx * 8;
+      const uint8_t* oth = planes + otherOff + (long long)(ty * 8 * gPitch + tx * 8);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        unsigned s0, s1, p0, p1;
+        ldg_row8(src + (size_t)r * gOrgPitch, s0, s1);
+        ldg_row8(oth + (size_t)r * gPitch, p0, p1);
+        o[4 * r + 0] = patPair(s0, p0, 0x4140); o[4 * r + 1] = patPair(s0, p0, 0x4342);
+        o[4 * r + 2] = patPair(s1, p1, 0x4140); o[4 * r + 3] = patPair(s1, p1, 0x4342);
+      }
+    } else if constexpr (BI) {
+      int t0 = 2 * u, t1 = 2 * u + 1;
+      int ty0 = t0 / ci.tilesX, tx0 = t0 - ty0 * ci.tilesX;
+      int ty1 = t1 / ci.tilesX, tx1 = t1 - ty1 * ci.tilesX;
+      uOff = ty0 * 4 * sg.RW + tx0 * 4;
+      u1Off = (ty1 * 4 * sg.RW + tx1 * 4) - uOff;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int ty = k ? ty1 : ty0, tx = k ? tx1 : tx0;
+        const uint8_t* src = org + (size_t)(oy + ty * 4) * gOrgPitch + ox + tx * 4;
+        const uint8_t* oth = planes + otherOff + (long long)(ty * 4 * gPitch + tx * 4);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const unsigned sw = ldg_row4(src + (size_t)r * gOrgPitch), pw = ldg_row4(oth + (size_t)r * gPitch);
+          o[8 * k + 2 * r + 0] = patPair(sw, pw, 0x4140);
+          o[8 * k + 2 * r + 1] = patPair(sw, pw, 0x4342);
+        }
+      }
+    } else if constexpr (TS == 8) {
       int ty = u / ci.tilesX, tx = u - ty * ci.tilesX;
       uOff = ty * 8 * sg.RW + tx * 8;
       const uint8_t* src = org + (size_t)(oy + ty * 8) * gOrgPitch + ox + tx * 8;
@@ -483,7 +611,7 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   [[maybe_unused]] uint2* const so2 = reinterpret_cast<uint2*>(smem + K2_STAGE_BYTES) + lane;  // [row][lane]
   [[maybe_unused]] int uOff2 = 0;
   [[maybe_unused]] bool uOn2 = false;
-  if constexpr (TS == 8 && A == 16) {
+  if constexpr (TS == 8 && A == 16 && !BI) {
     if (twoUnits) {
       const int u = unit0 + 32;
       uOn2 = laneActive && u < U;
@@ -544,8 +672,15 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
       const int bits = (ox3 < 0 ? bitsX[0] : ox3 == 0 ? bitsX[1] : bitsX[2]) +
                        (oy3 < 0 ? bitsY[0] : oy3 == 0 ? bitsY[1] : bitsY[2]);
       unsigned dist = 0;
-      if (uOn) dist = unit_dist<TS>(o, region + uOff + candOff, sg.RW, u1Off, had);
-      if constexpr (TS == 8 && A == 16) {
+      if (uOn) dist = unit_dist<TS, BI>(o, region + uOff + candOff, sg.RW, u1Off, had);
+      if constexpr (TS == 8 && A == 16 && BI) {
+        if (twoUnits) {  // rare (64x64, 64x48, 48x64 bi PUs): the second unit's pattern is rebuilt per candidate
+          loadUnit(unit0 + 32);
+          if (uOn) dist += unit_dist<TS, BI>(o, region + uOff + candOff, sg.RW, u1Off, had);
+          loadUnit(unit0);
+        }
+      }
+      if constexpr (TS == 8 && A == 16 && !BI) {
         if (uOn2) {
           auto row2 = [&](int r, unsigned& lo, unsigned& hi) { const uint2 v = so2[r * 32]; lo = v.x; hi = v.y; };
           dist += had ? satd8x8(row2, region + uOff2 + candOff, sg.RW) : sad8x8(row2, region + uOff2 + candOff, sg.RW);
@@ -588,6 +723,7 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   __syncwarp();
 }
 
+template <bool BI>
 #ifdef FME_K2_MAXREG
 __global__ void __maxnreg__(FME_K2_MAXREG)
 #else
@@ -632,12 +768,12 @@ k2_refine(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, const ui
     first += s_classOff[v];
 #define K2_ARGS ci, order, first, count, pus, res, planes, org, g, s_lut, useHad, smem
     if (ci.ts == 8) {
-      if (ci.w >= 16) k2_pack<8, 16>(K2_ARGS);
-      else k2_pack<8, 8>(K2_ARGS);
+      if (ci.w >= 16) k2_pack<8, 16, BI>(K2_ARGS);
+      else k2_pack<8, 8, BI>(K2_ARGS);
     } else {
-      if (ci.w >= 16) k2_pack<4, 16>(K2_ARGS);
-      else if (ci.w >= 8) k2_pack<4, 8>(K2_ARGS);
-      else k2_pack<4, 4>(K2_ARGS);
+      if (ci.w >= 16) k2_pack<4, 16, BI>(K2_ARGS);
+      else if (ci.w >= 8) k2_pack<4, 8, BI>(K2_ARGS);
+      else k2_pack<4, 4, BI>(K2_ARGS);
     }
 #undef K2_ARGS
   }
@@ -721,30 +857,42 @@ cudaError_t fme_launch_clear_results(fme_result* d_res, int n, cudaStream_t s, i
   return cudaGetLastError();
 }
 
-cudaError_t fme_launch_k2(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_pu* d_pus, int n,
-                          fme_result* d_res, const uint32_t* d_costLut, int useHad, const FmeK2Scratch& sc,
-                          int numSMs, cudaStream_t s, int64_t* launches) {
-  if (n <= 0) return cudaSuccess;
+template <bool BI>
+static cudaError_t launch_k2_pass(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_pu* d_pus, int n,
+                                  fme_result* d_res, const uint32_t* d_costLut, int useHad, const FmeK2Scratch& sc,
+                                  int numSMs, cudaStream_t s, int64_t* launches) {
   // classCount[64], classCursor[64] and the work counter are adjacent (fme_create)
   cudaError_t e = cudaMemsetAsync(sc.classCount, 0, sizeof(int) * (2 * FME_MAX_CLASSES + 1), s);
   if (e != cudaSuccess) return e;
   int blocks = min(numSMs * 4, (n + 255) / 256);
-  k2_count<<<blocks, 256, 0, s>>>(d_pus, n, sc.classCount);
-  k2_scatter<<<blocks, 256, 0, s>>>(d_pus, n, sc.classCount, sc.classOffset, sc.packOffset, sc.classCursor, sc.order);
+  k2_count<<<blocks, 256, 0, s>>>(d_pus, n, sc.classCount, BI ? 1 : 0);
+  k2_scatter<<<blocks, 256, 0, s>>>(d_pus, n, sc.classCount, sc.classOffset, sc.packOffset, sc.classCursor, sc.order,
+                                    BI ? 1 : 0);
   *launches += 2;
   static bool attrSet[64] = {};  // per device: the opt-in to > 48 KB dynamic shared memory is a per-device attribute
   const int smemBytes = K2_WARPS * K2_SMEM_PER_WARP;
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attrSet[dev & 63]) {
-    e = cudaFuncSetAttribute(k2_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
+    e = cudaFuncSetAttribute(k2_refine<BI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
     if (e != cudaSuccess) return e;
     attrSet[dev & 63] = true;
   }
-  k2_refine<<<numSMs, K2_THREADS, smemBytes, s>>>(d_pus, d_res, d_planes, d_org, g, d_costLut, useHad, sc.order,
-                                                  sc.classOffset, sc.packOffset, sc.workCounter);
+  k2_refine<BI><<<numSMs, K2_THREADS, smemBytes, s>>>(d_pus, d_res, d_planes, d_org, g, d_costLut, useHad, sc.order,
+                                                      sc.classOffset, sc.packOffset, sc.workCounter);
   ++*launches;
   return cudaGetLastError();
+}
+
+// biPred != 0: a second binning + refinement pass serves the bi-predictive refinement records (FME_PU_BI); with
+// biPred == 0 such records are left untouched (the synchronous entry points reject them).
+cudaError_t fme_launch_k2(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_pu* d_pus, int n,
+                          fme_result* d_res, const uint32_t* d_costLut, int useHad, int biPred, const FmeK2Scratch& sc,
+                          int numSMs, cudaStream_t s, int64_t* launches) {
+  if (n <= 0) return cudaSuccess;
+  cudaError_t e = launch_k2_pass<false>(g, d_planes, d_org, d_pus, n, d_res, d_costLut, useHad, sc, numSMs, s, launches);
+  if (e != cudaSuccess || !biPred) return e;
+  return launch_k2_pass<true>(g, d_planes, d_org, d_pus, n, d_res, d_costLut, useHad, sc, numSMs, s, launches);
 }
 
 cudaError_t fme_launch_pred_error(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_mc_pu* d_pus,

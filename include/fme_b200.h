@@ -45,6 +45,13 @@ typedef enum fme_status {
 
 /* fme_pu.flags */
 #define FME_PU_LOSSLESS 0x01 /* bIsLosslessCoded: SAD instead of Hadamard (TEncSearch.cpp:5258, 1604) */
+#define FME_PU_BI 0x04 /* bi-predictive refinement call (bBi, TEncSearch.cpp:4462-4472): the search pattern is
+                          2*org - P_other (TComYuv::removeHighFreq, no clipping), P_other = the other list's
+                          uni-prediction (xPredInterBlk, bi = false) from reference slot err[0] & 0xff at the
+                          quarter-pel MV packed in err[1] (x = low, y = high int16, after clipMv).  err[] carries no
+                          error grid for such records: the reference's NN_pred runs on stale globals there (its
+                          integer search is xPatternSearch, which never refreshes array_e), so the NN fields of the
+                          result are meaningless.  Needs fme_config.biPred = 1. */
 #define FME_PU_ERR_ON_GPU 0x02 /* err[] is ignored; the 3x3 integer error surface is computed on the
                                   device by the K0 pass (TEncSearch.cpp:5037-5050 semantics)         */
 
@@ -64,7 +71,9 @@ typedef struct fme_config {
                            oracle.  1: fused multiply-add in the dense layers of the compile-time fast paths -- half the
                            FP32 operations (measured: K3 0.153 -> 0.125 ms per 858 000 PUs), within BASELINE's NN
                            tolerance (class agreement >= 99.9 %), not bit-exact. */
-  int32_t reserved[6];
+  int32_t biPred;       /* 1: serve FME_PU_BI records with a second binning + refinement pass per submit (random
+                           access configurations); 0 (default): such records are rejected / left untouched */
+  int32_t reserved[5];
 } fme_config;
 
 /* One PU's integer-ME hand-off: what xMotionEstimation has in hand at

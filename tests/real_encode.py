@@ -1,7 +1,7 @@
 """Loader for tests/golden/real_encode_416x240*.npz: the reference encoder's own FME calls captured on real
 416x240 encodes (oracle/capture/make_capture.py): lowdelay_P QP22 (3 frames) and QP37 (2 frames, faster motion),
-and randomaccess QP32 (4 frames: B slices, two lists; the bi-prediction refinement calls are flagged `uni == False`
-and skipped -- that pattern is 2*org - pred, outside this path's scope)."""
+and randomaccess QP32 (4 frames: B slices, two lists; bi-predictive refinement calls are flagged `uni == False` and
+become FME_PU_BI records: pattern 2*org - other list's prediction, other slot / MV in err[0] / err[1])."""
 import os
 
 import numpy as np
