@@ -36,13 +36,15 @@ public:
 
   // TEncSearch::init (TEncSearch.cpp:377-1075): picture geometry + the QP that selects the NN weight set
   // (TEncSearch.cpp:472/625/775/925).  weightsDir = ".../DL/blowing" of the reference checkout.
+  // biPred: also serve bi-predictive refinement calls (enqueueBi; random-access configurations)
   Void init(Int picWidth, Int picHeight, Int numRefSlots, Int maxPUsPerBatch, Bool useHadME, Bool fen, Int qp,
-            const char* weightsDir, Int device = 0)
+            const char* weightsDir, Int device = 0, Bool biPred = false)
   {
     fme_config cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.device = device; cfg.width = picWidth; cfg.height = picHeight; cfg.margin = 80; cfg.bitDepth = 8;
     cfg.numRefSlots = numRefSlots; cfg.maxPUs = maxPUsPerBatch; cfg.useHadME = useHadME; cfg.fen = fen;
+    cfg.biPred = biPred;
     check(fme_create(&cfg, &m_ctx));
     const Int wq = (qp == 27 || qp == 32 || qp == 37) ? qp : 22;
     char dir[1024];
@@ -105,6 +107,23 @@ public:
     m_queue.push_back(p);
     return Int(m_queue.size()) - 1;
   }
+  // xMotionEstimation with bBi (TEncSearch.cpp:4462-4472): the search pattern is 2*org - (other list's prediction).
+  // Instead of the pattern buffer (m_cYuvPredTemp) the record names the other list's reference picture and the MV
+  // xPredInterUni used for it (i.e. after pcCU->clipMv); the engine rebuilds the pattern on the device.
+  Int enqueueBi(Int puX, Int puY, Int width, Int height, Int refSlot, const TComMv& mvInt, const TComMv& mvPred,
+                Int otherRefSlot, const TComMv& otherMvClipped, Bool lossless)
+  {
+    fme_pu p;
+    memset(&p, 0, sizeof(p));
+    p.x = Short(puX); p.y = Short(puY); p.w = UChar(width); p.h = UChar(height); p.refSlot = UChar(refSlot);
+    p.flags = UChar(FME_PU_BI | (lossless ? FME_PU_LOSSLESS : 0));
+    p.mvIntX = Short(mvInt.getHor()); p.mvIntY = Short(mvInt.getVer());
+    p.mvPredX = Short(mvPred.getHor()); p.mvPredY = Short(mvPred.getVer());
+    p.err[0] = UInt(otherRefSlot) & 0xff;
+    p.err[1] = (UInt(otherMvClipped.getHor()) & 0xffff) | (UInt(otherMvClipped.getVer()) << 16);
+    m_queue.push_back(p);
+    return Int(m_queue.size()) - 1;
+  }
   Void flush(Int mode = FME_MODE_BOTH)
   {
     m_results.resize(m_queue.size());
@@ -117,7 +136,7 @@ public:
   // TEncSearch::xPatternSearchFracDIF (TEncSearch.h:423-432).  The caller has done what xMotionEstimation does
   // before the call (setPredictor, TEncSearch.cpp:4499); the predictor is passed explicitly because
   // TComRdCost::m_mvPredictor is private.  pcPatternKey must view the source picture set by setOrgPicture
-  // (uni-prediction; the bi-pred refinement pattern of TEncSearch.cpp:4462-4472 is not a picture view).
+  // (uni-prediction; bi-predictive refinement calls, whose pattern is not a picture view, go through enqueueBi).
   Void xPatternSearchFracDIF(Bool bIsLosslessCoded, TComPattern* pcPatternKey, Pel* piRefY, Int iRefStride,
                              TComMv* pcMvInt, const TComMv& mvPred, TComMv& rcMvHalf, TComMv& rcMvQter,
                              Distortion& ruiCost)
