@@ -642,6 +642,8 @@ static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, 
           return fail(FME_ERR_STATE, "PU %d references slot %d which holds no picture", i, heads[i].refSlot);
         if (!valid_pu_size(heads[i].w, heads[i].h))
           return fail(FME_ERR_INVALID, "PU %d: %dx%d is not an HEVC PU size", i, heads[i].w, heads[i].h);
+        if (heads[i].flags & FME_PU_BI)
+          return fail(FME_ERR_INVALID, "PU %d: FME_PU_BI needs a full record (the other list's slot and MV live in err[])", i);
       }
     }
     for (int b = 0; b < FME_NBUF; ++b)
