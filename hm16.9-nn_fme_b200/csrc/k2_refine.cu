@@ -635,11 +635,12 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   unsigned hBest = 0xffffffffu, qBest = 0xffffffffu;
   int hBestI = 9, qBestI = 0;
   // MV bits per axis for offsets -1, 0, +1.  Half stage, cost scale 1 (TEncSearch.cpp:4531): ((int<<1)+h)<<1 - pred
-  int bitsX[3], bitsY[3];
+  // (bit counts are < 64: the three of an axis are packed into one register, byte t for offset t - 1)
+  unsigned bitsX = 0, bitsY = 0;
 #pragma unroll
   for (int t = 0; t < 3; ++t) {
-    bitsX[t] = golomb_bits((((mvIntX << 1) + (t - 1)) << 1) - predX);
-    bitsY[t] = golomb_bits((((mvIntY << 1) + (t - 1)) << 1) - predY);
+    bitsX |= (unsigned)golomb_bits((((mvIntX << 1) + (t - 1)) << 1) - predX) << (8 * t);
+    bitsY |= (unsigned)golomb_bits((((mvIntY << 1) + (t - 1)) << 1) - predY) << (8 * t);
   }
 #pragma unroll 1
   for (int s = 0; s < 12; ++s) {
@@ -669,8 +670,7 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
         candOff = (alignX + (qx >> 2)) & (A - 1);
       }
       // exp-Golomb bit counts of the three possible vector components per axis were computed once per stage
-      const int bits = (ox3 < 0 ? bitsX[0] : ox3 == 0 ? bitsX[1] : bitsX[2]) +
-                       (oy3 < 0 ? bitsY[0] : oy3 == 0 ? bitsY[1] : bitsY[2]);
+      const int bits = (int)(((bitsX >> (8 * ox3 + 8)) & 0xffu) + ((bitsY >> (8 * oy3 + 8)) & 0xffu));
       unsigned dist = 0;
       if (uOn) dist = unit_dist<TS, BI>(o, region + uOff + candOff, sg.RW, u1Off, had);
       if constexpr (TS == 8 && A == 16 && BI) {
@@ -706,10 +706,11 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
       qBestI = 0;
       stage(4);
       // quarter stage, cost scale 0 (TEncSearch.cpp:5260): (((int<<1)+half)<<1) + q - pred
+      bitsX = bitsY = 0;
 #pragma unroll
       for (int t = 0; t < 3; ++t) {
-        bitsX[t] = golomb_bits((((mvIntX << 1) + bhx) << 1) + (t - 1) - predX);
-        bitsY[t] = golomb_bits((((mvIntY << 1) + bhy) << 1) + (t - 1) - predY);
+        bitsX |= (unsigned)golomb_bits((((mvIntX << 1) + bhx) << 1) + (t - 1) - predX) << (8 * t);
+        bitsY |= (unsigned)golomb_bits((((mvIntY << 1) + bhy) << 1) + (t - 1) - predY) << (8 * t);
       }
     }
   }
