@@ -359,11 +359,11 @@ def run_gpu(args):
         dom = max(("k1_interp", "k2_refine"), key=lambda k: kavg[k])
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
         # (1080p workload only; the plane set of 4 references, 173 MB, does not fit the 126 MB L2)
-        ncu_traffic = {"k2_refine": 1.592214e9 + 22.156e6, "k1_interp": 2.09e6 + 111.36e6} if not banded else {}
+        ncu_traffic = {"k2_refine": 1.646401e9 + 20.994e6, "k1_interp": 2.09e6 + 111.36e6} if not banded else {}
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved"], "peak": peak, "unit": "GB/s",
                     "frac": kernels[dom]["frac"], "traffic": ncu_traffic.get(dom), "peak_source": peak_src,
                     "traffic_source": "profiles/r1_k2_metrics_v6.txt (ncu --set full, one launch)",
-                    "note": "K2 is INT-issue/pipe bound (ncu: issue_active 67 %, 596 thread instructions per 8x8 tile-candidate, "
+                    "note": "K2 is INT-issue/pipe bound (ncu: issue_active 67 %, 591 thread instructions per 8x8 tile-candidate, "
                             "DRAM 25 % busy); the HBM fraction is reported because the contract asks for bound in {hbm, tensor}; "
                             "kernels.k2_refine.int_lane_rate_frac is the fraction of the 148x128-lane integer rate; "
                             "the timed K2 pass includes the two binning launches (k2_count, k2_scatter, about 3 % of it)"}
