@@ -471,6 +471,41 @@ def test_submit_heads_equals_records_with_device_surface(small):
         eng.submit_heads(bad, fme.MODE_STD)
 
 
+def test_hostile_records_on_the_unvalidated_path_do_not_poison_the_context(small):
+    """The asynchronous entry points skip per-record validation.  Out-of-contract records (positions and vectors far
+    outside the picture, slots that do not exist, random flags incl. FME_PU_BI with random err[], sizes that are
+    not PU shapes) must neither fault nor disturb later work: coordinates are clamped on the device, unknown shapes
+    are skipped.  (compute-sanitizer is not available on this pool, so this is the memory-safety net.)"""
+    import torch
+    eng, g, recs = small
+    hostile = fme.Fme(128, 96, num_ref_slots=2, max_pus=60000, bi_pred=True)
+    hostile.set_slice(float(g["small_lambda"][0]))
+    hostile.set_nn_weights(fme.nn_weights.load_blob(22))
+    hostile.upload_org(g["small_org"])
+    for s in range(2):
+        hostile.upload_ref(s, g["small_refs"][s])
+    clean = golden_recs(g)
+    base = hostile.submit(clean, fme.MODE_STD)
+    rng = np.random.default_rng(99)
+    n = 60000
+    bad = np.zeros(n, fme.PU_DTYPE)
+    dims = np.array([4, 8, 12, 16, 24, 32, 48, 64, 0, 20, 255])
+    bad["x"] = rng.integers(-32768, 32768, n); bad["y"] = rng.integers(-32768, 32768, n)
+    bad["w"] = dims[rng.integers(0, len(dims), n)]; bad["h"] = dims[rng.integers(0, len(dims), n)]
+    bad["refSlot"] = rng.integers(0, 256, n); bad["flags"] = rng.integers(0, 256, n)
+    for f in ("mvIntX", "mvIntY", "mvPredX", "mvPredY"):
+        bad[f] = rng.integers(-32768, 32768, n)
+    bad["err"] = rng.integers(0, 1 << 32, bad["err"].shape, dtype=np.uint64).astype(np.uint32)
+    h_in = torch.from_numpy(bad.view(np.uint8).reshape(n, -1).copy()).pin_memory()
+    h_out = torch.zeros((n, 16), dtype=torch.uint8).pin_memory()
+    for mode in (fme.MODE_BOTH, fme.MODE_STD, fme.MODE_NN):
+        hostile.submit_async(h_in.data_ptr(), n, h_out.data_ptr(), mode)
+    hostile.synchronize()                       # raises if a kernel faulted
+    again = hostile.submit(clean, fme.MODE_STD)  # the context still computes the right answers
+    assert np.array_equal(again.view(np.uint8), base.view(np.uint8))
+    hostile.close()
+
+
 def test_pipelined_async_matches_synchronous():
     """fme_submit_async / fme_wait_oldest with pinned buffers: copies of frame i+1 overlap the kernels of frame i
     (and i+2: staging rings of three inside the ctx); results must equal the synchronous call frame by frame."""
