@@ -237,6 +237,8 @@ int fme_create(const fme_config* cfg, fme_ctx** out) {
   // at least one CTU: the kernels clamp a PU's source block into [0, W - w] x [0, H - h] and rely on w <= W, h <= H
   if (cfg->width < 64 || cfg->height < 64 || cfg->width > 16384 || cfg->height > 16384)
     return fail(FME_ERR_INVALID, "unsupported picture size %dx%d (64x64 .. 16384x16384)", cfg->width, cfg->height);
+  if ((cfg->width & 7) || (cfg->height & 7))
+    return fail(FME_ERR_INVALID, "picture size %dx%d is not a multiple of the minimum CU size 8", cfg->width, cfg->height);
   if (cfg->margin < 16 || (cfg->margin & 15)) return fail(FME_ERR_INVALID, "margin must be a multiple of 16, >= 16");
   if (cfg->bitDepth != 8) return fail(FME_ERR_INVALID, "frame-level passes support bitDepth 8 only");
   if (cfg->numRefSlots < 1 || cfg->numRefSlots > 64) return fail(FME_ERR_INVALID, "numRefSlots out of range");

@@ -292,6 +292,9 @@ def test_edge_cases(small):
 
 
 def test_state_errors():
+    for bad_size in ((32, 64), (64, 60), (100, 96)):   # smaller than a CTU / not a multiple of the minimum CU size
+        with pytest.raises(fme.FmeError):
+            fme.Fme(*bad_size)
     eng = fme.Fme(64, 64, num_ref_slots=1, max_pus=8)
     r = np.zeros(1, fme.PU_DTYPE)
     r["w"], r["h"] = 8, 8
