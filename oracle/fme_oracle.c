@@ -482,7 +482,7 @@ void orc_run_pu_list(const orc_pel* org, int os, const orc_pel* const* refs, int
       orc_mc_luma(refs[oslot] + (p->y + (omy >> 2)) * rs + p->x + (omx >> 2), rs, pred, 64, p->w, p->h, omx & 3, omy & 3);
       orc_bi_pattern(org + p->y * os + p->x, os, pred, 64, pat, 64, p->w, p->h);
       orc_frac_dif(pat, 64, p->w, p->h, refs[p->refSlot] + p->y * rs + p->x, rs, p->mvIntX, p->mvIntY, p->mvPredX,
-                   p->mvPredY, lambda, useHad, 0, hxy, qxy, &c);
+                   p->mvPredY, lambda, useHad, p->flags & 1 /* bIsLosslessCoded */, hxy, qxy, &c);
       r.halfX = (int8_t)hxy[0]; r.halfY = (int8_t)hxy[1];
       r.qterX = (int8_t)qxy[0]; r.qterY = (int8_t)qxy[1];
       r.cost = c;
@@ -490,7 +490,8 @@ void orc_run_pu_list(const orc_pel* org, int os, const orc_pel* const* refs, int
       int16_t hxy[2], qxy[2];
       uint32_t c;
       orc_frac_dif(org + p->y * os + p->x, os, p->w, p->h, refs[p->refSlot] + p->y * rs + p->x, rs, p->mvIntX,
-                   p->mvIntY, p->mvPredX, p->mvPredY, lambda, useHad, 0, hxy, qxy, &c);
+                   p->mvIntY, p->mvPredX, p->mvPredY, lambda, useHad, p->flags & 1 /* bIsLosslessCoded */, hxy,
+                   qxy, &c);
       r.halfX = (int8_t)hxy[0]; r.halfY = (int8_t)hxy[1];
       r.qterX = (int8_t)qxy[0]; r.qterY = (int8_t)qxy[1];
       r.cost = c;

@@ -229,7 +229,7 @@ void hmref_run_pu_list(short* org, int orgStride, short* const* refs, int refStr
       short hxy[2], qxy[2];
       unsigned c;
       hmref_frac_dif(org + p.y * orgStride + p.x, orgStride, p.w, p.h, refs[p.refSlot] + p.y * refStride + p.x,
-                     refStride, p.mvIntX, p.mvIntY, p.mvPredX, p.mvPredY, 0, hxy, qxy, &c);
+                     refStride, p.mvIntX, p.mvIntY, p.mvPredX, p.mvPredY, p.flags & 1 /* bIsLosslessCoded */, hxy, qxy, &c);
       r.halfX = hxy[0]; r.halfY = hxy[1]; r.qterX = qxy[0]; r.qterY = qxy[1]; r.cost = c;
     }
     if (mode & 2) {

@@ -246,6 +246,7 @@ def test_full_416x240_list_vs_oracle(use_had):
     W, H = 416, 240
     org, refs, motions = fme.pu_list.synth_frames(W, H, n_refs=4, seed=1000)
     recs = fme.pu_list.make_records(W, H, motions, seed=1, amp=True)
+    recs["flags"][::7] |= fme.PU_LOSSLESS   # bIsLosslessCoded PUs take SAD even with HadamardME (TEncSearch.cpp:5258)
     frame = ob.CpuFrame(org, refs)
     frame.oracle_fill_surface(recs)
     blob = fme.nn_weights.load_blob(22)
@@ -263,6 +264,43 @@ def test_full_416x240_list_vs_oracle(use_had):
             bad = np.nonzero(got[f] != want[f])[0]
             assert len(bad) == 0, (f, len(bad), recs[bad[:4]], got[bad[:4]], want[bad[:4]])
         eng.close()
+
+
+@pytest.mark.parametrize("use_had", [True, False])
+def test_bi_predictive_refinement_all_shapes_vs_oracle(use_had):
+    """FME_PU_BI records (pattern 2*org - other list's prediction) for every PU shape incl. AMP and the > 32-tile
+    shapes, random other-list slots and quarter-pel MVs, Hadamard and SAD, a few lossless: engine == oracle (whose bi
+    path is pinned by the reference encoder's own 20 291 bi calls, tests/test_real_encode_cpu.py)."""
+    W, H = 416, 240
+    org, refs, motions = fme.pu_list.synth_frames(W, H, n_refs=4, seed=1700)
+    recs = fme.pu_list.make_records(W, H, motions, seed=3, amp=True)
+    rng = np.random.default_rng(17)
+    recs = recs[rng.permutation(len(recs))[:12000]].copy()
+    recs["flags"] = fme.PU_BI | np.where(rng.random(len(recs)) < 0.05, fme.PU_LOSSLESS, 0).astype(np.uint8)
+    recs["err"] = 0
+    recs["err"][:, 0] = rng.integers(0, 4, len(recs))
+    omx, omy = rng.integers(-60, 61, len(recs)), rng.integers(-60, 61, len(recs))
+    recs["err"][:, 1] = (omx & 0xffff) | ((omy & 0xffff) << 16)
+    mixed = recs.copy()
+    mixed["flags"][::3] &= ~np.uint8(fme.PU_BI)          # uni and bi records interleaved in one batch
+    frame = ob.CpuFrame(org, refs)
+    lam = fme.pu_list.slice_lambda(32, had_me=use_had)
+    eng = fme.Fme(W, H, num_ref_slots=4, max_pus=len(recs), use_had=use_had, bi_pred=True)
+    eng.set_slice(lam)
+    eng.upload_org(org)
+    for s in range(4):
+        eng.upload_ref(s, refs[s])
+    for batch in (recs, mixed):
+        got = eng.submit(batch, fme.MODE_STD)
+        want = frame.oracle_run(batch, 1, lam, use_had, None)
+        for f in ("halfX", "halfY", "qterX", "qterY", "cost"):
+            bad = np.nonzero(got[f] != want[f])[0]
+            assert len(bad) == 0, (f, len(bad), batch[bad[:4]], got[bad[:4]], want[bad[:4]])
+    plain = fme.Fme(W, H, num_ref_slots=4, max_pus=len(recs), use_had=use_had)     # biPred = 0
+    with pytest.raises(fme.FmeError):
+        plain.submit(recs[:8], fme.MODE_STD)
+    plain.close()
+    eng.close()
 
 
 def test_edge_cases(small):
