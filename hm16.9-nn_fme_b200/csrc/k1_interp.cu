@@ -78,16 +78,19 @@ constexpr int K1_PREF = (K1_IN_WORDS + K1_THREADS - 1) / K1_THREADS;  // input w
 
 // Persistent: gridDim.x CTAs walk the tile list; the next tile's input words are fetched into registers before the
 // current tile's filtering starts and parked in shared memory after it, so global latency hides behind stages B/C.
-__global__ void __launch_bounds__(K1_THREADS, 2)
+#ifndef FME_K1_CTAS
+#define FME_K1_CTAS 3
+#endif
+__global__ void __launch_bounds__(K1_THREADS, FME_K1_CTAS)
 k1_interp_planes(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int M, int Wp, int Hp, int pitch,
-                 size_t planeBytes, uint8_t* __restrict__ planes, int tilesX, int nTiles) {
+                 size_t planeBytes, uint8_t* __restrict__ planes, int tilesX, unsigned tilesXRcp, int nTiles) {
   __shared__ __align__(16) uint8_t s_in[IN_H][IN_W];
   __shared__ __align__(16) int16_t s_t[4][IN_H][TW];
 
   const int tid = threadIdx.x;
   unsigned pref[K1_PREF];
   auto fetch = [&](int tile) {
-    const int ty = tile / tilesX, tx = tile - ty * tilesX;
+    const int ty = (int)__umulhi((unsigned)tile, tilesXRcp), tx = tile - ty * tilesX;  // tilesXRcp = ceil(2^32 / tilesX)
     const int pxBase = tx * TW - M - 4, pyBase = ty * TH - M - 3;  // picture coords of input (0,0); pxBase % 4 == 0
 #pragma unroll
     for (int k = 0; k < K1_PREF; ++k) {
@@ -106,7 +109,7 @@ k1_interp_planes(const uint8_t* __restrict__ pic, int picPitch, int W, int H, in
   int tile = blockIdx.x;
   if (tile < nTiles) fetch(tile);
   for (; tile < nTiles; tile += gridDim.x) {
-    const int tyI = tile / tilesX, txI = tile - tyI * tilesX;
+    const int tyI = (int)__umulhi((unsigned)tile, tilesXRcp), txI = tile - tyI * tilesX;
     const int x0 = txI * TW, y0 = tyI * TH;  // padded-plane coordinates of the tile
     __syncthreads();  // every thread is done with s_in / s_t of the previous tile
     park();
@@ -160,6 +163,7 @@ k1_interp_planes(const uint8_t* __restrict__ pic, int picPitch, int W, int H, in
     const int gy0 = y0 + r0, gx = x0 + q * 4;
     const bool inside = gx < Wp && gy0 < Hp;  // Wp is a multiple of 4
     uint8_t* outBase = planes + (size_t)gy0 * pitch + gx;
+    const int planeBytes32 = (int)planeBytes;  // 16 planes of an 8K picture stay below 2^31 bytes
 #pragma unroll 1
     for (int fx = fxHalf; fx < 4 && inside; fx += 2) {
       int2 v[11];  // rows r0 .. r0+10 of T_fx (output row r is centred on input row r+3)
@@ -172,7 +176,7 @@ k1_interp_planes(const uint8_t* __restrict__ pic, int picPitch, int W, int H, in
           const int2 c = v[r + 3];
           int a0 = dp2a_lo(c.x, 0x0001, 8224) >> 6, a1 = dp2a_lo(c.x, 0x0100, 8224) >> 6;
           int a2 = dp2a_lo(c.y, 0x0001, 8224) >> 6, a3 = dp2a_lo(c.y, 0x0100, 8224) >> 6;
-          *reinterpret_cast<unsigned*>(outBase + (size_t)(0 * 4 + fx) * planeBytes + (size_t)r * pitch) =
+          *reinterpret_cast<unsigned*>(outBase + (fx * planeBytes32 + r * pitch)) =
               pack_sat_u8x4(a0, a1, a2, a3);
         }
       }
@@ -204,7 +208,7 @@ k1_interp_planes(const uint8_t* __restrict__ pic, int picPitch, int W, int H, in
 #ifdef K1_PROBE_NOSTORE
               if (planeBytes == 1)
 #endif
-              *reinterpret_cast<unsigned*>(outBase + (size_t)(fy * 4 + fx) * planeBytes + (size_t)r * pitch) =
+              *reinterpret_cast<unsigned*>(outBase + ((fy * 4 + fx) * planeBytes32 + r * pitch)) =
                   pack_sat_u8x2(acc0 >> 12, acc1 >> 12, hi16[fy - 1][r]);
             }
           }
@@ -251,9 +255,11 @@ cudaError_t fme_launch_k1(const FmeGeom& g, const uint8_t* d_pic, int picPitch, 
   cudaGetDevice(&dev);
   if (!smCount[dev & 63]) cudaDeviceGetAttribute(&smCount[dev & 63], cudaDevAttrMultiProcessorCount, dev);
   const int numSMs = smCount[dev & 63];
-  const int grid = nTiles < numSMs * 2 ? nTiles : numSMs * 2;
+  const int grid = nTiles < numSMs * FME_K1_CTAS ? nTiles : numSMs * FME_K1_CTAS;
+  // ceil(2^32 / tilesX): __umulhi(tile, rcp) == tile / tilesX for every tile < 2^32 / tilesX (tiles are < 2^17 at 8K)
+  const unsigned tilesXRcp = (unsigned)((0x100000000ull + tilesX - 1) / tilesX);
   k1_interp_planes<<<grid, K1_THREADS, 0, s>>>(d_pic, picPitch, g.W, g.H, g.M, g.Wp, g.Hp, g.pitch, g.planeBytes,
-                                                d_planes, tilesX, nTiles);
+                                                d_planes, tilesX, tilesXRcp, nTiles);
   ++*launches;
   return cudaGetLastError();
 }
