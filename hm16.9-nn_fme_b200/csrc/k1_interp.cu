@@ -205,9 +205,6 @@ k1_interp_planes(const uint8_t* __restrict__ pic, int picPitch, int W, int H, in
             if (half) {
               hi16[fy - 1][r] = pack_sat_u8x2(acc0 >> 12, acc1 >> 12, 0);
             } else if (gy0 + r < Hp) {
-#ifdef K1_PROBE_NOSTORE
-              if (planeBytes == 1)
-#endif
               *reinterpret_cast<unsigned*>(outBase + ((fy * 4 + fx) * planeBytes32 + r * pitch)) =
                   pack_sat_u8x2(acc0 >> 12, acc1 >> 12, hi16[fy - 1][r]);
             }
