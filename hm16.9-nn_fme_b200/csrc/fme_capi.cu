@@ -78,6 +78,7 @@ struct fme_ctx {
   size_t nnBytes = 0;
   FmeNnHeader nnHeader{};
   uint32_t* d_costLut = nullptr;
+  int* d_k1Counter = nullptr;    // K1's dynamic tile hand-out (2 ints, re-armed by the kernel)
   uint32_t* d_scratchU32 = nullptr;
   size_t scratchU32Capacity = 0;
   FmeK2Scratch k2{};
@@ -162,7 +163,7 @@ struct StageTimer {
 
 int run_k1(fme_ctx* c, int slot) {
   StageTimer t(c, 0);
-  CU_CHECK(fme_launch_k1(c->g, c->d_pic, c->picPitch, c->d_planes + (size_t)slot * c->g.slotBytes, c->stream,
+  CU_CHECK(fme_launch_k1(c->g, c->d_pic, c->picPitch, c->d_planes + (size_t)slot * c->g.slotBytes, c->d_k1Counter, c->stream,
                          &c->launches));
   c->refValid[slot] = 1;
   return FME_OK;
@@ -306,6 +307,8 @@ int fme_create(const fme_config* cfg, fme_ctx** out) {
   }
   c->d_org = c->d_orgBuf[0]; c->d_pic = c->d_picBuf[0]; c->d_pus = c->d_pusBuf[0]; c->d_res = c->d_resBuf[0];
   CREATE_CHECK(cudaMalloc(&c->d_costLut, sizeof(uint32_t) * FME_COST_LUT_SIZE));
+  CREATE_CHECK(cudaMalloc(&c->d_k1Counter, 2 * sizeof(int)));
+  CREATE_CHECK(cudaMemsetAsync(c->d_k1Counter, 0, 2 * sizeof(int), c->stream));
   CREATE_CHECK(cudaMalloc(&c->k2.classCount, sizeof(int) * (4 * FME_MAX_CLASSES + 16)));
   c->k2.classCursor = c->k2.classCount + FME_MAX_CLASSES;
   c->k2.workCounter = c->k2.classCursor + FME_MAX_CLASSES;  // counts, cursors and the work counter are cleared together
@@ -330,7 +333,7 @@ void fme_destroy(fme_ctx* c) {
       if (e) cudaEventDestroy(e);
   }
   cudaFree(c->d_cb); cudaFree(c->d_cr); cudaFree(c->d_nn);
-  cudaFree(c->d_costLut); cudaFree(c->d_scratchU32); cudaFree(c->k2.classCount); cudaFree(c->k2.order);
+  cudaFree(c->d_costLut); cudaFree(c->d_k1Counter); cudaFree(c->d_scratchU32); cudaFree(c->k2.classCount); cudaFree(c->k2.order);
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
   if (c->ownStream) cudaStreamDestroy(c->ownStream);

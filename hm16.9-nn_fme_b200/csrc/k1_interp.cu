@@ -79,11 +79,11 @@ constexpr int K1_PREF = (K1_IN_WORDS + K1_THREADS - 1) / K1_THREADS;  // input w
 // Persistent: gridDim.x CTAs walk the tile list; the next tile's input words are fetched into registers before the
 // current tile's filtering starts and parked in shared memory after it, so global latency hides behind stages B/C.
 #ifndef FME_K1_CTAS
-#define FME_K1_CTAS 3
+#define FME_K1_CTAS 4
 #endif
 __global__ void __launch_bounds__(K1_THREADS, FME_K1_CTAS)
 k1_interp_planes(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int M, int Wp, int Hp, int pitch,
-                 size_t planeBytes, uint8_t* __restrict__ planes, int tilesX, unsigned tilesXRcp, int nTiles) {
+                 size_t planeBytes, uint8_t* __restrict__ planes, int tilesX, unsigned tilesXRcp, int nTiles, int* __restrict__ tileCounter) {
   __shared__ __align__(16) uint8_t s_in[IN_H][IN_W];
   __shared__ __align__(16) int16_t s_t[4][IN_H][TW];
 
@@ -106,15 +106,21 @@ k1_interp_planes(const uint8_t* __restrict__ pic, int picPitch, int W, int H, in
     }
   };
 
+  // Tiles beyond the first one per CTA are handed out dynamically (tileCounter[0]), so that all resident CTAs of an
+  // SM finish together whatever the ratio of tiles to CTAs; the last CTA to leave re-arms the counters
+  // (tileCounter[1] counts finished CTAs), so no memset is needed between launches.
+  __shared__ int s_next;
   int tile = blockIdx.x;
   if (tile < nTiles) fetch(tile);
-  for (; tile < nTiles; tile += gridDim.x) {
+  while (tile < nTiles) {
     const int tyI = (int)__umulhi((unsigned)tile, tilesXRcp), txI = tile - tyI * tilesX;
     const int x0 = txI * TW, y0 = tyI * TH;  // padded-plane coordinates of the tile
-    __syncthreads();  // every thread is done with s_in / s_t of the previous tile
+    if (tid == 0) s_next = (int)gridDim.x + atomicAdd(&tileCounter[0], 1);
+    __syncthreads();  // every thread is done with s_in / s_t of the previous tile; s_next is published
     park();
+    const int nextTile = s_next;
     __syncthreads();
-    if (tile + (int)gridDim.x < nTiles) fetch(tile + gridDim.x);  // in flight during stages B and C
+    if (nextTile < nTiles) fetch(nextTile);  // in flight during stages B and C
 
   // ---- stage B: horizontal filters -> int16 T_fx ---------------------------------------------
   // item = (row, quad of 4 output columns).  Output column x uses input columns x+1 .. x+8
@@ -213,7 +219,12 @@ k1_interp_planes(const uint8_t* __restrict__ pic, int picPitch, int W, int H, in
       }
     }
   }
+    tile = nextTile;
   }  // tile loop
+  if (tid == 0 && atomicAdd(&tileCounter[1], 1) == (int)gridDim.x - 1) {
+    tileCounter[0] = 0;
+    tileCounter[1] = 0;
+  }
 }
 
 // Edge-replicating copy of a chroma picture into its padded plane (used by MC only).
@@ -243,8 +254,8 @@ __global__ void k_pel_to_u8(const int16_t* __restrict__ src, int srcStride, uint
 
 }  // namespace
 
-cudaError_t fme_launch_k1(const FmeGeom& g, const uint8_t* d_pic, int picPitch, uint8_t* d_planes, cudaStream_t s,
-                          int64_t* launches) {
+cudaError_t fme_launch_k1(const FmeGeom& g, const uint8_t* d_pic, int picPitch, uint8_t* d_planes, int* d_tileCounter,
+                          cudaStream_t s, int64_t* launches) {
   const int tilesX = (g.Wp + TW - 1) / TW, tilesY = (g.Hp + TH - 1) / TH;
   const int nTiles = tilesX * tilesY;
   static int smCount[64] = {};  // per device
@@ -256,7 +267,7 @@ cudaError_t fme_launch_k1(const FmeGeom& g, const uint8_t* d_pic, int picPitch, 
   // ceil(2^32 / tilesX): __umulhi(tile, rcp) == tile / tilesX for every tile < 2^32 / tilesX (tiles are < 2^17 at 8K)
   const unsigned tilesXRcp = (unsigned)((0x100000000ull + tilesX - 1) / tilesX);
   k1_interp_planes<<<grid, K1_THREADS, 0, s>>>(d_pic, picPitch, g.W, g.H, g.M, g.Wp, g.Hp, g.pitch, g.planeBytes,
-                                                d_planes, tilesX, tilesXRcp, nTiles);
+                                                d_planes, tilesX, tilesXRcp, nTiles, d_tileCounter);
   ++*launches;
   return cudaGetLastError();
 }
