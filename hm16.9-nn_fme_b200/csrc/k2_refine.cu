@@ -686,7 +686,9 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
           dist += had ? satd8x8(row2, region + uOff2 + candOff, sg.RW) : sad8x8(row2, region + uOff2 + candOff, sg.RW);
         }
       }
-      for (int d = lanesPerPu >> 1; d > 0; d >>= 1) dist += __shfl_xor_sync(0xffffffffu, dist, d);  // per-PU sum
+      // per-PU sum: one REDUX when the PU owns the whole warp, xor-shuffles over the lane group otherwise
+      if (lanesPerPu == 32) dist = __reduce_add_sync(0xffffffffu, dist);
+      else for (int d = lanesPerPu >> 1; d > 0; d >>= 1) dist += __shfl_xor_sync(0xffffffffu, dist, d);
       if (laneActive) {
         dist += costLut[bits];
         if (s < 4) {
