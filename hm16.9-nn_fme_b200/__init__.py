@@ -18,7 +18,8 @@ from . import formats  # noqa: F401
 from .pu_list import PU_DTYPE, HEAD_DTYPE, RESULT_DTYPE, MC_PU_DTYPE, MC_BI_PU_DTYPE  # noqa: F401
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libfme_b200.so")
+# FME_B200_LIB selects another build of the same library (A/B builds for profiling, e.g. variants/libfme_swar8.so)
+LIB_PATH = os.environ.get("FME_B200_LIB") or os.path.join(PKG_DIR, "libfme_b200.so")
 
 MODE_STD, MODE_NN, MODE_BOTH = 1, 2, 3
 PU_LOSSLESS, PU_ERR_ON_GPU, PU_BI = 0x01, 0x02, 0x04

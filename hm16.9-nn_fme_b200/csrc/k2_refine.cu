@@ -312,6 +312,133 @@ __device__ __forceinline__ unsigned ldg_row4(const uint8_t* base) {
   return __funnelshift_r(__ldg(p), __ldg(p + 1), sh);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// 8x8 SATD on the tensor pipe (fp16 in, fp32 accumulate -- the variant BASELINE.json's north_star names)
+// ------------------------------------------------------------------------------------------------
+// xCalcHADs8x8 (TComRdCost.cpp:1330-1425) is sum |H8 D H8| = sum |(H8 (x) H8) vec(D)|, a 64x64 +-1 matrix applied to the
+// 64 residuals of a tile.  One warp evaluates eight tiles at a time ("column block"): lane (g, t), g = lane >> 2,
+// t = lane & 3, feeds rows 2t and 2t+1 of tile g.  With pixel (y, x), y = 2t + ks1, x = 4 ks0 + 2 c1 + c0 and
+// coefficient (u, v), u = 2 uh + u0, v = 4 v2 + 2 v1 + v0, the sign (-1)^(popc(u&y) + popc(v&x)) splits into
+//   (-1)^(u0 ks1 + v2 ks0)  *  (-1)^(popc(uh & t) + v1 c1 + v0 c0):
+// the first factor is a 2x2 butterfly over the four 4-pixel groups (ks1, ks0) a lane holds -- done on packed f16x2
+// (values <= 4 * 255, exact) -- and the second is the natural 16x16 Hadamard matrix over k = 8 c1 + 2 t + c0, which is
+// exactly how mma.m16n8k16 spreads its K index over the lanes.  So 16 HADD2 + 4 HMMA (one constant A fragment)
+// replace the 64x64 product; all values are integers below 2^24, so fp32 accumulation is exact.
+// u8 -> f16 is one PRMT per pixel pair: byte b under the high byte 0x64 is the f16 number 1024 + b.
+__device__ __forceinline__ unsigned f16pair_lo(unsigned w) {
+  unsigned r;
+  asm("prmt.b32 %0, %1, %2, 0x4140;" : "=r"(r) : "r"(w), "r"(0x64646464u));
+  return r;
+}
+__device__ __forceinline__ unsigned f16pair_hi(unsigned w) {
+  unsigned r;
+  asm("prmt.b32 %0, %1, %2, 0x4342;" : "=r"(r) : "r"(w), "r"(0x64646464u));
+  return r;
+}
+__device__ __forceinline__ unsigned hadd2u(unsigned a, unsigned b) {
+  unsigned r;
+  asm("add.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned hsub2u(unsigned a, unsigned b) {
+  unsigned r;
+  asm("sub.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned lds_u32(unsigned sa) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa));
+  return v;
+}
+__device__ __forceinline__ void hmma16816(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
+// A fragment of the natural 16x16 Hadamard matrix, A[row][k] = (-1)^popc(row & k) as f16 +-1
+// (m16n8k16 .row layout: a0,a1 = (g; 2t, 2t+1)  a2,a3 = (g+8; 2t, 2t+1)  a4,a5 = (g; 2t+8, 2t+9)  a6,a7 = (g+8; 2t+8, 2t+9))
+__device__ __forceinline__ void had16_afrag(int lane, unsigned (&a)[4]) {
+  const int g = lane >> 2, t = lane & 3;
+  auto one = [](int row, int k) { return (__popc(row & k) & 1) ? 0xbc00u : 0x3c00u; };
+  auto pair = [&](int row, int k) { return one(row, k) | (one(row, k + 1) << 16); };
+  a[0] = pair(g, 2 * t);
+  a[1] = pair(g + 8, 2 * t);
+  a[2] = pair(g, 2 * t + 8);
+  a[3] = pair(g + 8, 2 * t + 8);
+}
+// The eight f16x2 words of a lane's two tile rows: f[2 ks + r], ks = 2 ks1 + ks0 (row 2t + ks1, columns 4 ks0 ..),
+// r = 0: columns +0,+1 (k = 2t, 2t+1), r = 1: columns +2,+3 (k = 2t+8, 2t+9).
+__device__ __forceinline__ void f16_rows(unsigned lo0, unsigned hi0, unsigned lo1, unsigned hi1, unsigned (&f)[8]) {
+  f[0] = f16pair_lo(lo0); f[1] = f16pair_hi(lo0);
+  f[2] = f16pair_lo(hi0); f[3] = f16pair_hi(hi0);
+  f[4] = f16pair_lo(lo1); f[5] = f16pair_hi(lo1);
+  f[6] = f16pair_lo(hi1); f[7] = f16pair_hi(hi1);
+}
+// Residual rows of one column block -> the four B fragments of its 2x2-butterflied pixel groups (f[2 mt], f[2 mt + 1]).
+__device__ __forceinline__ void cand_bfrags(unsigned cAddr, int RW, const unsigned (&o)[8], int lane, unsigned (&f)[8]) {
+  const unsigned a0 = cAddr + 2 * (lane & 3) * RW;
+  const unsigned base = a0 & ~3u, sh = (a0 & 3u) * 8u;
+  const unsigned w0 = lds_u32(base), w1 = lds_u32(base + 4), w2 = lds_u32(base + 8);
+  const unsigned x0 = lds_u32(base + RW), x1 = lds_u32(base + RW + 4), x2 = lds_u32(base + RW + 8);
+  f16_rows(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(x0, x1, sh),
+           __funnelshift_r(x1, x2, sh), f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = hsub2u(f[i], o[i]);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const unsigned s0 = hadd2u(f[0 + r], f[2 + r]), d0 = hsub2u(f[0 + r], f[2 + r]);  // over ks0, ks1 = 0
+    const unsigned s1 = hadd2u(f[4 + r], f[6 + r]), d1 = hsub2u(f[4 + r], f[6 + r]);  // over ks0, ks1 = 1
+    f[0 + r] = hadd2u(s0, s1); f[2 + r] = hadd2u(d0, d1);
+    f[4 + r] = hsub2u(s0, s1); f[6 + r] = hsub2u(d0, d1);
+  }
+}
+// sum |coefficients| of one column block: acc0 = this lane's share of tile 2t, acc1 of tile 2t+1
+__device__ __forceinline__ void had_abs_sums(const unsigned (&f)[8], const unsigned (&afrag)[4], float& acc0, float& acc1) {
+  float d[4][4];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) hmma16816(d[mt], afrag, f[2 * mt], f[2 * mt + 1]);
+  acc0 = (fabsf(d[0][0]) + fabsf(d[0][2])) + (fabsf(d[1][0]) + fabsf(d[1][2])) +
+         ((fabsf(d[2][0]) + fabsf(d[2][2])) + (fabsf(d[3][0]) + fabsf(d[3][2])));
+  acc1 = (fabsf(d[0][1]) + fabsf(d[0][3])) + (fabsf(d[1][1]) + fabsf(d[1][3])) +
+         ((fabsf(d[2][1]) + fabsf(d[2][3])) + (fabsf(d[3][1]) + fabsf(d[3][3])));
+}
+// SATD of the 32 tiles of a pack (four column blocks).  cOwn: shared-window address of row 0 of the candidate tile
+// this lane OWNS; orow(cb, o): source rows 2t, 2t+1 (f16 pairs) of the tile this lane FEEDS in block cb (tile
+// 8 cb + g).  The eight per-lane partial sums (4 blocks x 2 columns) are reduced over the eight lanes g with a
+// transposing butterfly, which leaves lane (g, t) with tile 8 (g >> 1) + 2 t + (g & 1); one more shuffle hands every
+// lane the SATD of its own tile, rounded as TComRdCost.cpp:1421.
+template <typename OrgRows>
+__device__ __forceinline__ unsigned satd8x8_pack_mma(unsigned cOwn, int RW, OrgRows orow, const unsigned (&afrag)[4],
+                                                     int lane, int gatherLane) {
+  float a0[4], a1[4];
+#pragma unroll
+  for (int cb = 0; cb < 4; ++cb) {
+    const unsigned ca = __shfl_sync(0xffffffffu, cOwn, 8 * cb + (lane >> 2));
+    unsigned f[8];
+    cand_bfrags(ca, RW, orow(cb), lane, f);
+    had_abs_sums(f, afrag, a0[cb], a1[cb]);
+  }
+  const bool g0 = (lane & 4) != 0, g1 = (lane & 8) != 0, g2 = (lane & 16) != 0;
+  float w[4];
+#pragma unroll
+  for (int cb = 0; cb < 4; ++cb) {  // lanes with g0 = j keep column j
+    const float keep = g0 ? a1[cb] : a0[cb], send = g0 ? a0[cb] : a1[cb];
+    w[cb] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  float x[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {     // lanes with g1 = i keep block 2k + i
+    const float keep = g1 ? w[2 * k + 1] : w[2 * k], send = g1 ? w[2 * k] : w[2 * k + 1];
+    x[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  const float keep = g2 ? x[1] : x[0], send = g2 ? x[0] : x[1];
+  const float z = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  // exact integer < 2^23: read it from the mantissa of z + 2^23
+  const unsigned v = (unsigned)__float_as_int(z + 8388608.0f) - 0x4b000000u;
+  return __shfl_sync(0xffffffffu, (v + 2) >> 2, gatherLane);
+}
+
 // TComRdCost.cpp:172-185
 __device__ __forceinline__ int golomb_bits(int v) {
   unsigned u = (v <= 0) ? (((unsigned)(-v)) << 1) + 1u : ((unsigned)v << 1);
@@ -434,7 +561,11 @@ __device__ __forceinline__ unsigned unit_dist(const unsigned* o, const uint8_t* 
                : sad4x4_p(o, cand, candPitch) + sad4x4_p(o + 8, cand + tile1Off, candPitch);
   } else if constexpr (TS == 8) {
     auto row = [&](int r, unsigned& lo, unsigned& hi) { lo = o[2 * r]; hi = o[2 * r + 1]; };
+#ifdef FME_K2_SWAR8
     return had ? satd8x8(row, cand, candPitch) : sad8x8(row, cand, candPitch);
+#else
+    return sad8x8(row, cand, candPitch);  // 8x8 SATD of uni-prediction packs runs on the tensor pipe (k2_pack)
+#endif
   } else {
     const unsigned(&oa)[4] = *reinterpret_cast<const unsigned(*)[4]>(o);
     const unsigned(&ob)[4] = *reinterpret_cast<const unsigned(*)[4]>(o + 4);
@@ -544,6 +675,15 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   constexpr int OW = BI ? (TS == 8 ? 32 : 16) : (TS == 8 ? 16 : 8);
   unsigned o[OW];
   const bool had = useHad && !lossless;
+  // 8x8 SATD of uni-prediction packs: tensor pipe (satd8x8_block_mma).  Warp-uniform; lossless PUs inside such a pack
+  // get their SAD from the SWAR path afterwards.
+#ifdef FME_K2_SWAR8
+  constexpr bool kMma = false;
+#else
+  constexpr bool kMma = TS == 8 && !BI;
+#endif
+  const bool useMma = kMma && useHad;
+  [[maybe_unused]] int orgOffOwn = 0;  // byte offset of this lane's (first) source tile in the source picture
   // unit -> byte offset of its (first) tile inside a staged region, offset of the second 4x4 tile, source load
   int uOff = 0, u1Off = 0;
   bool uOn = false;
@@ -589,9 +729,12 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
     } else if constexpr (TS == 8) {
       int ty = u / ci.tilesX, tx = u - ty * ci.tilesX;
       uOff = ty * 8 * sg.RW + tx * 8;
-      const uint8_t* src = org + (size_t)(oy + ty * 8) * gOrgPitch + ox + tx * 8;
+      orgOffOwn = (oy + ty * 8) * gOrgPitch + ox + tx * 8;  // < 2^31 (8K picture)
+      if (!useMma) {
+        const uint8_t* src = org + orgOffOwn;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) ldg_row8(src + (size_t)r * gOrgPitch, o[2 * r], o[2 * r + 1]);
+        for (int r = 0; r < 8; ++r) ldg_row8(src + (size_t)r * gOrgPitch, o[2 * r], o[2 * r + 1]);
+      }
     } else {
       int t0 = 2 * u, t1 = 2 * u + 1;
       int ty0 = t0 / ci.tilesX, tx0 = t0 - ty0 * ci.tilesX;
@@ -628,6 +771,27 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
       }
     }
   }
+
+  // ---- tensor-pipe state: Hadamard A fragment, source rows of the tiles this lane feeds, as f16 pairs ----
+  [[maybe_unused]] unsigned afrag[4];
+  [[maybe_unused]] unsigned o16[4][8];
+  // owner lane L = 8 cb + 2 t' + b reads its tile's SATD from lane (g = 2 cb + b, t = t')
+  [[maybe_unused]] const int gatherLane = (lane & 24) + 4 * (lane & 1) + ((lane & 7) >> 1);
+  if constexpr (kMma) {
+    if (useMma) {
+      had16_afrag(lane, afrag);
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        const int off = __shfl_sync(0xffffffffu, orgOffOwn, 8 * cb + (lane >> 2));
+        const uint8_t* src = org + off + (size_t)(2 * (lane & 3)) * gOrgPitch;
+        unsigned lo0, hi0, lo1, hi1;
+        ldg_row8(src, lo0, hi0);
+        ldg_row8(src + gOrgPitch, lo1, hi1);
+        f16_rows(lo0, hi0, lo1, hi1, o16[cb]);
+      }
+    }
+  }
+  [[maybe_unused]] const unsigned bufSA = (unsigned)__cvta_generic_to_shared(smem);
 
   // ---- 12 steps: prefetch step s+1 while evaluating the candidates served by step s ----
   // running first-minimum: candidates of the half-pel stage are evaluated plane by plane, i.e. out of table
@@ -672,6 +836,54 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
       // exp-Golomb bit counts of the three possible vector components per axis were computed once per stage
       const int bits = (int)(((bitsX >> (8 * ox3 + 8)) & 0xffu) + ((bitsY >> (8 * oy3 + 8)) & 0xffu));
       unsigned dist = 0;
+      bool swar = true;
+      if constexpr (kMma) {
+        if (useMma) {
+          swar = false;
+          // every lane publishes the address of its own tile's candidate; the lanes of a column block fetch the
+          // address of the tile they feed
+          const unsigned cOwn = bufSA + ((s & 1) ? bufBytes : 0) + myPu * sg.RB + uOff + candOff;
+          struct OrgRegs {
+            const unsigned (*o)[8];
+            __device__ __forceinline__ const unsigned (&operator()(int cb) const)[8] { return o[cb]; }
+          };
+          dist = satd8x8_pack_mma(cOwn, sg.RW, OrgRegs{o16}, afrag, lane, gatherLane);
+          if (!uOn) dist = 0;
+          if constexpr (A == 16) {
+            if (twoUnits) {  // units 32.. of a 64x64 / 64x48 / 48x64 PU: source rows come from the parked tiles
+              struct OrgSmem {
+                const uint2* sp;
+                int lane;
+                mutable unsigned o2[8];
+                __device__ __forceinline__ const unsigned (&operator()(int cb) const)[8] {
+                  const uint2* q = sp + 8 * cb + (lane >> 2);
+                  const uint2 r0 = q[(2 * (lane & 3)) * 32], r1 = q[(2 * (lane & 3) + 1) * 32];
+                  f16_rows(r0.x, r0.y, r1.x, r1.y, o2);
+                  return o2;
+                }
+              };
+              const unsigned d2 = satd8x8_pack_mma(cOwn - uOff + uOff2, sg.RW,
+                                                   OrgSmem{reinterpret_cast<const uint2*>(smem + K2_STAGE_BYTES), lane, {}},
+                                                   afrag, lane, gatherLane);
+              if (uOn2) dist += d2;
+            }
+          }
+          if (__any_sync(0xffffffffu, laneActive && !had)) {  // lossless PUs in a Hadamard pack: SAD (TEncSearch.cpp:5258)
+            if (uOn && !had) {
+              const uint8_t* src = org + orgOffOwn;
+              auto rowG = [&](int r, unsigned& lo, unsigned& hi) { ldg_row8(src + (size_t)r * gOrgPitch, lo, hi); };
+              dist = sad8x8(rowG, region + uOff + candOff, sg.RW);
+              if constexpr (A == 16) {
+                if (uOn2) {
+                  auto row2 = [&](int r, unsigned& lo, unsigned& hi) { const uint2 v = so2[r * 32]; lo = v.x; hi = v.y; };
+                  dist += sad8x8(row2, region + uOff2 + candOff, sg.RW);
+                }
+              }
+            }
+          }
+        }
+      }
+      if (swar) {
       if (uOn) dist = unit_dist<TS, BI>(o, region + uOff + candOff, sg.RW, u1Off, had);
       if constexpr (TS == 8 && A == 16 && BI) {
         if (twoUnits) {  // rare (64x64, 64x48, 48x64 bi PUs): the second unit's pattern is rebuilt per candidate
@@ -683,9 +895,14 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
       if constexpr (TS == 8 && A == 16 && !BI) {
         if (uOn2) {
           auto row2 = [&](int r, unsigned& lo, unsigned& hi) { const uint2 v = so2[r * 32]; lo = v.x; hi = v.y; };
+#ifdef FME_K2_SWAR8
           dist += had ? satd8x8(row2, region + uOff2 + candOff, sg.RW) : sad8x8(row2, region + uOff2 + candOff, sg.RW);
+#else
+          dist += sad8x8(row2, region + uOff2 + candOff, sg.RW);
+#endif
         }
       }
+      }  // swar
       // per-PU sum: one REDUX when the PU owns the whole warp, xor-shuffles over the lane group otherwise
       if (lanesPerPu == 32) dist = __reduce_add_sync(0xffffffffu, dist);
       else for (int d = lanesPerPu >> 1; d > 0; d >>= 1) dist += __shfl_xor_sync(0xffffffffu, dist, d);
