@@ -22,6 +22,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FME_B200_LIB") or os.path.join(PKG_DIR, "libfme_b200.so")
 
 MODE_STD, MODE_NN, MODE_BOTH = 1, 2, 3
+K2_PATH_AUTO, K2_PATH_SWAR, K2_PATH_MMA_PACK, K2_PATH_MMA_GROUP = 0, 1, 2, 3
 PU_LOSSLESS, PU_ERR_ON_GPU, PU_BI = 0x01, 0x02, 0x04
 
 # every symbol include/fme_b200.h declares (checked by tests/test_abi.py against the header)
@@ -38,7 +39,8 @@ EXPORTS = [
 class FmeConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("margin", C.c_int32),
                 ("bitDepth", C.c_int32), ("numRefSlots", C.c_int32), ("maxPUs", C.c_int32), ("useHadME", C.c_int32),
-                ("fen", C.c_int32), ("nnFma", C.c_int32), ("biPred", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("fen", C.c_int32), ("nnFma", C.c_int32), ("biPred", C.c_int32), ("k2Path", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
 
 
 class FmeError(RuntimeError):
@@ -107,11 +109,13 @@ class Fme:
     """One engine context (= one encoder instance's TEncSearch for the fractional-ME path)."""
 
     def __init__(self, width, height, num_ref_slots=4, max_pus=1 << 20, margin=80, use_had=True, fen=True, device=0,
-                 nn_fma=False, bi_pred=False):
+                 nn_fma=False, bi_pred=False, k2_path=None):
         self.lib = load_library()
+        if k2_path is None:   # FME_K2_PATH=1|2|3 runs a whole test / bench session on one K2 path (all are bit-identical)
+            k2_path = int(os.environ.get("FME_K2_PATH", "0"))
         self.cfg = FmeConfig(device=device, width=width, height=height, margin=margin, bitDepth=8,
                              numRefSlots=num_ref_slots, maxPUs=max_pus, useHadME=int(use_had), fen=int(fen),
-                             nnFma=int(nn_fma), biPred=int(bi_pred))
+                             nnFma=int(nn_fma), biPred=int(bi_pred), k2Path=int(k2_path))
         self.h = C.c_void_p()
         self._check(self.lib.fme_create(C.byref(self.cfg), C.byref(self.h)))
         self.width, self.height, self.margin = width, height, margin

@@ -41,6 +41,11 @@ inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 // against a 1.05 ms PCIe floor); three keep it busy.
 constexpr int FME_NBUF = 3;
 
+// What FME_K2_PATH_AUTO resolves to: the fastest measured path (profiles/r2_k2_paths.txt).
+#ifndef FME_K2_PATH_DEFAULT
+#define FME_K2_PATH_DEFAULT FME_K2_PATH_SWAR
+#endif
+
 struct fme_ctx {
   fme_config cfg;
   FmeGeom g;
@@ -163,8 +168,8 @@ struct StageTimer {
 
 int run_k1(fme_ctx* c, int slot) {
   StageTimer t(c, 0);
-  CU_CHECK(fme_launch_k1(c->g, c->d_pic, c->picPitch, c->d_planes + (size_t)slot * c->g.slotBytes, c->d_k1Counter, c->stream,
-                         &c->launches));
+  CU_CHECK(fme_launch_k1(c->g, c->d_pic, c->picPitch, c->d_planes + (size_t)slot * c->g.slotBytes, c->d_k1Counter, c->numSMs,
+                         c->stream, &c->launches));
   c->refValid[slot] = 1;
   return FME_OK;
 }
@@ -198,8 +203,9 @@ int run_search(fme_ctx* c, fme_pu* d_pus, int n, fme_result* d_out, int mode) {
   if (mode != FME_MODE_BOTH) CU_CHECK(fme_launch_clear_results(d_out, n, c->stream, &c->launches));
   if (mode & FME_MODE_STD) {
     StageTimer t(c, 1);
-    CU_CHECK(fme_launch_k2(c->g, c->d_planes, c->d_org, d_pus, n, d_out, c->d_costLut, c->cfg.useHadME, c->cfg.biPred, c->k2,
-                           c->numSMs, c->stream, &c->launches));
+    CU_CHECK(fme_launch_k2(c->g, c->d_planes, c->d_org, d_pus, n, d_out, c->d_costLut, c->cfg.useHadME, c->cfg.biPred,
+                           c->cfg.k2Path == FME_K2_PATH_AUTO ? FME_K2_PATH_DEFAULT : c->cfg.k2Path, c->k2, c->numSMs, c->stream,
+                           &c->launches));
   }
   if (mode & FME_MODE_NN) {
     StageTimer t(c, 2);
@@ -244,6 +250,7 @@ int fme_create(const fme_config* cfg, fme_ctx** out) {
   if (cfg->bitDepth != 8) return fail(FME_ERR_INVALID, "frame-level passes support bitDepth 8 only");
   if (cfg->numRefSlots < 1 || cfg->numRefSlots > 64) return fail(FME_ERR_INVALID, "numRefSlots out of range");
   if (cfg->maxPUs < 1) return fail(FME_ERR_INVALID, "maxPUs must be positive");
+  if (cfg->k2Path < FME_K2_PATH_AUTO || cfg->k2Path > FME_K2_PATH_MMA_GROUP) return fail(FME_ERR_INVALID, "k2Path out of range");
 
   int nDev = 0;
   if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) {
@@ -628,9 +635,9 @@ int fme_upload_ref_chroma(fme_ctx* c, int slot, const int16_t* cb, const int16_t
   return FME_OK;
 }
 
-// Inter PU shapes of HEVC: both sides in {4,8,12,16,24,32,48,64}; 4x4 does not exist (8x4 / 4x8 are the smallest)
-// and K2's lane units are 8x8 tiles or PAIRS of 4x4 tiles.
-static bool valid_pu_size(int w, int h) { return fme_dim_index(w) >= 0 && fme_dim_index(h) >= 0 && w * h >= 32; }
+// Inter PU shapes of HEVC (fme_hevc_pu_shape): K2's lane units are 8x8 tiles or PAIRS of 4x4 tiles, and every HEVC
+// shape that is 4x4-tiled has an even tile count.
+static bool valid_pu_size(int w, int h) { return fme_hevc_pu_shape(w, h); }
 
 // ---- the batched search ------------------------------------------------------------------------
 static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, int mode, bool sync,
@@ -896,7 +903,7 @@ int fme_pred_error(fme_ctx* c, const fme_mc_pu* pus, int n, uint32_t* out) {
   for (int i = 0; i < n; ++i) {
     if (pus[i].refSlot >= c->cfg.numRefSlots || !c->refValid[pus[i].refSlot])
       return fail(FME_ERR_STATE, "PU %d references slot %d which holds no picture", i, pus[i].refSlot);
-    if (fme_dim_index(pus[i].w) < 0 || fme_dim_index(pus[i].h) < 0) return fail(FME_ERR_INVALID, "PU %d: bad size", i);
+    if (!fme_hevc_pu_shape(pus[i].w, pus[i].h)) return fail(FME_ERR_INVALID, "PU %d: %dx%d is not an HEVC PU size", i, pus[i].w, pus[i].h);
   }
   CU_CHECK(cudaSetDevice(c->cfg.device));
   int rc = sync_all(c);  // the record staging buffer is shared with the async submit path

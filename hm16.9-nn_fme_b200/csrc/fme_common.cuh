@@ -50,6 +50,16 @@ __host__ __device__ inline int fme_index_dim(int i) {
   return i < 4 ? 4 * (i + 1) : ((i & 1) ? 32 : 24) << ((i - 4) >> 1);
 }
 
+// The inter PU shapes HEVC can produce (2Nx2N, 2NxN, Nx2N and the AMP splits of CUs 8..64, TypeDef.h PartSize):
+// one side is the CU size S in {8,16,32,64} and the other is S, S/2, S/4 or 3S/4 (quarter splits from S = 16 up;
+// 4x4 does not exist).  Anything else (12x12, 24x8, ...) is rejected on the host and skipped by the kernels.
+__host__ __device__ inline bool fme_hevc_pu_shape(int w, int h) {
+  const int S = w > h ? w : h, m = w > h ? h : w;
+  if (S != 8 && S != 16 && S != 32 && S != 64) return false;
+  if (m == S || 2 * m == S) return true;
+  return S >= 16 && (4 * m == S || 4 * m == 3 * S);
+}
+
 // ---- launchers implemented in the kernel translation units ----------------------------------
 struct FmeK2Scratch {
   int* classCount;   // [FME_MAX_CLASSES]
@@ -62,12 +72,12 @@ struct FmeK2Scratch {
 
 // d_tileCounter: two zero-initialised ints owned by the ctx (dynamic tile hand-out; the kernel re-arms them itself)
 cudaError_t fme_launch_k1(const FmeGeom& g, const uint8_t* d_pic, int picPitch, uint8_t* d_planes, int* d_tileCounter,
-                          cudaStream_t s, int64_t* launches);
+                          int numSMs, cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_pad_chroma(const FmeGeom& g, const uint8_t* d_pic, int picPitch, uint8_t* d_plane,
                                   cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_k2(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_pu* d_pus, int n,
-                          fme_result* d_res, const uint32_t* d_costLut, int useHad, int biPred, const FmeK2Scratch& sc,
-                          int numSMs, cudaStream_t s, int64_t* launches);
+                          fme_result* d_res, const uint32_t* d_costLut, int useHad, int biPred, int k2Path,
+                          const FmeK2Scratch& sc, int numSMs, cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_k3(const fme_pu* d_pus, int n, fme_result* d_res, const float* d_nn, size_t nnBytes,
                           const FmeNnHeader& h, int fma, cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_k0(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, fme_pu* d_pus, int n,

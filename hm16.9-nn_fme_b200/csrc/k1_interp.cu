@@ -255,14 +255,9 @@ __global__ void k_pel_to_u8(const int16_t* __restrict__ src, int srcStride, uint
 }  // namespace
 
 cudaError_t fme_launch_k1(const FmeGeom& g, const uint8_t* d_pic, int picPitch, uint8_t* d_planes, int* d_tileCounter,
-                          cudaStream_t s, int64_t* launches) {
+                          int numSMs, cudaStream_t s, int64_t* launches) {
   const int tilesX = (g.Wp + TW - 1) / TW, tilesY = (g.Hp + TH - 1) / TH;
   const int nTiles = tilesX * tilesY;
-  static int smCount[64] = {};  // per device
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!smCount[dev & 63]) cudaDeviceGetAttribute(&smCount[dev & 63], cudaDevAttrMultiProcessorCount, dev);
-  const int numSMs = smCount[dev & 63];
   const int grid = nTiles < numSMs * FME_K1_CTAS ? nTiles : numSMs * FME_K1_CTAS;
   // ceil(2^32 / tilesX): __umulhi(tile, rcp) == tile / tilesX for every tile < 2^32 / tilesX (tiles are < 2^17 at 8K)
   const unsigned tilesXRcp = (unsigned)((0x100000000ull + tilesX - 1) / tilesX);

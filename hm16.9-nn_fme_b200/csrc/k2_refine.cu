@@ -29,7 +29,6 @@ namespace {
 #define FME_K2_WARPS 12
 #endif
 constexpr int K2_WARPS = FME_K2_WARPS;
-constexpr int K2_THREADS = K2_WARPS * 32;
 constexpr int K2_STAGE_BYTES = 10496;  // two staging buffers of max P*(h+1)*RW + 16 bytes (64x64: 65*80 = 5200)
 constexpr int K2_ORG2_BYTES = 2048;    // second source tile of every lane for PUs with more than 32 tiles (8 rows x 32 lanes x 8 B)
 constexpr int K2_SMEM_PER_WARP = K2_STAGE_BYTES + K2_ORG2_BYTES;
@@ -65,6 +64,15 @@ __host__ __device__ inline ClassInfo class_info(int cls) {
   return c;
 }
 
+// PUs per pack.  8x8-tiled classes served by k2_group_mma (mmaGroups) use "groups" of eight tiles instead of 32-lane packs.
+__host__ __device__ inline int group_pus(int w, int h) {
+  const int tpp = (w >> 3) * (h >> 3);  // 8x8 tiles per PU
+  return tpp <= 4 ? 8 / tpp : 1;
+}
+__host__ __device__ inline int pack_pus(const ClassInfo& c, int mmaGroups) {
+  return (mmaGroups && c.ts == 8) ? group_pus(c.w, c.h) : c.P;
+}
+
 // ------------------------------------------------------------------------------------------------
 // prepass: counting sort of PU indices by shape class
 // ------------------------------------------------------------------------------------------------
@@ -72,8 +80,8 @@ __host__ __device__ inline ClassInfo class_info(int cls) {
 // refinement records (FME_PU_BI, wantBi = 1) -- a pack never mixes the two kinds (different k2_pack instantiations).
 __device__ __forceinline__ int k2_class_of(const fme_pu& p, int wantBi) {
   if (((p.flags & FME_PU_BI) != 0) != (wantBi != 0)) return -1;
-  const int wi = fme_dim_index(p.w), hi = fme_dim_index(p.h);
-  return (wi >= 0 && hi >= 0) ? wi * 8 + hi : -1;
+  if (!fme_hevc_pu_shape(p.w, p.h)) return -1;
+  return fme_dim_index(p.w) * 8 + fme_dim_index(p.h);
 }
 
 __global__ void k2_count(const fme_pu* __restrict__ pus, int n, int* __restrict__ classCount, int wantBi) {
@@ -93,7 +101,7 @@ __global__ void k2_count(const fme_pu* __restrict__ pus, int n, int* __restrict_
 // class counts (a warp scan, cheaper than a separate launch); block 0 also publishes them for k2_refine.
 __global__ void k2_scatter(const fme_pu* __restrict__ pus, int n, const int* __restrict__ classCount,
                            int* __restrict__ classOffset, int* __restrict__ packOffset,
-                           int* __restrict__ classCursor, int* __restrict__ order, int wantBi) {
+                           int* __restrict__ classCursor, int* __restrict__ order, int wantBi, int mmaGroups) {
   __shared__ int s_cnt[FME_MAX_CLASSES];
   __shared__ int s_base[FME_MAX_CLASSES];
   __shared__ int s_classOff[FME_MAX_CLASSES];
@@ -103,8 +111,9 @@ __global__ void k2_scatter(const fme_pu* __restrict__ pus, int n, const int* __r
     const int lane = threadIdx.x;  // two classes per lane
     const int k0 = FME_MAX_CLASSES - 1 - 2 * lane, k1 = k0 - 1;
     const int c0 = classCount[k0], c1 = classCount[k1];
-    const int p0 = c0 ? (c0 + class_info(k0).P - 1) / class_info(k0).P : 0;
-    const int p1 = c1 ? (c1 + class_info(k1).P - 1) / class_info(k1).P : 0;
+    const int P0 = pack_pus(class_info(k0), mmaGroups), P1 = pack_pus(class_info(k1), mmaGroups);
+    const int p0 = c0 ? (c0 + P0 - 1) / P0 : 0;
+    const int p1 = c1 ? (c1 + P1 - 1) / P1 : 0;
     int sc = c0 + c1, sp = p0 + p1;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -551,7 +560,7 @@ __device__ __forceinline__ unsigned sad4x4_p(const unsigned* ou, const uint8_t* 
 }
 
 // Distortion of one lane unit against the candidate at `cand` (row 0 of the unit's first tile).
-template <int TS, bool BI = false>
+template <int TS, bool BI = false, bool SWAR8 = true>
 __device__ __forceinline__ unsigned unit_dist(const unsigned* o, const uint8_t* cand, int candPitch, int tile1Off,
                                               bool had) {
   if constexpr (BI && TS == 8) {
@@ -561,11 +570,8 @@ __device__ __forceinline__ unsigned unit_dist(const unsigned* o, const uint8_t* 
                : sad4x4_p(o, cand, candPitch) + sad4x4_p(o + 8, cand + tile1Off, candPitch);
   } else if constexpr (TS == 8) {
     auto row = [&](int r, unsigned& lo, unsigned& hi) { lo = o[2 * r]; hi = o[2 * r + 1]; };
-#ifdef FME_K2_SWAR8
-    return had ? satd8x8(row, cand, candPitch) : sad8x8(row, cand, candPitch);
-#else
-    return sad8x8(row, cand, candPitch);  // 8x8 SATD of uni-prediction packs runs on the tensor pipe (k2_pack)
-#endif
+    if constexpr (SWAR8) return had ? satd8x8(row, cand, candPitch) : sad8x8(row, cand, candPitch);
+    else return sad8x8(row, cand, candPitch);  // the 8x8 SATD of these packs runs on the tensor pipe (k2_pack)
   } else {
     const unsigned(&oa)[4] = *reinterpret_cast<const unsigned(*)[4]>(o);
     const unsigned(&ob)[4] = *reinterpret_cast<const unsigned(*)[4]>(o + 4);
@@ -577,7 +583,9 @@ __device__ __forceinline__ unsigned unit_dist(const unsigned* o, const uint8_t* 
 // BI = bi-predictive refinement records (FME_PU_BI): the source block is the pattern 2*org - P_other, P_other being
 // the other list's uni-prediction = plane P[mvY&3][mvX&3] of slot err[0] at the integer part of the MV packed in err[1]
 // (TEncSearch.cpp:4462-4472, TComYuv::removeHighFreq without clipping).  Everything else is the same search.
-template <int TS, int A, bool BI>
+// PATH selects how the 8x8 SATD of uni-prediction Hadamard packs is computed: 0 = SWAR integer (registers),
+// 1 / 2 = tensor pipe (satd8x8_pack_mma; with PATH 2 only the groups k2_group_mma hands back land here).
+template <int TS, int A, bool BI, int PATH>
 __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__ order, int first, int count,
                                      const fme_pu* __restrict__ pus, fme_result* __restrict__ res,
                                      const uint8_t* __restrict__ planes, const uint8_t* __restrict__ org,
@@ -677,11 +685,7 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   const bool had = useHad && !lossless;
   // 8x8 SATD of uni-prediction packs: tensor pipe (satd8x8_block_mma).  Warp-uniform; lossless PUs inside such a pack
   // get their SAD from the SWAR path afterwards.
-#ifdef FME_K2_SWAR8
-  constexpr bool kMma = false;
-#else
-  constexpr bool kMma = TS == 8 && !BI;
-#endif
+  constexpr bool kMma = TS == 8 && !BI && PATH != 0;
   const bool useMma = kMma && useHad;
   [[maybe_unused]] int orgOffOwn = 0;  // byte offset of this lane's (first) source tile in the source picture
   // unit -> byte offset of its (first) tile inside a staged region, offset of the second 4x4 tile, source load
@@ -884,22 +888,19 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
         }
       }
       if (swar) {
-      if (uOn) dist = unit_dist<TS, BI>(o, region + uOff + candOff, sg.RW, u1Off, had);
+      if (uOn) dist = unit_dist<TS, BI, !kMma>(o, region + uOff + candOff, sg.RW, u1Off, had);
       if constexpr (TS == 8 && A == 16 && BI) {
         if (twoUnits) {  // rare (64x64, 64x48, 48x64 bi PUs): the second unit's pattern is rebuilt per candidate
           loadUnit(unit0 + 32);
-          if (uOn) dist += unit_dist<TS, BI>(o, region + uOff + candOff, sg.RW, u1Off, had);
+          if (uOn) dist += unit_dist<TS, BI, !kMma>(o, region + uOff + candOff, sg.RW, u1Off, had);
           loadUnit(unit0);
         }
       }
       if constexpr (TS == 8 && A == 16 && !BI) {
         if (uOn2) {
           auto row2 = [&](int r, unsigned& lo, unsigned& hi) { const uint2 v = so2[r * 32]; lo = v.x; hi = v.y; };
-#ifdef FME_K2_SWAR8
-          dist += had ? satd8x8(row2, region + uOff2 + candOff, sg.RW) : sad8x8(row2, region + uOff2 + candOff, sg.RW);
-#else
-          dist += sad8x8(row2, region + uOff2 + candOff, sg.RW);
-#endif
+          if constexpr (!kMma) dist += had ? satd8x8(row2, region + uOff2 + candOff, sg.RW) : sad8x8(row2, region + uOff2 + candOff, sg.RW);
+          else dist += sad8x8(row2, region + uOff2 + candOff, sg.RW);
         }
       }
       }  // swar
@@ -943,16 +944,321 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
   __syncwarp();
 }
 
-template <bool BI>
-#ifdef FME_K2_MAXREG
-__global__ void __maxnreg__(FME_K2_MAXREG)
-#else
-__global__ void __launch_bounds__(K2_THREADS, 1)
+
+// ------------------------------------------------------------------------------------------------
+// MMA-native decomposition for 8x8-tiled uni-prediction PUs with Hadamard distortion (the default path)
+// ------------------------------------------------------------------------------------------------
+// A warp takes a "group": the eight tiles an m16n8k16 column block holds -- 8 / 4 / 2 PUs of 1 / 2 / 4 tiles, or one
+// strip (R tile rows, R * tilesX <= 8 tiles) of a larger PU, strips being walked one after the other.  The four column
+// blocks of one evaluation are four CANDIDATES of the same eight tiles, so a lane feeds rows 2t, 2t+1 of one tile
+// (column g = lane >> 2) for all of them: the source rows are 8 registers instead of 32, the four fetch -> butterfly
+// -> HMMA chains are independent (ILP), and the transposing reduction leaves lane (g, t) with tile column 2t + (g & 1)
+// of candidate g >> 1.  Half-pel phase: the 4 planes of the strip are staged at once and the 9 candidates evaluated
+// as 4 + 4 + 1; quarter-pel phase: the 8 candidate regions are staged as two batches of 4 into the two halves of the
+// buffer (the second batch lands while the first is evaluated; with several strips the copies roll on).
+// Lane roles: FEEDER of column g (PU pf, tile (tyF, txF)) and holder of the RESULT of column 2t + (g & 1) (PU pr);
+// staging uses lane = [pf][plane k][sub], so the staging PU is the feeder PU.
+constexpr int K2_GROUP_BYTES = 2 * 4608 + 16;  // two halves of 4 regions x P PUs (max: 8x8 and 16x8, 4 * 8 * 9 * 16) + read slack
+static_assert(K2_GROUP_BYTES <= K2_SMEM_PER_WARP, "a group's staging buffer must fit the warp's shared-memory slice");
+
+// row-2t address variant of cand_bfrags
+__device__ __forceinline__ void cand_bfrags_at(unsigned a0, int RW, const unsigned (&o)[8], unsigned (&f)[8]) {
+  const unsigned base = a0 & ~3u, sh = (a0 & 3u) * 8u;
+  const unsigned w0 = lds_u32(base), w1 = lds_u32(base + 4), w2 = lds_u32(base + 8);
+  const unsigned x0 = lds_u32(base + RW), x1 = lds_u32(base + RW + 4), x2 = lds_u32(base + RW + 8);
+  f16_rows(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(x0, x1, sh),
+           __funnelshift_r(x1, x2, sh), f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = hsub2u(f[i], o[i]);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const unsigned s0 = hadd2u(f[0 + r], f[2 + r]), d0 = hsub2u(f[0 + r], f[2 + r]);
+    const unsigned s1 = hadd2u(f[4 + r], f[6 + r]), d1 = hsub2u(f[4 + r], f[6 + r]);
+    f[0 + r] = hadd2u(s0, s1); f[2 + r] = hadd2u(d0, d1);
+    f[4 + r] = hsub2u(s0, s1); f[6 + r] = hsub2u(d0, d1);
+  }
+}
+__device__ __forceinline__ unsigned round_satd8(float z) {  // exact integer < 2^23 -> (z + 2) >> 2, TComRdCost.cpp:1421
+  const unsigned v = (unsigned)__float_as_int(z + 8388608.0f) - 0x4b000000u;
+  return (v + 2) >> 2;
+}
+// NC candidates of the group's eight tiles.  addr[j]: shared-window address of row 2t of the tile this lane feeds in
+// candidate j.  NC == 4: lane (g, t) gets the SATD of tile column 2t + (g & 1) for candidate g >> 1;
+// NC == 1: for the one candidate, replicated over g >> 1.
+template <int NC>
+__device__ __forceinline__ unsigned satd8x8_cands_mma(const unsigned (&addr)[NC], int RW, const unsigned (&o)[8],
+                                                      const unsigned (&afrag)[4], int lane) {
+  float a0[NC], a1[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    unsigned f[8];
+    cand_bfrags_at(addr[j], RW, o, f);
+    had_abs_sums(f, afrag, a0[j], a1[j]);
+  }
+  const bool g0 = (lane & 4) != 0, g1 = (lane & 8) != 0, g2 = (lane & 16) != 0;
+  if constexpr (NC == 4) {
+    float w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float keep = g0 ? a1[j] : a0[j], send = g0 ? a0[j] : a1[j];
+      w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    float x[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float keep = g1 ? w[2 * k + 1] : w[2 * k], send = g1 ? w[2 * k] : w[2 * k + 1];
+      x[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const float keep = g2 ? x[1] : x[0], send = g2 ? x[0] : x[1];
+    return round_satd8(keep + __shfl_xor_sync(0xffffffffu, send, 16));
+  } else {
+    float keep = g0 ? a1[0] : a0[0];
+    const float send = g0 ? a0[0] : a1[0];
+    keep += __shfl_xor_sync(0xffffffffu, send, 4);
+    keep += __shfl_xor_sync(0xffffffffu, keep, 8);
+    keep += __shfl_xor_sync(0xffffffffu, keep, 16);
+    return round_satd8(keep);
+  }
+}
+
+// Returns false (nothing done) when the group holds a lossless PU: the caller then runs it through k2_pack.
+template <int A>
+__device__ __noinline__ bool k2_group_mma(int w, int h, const int* __restrict__ order, int first, int count,
+                                          const fme_pu* __restrict__ pus, fme_result* __restrict__ res,
+                                          const uint8_t* __restrict__ planes, const uint8_t* __restrict__ org,
+                                          const FmeGeom& g, const uint32_t* __restrict__ costLut, uint8_t* smem) {
+  const int lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
+  const int tilesX = w >> 3, tilesY = h >> 3, tpp = tilesX * tilesY;
+  const bool small = tpp <= 4;                        // several whole PUs per group
+  const int lt = small ? (tpp >> 1) : 0;              // log2(tpp) for 1, 2, 4
+  const int P = small ? (8 >> lt) : 1;                // PUs per group
+  const int R = small ? tilesY : 8 / tilesX;          // tile rows per strip
+  const int nStrips = small ? 1 : (tilesY + R - 1) / R;
+  auto tile_row = [&](int j) { return small ? j >> (tilesX >> 1) : (j >= tilesX) + (j >= 2 * tilesX) + (j >= 3 * tilesX); };
+  // feeder role: column gq
+  const int pf = small ? gq >> lt : 0;
+  const int jF = small ? gq & (tpp - 1) : gq;
+  const int tyF = tile_row(jF), txF = jF - tyF * tilesX;
+  // result role: column 2t + (gq & 1)
+  const int nR = 2 * t + (gq & 1);
+  const int pr = small ? nR >> lt : 0;
+  const int tyR = tile_row(small ? nR & (tpp - 1) : nR);
+
+  const int gPitch = g.pitch, gOrgPitch = g.orgPitch, gPlaneBytes = (int)g.planeBytes;
+  // ---- records: the feeder's PU and the result holder's PU (16-byte heads; lanes past `count` reuse the last PU) ----
+  const int idxF = order[first + min(pf, count - 1)], idxR = order[first + min(pr, count - 1)];
+  const unsigned* hF = reinterpret_cast<const unsigned*>(pus + idxF);
+  const unsigned* hR = reinterpret_cast<const unsigned*>(pus + idxR);
+  const unsigned f0 = __ldg(hF), f1 = __ldg(hF + 1), f2 = __ldg(hF + 2);
+  const unsigned r1 = __ldg(hR + 1), r2 = __ldg(hR + 2), r3 = __ldg(hR + 3);
+  if (__any_sync(0xffffffffu, (((f1 | r1) >> 24) & FME_PU_LOSSLESS) != 0)) return false;
+  const int px = (short)(f0 & 0xffff), py = (short)(f0 >> 16);
+  const int X = min(max(px + (short)(f2 & 0xffff), -(g.M - 8)), g.W + g.M - 8 - w);  // as k2_pack: guards memory only
+  const int Y = min(max(py + (short)(f2 >> 16), -(g.M - 8)), g.H + g.M - 8 - h);
+  const int alignX = X + g.M;
+  const uint8_t* const slotBase = planes + (size_t)min((int)((f1 >> 16) & 0xff), g.numSlots - 1) * g.slotBytes;
+  const int ox = min(max(px, 0), g.W - w), oy = min(max(py, 0), g.H - h);
+  const int mvIntX = (short)(r2 & 0xffff), mvIntY = (short)(r2 >> 16);
+  const int predX = (short)(r3 & 0xffff), predY = (short)(r3 >> 16);
+
+  // ---- staging geometry (granule A, as in k2_pack) ----
+  const int RW = ((w + A + A - 1) / A) * A;
+  const int G = RW / A;
+  const int hsMax = small ? h : R * 8;
+  const int RB = (hsMax + 1) * RW;
+  const int PRB = P * RB;                  // one plane / candidate slot: the regions of the group's PUs
+  const int HALF = (4 * PRB + 15) & ~15;
+  const int LPI = small ? tpp : 8;         // lanes per (plane, PU) item
+  const int lpiShift = small ? lt : 3;
+  const int kS = (lane >> lpiShift) & 3, subS = lane & (LPI - 1);
+  int gpShift = 0;
+  while ((1 << gpShift) < G && (1 << gpShift) < LPI) ++gpShift;
+  const int stGi = subS & ((1 << gpShift) - 1), stRow0 = subS >> gpShift, stRowStep = LPI >> gpShift;
+  const bool stSecond = (1 << gpShift) < G;  // single-lane items (8x8 PUs): both granules of a row
+  const bool stOn = pf < count && stGi < G;
+  const unsigned bufSA = (unsigned)__cvta_generic_to_shared(smem);
+  const unsigned stDst = bufSA + (kS * P + pf) * RB + stRow0 * RW + stGi * A;
+  const int stSrcOff = stRow0 * gPitch + stGi * A;
+
+  unsigned afrag[4];
+  had16_afrag(lane, afrag);
+
+  // feeder address parts that do not depend on the candidate
+  const int feedTile = pf * RB + (tyF * 8 + 2 * t) * RW + txF * 8;
+  const unsigned feedH = bufSA + feedTile + RW + ((alignX - 1) & (A - 1)) + 1;  // half-pel regions start at (X-1, Y-1)
+
+  unsigned o[8];
+  auto load_org = [&](int y0) {  // source rows 2t, 2t+1 of the fed tile (idle columns read the PU's first tile rows)
+    const uint8_t* src = org + (size_t)(oy + min(y0 + tyF * 8, h - 8) + 2 * t) * gOrgPitch + ox + txF * 8;
+    unsigned lo0, hi0, lo1, hi1;
+    ldg_row8(src, lo0, hi0);
+    ldg_row8(src + gOrgPitch, lo1, hi1);
+    f16_rows(lo0, hi0, lo1, hi1, o);
+  };
+  // PU sums of the result columns: tiles of one PU sit in columns [pr * tps, (pr + 1) * tps)
+  const int tps = small ? tpp : 8;
+  auto pu_sum = [&](unsigned v, bool on) {
+    v = on ? v : 0u;
+    if (tps >= 2) v += __shfl_xor_sync(0xffffffffu, v, 4);   // column bit 0 = g & 1
+    if (tps >= 4) v += __shfl_xor_sync(0xffffffffu, v, 1);   // column bits 1, 2 = t
+    if (tps >= 8) v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+  };
+
+  // ================= half-pel phase =================
+  // staging slot k: plane (fx = 2 (k & 1), fy = 2 (k >> 1)), rows Y - 1 .. Y + hs of the strip
+  auto stage_half = [&](int strip, int half) {
+    if (stOn) {
+      const int y0 = strip * R * 8;
+      const int rows = (small ? h : min(R, tilesY - strip * R) * 8) + 1;
+      const int plane = (kS & 1) * 2 + (kS >> 1) * 8;
+      const int off = plane * gPlaneBytes + (Y + g.M + y0 - 1) * gPitch + ((alignX - 1) & ~(A - 1));
+      stage_rows<A>(stDst + half * HALF, slotBase + off + stSrcOff, stRow0, stRowStep, rows, RW, gPitch, stSecond);
+    }
+    cp_async_commit();
+  };
+  unsigned hAcc[3] = {0, 0, 0};
+  stage_half(0, 0);
+#pragma unroll 1
+  for (int s = 0; s < nStrips; ++s) {
+    const int rowsIn = small ? tilesY : min(R, tilesY - s * R);
+    if (s + 1 < nStrips) { stage_half(s + 1, (s + 1) & 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    load_org(s * R * 8);
+    __syncwarp();
+    const bool onR = pr < count && tyR < rowsIn;
+    const unsigned base = feedH + (s & 1) * HALF;
+    // candidate i of s_acMvRefineH: slot k_i, (dx, dy) = ((2hx)>>2, (2hy)>>2)
+    //   i:  0      1       2      3       4      5        6       7       8
+    //  hx,hy (0,0) (0,-1) (0,1) (-1,0)  (1,0) (-1,-1)  (1,-1)  (-1,1)  (1,1)
+    {
+      const unsigned a[4] = {base, base + 2 * PRB - RW, base + 2 * PRB, base + PRB - 1};
+      hAcc[0] += pu_sum(satd8x8_cands_mma<4>(a, RW, o, afrag, lane), onR);
+    }
+    {
+      const unsigned a[4] = {base + PRB, base + 3 * PRB - RW - 1, base + 3 * PRB - RW, base + 3 * PRB - 1};
+      hAcc[1] += pu_sum(satd8x8_cands_mma<4>(a, RW, o, afrag, lane), onR);
+    }
+    {
+      const unsigned a[1] = {base + 3 * PRB};
+      hAcc[2] += pu_sum(satd8x8_cands_mma<1>(a, RW, o, afrag, lane), onR);
+    }
+    __syncwarp();  // the buffer half is free for strip s + 2
+  }
+  // ---- half-pel decision (TEncSearch.cpp:1634 strict <, first minimum in table order) ----
+  // MV bits, cost scale 1 (TEncSearch.cpp:4531): ((int << 1) + h) << 1 against the predictor
+  const int cq = gq >> 1;  // this lane's candidate inside a batch
+  auto half_cost = [&](int i, unsigned dist) {
+    const int hx = c_refineH[i][0], hy = c_refineH[i][1];
+    const int bits = golomb_bits((((mvIntX << 1) + hx) << 1) - predX) + golomb_bits((((mvIntY << 1) + hy) << 1) - predY);
+    return dist + costLut[bits];
+  };
+  unsigned bestC = half_cost(cq, hAcc[0]);
+  int bestI = cq;
+  {
+    const unsigned c1 = half_cost(4 + cq, hAcc[1]);
+    if (c1 < bestC) { bestC = c1; bestI = 4 + cq; }
+    const unsigned c2 = half_cost(8, hAcc[2]);
+    if (c2 < bestC) { bestC = c2; bestI = 8; }
+  }
+#pragma unroll
+  for (int d = 8; d <= 16; d <<= 1) {  // across the four candidate lanes of a batch
+    const unsigned oc = __shfl_xor_sync(0xffffffffu, bestC, d);
+    const int oi = __shfl_xor_sync(0xffffffffu, bestI, d);
+    if (oc < bestC || (oc == bestC && oi < bestI)) { bestC = oc; bestI = oi; }
+  }
+  const int bhxR = c_refineH[bestI][0], bhyR = c_refineH[bestI][1];
+  // the feeder needs the winner of ITS PU: held by the lane with result column pf * tps (candidate bits 0)
+  const int colF = pf * tps;
+  const int bhPackF = __shfl_sync(0xffffffffu, (bhxR & 0xff) | ((bhyR & 0xff) << 8), 4 * (colF & 1) + (colF >> 1));
+  const int bhxF = (int)(signed char)(bhPackF & 0xff), bhyF = (int)(signed char)((bhPackF >> 8) & 0xff);
+
+  // ================= quarter-pel phase =================
+  // candidate q = 1..8 of s_acMvRefineQ around the winner; batch b holds q = 4b + 1 + k in slot k of half b
+  auto stage_qter = [&](int strip, int b) {
+    if (stOn) {
+      const int y0 = strip * R * 8;
+      const int rows = small ? h : min(R, tilesY - strip * R) * 8;
+      const int q = 4 * b + 1 + kS;
+      const int qx = 2 * bhxF + c_refineQ[q][0], qy = 2 * bhyF + c_refineQ[q][1];
+      const int plane = (qy & 3) * 4 + (qx & 3);
+      const int off = plane * gPlaneBytes + (Y + g.M + y0 + (qy >> 2)) * gPitch + ((alignX + (qx >> 2)) & ~(A - 1));
+      stage_rows<A>(stDst + b * HALF, slotBase + off + stSrcOff, stRow0, stRowStep, rows, RW, gPitch, stSecond);
+    }
+    cp_async_commit();
+  };
+  // feeder addresses for x offsets -1, 0, +1 of the quarter stage (rows are handled by the staging origin)
+  unsigned feedQ[3];
+#pragma unroll
+  for (int e = 0; e < 3; ++e) feedQ[e] = bufSA + feedTile + ((alignX + ((2 * bhxF + e - 1) >> 2)) & (A - 1));
+  unsigned qAcc[2] = {0, 0};
+  const int nJobs = 2 * nStrips;  // job j = (strip j >> 1, batch j & 1) uses buffer half j & 1
+  stage_qter(0, 0);
+  stage_qter(0, 1);
+#pragma unroll 1
+  for (int j = 0; j < nJobs; ++j) {
+    const int s = j >> 1, b = j & 1;
+    const int rowsIn = small ? tilesY : min(R, tilesY - s * R);
+    if (j + 1 < nJobs) cp_async_wait<1>(); else cp_async_wait<0>();
+    if (b == 0 && nStrips > 1) load_org(s * R * 8);
+    __syncwarp();
+    const bool onR = pr < count && tyR < rowsIn;
+    const unsigned hb = b * HALF;
+    // q:    1      2       3       4       5      6      7      8
+    // ox:   0      0      -1       1      -1      1     -1      1
+    if (b == 0) {
+      const unsigned a[4] = {feedQ[1] + hb, feedQ[1] + hb + PRB, feedQ[0] + hb + 2 * PRB, feedQ[2] + hb + 3 * PRB};
+      qAcc[0] += pu_sum(satd8x8_cands_mma<4>(a, RW, o, afrag, lane), onR);
+    } else {
+      const unsigned a[4] = {feedQ[0] + hb, feedQ[2] + hb + PRB, feedQ[0] + hb + 2 * PRB, feedQ[2] + hb + 3 * PRB};
+      qAcc[1] += pu_sum(satd8x8_cands_mma<4>(a, RW, o, afrag, lane), onR);
+    }
+    __syncwarp();
+    if (j + 2 < nJobs) stage_qter((j + 2) >> 1, b);
+  }
+  // ---- quarter-pel decision: candidate 0 is the half-pel winner itself (same block, same bits) ----
+  // cost scale 0 (TEncSearch.cpp:5260): (((int << 1) + half) << 1) + q against the predictor
+  auto qter_cost = [&](int q, unsigned dist) {
+    const int bx = (((mvIntX << 1) + bhxR) << 1) + c_refineQ[q][0], by = (((mvIntY << 1) + bhyR) << 1) + c_refineQ[q][1];
+    return dist + costLut[golomb_bits(bx - predX) + golomb_bits(by - predY)];
+  };
+  unsigned qC = qter_cost(1 + cq, qAcc[0]);
+  int qI = 1 + cq;
+  {
+    const unsigned c1 = qter_cost(5 + cq, qAcc[1]);
+    if (c1 < qC) { qC = c1; qI = 5 + cq; }
+  }
+#pragma unroll
+  for (int d = 8; d <= 16; d <<= 1) {
+    const unsigned oc = __shfl_xor_sync(0xffffffffu, qC, d);
+    const int oi = __shfl_xor_sync(0xffffffffu, qI, d);
+    if (oc < qC || (oc == qC && oi < qI)) { qC = oc; qI = oi; }
+  }
+  if (bestC <= qC) { qC = bestC; qI = 0; }  // strict < against the running best that starts at candidate 0
+
+  if (pr < count && nR == pr * tps && cq == 0) {
+    fme_result* r = &res[idxR];
+    r->halfX = (int8_t)bhxR; r->halfY = (int8_t)bhyR;
+    r->qterX = c_refineQ[qI][0]; r->qterY = c_refineQ[qI][1];
+    r->cost = qC;
+  }
+  __syncwarp();
+  return true;
+}
+
+// warps per CTA (one CTA per SM): SWAR k2_pack needs 168 registers (12 warps); k2_group_mma runs at 128 (16 warps)
+#ifndef FME_K2_WARPS_GROUP
+#define FME_K2_WARPS_GROUP 16
 #endif
+template <int PATH>
+constexpr int k2_warps() { return PATH == 2 ? FME_K2_WARPS_GROUP : K2_WARPS; }
+
+template <bool BI, int PATH>
+__global__ void __launch_bounds__(k2_warps<PATH>() * 32, 1)
 k2_refine(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, const uint8_t* __restrict__ planes,
           const uint8_t* __restrict__ org, const FmeGeom g, const uint32_t* __restrict__ costLutG, int useHad,
           const int* __restrict__ order, const int* __restrict__ classOffset, const int* __restrict__ packOffset,
           int* __restrict__ workCounter) {
+  constexpr int mmaGroups = PATH == 2 ? 1 : 0;
   extern __shared__ __align__(16) uint8_t dynSmem[];
   __shared__ uint32_t s_lut[FME_COST_LUT_SIZE];
   __shared__ int s_packOff[FME_MAX_CLASSES + 1];
@@ -983,17 +1289,25 @@ k2_refine(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, const ui
     const int v = hit ? (__ffs(hit) - 1) : (32 + __ffs(hit2) - 1);
     ClassInfo ci = class_info(FME_MAX_CLASSES - 1 - v);
     int inClass = s_classOff[v + 1] - s_classOff[v];
-    int first = (pack - s_packOff[v]) * ci.P;
-    int count = min(ci.P, inClass - first);
+    const int packP = pack_pus(ci, mmaGroups);
+    int first = (pack - s_packOff[v]) * packP;
+    int count = min(packP, inClass - first);
     first += s_classOff[v];
 #define K2_ARGS ci, order, first, count, pus, res, planes, org, g, s_lut, useHad, smem
+    if constexpr (PATH == 2) {
+      if (ci.ts == 8) {
+        const bool done = ci.w >= 16 ? k2_group_mma<16>(ci.w, ci.h, order, first, count, pus, res, planes, org, g, s_lut, smem)
+                                     : k2_group_mma<8>(ci.w, ci.h, order, first, count, pus, res, planes, org, g, s_lut, smem);
+        if (done) continue;  // otherwise (a lossless PU in the group) the generic path below serves it
+      }
+    }
     if (ci.ts == 8) {
-      if (ci.w >= 16) k2_pack<8, 16, BI>(K2_ARGS);
-      else k2_pack<8, 8, BI>(K2_ARGS);
+      if (ci.w >= 16) k2_pack<8, 16, BI, PATH>(K2_ARGS);
+      else k2_pack<8, 8, BI, PATH>(K2_ARGS);
     } else {
-      if (ci.w >= 16) k2_pack<4, 16, BI>(K2_ARGS);
-      else if (ci.w >= 8) k2_pack<4, 8, BI>(K2_ARGS);
-      else k2_pack<4, 4, BI>(K2_ARGS);
+      if (ci.w >= 16) k2_pack<4, 16, BI, PATH>(K2_ARGS);
+      else if (ci.w >= 8) k2_pack<4, 8, BI, PATH>(K2_ARGS);
+      else k2_pack<4, 4, BI, PATH>(K2_ARGS);
     }
 #undef K2_ARGS
   }
@@ -1019,7 +1333,7 @@ __global__ void __launch_bounds__(PE_WARPS * 32) k_pred_error(const fme_mc_pu* _
   for (int i = blockIdx.x * PE_WARPS + warp; i < n; i += gridDim.x * PE_WARPS) {
     const fme_mc_pu p = pus[i];
     const int w = p.w, h = p.h;
-    if (fme_dim_index(w) < 0 || fme_dim_index(h) < 0) {
+    if (!fme_hevc_pu_shape(w, h)) {
       if (lane == 0) out[i] = 0xffffffffu;
       continue;
     }
@@ -1077,7 +1391,7 @@ cudaError_t fme_launch_clear_results(fme_result* d_res, int n, cudaStream_t s, i
   return cudaGetLastError();
 }
 
-template <bool BI>
+template <bool BI, int PATH>
 static cudaError_t launch_k2_pass(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_pu* d_pus, int n,
                                   fme_result* d_res, const uint32_t* d_costLut, int useHad, const FmeK2Scratch& sc,
                                   int numSMs, cudaStream_t s, int64_t* launches) {
@@ -1087,32 +1401,37 @@ static cudaError_t launch_k2_pass(const FmeGeom& g, const uint8_t* d_planes, con
   int blocks = min(numSMs * 4, (n + 255) / 256);
   k2_count<<<blocks, 256, 0, s>>>(d_pus, n, sc.classCount, BI ? 1 : 0);
   k2_scatter<<<blocks, 256, 0, s>>>(d_pus, n, sc.classCount, sc.classOffset, sc.packOffset, sc.classCursor, sc.order,
-                                    BI ? 1 : 0);
+                                    BI ? 1 : 0, PATH == 2 ? 1 : 0);
   *launches += 2;
-  static bool attrSet[64] = {};  // per device: the opt-in to > 48 KB dynamic shared memory is a per-device attribute
-  const int smemBytes = K2_WARPS * K2_SMEM_PER_WARP;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!attrSet[dev & 63]) {
-    e = cudaFuncSetAttribute(k2_refine<BI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
-    if (e != cudaSuccess) return e;
-    attrSet[dev & 63] = true;
-  }
-  k2_refine<BI><<<numSMs, K2_THREADS, smemBytes, s>>>(d_pus, d_res, d_planes, d_org, g, d_costLut, useHad, sc.order,
-                                                      sc.classOffset, sc.packOffset, sc.workCounter);
+  const int smemBytes = k2_warps<PATH>() * K2_SMEM_PER_WARP;
+  // the opt-in to > 48 KB dynamic shared memory is a per-device, per-function attribute; setting it is cheap and
+  // idempotent, so it is simply set before every launch (no shared state between host threads / contexts)
+  e = cudaFuncSetAttribute(k2_refine<BI, PATH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
+  if (e != cudaSuccess) return e;
+  k2_refine<BI, PATH><<<numSMs, k2_warps<PATH>() * 32, smemBytes, s>>>(d_pus, d_res, d_planes, d_org, g, d_costLut, useHad,
+                                                                      sc.order, sc.classOffset, sc.packOffset, sc.workCounter);
   ++*launches;
   return cudaGetLastError();
 }
 
+// k2Path: how the 8x8 SATD of uni-prediction Hadamard PUs is computed (fme_config.k2Path): FME_K2_PATH_SWAR (integer
+// SWAR in registers), FME_K2_PATH_MMA_PACK (tensor pipe inside the 32-lane packs) or FME_K2_PATH_MMA_GROUP (tensor pipe,
+// eight-tile groups x four candidates).  All three are bit-identical; SAD mode and bi-predictive records always take
+// the SWAR kernels.
 // biPred != 0: a second binning + refinement pass serves the bi-predictive refinement records (FME_PU_BI); with
 // biPred == 0 such records are left untouched (the synchronous entry points reject them).
 cudaError_t fme_launch_k2(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_pu* d_pus, int n,
-                          fme_result* d_res, const uint32_t* d_costLut, int useHad, int biPred, const FmeK2Scratch& sc,
-                          int numSMs, cudaStream_t s, int64_t* launches) {
+                          fme_result* d_res, const uint32_t* d_costLut, int useHad, int biPred, int k2Path,
+                          const FmeK2Scratch& sc, int numSMs, cudaStream_t s, int64_t* launches) {
   if (n <= 0) return cudaSuccess;
-  cudaError_t e = launch_k2_pass<false>(g, d_planes, d_org, d_pus, n, d_res, d_costLut, useHad, sc, numSMs, s, launches);
+  cudaError_t e;
+#define K2_UNI(PATH) launch_k2_pass<false, PATH>(g, d_planes, d_org, d_pus, n, d_res, d_costLut, useHad, sc, numSMs, s, launches)
+  if (!useHad || k2Path == FME_K2_PATH_SWAR) e = K2_UNI(0);
+  else if (k2Path == FME_K2_PATH_MMA_PACK) e = K2_UNI(1);
+  else e = K2_UNI(2);
+#undef K2_UNI
   if (e != cudaSuccess || !biPred) return e;
-  return launch_k2_pass<true>(g, d_planes, d_org, d_pus, n, d_res, d_costLut, useHad, sc, numSMs, s, launches);
+  return launch_k2_pass<true, 0>(g, d_planes, d_org, d_pus, n, d_res, d_costLut, useHad, sc, numSMs, s, launches);
 }
 
 cudaError_t fme_launch_pred_error(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_mc_pu* d_pus,

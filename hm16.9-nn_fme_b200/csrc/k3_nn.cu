@@ -312,13 +312,9 @@ cudaError_t launch_fixed(const fme_pu* d_pus, int n, fme_result* d_res, const fl
                         (H3 > 0 ? LayerSmem<H2, (H3 > 0 ? H3 : 1)>::WORDS : 0) + LayerSmem<HLAST, NOUT>::WORDS +
                         HMAX * K3F_NPU * K3F_THREADS;
   const int smem = words * 4;
-  static bool attr[64] = {};  // per device
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!attr[dev & 63] && smem > 48 * 1024) {
+  if (smem > 48 * 1024) {  // per-device, per-function opt-in; idempotent and cheap, so no cached state shared between host threads
     cudaError_t e = cudaFuncSetAttribute(k3_nn_fixed<NEMB, H1, H2, H3, NOUT, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    attr[dev & 63] = true;
   }
   int blocks = (n + K3F_NPU * K3F_THREADS - 1) / (K3F_NPU * K3F_THREADS);
   if (blocks > 148 * 6) blocks = 148 * 6;

@@ -74,8 +74,8 @@ __global__ void __launch_bounds__(256) k0_int_surface(fme_pu* __restrict__ pus, 
       w = r1 & 0xff; h = (r1 >> 8) & 0xff; slot = (r1 >> 16) & 0xff; flags = r1 >> 24;
       mvx = (int)(short)(r2 & 0xffff); mvy = (int)(short)(r2 >> 16);
     }
-    const bool doit = valid && (flags & FME_PU_ERR_ON_GPU) && !(flags & FME_PU_BI) && fme_dim_index(w) >= 0 &&
-                      fme_dim_index(h) >= 0;  // FME_PU_BI records carry the other list's prediction in err[]
+    const bool doit = valid && (flags & FME_PU_ERR_ON_GPU) && !(flags & FME_PU_BI) &&
+                      fme_hevc_pu_shape(w, h);  // FME_PU_BI records carry the other list's prediction in err[]
     unsigned acc[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[k] = 0;

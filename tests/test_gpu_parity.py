@@ -266,6 +266,37 @@ def test_full_416x240_list_vs_oracle(use_had):
         eng.close()
 
 
+@pytest.mark.parametrize("k2_path", [fme.K2_PATH_SWAR, fme.K2_PATH_MMA_PACK, fme.K2_PATH_MMA_GROUP])
+def test_k2_paths_bit_identical_vs_oracle(k2_path):
+    """fme_config.k2Path: the SWAR integer Hadamard and the two fp16-in / fp32-accumulate tensor-pipe formulations must
+    give the reference's costs and vectors bit for bit (TComRdCost.cpp:1330-1425), on every HEVC PU shape (AMP
+    included), with lossless PUs mixed into the packs, partial packs and a saturating-content frame."""
+    W, H = 416, 240
+    for content in ("synthetic", "extreme"):
+        org, refs, motions = fme.pu_list.synth_frames(W, H, n_refs=2, seed=77)
+        if content == "extreme":   # 0/255 checkerboards and steps: the largest residuals and coefficients
+            yy, xx = np.mgrid[0:H, 0:W]
+            org = (((xx ^ yy) & 1) * 255).astype(np.uint8)
+            refs = [(((xx // 3 + yy // 5) & 1) * 255).astype(np.uint8), (255 - org).astype(np.uint8)]
+        recs = fme.pu_list.make_records(W, H, motions, seed=5, amp=True)
+        recs["flags"][::11] |= fme.PU_LOSSLESS
+        recs = np.ascontiguousarray(recs[:len(recs) - 3])        # ragged tail: partial packs / groups
+        frame = ob.CpuFrame(org, refs)
+        frame.oracle_fill_surface(recs)
+        lam = fme.pu_list.slice_lambda(27)
+        eng = fme.Fme(W, H, num_ref_slots=2, max_pus=len(recs), k2_path=k2_path)
+        eng.set_slice(lam)
+        eng.upload_org(org)
+        for s in range(2):
+            eng.upload_ref(s, refs[s])
+        got = eng.submit(recs, fme.MODE_STD)
+        eng.close()
+        want = frame.oracle_run(recs, 1, lam, 1, None)
+        for f in ("halfX", "halfY", "qterX", "qterY", "cost"):
+            bad = np.nonzero(got[f] != want[f])[0]
+            assert len(bad) == 0, (content, f, len(bad), recs[bad[:4]], got[bad[:4]], want[bad[:4]])
+
+
 @pytest.mark.parametrize("use_had", [True, False])
 def test_bi_predictive_refinement_all_shapes_vs_oracle(use_had):
     """FME_PU_BI records (pattern 2*org - other list's prediction) for every PU shape incl. AMP and the > 32-tile
