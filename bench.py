@@ -162,9 +162,15 @@ def run_gpu(args):
         d_recs[i].copy_(torch.from_numpy(full.view(np.uint8).reshape(len(full), -1)))
     torch.cuda.synchronize(dev)
 
+    # lowdelay_P changes lambda every picture (QP offsets 3,2,3,1 / factors, cfg/encoder_lowdelay_P_main.cfg:24-27):
+    # fme_set_slice is part of every step, device-resident and end-to-end alike
+    lams = [fme.pu_list.slice_lambda(QP, off, fac) for off, fac in
+            zip(fme.pu_list.LOWDELAY_P_QP_OFFSETS, fme.pu_list.LOWDELAY_P_QP_FACTORS)]
+
     def step_device(i):
         k = i % n_sets
         slot = i % N_REFS
+        eng.set_slice(lams[i % len(lams)])
         if banded and world > 1:
             # the rank that "reconstructed" the new reference broadcasts it over NVLink
             dist.broadcast(d_refs[k][slot], src=i % world)
@@ -234,6 +240,7 @@ def run_gpu(args):
             i = first + j
             k = i % n_sets
             slot = i % N_REFS
+            eng.set_slice(lams[i % len(lams)])      # per-picture lambda, as TEncSlice sets it before the CTU loop
             if banded and world > 1:
                 dist.broadcast(d_refs[k][slot], src=i % world)
                 torch.cuda.current_stream(dev).synchronize()
@@ -306,12 +313,12 @@ def run_gpu(args):
     kavg = {k: float(np.mean(v)) for k, v in kms.items()}
     # K1 alone, back to back over the 4 slots (4 x 43 MB of output > L2), no picture copy in between
     for s_ in range(N_REFS):
-        eng.interp_slot(s_)
+        eng.upload_ref_device_u8(s_, d_refs[0][s_].data_ptr(), width)
     k1e0, k1e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k1e0.record(stream)
     K1_REPS = 16
-    for r_ in range(K1_REPS):
-        eng.interp_slot(r_ % N_REFS)
+    for r_ in range(K1_REPS):   # device pictures are interpolated in place: these launches are K1 and nothing else
+        eng.upload_ref_device_u8(r_ % N_REFS, d_refs[r_ % n_sets][r_ % N_REFS].data_ptr(), width)
     k1e1.record(stream)
     torch.cuda.synchronize(dev)
     kavg["k1_interp_alone"] = k1e0.elapsed_time(k1e1) / K1_REPS

@@ -82,7 +82,6 @@ struct fme_ctx {
   float* d_nn = nullptr;
   size_t nnBytes = 0;
   FmeNnHeader nnHeader{};
-  uint32_t* d_costLut = nullptr;
   int* d_k1Counter = nullptr;    // K1's dynamic tile hand-out (2 ints, re-armed by the kernel)
   uint32_t* d_scratchU32 = nullptr;
   size_t scratchU32Capacity = 0;
@@ -91,7 +90,7 @@ struct fme_ctx {
   std::vector<char> refValid;
   bool orgValid = false, sliceValid = false, nnValid = false;
   double lambda = 0.0;
-  uint32_t costLut[FME_COST_LUT_SIZE];
+  FmeCostLut costLut;            // the current slice's table; copied into every K2 launch as a kernel argument
   // profiling
   bool profiling = false;
   cudaEvent_t ev[8] = {};
@@ -166,9 +165,10 @@ struct StageTimer {
   ~StageTimer() { rec(2 * idx + 1); }
 };
 
-int run_k1(fme_ctx* c, int slot) {
+int run_k1(fme_ctx* c, int slot, const uint8_t* d_pic = nullptr, int picPitch = 0) {
   StageTimer t(c, 0);
-  CU_CHECK(fme_launch_k1(c->g, c->d_pic, c->picPitch, c->d_planes + (size_t)slot * c->g.slotBytes, c->d_k1Counter, c->numSMs,
+  if (!d_pic) { d_pic = c->d_pic; picPitch = c->picPitch; }
+  CU_CHECK(fme_launch_k1(c->g, d_pic, picPitch, c->d_planes + (size_t)slot * c->g.slotBytes, c->d_k1Counter, c->numSMs,
                          c->stream, &c->launches));
   c->refValid[slot] = 1;
   return FME_OK;
@@ -203,7 +203,7 @@ int run_search(fme_ctx* c, fme_pu* d_pus, int n, fme_result* d_out, int mode) {
   if (mode != FME_MODE_BOTH) CU_CHECK(fme_launch_clear_results(d_out, n, c->stream, &c->launches));
   if (mode & FME_MODE_STD) {
     StageTimer t(c, 1);
-    CU_CHECK(fme_launch_k2(c->g, c->d_planes, c->d_org, d_pus, n, d_out, c->d_costLut, c->cfg.useHadME, c->cfg.biPred,
+    CU_CHECK(fme_launch_k2(c->g, c->d_planes, c->d_org, d_pus, n, d_out, c->costLut, c->cfg.useHadME, c->cfg.biPred,
                            c->cfg.k2Path == FME_K2_PATH_AUTO ? FME_K2_PATH_DEFAULT : c->cfg.k2Path, c->k2, c->numSMs, c->stream,
                            &c->launches));
   }
@@ -280,6 +280,12 @@ int fme_create(const fme_config* cfg, fme_ctx** out) {
   g.cPitch = round_up(g.Wcp, 128);
   g.cPlaneBytes = (size_t)g.Hcp * g.cPitch;
   g.numSlots = cfg->numRefSlots;
+  if (g.slotBytes > (size_t)INT32_MAX) {  // the kernels form plane offsets (plane * planeBytes + row * pitch) in 32-bit int
+    int rc = fail(FME_ERR_INVALID, "picture %dx%d with margin %d: a 16-plane slot of %zu bytes exceeds the 2^31 offset range",
+                  g.W, g.H, g.M, g.slotBytes);
+    delete c;
+    return rc;
+  }
   c->picPitch = round_up(g.W, 256);
   c->refValid.assign(cfg->numRefSlots, 0);
 
@@ -313,7 +319,6 @@ int fme_create(const fme_config* cfg, fme_ctx** out) {
     CREATE_CHECK(cudaMalloc(&c->d_resBuf[b], sizeof(fme_result) * (size_t)cfg->maxPUs));
   }
   c->d_org = c->d_orgBuf[0]; c->d_pic = c->d_picBuf[0]; c->d_pus = c->d_pusBuf[0]; c->d_res = c->d_resBuf[0];
-  CREATE_CHECK(cudaMalloc(&c->d_costLut, sizeof(uint32_t) * FME_COST_LUT_SIZE));
   CREATE_CHECK(cudaMalloc(&c->d_k1Counter, 2 * sizeof(int)));
   CREATE_CHECK(cudaMemsetAsync(c->d_k1Counter, 0, 2 * sizeof(int), c->stream));
   CREATE_CHECK(cudaMalloc(&c->k2.classCount, sizeof(int) * (4 * FME_MAX_CLASSES + 16)));
@@ -340,7 +345,7 @@ void fme_destroy(fme_ctx* c) {
       if (e) cudaEventDestroy(e);
   }
   cudaFree(c->d_cb); cudaFree(c->d_cr); cudaFree(c->d_nn);
-  cudaFree(c->d_costLut); cudaFree(c->d_k1Counter); cudaFree(c->d_scratchU32); cudaFree(c->k2.classCount); cudaFree(c->k2.order);
+  cudaFree(c->d_k1Counter); cudaFree(c->d_scratchU32); cudaFree(c->k2.classCount); cudaFree(c->k2.order);
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
   if (c->ownStream) cudaStreamDestroy(c->ownStream);
@@ -505,18 +510,14 @@ int fme_load_nn_csv_dir(fme_ctx* c, const char* dir) {
 // ---- slice lambda ----------------------------------------------------------------------------
 int fme_set_slice(fme_ctx* c, double lambda) {
   if (!c || !(lambda > 0.0)) return fail(FME_ERR_INVALID, "lambda must be positive");
-  CU_CHECK(cudaSetDevice(c->cfg.device));
   c->lambda = lambda;
   // TComRdCost.cpp:108 m_dLambdaMotionSAD[0]; TComRdCost.h:159 selectMotionLambda(true, 0, false);
   // TComRdCost.h:165-169 Distortion((m_motionLambda * bits) / 65536.0)
+  // (FME_PU_LOSSLESS records use the same table: bit-exact for the standard lossy and the all-lossless cost modes;
+  //  COST_MIXED_LOSSLESS_LOSSY_CODING would select m_dLambdaMotionSAD[1] for transquant-bypass PUs, TComRdCost.cpp:110-116)
   const double motionLambda = 65536.0 * sqrt(lambda);
-  for (unsigned b = 0; b < FME_COST_LUT_SIZE; ++b) c->costLut[b] = (uint32_t)((motionLambda * b) / 65536.0);
-  {
-    int rc = sync_all(c);  // in-flight submits still read the previous table
-    if (rc) return rc;
-  }
-  CU_CHECK(cudaMemcpyAsync(c->d_costLut, c->costLut, sizeof(c->costLut), cudaMemcpyHostToDevice, c->stream));
-  CU_CHECK(cudaStreamSynchronize(c->stream));
+  for (unsigned b = 0; b < FME_COST_LUT_SIZE; ++b) c->costLut.v[b] = (uint32_t)((motionLambda * b) / 65536.0);
+  // No synchronisation and no device copy: submits already issued carry the previous table in their launch arguments.
   c->sliceValid = true;
   return FME_OK;
 }
@@ -531,7 +532,7 @@ int fme_mv_cost(fme_ctx* c, int x, int y, int scale, int predX, int predY, uint3
   };
   unsigned b = bits((x << scale) - predX) + bits((y << scale) - predY);
   if (b >= FME_COST_LUT_SIZE) return fail(FME_ERR_INVALID, "vector out of range");
-  *out = c->costLut[b];
+  *out = c->costLut.v[b];
   return FME_OK;
 }
 
@@ -558,7 +559,10 @@ int fme_upload_ref_device_u8(fme_ctx* c, int slot, const uint8_t* d_y, int pitch
   if (rc) return rc;
   if (!d_y || pitch < c->g.W) return fail(FME_ERR_INVALID, "bad device picture");
   CU_CHECK(cudaSetDevice(c->cfg.device));
-  // device-resident input: ordered on the kernel stream, no copy-in stream involved
+  // device-resident input, ordered on the kernel stream.  K1 reads 32-bit words: a 4-byte aligned picture is
+  // interpolated straight from the caller's buffer (which must stay unchanged until the work issued here has run, as
+  // with any stream-ordered call); anything else goes through a staging copy.
+  if (((size_t)d_y & 3) == 0 && (pitch & 3) == 0) return run_k1(c, slot, d_y, pitch);
   int idx = (int)(c->picSeq++ % FME_NBUF);
   CU_CHECK(cudaStreamWaitEvent(c->stream, c->evPicFree[idx], 0));
   c->d_pic = c->d_picBuf[idx];
@@ -570,8 +574,16 @@ int fme_upload_ref_device_u8(fme_ctx* c, int slot, const uint8_t* d_y, int pitch
 int fme_interp_slot(fme_ctx* c, int slot) {
   int rc = check_slot(c, slot);
   if (rc) return rc;
+  if (!c->refValid[slot]) return fail(FME_ERR_STATE, "fme_interp_slot: slot %d holds no picture", slot);
   CU_CHECK(cudaSetDevice(c->cfg.device));
-  return run_k1(c, slot);
+  // the slot's own picture = the picture area of its plane 0 (integer-pel copy, margin M on every side)
+  int idx = (int)(c->picSeq++ % FME_NBUF);
+  CU_CHECK(cudaStreamWaitEvent(c->stream, c->evPicFree[idx], 0));
+  c->d_pic = c->d_picBuf[idx];
+  const uint8_t* plane0 = c->d_planes + (size_t)slot * c->g.slotBytes + (size_t)c->g.M * c->g.pitch + c->g.M;
+  CU_CHECK(cudaMemcpy2DAsync(c->d_pic, c->picPitch, plane0, c->g.pitch, c->g.W, c->g.H, cudaMemcpyDeviceToDevice, c->stream));
+  if ((rc = run_k1(c, slot))) return rc;
+  return release_picture(c, idx);
 }
 
 // The source picture lives in a ring: a new upload goes to a buffer no in-flight submit reads.
@@ -680,7 +692,9 @@ static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, 
       }
     }
   } else {
-    needK0 = (pus[0].flags & FME_PU_ERR_ON_GPU) != 0;
+    // unvalidated path: nothing is read from the caller's (pinned) records here.  K0 is launched whenever NN_pred runs --
+    // it skips records without FME_PU_ERR_ON_GPU itself -- so a mixed batch can never feed K3 an unfilled err[].
+    needK0 = (mode & FME_MODE_NN) != 0;
   }
   if (needK0 && !c->orgValid) return fail(FME_ERR_STATE, "FME_PU_ERR_ON_GPU needs fme_upload_org first");
   if (c->fifoCount == FME_NBUF) {  // at most FME_NBUF submits in flight: retire the oldest before reusing its buffers

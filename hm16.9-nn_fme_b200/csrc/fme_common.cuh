@@ -10,6 +10,13 @@
 #define FME_COST_LUT_SIZE 160 // MV bit counts: 2 * (1 + 2*17) = 70 max for 16-bit components, padded
 #define FME_MAX_CLASSES 64    // (w index) * 8 + (h index), w,h in {4,8,12,16,24,32,48,64}
 
+// MV-bit cost table of one slice, cost[bits] (fme_set_slice).  It travels BY VALUE as a kernel argument of k2_refine:
+// every launch carries the table of the slice it was submitted under, so changing lambda never has to wait for
+// submits in flight (lowdelay_P changes lambda every frame, cfg/encoder_lowdelay_P_main.cfg:24-27).
+struct FmeCostLut {
+  uint32_t v[FME_COST_LUT_SIZE];
+};
+
 // Geometry of one padded plane set (all slots share it).
 struct FmeGeom {
   int W, H;        // picture
@@ -76,7 +83,7 @@ cudaError_t fme_launch_k1(const FmeGeom& g, const uint8_t* d_pic, int picPitch, 
 cudaError_t fme_launch_pad_chroma(const FmeGeom& g, const uint8_t* d_pic, int picPitch, uint8_t* d_plane,
                                   cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_k2(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_pu* d_pus, int n,
-                          fme_result* d_res, const uint32_t* d_costLut, int useHad, int biPred, int k2Path,
+                          fme_result* d_res, const FmeCostLut& costLut, int useHad, int biPred, int k2Path,
                           const FmeK2Scratch& sc, int numSMs, cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_k3(const fme_pu* d_pus, int n, fme_result* d_res, const float* d_nn, size_t nnBytes,
                           const FmeNnHeader& h, int fma, cudaStream_t s, int64_t* launches);

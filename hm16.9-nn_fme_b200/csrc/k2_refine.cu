@@ -84,13 +84,20 @@ __device__ __forceinline__ int k2_class_of(const fme_pu& p, int wantBi) {
   return fme_dim_index(p.w) * 8 + fme_dim_index(p.h);
 }
 
-__global__ void k2_count(const fme_pu* __restrict__ pus, int n, int* __restrict__ classCount, int wantBi) {
+// res != nullptr (the uni-prediction pass): records no K2 pass will serve -- a shape HEVC cannot produce, or FME_PU_BI
+// on a ctx without biPred -- get the sentinel result (zero vectors, cost 0xffffffff) instead of whatever the result
+// buffer held (the unvalidated async / device entry points, include/fme_b200.h).
+__global__ void k2_count(const fme_pu* __restrict__ pus, int n, int* __restrict__ classCount, int wantBi,
+                         fme_result* __restrict__ res, int biServed) {
   __shared__ int s_cnt[FME_MAX_CLASSES];
   for (int i = threadIdx.x; i < FME_MAX_CLASSES; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int c = k2_class_of(pus[i], wantBi);
+    const fme_pu p = pus[i];
+    const int c = k2_class_of(p, wantBi);
     if (c >= 0) atomicAdd(&s_cnt[c], 1);
+    else if (res && (!fme_hevc_pu_shape(p.w, p.h) || ((p.flags & FME_PU_BI) && !biServed)))
+      *reinterpret_cast<uint2*>(&res[i]) = make_uint2(0u, 0xffffffffu);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < FME_MAX_CLASSES; i += blockDim.x)
@@ -1255,7 +1262,7 @@ constexpr int k2_warps() { return PATH == 2 ? FME_K2_WARPS_GROUP : K2_WARPS; }
 template <bool BI, int PATH>
 __global__ void __launch_bounds__(k2_warps<PATH>() * 32, 1)
 k2_refine(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, const uint8_t* __restrict__ planes,
-          const uint8_t* __restrict__ org, const FmeGeom g, const uint32_t* __restrict__ costLutG, int useHad,
+          const uint8_t* __restrict__ org, const FmeGeom g, const FmeCostLut costLutG, int useHad,
           const int* __restrict__ order, const int* __restrict__ classOffset, const int* __restrict__ packOffset,
           int* __restrict__ workCounter) {
   constexpr int mmaGroups = PATH == 2 ? 1 : 0;
@@ -1264,7 +1271,7 @@ k2_refine(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, const ui
   __shared__ int s_packOff[FME_MAX_CLASSES + 1];
   __shared__ int s_classOff[FME_MAX_CLASSES + 1];
 
-  for (int i = threadIdx.x; i < FME_COST_LUT_SIZE; i += blockDim.x) s_lut[i] = costLutG[i];
+  for (int i = threadIdx.x; i < FME_COST_LUT_SIZE; i += blockDim.x) s_lut[i] = costLutG.v[i];
   for (int i = threadIdx.x; i <= FME_MAX_CLASSES; i += blockDim.x) {
     s_packOff[i] = packOffset[i];
     s_classOff[i] = classOffset[i];
@@ -1393,13 +1400,13 @@ cudaError_t fme_launch_clear_results(fme_result* d_res, int n, cudaStream_t s, i
 
 template <bool BI, int PATH>
 static cudaError_t launch_k2_pass(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_pu* d_pus, int n,
-                                  fme_result* d_res, const uint32_t* d_costLut, int useHad, const FmeK2Scratch& sc,
+                                  fme_result* d_res, const FmeCostLut& costLut, int useHad, int biServed, const FmeK2Scratch& sc,
                                   int numSMs, cudaStream_t s, int64_t* launches) {
   // classCount[64], classCursor[64] and the work counter are adjacent (fme_create)
   cudaError_t e = cudaMemsetAsync(sc.classCount, 0, sizeof(int) * (2 * FME_MAX_CLASSES + 1), s);
   if (e != cudaSuccess) return e;
   int blocks = min(numSMs * 4, (n + 255) / 256);
-  k2_count<<<blocks, 256, 0, s>>>(d_pus, n, sc.classCount, BI ? 1 : 0);
+  k2_count<<<blocks, 256, 0, s>>>(d_pus, n, sc.classCount, BI ? 1 : 0, BI ? nullptr : d_res, biServed);
   k2_scatter<<<blocks, 256, 0, s>>>(d_pus, n, sc.classCount, sc.classOffset, sc.packOffset, sc.classCursor, sc.order,
                                     BI ? 1 : 0, PATH == 2 ? 1 : 0);
   *launches += 2;
@@ -1408,7 +1415,7 @@ static cudaError_t launch_k2_pass(const FmeGeom& g, const uint8_t* d_planes, con
   // idempotent, so it is simply set before every launch (no shared state between host threads / contexts)
   e = cudaFuncSetAttribute(k2_refine<BI, PATH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
   if (e != cudaSuccess) return e;
-  k2_refine<BI, PATH><<<numSMs, k2_warps<PATH>() * 32, smemBytes, s>>>(d_pus, d_res, d_planes, d_org, g, d_costLut, useHad,
+  k2_refine<BI, PATH><<<numSMs, k2_warps<PATH>() * 32, smemBytes, s>>>(d_pus, d_res, d_planes, d_org, g, costLut, useHad,
                                                                       sc.order, sc.classOffset, sc.packOffset, sc.workCounter);
   ++*launches;
   return cudaGetLastError();
@@ -1421,17 +1428,17 @@ static cudaError_t launch_k2_pass(const FmeGeom& g, const uint8_t* d_planes, con
 // biPred != 0: a second binning + refinement pass serves the bi-predictive refinement records (FME_PU_BI); with
 // biPred == 0 such records are left untouched (the synchronous entry points reject them).
 cudaError_t fme_launch_k2(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_pu* d_pus, int n,
-                          fme_result* d_res, const uint32_t* d_costLut, int useHad, int biPred, int k2Path,
+                          fme_result* d_res, const FmeCostLut& costLut, int useHad, int biPred, int k2Path,
                           const FmeK2Scratch& sc, int numSMs, cudaStream_t s, int64_t* launches) {
   if (n <= 0) return cudaSuccess;
   cudaError_t e;
-#define K2_UNI(PATH) launch_k2_pass<false, PATH>(g, d_planes, d_org, d_pus, n, d_res, d_costLut, useHad, sc, numSMs, s, launches)
+#define K2_UNI(PATH) launch_k2_pass<false, PATH>(g, d_planes, d_org, d_pus, n, d_res, costLut, useHad, biPred, sc, numSMs, s, launches)
   if (!useHad || k2Path == FME_K2_PATH_SWAR) e = K2_UNI(0);
   else if (k2Path == FME_K2_PATH_MMA_PACK) e = K2_UNI(1);
   else e = K2_UNI(2);
 #undef K2_UNI
   if (e != cudaSuccess || !biPred) return e;
-  return launch_k2_pass<true, 0>(g, d_planes, d_org, d_pus, n, d_res, d_costLut, useHad, sc, numSMs, s, launches);
+  return launch_k2_pass<true, 0>(g, d_planes, d_org, d_pus, n, d_res, costLut, useHad, biPred, sc, numSMs, s, launches);
 }
 
 cudaError_t fme_launch_pred_error(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_mc_pu* d_pus,

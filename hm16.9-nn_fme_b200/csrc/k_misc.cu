@@ -327,7 +327,9 @@ __global__ void k_expand_heads(const fme_pu_head* __restrict__ heads, int n, fme
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint4 v = reinterpret_cast<const uint4*>(heads)[i];
-  v.y |= (unsigned)FME_PU_ERR_ON_GPU << 24;  // flags is byte 7 of the record
+  // flags is byte 7 of the record.  FME_PU_BI is dropped: a bi-predictive record names the other list's prediction in
+  // err[], which a head does not have (the synchronous entry points reject such heads).
+  v.y = (v.y & ~((unsigned)FME_PU_BI << 24)) | ((unsigned)FME_PU_ERR_ON_GPU << 24);
   unsigned* d = reinterpret_cast<unsigned*>(&pus[i]);  // 52-byte records are 4-byte aligned
   d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
 }

@@ -133,6 +133,11 @@ int fme_load_nn_csv_dir(fme_ctx* ctx, const char* dir);
  * (TComRdCost.cpp:104-117, TComRdCost.h:159).  Builds cost[bits] = uint32((65536*sqrt(lambda)*bits)/65536.0)
  * on the host with the reference's exact double expression (TComRdCost.h:165-169). */
 int fme_set_slice(fme_ctx* ctx, double lambda);
+/* fme_set_slice never waits for the device: the table travels with every K2 launch as a kernel argument, so submits
+ * already issued keep the lambda they were submitted under and the call may be made once per slice between
+ * fme_submit_async calls without draining the pipeline.  FME_PU_LOSSLESS records use the same table, which is what
+ * the reference does in the standard lossy and all-lossless cost modes (COST_MIXED_LOSSLESS_LOSSY_CODING, which
+ * selects a second lambda for transquant-bypass PUs, TComRdCost.cpp:110-116, is not reproduced). */
 
 /* ---- frame data --------------------------------------------------------------------------- */
 /* Reference picture: y points at picture sample (0,0) of a TComPicYuv luma plane (Pel, stride in
@@ -153,6 +158,14 @@ int fme_submit(fme_ctx* ctx, const fme_pu* pus, int n, fme_result* out, int mode
 /* Asynchronous halves for pipelining: records/results in pinned host memory owned by the caller.
  * fme_submit_async enqueues H2D + kernels + D2H on the ctx stream; fme_synchronize completes it. */
 int fme_submit_async(fme_ctx* ctx, const fme_pu* pus, int n, fme_result* out, int mode);
+/* Contract of the asynchronous and device-resident entry points (fme_submit_async, fme_submit_heads_async,
+ * fme_submit_device): the records are NOT validated on the host (they are still being DMA'd).  On the device
+ *   - records whose shape HEVC cannot produce, and FME_PU_BI records on a ctx without biPred, are served by no pass:
+ *     their result is the sentinel {half = qter = (0,0), cost = 0xffffffff} (the NN fields are still written);
+ *   - reference slots beyond numRefSlots and integer MVs beyond the padded plane are clamped (memory safety only);
+ *   - the K0 pass runs whenever mode includes FME_MODE_NN and fills err[] of exactly the records flagged
+ *     FME_PU_ERR_ON_GPU, so flagged and unflagged records may be mixed freely in one batch;
+ *   - FME_PU_BI is ignored on head records (a head has no err[] to name the other list's prediction). */
 /* fme_submit / fme_submit_async for records without the error grid: equivalent to full records carrying
  * FME_PU_ERR_ON_GPU (the 3x3 surface of TEncSearch.cpp:5037-5050 is computed on the device before K2 / K3). */
 int fme_submit_heads(fme_ctx* ctx, const fme_pu_head* heads, int n, fme_result* out, int mode);
@@ -163,10 +176,12 @@ int fme_submit_heads_async(fme_ctx* ctx, const fme_pu_head* heads, int n, fme_re
 int fme_wait_oldest(fme_ctx* ctx);
 /* Device-resident variant: d_pus / d_out are device pointers; nothing is copied. */
 int fme_submit_device(fme_ctx* ctx, const fme_pu* d_pus, int n, fme_result* d_out, int mode);
-/* Re-run K1 on the reference already resident in `slot` (device-resident benchmarking). */
+/* Re-run K1 on the reference picture already resident in `slot` (device-resident benchmarking): the picture is taken
+ * from the slot's own integer-pel plane.  FME_ERR_STATE when the slot holds no picture. */
 int fme_interp_slot(fme_ctx* ctx, int slot);
-/* Device-to-device upload of an 8-bit picture (d_y: device pointer, pitch in bytes), then K1.
- * Used with torch/NCCL buffers in the multi-GPU banded mode. */
+/* Reference picture already on the device (d_y: device pointer to 8-bit samples, pitch in bytes), then K1.  A 4-byte
+ * aligned picture is read in place -- it must stay unchanged until the work issued by this call has run on the ctx
+ * stream --, anything else is staged through a device copy.  Used with torch/NCCL buffers in the banded mode. */
 int fme_upload_ref_device_u8(fme_ctx* ctx, int slot, const uint8_t* d_y, int pitch);
 int fme_upload_org_device_u8(fme_ctx* ctx, const uint8_t* d_y, int pitch);
 /* K0: fill fme_pu.err[] of device-resident records from the 3x3 integer error surface

@@ -767,3 +767,117 @@ def test_c5_2160p_ctu_row_bands():
     for f in ("halfX", "halfY", "qterX", "qterY", "cost", "nnClass"):
         assert np.array_equal(full[f][idx], want[f]), f
     eng.close()
+
+
+@pytest.mark.gpu
+def test_set_slice_between_submits_in_flight_matches_synchronous():
+    """fme_set_slice must not drain the pipeline and must not leak into submits already issued: lowdelay_P changes
+    lambda every picture (QP offsets 3,2,3,1, cfg/encoder_lowdelay_P_main.cfg:24-27).  Three submits are in flight,
+    each under its own lambda; results equal the synchronous per-lambda runs."""
+    import torch
+    W, H = 416, 240
+    org, refs, motions = fme.pu_list.synth_frames(W, H, n_refs=2, seed=31)
+    recs = fme.pu_list.make_records(W, H, motions, seed=3, amp=True)
+    frame = ob.CpuFrame(org, refs)
+    frame.oracle_fill_surface(recs)
+    lams = [fme.pu_list.slice_lambda(22, off, fac) for off, fac in
+            zip(fme.pu_list.LOWDELAY_P_QP_OFFSETS, fme.pu_list.LOWDELAY_P_QP_FACTORS)] + [400.0, 0.37]
+    eng = fme.Fme(W, H, num_ref_slots=2, max_pus=len(recs))
+    eng.set_nn_weights(fme.nn_weights.load_blob(22))
+    eng.upload_org(org)
+    for s in range(2):
+        eng.upload_ref(s, refs[s])
+    want = []
+    for lam in lams:
+        eng.set_slice(lam)
+        want.append(eng.submit(recs, fme.MODE_BOTH))
+    assert any(not np.array_equal(want[0]["cost"], w["cost"]) for w in want[1:])   # the lambdas do matter
+    h_in = torch.from_numpy(recs.view(np.uint8).reshape(len(recs), -1).copy()).pin_memory()
+    h_out = [torch.zeros((len(recs), 16), dtype=torch.uint8).pin_memory() for _ in lams]
+    for k, lam in enumerate(lams):           # no wait in between: up to three submits in flight, lambda changing under them
+        eng.set_slice(lam)
+        eng.submit_async(h_in.data_ptr(), len(recs), h_out[k].data_ptr(), fme.MODE_BOTH)
+    eng.synchronize()
+    for k in range(len(lams)):
+        np.testing.assert_array_equal(h_out[k].numpy().view(np.uint8), want[k].view(np.uint8).reshape(len(recs), -1),
+                                      err_msg="lambda %d" % k)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_interp_slot_reinterpolates_the_slots_own_picture():
+    """fme_interp_slot(s) re-runs K1 on the picture resident in slot s -- not on whatever was uploaded last, chroma
+    included -- and refuses empty slots."""
+    W, H = 128, 96
+    org, refs, _ = fme.pu_list.synth_frames(W, H, n_refs=2, seed=8)
+    eng = fme.Fme(W, H, num_ref_slots=3, max_pus=16)
+    for s in range(2):
+        eng.upload_ref(s, refs[s])
+    before = [[eng.download_plane(s, fy, fx) for fy in range(4) for fx in range(4)] for s in range(2)]
+    half = np.full((H // 2, W // 2), 77, np.int16)
+    eng.upload_ref_chroma(1, half, half)       # the staging buffer now holds a chroma plane
+    eng.interp_slot(0)
+    eng.interp_slot(1)
+    eng.interp_slot(0)
+    for s in range(2):
+        for k, p in enumerate(before[s]):
+            np.testing.assert_array_equal(eng.download_plane(s, k // 4, k % 4), p, err_msg="slot %d plane %d" % (s, k))
+    with pytest.raises(fme.FmeError):
+        eng.interp_slot(2)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_async_batch_with_mixed_surface_flags_and_unservable_records(small):
+    """The unvalidated entry points: K0 fills err[] of exactly the flagged records wherever they sit in the batch (the
+    first record is NOT flagged), unservable records (non-HEVC shapes, FME_PU_BI without biPred) come back with the
+    sentinel cost instead of stale results, and BI is ignored on head records."""
+    import torch
+    eng0, g, recs = small
+    recs = recs.copy()
+    org, refs, lam = g["small_org"], g["small_refs"], float(g["small_lambda"][0])
+    blob = fme.nn_weights.load_blob(22)
+    eng = fme.Fme(128, 96, num_ref_slots=2, max_pus=len(recs) + 8)
+    eng.set_nn_weights(blob)
+    eng.set_slice(lam)
+    eng.upload_org(org)
+    for s in range(2):
+        eng.upload_ref(s, refs[s])
+    want = eng.submit(recs, fme.MODE_BOTH)                       # complete records, validated path
+    mixed = recs.copy()
+    flagged = np.arange(len(recs)) % 3 != 0                      # record 0 keeps its grid, two of three lose it
+    mixed["err"][flagged] = 0xdeadbeef
+    mixed["flags"][flagged] |= fme.PU_ERR_ON_GPU
+    junk = np.zeros(3, fme.PU_DTYPE)
+    junk["w"], junk["h"] = [12, 24, 16], [12, 8, 16]             # 12x12 and 24x8 are not HEVC PUs; 16x16 + BI below
+    junk["flags"][2] = fme.PU_BI
+    batch = np.concatenate([mixed, junk])
+    h_in = torch.from_numpy(batch.view(np.uint8).reshape(len(batch), -1).copy()).pin_memory()
+    h_out = torch.full((len(batch), 16), 0x5a, dtype=torch.uint8).pin_memory()
+    # surface records must reproduce the grid the (same-metric) reference fixture holds, hence the same NN decision
+    eng.submit_async(h_in.data_ptr(), len(batch), h_out.data_ptr(), fme.MODE_BOTH)
+    eng.synchronize()
+    got = h_out.numpy().copy().view(fme.RESULT_DTYPE).reshape(-1)
+    surf = ob.CpuFrame(org, list(refs))
+    cpu = recs.copy()
+    cpu["flags"] |= fme.PU_ERR_ON_GPU
+    surf.oracle_fill_surface(cpu)
+    same_grid = np.all(cpu["err"] == recs["err"], axis=1)        # where the fixture's grid IS the 3x3 surface
+    assert same_grid.sum() > len(recs) // 2
+    for f in ("halfX", "halfY", "qterX", "qterY", "cost"):
+        np.testing.assert_array_equal(got[f][:len(recs)], want[f], err_msg=f)
+    chk = same_grid | ~flagged
+    for f in ("nnHalfX", "nnHalfY", "nnQterX", "nnQterY", "nnClass"):
+        np.testing.assert_array_equal(got[f][:len(recs)][chk], want[f][chk], err_msg=f)
+    tail = got[len(recs):]
+    assert (tail["cost"] == 0xffffffff).all() and not tail["halfX"].any() and not tail["qterY"].any()
+    # heads: BI on a head is ignored, the record is served as a uni-prediction PU
+    heads = fme.pu_list.heads_of(recs)
+    heads["flags"] |= fme.PU_BI
+    h_h = torch.from_numpy(heads.view(np.uint8).reshape(len(heads), -1).copy()).pin_memory()
+    h_o2 = torch.zeros((len(heads), 16), dtype=torch.uint8).pin_memory()
+    eng.submit_heads_async(h_h.data_ptr(), len(heads), h_o2.data_ptr(), fme.MODE_STD)
+    eng.synchronize()
+    got2 = h_o2.numpy().copy().view(fme.RESULT_DTYPE).reshape(-1)
+    np.testing.assert_array_equal(got2["cost"], want["cost"])
+    eng.close()
