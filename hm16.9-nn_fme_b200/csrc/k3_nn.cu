@@ -108,7 +108,11 @@ __global__ void __launch_bounds__(K3_THREADS) k3_nn_pred(const fme_pu* __restric
       float acc = __fmul_rn(W[o * nIn], x[0]);
       for (int k = 1; k < nIn; ++k) acc = __fadd_rn(acc, __fmul_rn(W[o * nIn + k], x[k]));
       acc = __fadd_rn(acc, b[o]);
-      if (H->outSigmoid) acc = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-acc)));
+      // outSigmoid (the reference's 3-layer backup network): the sigmoid is monotonic, the class is the first maximum
+      // of the pre-activation -- no transcendental on the decision path
+      // (evaluated in double, as the reference does, the sigmoid is exactly 1.0 from 53 ln 2 on: saturated outputs tie
+      //  and the first wins -- the clamp reproduces that)
+      if (H->outSigmoid) acc = fminf(acc, 36.7368f);
       if (o == 0 || acc > bestV) { bestV = acc; best = o; }
     }
     store_class(&res[i], best);
@@ -190,7 +194,7 @@ struct LayerSmem {
 template <int NEMB, int H1, int H2, int H3, int NOUT, bool FMA>
 __global__ void __launch_bounds__(K3F_THREADS) k3_nn_fixed(const fme_pu* __restrict__ pus, int n,
                                                           fme_result* __restrict__ res,
-                                                          const float* __restrict__ blob) {
+                                                          const float* __restrict__ blob, float outClamp) {
   constexpr int IN0 = 9 + 4 * NEMB;
   constexpr int HLAST = H3 > 0 ? H3 : H2;
   using L1 = LayerSmem<IN0, H1>;
@@ -277,7 +281,10 @@ __global__ void __launch_bounds__(K3F_THREADS) k3_nn_fixed(const fme_pu* __restr
     auto argmax = [&](int o, const float (&acc)[K3F_NPU]) {
 #pragma unroll
       for (int u = 0; u < K3F_NPU; ++u)
-        if (o == 0 || acc[u] > bestV[u]) { bestV[u] = acc[u]; best[u] = o; }  // first maximum (TEncSearch.cpp:134)
+      {  // first maximum (TEncSearch.cpp:134); outClamp = 53 ln 2 for sigmoid-output nets (double saturation ties), else +inf
+        const float v = fminf(acc[u], outClamp);
+        if (o == 0 || v > bestV[u]) { bestV[u] = v; best[u] = o; }
+      }
     };
     if constexpr (H3 > 0) {
       dense_rows<FMA, H2, H3>(L3::W(s_l3), L3::b(s_l3), x2, [&](int o, const float (&acc)[K3F_NPU]) {
@@ -304,7 +311,7 @@ __global__ void __launch_bounds__(K3F_THREADS) k3_nn_fixed(const fme_pu* __restr
 }
 
 template <int NEMB, int H1, int H2, int H3, int NOUT, bool FMA>
-cudaError_t launch_fixed(const fme_pu* d_pus, int n, fme_result* d_res, const float* d_nn, cudaStream_t s) {
+cudaError_t launch_fixed(const fme_pu* d_pus, int n, fme_result* d_res, const float* d_nn, bool outSigmoid, cudaStream_t s) {
   constexpr int IN0 = 9 + 4 * NEMB;
   constexpr int HLAST = H3 > 0 ? H3 : H2;
   constexpr int HMAX = (H1 > H2 ? (H1 > H3 ? H1 : H3) : (H2 > H3 ? H2 : H3));
@@ -318,7 +325,8 @@ cudaError_t launch_fixed(const fme_pu* d_pus, int n, fme_result* d_res, const fl
   }
   int blocks = (n + K3F_NPU * K3F_THREADS - 1) / (K3F_NPU * K3F_THREADS);
   if (blocks > 148 * 6) blocks = 148 * 6;
-  k3_nn_fixed<NEMB, H1, H2, H3, NOUT, FMA><<<blocks, K3F_THREADS, smem, s>>>(d_pus, n, d_res, d_nn);
+  k3_nn_fixed<NEMB, H1, H2, H3, NOUT, FMA><<<blocks, K3F_THREADS, smem, s>>>(d_pus, n, d_res, d_nn,
+                                                                             outSigmoid ? 36.7368f : 3.0e38f);
   return cudaGetLastError();
 }
 
@@ -328,13 +336,13 @@ cudaError_t fme_launch_k3(const fme_pu* d_pus, int n, fme_result* d_res, const f
                           const FmeNnHeader& h, int fma, cudaStream_t s, int64_t* launches) {
   if (n <= 0) return cudaSuccess;
   ++*launches;
-  if (!h.outSigmoid && h.nOut == 49) {
+  if (h.nOut == 49) {  // (a sigmoid on the outputs does not change the first maximum: same kernels)
     if (h.nEmb == 2 && h.embDim == 4 && h.nHidden == 2 && h.hidden[0] == 22 && h.hidden[1] == 20)
-      return fma ? launch_fixed<2, 22, 20, 0, 49, true>(d_pus, n, d_res, d_nn, s)
-                 : launch_fixed<2, 22, 20, 0, 49, false>(d_pus, n, d_res, d_nn, s);  // shipped per-QP nets (master)
+      return fma ? launch_fixed<2, 22, 20, 0, 49, true>(d_pus, n, d_res, d_nn, h.outSigmoid != 0, s)
+                 : launch_fixed<2, 22, 20, 0, 49, false>(d_pus, n, d_res, d_nn, h.outSigmoid != 0, s);  // shipped per-QP nets (master)
     if (h.nEmb == 0 && h.nHidden == 3 && h.hidden[0] == 40 && h.hidden[1] == 40 && h.hidden[2] == 40)
-      return fma ? launch_fixed<0, 40, 40, 40, 49, true>(d_pus, n, d_res, d_nn, s)
-                 : launch_fixed<0, 40, 40, 40, 49, false>(d_pus, n, d_res, d_nn, s);  // "3-layer" 9-40-40-40-49 shape
+      return fma ? launch_fixed<0, 40, 40, 40, 49, true>(d_pus, n, d_res, d_nn, h.outSigmoid != 0, s)
+                 : launch_fixed<0, 40, 40, 40, 49, false>(d_pus, n, d_res, d_nn, h.outSigmoid != 0, s);  // "3-layer" 9-40-40-40-49 shape
   }
   int blocks = (n + K3_THREADS - 1) / K3_THREADS;
   if (blocks > 148 * 16) blocks = 148 * 16;

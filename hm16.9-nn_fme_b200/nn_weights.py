@@ -91,6 +91,31 @@ def synthetic_blob(hidden_sizes=(40, 40, 40), n_emb=0, seed=0, n_out=49):
                      rng.normal(0, 0.3, n_out))
 
 
+def backup3_arrays(npz):
+    """The reference's own 3-layer network (Backups/4...cpp, extracted by tests/golden/make_backup3_weights.py):
+    (mean, stdev, gamma_in, hidden=[(W, b, gamma, beta)] * 3, out_w, out_b) as float64 arrays."""
+    g = npz
+    hidden = [(g["in_h1"], g["b1"], g["BN_gamma_1"], g["BN_beta_1"]), (g["h1_h2"], g["b2"], g["BN_gamma_2"], g["BN_beta_2"]),
+              (g["h2_h3"], g["b3"], g["BN_gamma_3"], g["BN_beta_3"])]
+    return g["mean"], g["stdev"], g["BN_gamma_in"], hidden, g["h3_out"], g["bout"]
+
+
+def blob_from_backup3(npz):
+    """FMNN blob (float32, 9-40-40-40-49, sigmoid output, no embeddings) of the reference's 3-layer backup network."""
+    mean, stdev, gin, hidden, ow, ob = backup3_arrays(npz)
+    return pack_blob(mean, stdev, gin, [], hidden, ow, ob, out_sigmoid=True)
+
+
+def payload_f64(npz):
+    """The same payload sequence as doubles, for the oracle's double-precision restatement (orc_nn_pred_f64)."""
+    mean, stdev, gin, hidden, ow, ob = backup3_arrays(npz)
+    parts = [mean, stdev, gin]
+    for (w, b, g, be) in hidden:
+        parts += [np.asarray(w).reshape(-1), b, g, be]
+    parts += [np.asarray(ow).reshape(-1), ob]
+    return np.concatenate([np.asarray(p, np.float64) for p in parts])
+
+
 def load_blob(qp):
     """Shipped blob for a QP (generated from the reference's DL/blowing/<qp> by tools/pack_weights.py)."""
     with open(os.path.join(WEIGHTS_DIR, "qp%d.fmnn" % select_qp(qp)), "rb") as f:

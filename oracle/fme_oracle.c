@@ -425,14 +425,63 @@ int orc_nn_pred(const void* blob, const uint32_t err9[9], int puHeight, int puWi
     float acc = W[o * n] * x[0];
     for (int k = 1; k < n; ++k) acc = acc + W[o * n + k] * x[k];
     acc = acc + b[o];
-    if (H->outSigmoid) acc = 1.0f / (1.0f + expf(-acc));
-    if (logits) logits[o] = acc;
+    /* outSigmoid (the 3-layer backup network, Backups/4...cpp:4476): the sigmoid is monotonic, so the class is decided
+     * on the pre-activation (first maximum); the reported outputs carry the activation */
+    if (logits) logits[o] = H->outSigmoid ? 1.0f / (1.0f + expf(-acc)) : acc;
+    /* the reference evaluates that sigmoid in double, where it is exactly 1.0 from 53 ln 2 = 36.7368 on: saturated
+     * outputs tie and std::max_element keeps the first of them -- the clamp reproduces that */
+    if (H->outSigmoid && acc > 36.7368f) acc = 36.7368f;
     if (o == 0 || acc > bestV) { /* first maximum, TES:134 */
       bestV = acc;
       best = o;
     }
   }
   if (halfXY && qterXY) orc_nn_class_to_mv(best, halfXY, qterXY);
+  return best;
+}
+
+/* The reference's own 3-layer network, restated as it computes: double precision throughout
+ * (source/Lib/TLibEncoder/Backups/4. TEncSearch - SCR 3 layers - no normalization.cpp:4408-4490):
+ *   IN[i] = (E_i - mean_i) / stdev_i (:4427-4435), IN_norm = IN * BN_gamma_in (:4439-4441),
+ *   X = relu(W X + b) * gamma + beta per hidden layer (:4445-4471, accumulation in index order starting from 0),
+ *   OUT = sigmoid(W X + b) (:4475-4481), class = first maximum (std::max_element, :4486).
+ * `payload` holds the same sequence as an FMNN blob's payload, as doubles (tests/golden/backup3_*.npz). */
+int orc_nn_pred_f64(const void* header, const double* payload, const uint32_t err9[9], double* outs) {
+  const orc_nn_header* H = (const orc_nn_header*)header;
+  const double* p = payload;
+  const double* mean = p; p += H->nErr;
+  const double* stdev = p; p += H->nErr;
+  const double* gin = p; p += H->nErr;
+  double x[64], y[64];
+  int n = H->nErr;
+  for (int i = 0; i < n; ++i) x[i] = (((double)err9[i] - mean[i]) / stdev[i]) * gin[i];
+  for (int l = 0; l < H->nHidden; ++l) {
+    int out = H->hidden[l];
+    const double* W = p; p += (size_t)out * n;
+    const double* b = p; p += out;
+    const double* g = p; p += out;
+    const double* be = p; p += out;
+    for (int o = 0; o < out; ++o) {
+      double acc = 0.0;
+      for (int k = 0; k < n; ++k) acc += W[o * n + k] * x[k];
+      acc += b[o];
+      y[o] = ((acc > 0.0 ? acc : 0.0) * g[o]) + be[o];
+    }
+    memcpy(x, y, sizeof(double) * (size_t)out);
+    n = out;
+  }
+  const double* W = p; p += (size_t)H->nOut * n;
+  const double* b = p;
+  int best = 0;
+  double bestV = 0.0;
+  for (int o = 0; o < H->nOut; ++o) {
+    double acc = 0.0;
+    for (int k = 0; k < n; ++k) acc += W[o * n + k] * x[k];
+    acc += b[o];
+    if (H->outSigmoid) acc = 1.0 / (1.0 + exp(-acc));
+    if (outs) outs[o] = acc;
+    if (o == 0 || acc > bestV) { bestV = acc; best = o; }
+  }
   return best;
 }
 

@@ -94,6 +94,9 @@ size_t orc_nn_blob_floats(const orc_nn_header* h);
 int orc_nn_pred(const void* blob, const uint32_t err9[9], int puHeight, int puWidth, float* logits,
                 int16_t halfXY[2], int16_t qterXY[2]);
 void orc_nn_class_to_mv(int cls, int16_t halfXY[2], int16_t qterXY[2]);
+/* the reference's 3-layer backup network in double precision (Backups/4...cpp:4408-4490); payload = the FMNN payload
+ * sequence as doubles.  Returns the class (first maximum of the sigmoid outputs); outs may be NULL. */
+int orc_nn_pred_f64(const void* header, const double* payload, const uint32_t err9[9], double* outs);
 
 /* ---- PU-list runner (same record layout as include/fme_b200.h) ---- */
 typedef struct {

@@ -72,6 +72,8 @@ class Oracle:
         L.orc_filtered_block.restype = c_short_p
         L.orc_nn_pred.restype = C.c_int
         L.orc_nn_pred.argtypes = [C.c_void_p, c_uint_p, C.c_int, C.c_int, C.POINTER(C.c_float), c_short_p, c_short_p]
+        L.orc_nn_pred_f64.restype = C.c_int
+        L.orc_nn_pred_f64.argtypes = [C.c_void_p, C.POINTER(C.c_double), c_uint_p, C.POINTER(C.c_double)]
         L.orc_run_pu_list.argtypes = [c_short_p, C.c_int, C.POINTER(c_short_p), C.c_int, C.c_void_p, C.c_int,
                                       C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_subpel_plane.argtypes = [c_short_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -144,6 +146,15 @@ class Oracle:
         buf = C.create_string_buffer(bytes(blob), len(blob))
         cls = self.L.orc_nn_pred(buf, e, h, w, logits, hxy, qxy)
         return cls, np.array(logits[:49], np.float32), (hxy[0], hxy[1]), (qxy[0], qxy[1])
+
+    def nn_pred_f64(self, blob, payload, err9):
+        """Double-precision forward of the reference's 3-layer backup network: (class, outputs[49])."""
+        e = (C.c_uint * 9)(*[int(v) for v in err9])
+        outs = (C.c_double * 64)()
+        buf = C.create_string_buffer(bytes(blob[:64]), 64)
+        pl = np.ascontiguousarray(payload, np.float64)
+        cls = self.L.orc_nn_pred_f64(buf, pl.ctypes.data_as(C.POINTER(C.c_double)), e, outs)
+        return cls, np.array(outs[:49])
 
     def fill_surface(self, org, ostride, refs, ref_offs, rstride, pus, fen=1):
         arr = (c_short_p * len(refs))(*[_ptr(r, o) for r, o in zip(refs, ref_offs)])

@@ -881,3 +881,50 @@ def test_async_batch_with_mixed_surface_flags_and_unservable_records(small):
     got2 = h_o2.numpy().copy().view(fme.RESULT_DTYPE).reshape(-1)
     np.testing.assert_array_equal(got2["cost"], want["cost"])
     eng.close()
+
+
+@pytest.mark.gpu
+def test_k3_references_own_three_layer_network(orc):
+    """BASELINE config C4 on the reference's OWN 3-layer weights (Backups/4...cpp:65-288, sigmoid outputs,
+    tests/golden/make_backup3_weights.py): K3 (compile-time 9-40-40-40-49 path and, with a 48-output copy, the generic
+    path -- the `outSigmoid` branch of both) equals the float32 oracle bit for bit, and agrees with the reference's
+    double-precision forward (Backups/4...cpp:4408-4490) on >= 99.9 % of the PUs; the rate is printed."""
+    import os
+    from common import HERE
+    npz = np.load(os.path.join(HERE, "golden", "backup3_9_40_40_40_49.npz"))
+    blob = fme.nn_weights.blob_from_backup3(npz)
+    payload = fme.nn_weights.payload_f64(npz)
+    cap = np.load(os.path.join(HERE, "golden", "real_encode_416x240.npz"))["recs"]
+    cap = cap[cap[:, 11] == 8]
+    pick = cap[np.random.default_rng(3).choice(len(cap), 6000, replace=False)]
+    rng = np.random.default_rng(4)
+    centre = np.exp(rng.uniform(np.log(1e2), np.log(1e6), 6000))
+    syn = (centre[:, None] * rng.uniform(0.8, 6.0, (6000, 9))).astype(np.uint32)
+    recs = np.zeros(12000, fme.PU_DTYPE)
+    recs["w"], recs["h"] = 16, 16
+    recs["err"][:6000] = np.concatenate([pick[:, 12:16], pick[:, 20:21], pick[:, 16:20]], 1).astype(np.uint32)
+    recs["err"][6000:] = syn
+    eng = fme.Fme(128, 96, num_ref_slots=1, max_pus=len(recs))
+    eng.set_nn_weights(blob)
+    got = eng.submit(recs, fme.MODE_NN)
+    want32 = np.array([orc.nn_pred(blob, e, 16, 16)[0] for e in recs["err"]])
+    want64 = np.array([orc.nn_pred_f64(blob, payload, e)[0] for e in recs["err"]])
+    np.testing.assert_array_equal(got["nnClass"], want32)          # same arithmetic, same classes
+    mism = got["nnClass"] != want64
+    print("K3 on the reference's 3-layer network: class mismatch rate vs the double-precision reference forward: "
+          "%.5f on captured surfaces (%d of 6000), %.5f on synthetic near-saturation surfaces (%d of 6000)"
+          % (mism[:6000].mean(), mism[:6000].sum(), mism[6000:].mean(), mism[6000:].sum()))
+    assert mism[:6000].mean() <= 1e-3 and mism[6000:].mean() <= 0.02
+    # generic kernel (k3_nn_pred): the same network with its last output row dropped is not a compile-time shape
+    import struct
+    hdr = list(struct.unpack("<16i", blob[:64]))
+    pay = np.frombuffer(blob, "<f4", offset=64)
+    n_out_w = 49 * 40
+    w_out, b_out = pay[-(n_out_w + 49):-49].reshape(49, 40), pay[-49:]
+    hdr[11] = 48
+    blob48 = struct.pack("<16i", *hdr) + np.concatenate([pay[:-(n_out_w + 49)], w_out[:48].reshape(-1), b_out[:48]]).astype("<f4").tobytes()
+    eng.set_nn_weights(blob48)
+    got48 = eng.submit(recs, fme.MODE_NN)
+    want48 = np.array([orc.nn_pred(blob48, e, 16, 16)[0] for e in recs["err"][:3000]])
+    np.testing.assert_array_equal(got48["nnClass"][:3000], want48)
+    eng.close()
