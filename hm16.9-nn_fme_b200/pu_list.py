@@ -154,3 +154,23 @@ def band_of_pus(recs, band, n_bands, height, ctu=64):
 def band_rows(band, n_bands, height, ctu=64):
     rows = (height + ctu - 1) // ctu
     return band * rows // n_bands, (band + 1) * rows // n_bands
+
+
+def band_mask_balanced(recs, band, n_bands, width, ctu=64):
+    """Boolean mask of band `band` when the PU list is cut into n_bands contiguous runs of CTUs (raster order) carrying
+    equal PU-pixel work: boundaries fall wherever the cumulative sum of w*h says, i.e. also in the middle of a CTU row
+    (whole-row bands leave 34 CTU rows / 8 GPUs = 5-row and 4-row bands, a 25 % imbalance at 2160p).  Every PU of a
+    CTU stays with its CTU; the union of the bands is the list and the bands are disjoint."""
+    ctus_x = (width + ctu - 1) // ctu
+    cid = (recs["y"].astype(np.int64) // ctu) * ctus_x + recs["x"].astype(np.int64) // ctu
+    work = np.bincount(cid, weights=recs["w"].astype(np.float64) * recs["h"])
+    cum = np.cumsum(work)
+    total = cum[-1] if len(cum) else 0.0
+    # CTU c belongs to band floor(n * (work before c) / total)
+    before = cum - work
+    owner = np.minimum((before * n_bands / max(total, 1.0)).astype(np.int64), n_bands - 1)
+    return owner[cid] == band
+
+
+def band_of_pus_balanced(recs, band, n_bands, width, ctu=64):
+    return recs[band_mask_balanced(recs, band, n_bands, width, ctu)]

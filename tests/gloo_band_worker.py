@@ -25,7 +25,9 @@ recs = fme.pu_list.make_records(W, H, motions, seed=1)
 frame = ob.CpuFrame(org, refs)
 frame.oracle_fill_surface(recs)
 lam = fme.pu_list.slice_lambda(22)
-mine = fme.pu_list.band_of_pus(recs, rank, world, H)
+# bench.py's banded leg: pixel-balanced contiguous CTU runs (argv[1] == "balanced"), else whole CTU rows
+balanced = len(sys.argv) > 1 and sys.argv[1] == "balanced"
+mine = fme.pu_list.band_of_pus_balanced(recs, rank, world, W) if balanced else fme.pu_list.band_of_pus(recs, rank, world, H)
 res = frame.oracle_run(np.ascontiguousarray(mine), 3, lam, 1, fme.nn_weights.load_blob(22))
 gathered = [None] * world
 dist.all_gather_object(gathered, res.tobytes())
@@ -33,7 +35,10 @@ if rank == 0:
     full = frame.oracle_run(recs, 3, lam, 1, fme.nn_weights.load_blob(22))
     merged = np.concatenate([np.frombuffer(b, fme.RESULT_DTYPE) for b in gathered])
     bands = [fme.pu_list.band_rows(b, world, H) for b in range(world)]
-    order = np.concatenate([np.nonzero((recs["y"] // 64 >= lo) & (recs["y"] // 64 < hi))[0] for lo, hi in bands])
+    if balanced:
+        order = np.concatenate([np.nonzero(fme.pu_list.band_mask_balanced(recs, b, world, W))[0] for b in range(world)])
+    else:
+        order = np.concatenate([np.nonzero((recs["y"] // 64 >= lo) & (recs["y"] // 64 < hi))[0] for lo, hi in bands])
     assert np.array_equal(merged.view(np.uint8), full[order].view(np.uint8))
     print("BAND_MERGE_OK", len(merged))
 dist.barrier()

@@ -67,13 +67,19 @@ def test_band_sharding_partitions_the_list():
     assert all(hi > lo for lo, hi in (fme.pu_list.band_rows(b, 8, 2160) for b in range(8)))
 
 
-def test_two_rank_gloo_band_merge():
-    """world_size-2 run of the banded host logic over gloo: each rank owns a CTU-row band, computes its PUs
-    (oracle as the stand-in compute on CPU), results gathered on rank 0 equal the single-process run."""
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("split", ["rows", "balanced"])
+def test_two_rank_gloo_band_merge(split):
+    """world_size-2 run of the banded host logic over gloo: each rank owns a band of CTUs (whole rows, or the
+    pixel-balanced runs bench.py uses), computes its PUs (oracle as the stand-in compute on CPU), results gathered on
+    rank 0 equal the single-process run."""
     script = os.path.join(ROOT, "tests", "gloo_band_worker.py")
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29541")
+    port = "29541" if split == "rows" else "29543"
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29541", script],
+                          "--master-addr", "127.0.0.1", "--master-port", port, script, split],
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "BAND_MERGE_OK" in out.stdout
@@ -109,3 +115,25 @@ def test_h5_models_equal_csv_weights():
     assert a[:64] == b[:64]
     fa, fb = np.frombuffer(a[64:], "<f4"), np.frombuffer(b[64:], "<f4")
     assert np.allclose(fa, fb, rtol=2e-6, atol=1e-7)
+
+
+def test_balanced_bands_partition_the_list_and_even_out_the_work():
+    """Pixel-balanced CTU bands (bench.py banded leg): a partition of the list, CTUs never split, work within a CTU's
+    worth of the mean -- against whole-row bands, which at 2160p / 8 differ by a full CTU row."""
+    motions = [(1.25, 0.75), (2.5, 1.5)]
+    for (W, H, nb) in ((416, 240, 3), (3840, 2160, 8), (1920, 1080, 4)):
+        recs = fme.pu_list.make_records(W, H, motions[:1], seed=2)
+        masks = [fme.pu_list.band_mask_balanced(recs, b, nb, W) for b in range(nb)]
+        assert np.array_equal(np.sum(masks, axis=0), np.ones(len(recs), np.int64))       # disjoint cover
+        px = recs["w"].astype(np.int64) * recs["h"]
+        work = np.array([px[m].sum() for m in masks], np.float64)
+        ctu_work = 12.0 * 64 * 64                                                        # 12 coverings of a CTU's pixels
+        assert work.max() - work.min() <= 2 * ctu_work, (W, H, work)
+        ctus_x = (W + 63) // 64
+        cid = (recs["y"] // 64).astype(np.int64) * ctus_x + recs["x"] // 64
+        owners = [set(np.unique(cid[m]).tolist()) for m in masks]
+        assert sum(len(o) for o in owners) == len(set(cid.tolist()))                      # a CTU has one owner
+        if (W, H) == (3840, 2160):
+            rows = np.array([px[(recs["y"] // 64 >= lo) & (recs["y"] // 64 < hi)].sum()
+                             for lo, hi in (fme.pu_list.band_rows(b, nb, H) for b in range(nb))], np.float64)
+            assert work.max() / work.mean() < 1.01 < rows.max() / rows.mean()
