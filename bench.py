@@ -255,12 +255,17 @@ def run_gpu(args):
     h_outs = [h_out] + [torch.zeros((n_pus, 16), dtype=torch.uint8).pin_memory() for _ in range(LAG)]
 
     h_heads = [pin(fme.pu_list.heads_of(r).view(np.uint8).reshape(len(r), -1)) for r in h_recs]
+    h_org8 = [pin(o) for (o, _, _) in sets]                              # the same pictures as 8-bit planes
+    h_ref8 = [[pin(r) for r in refs] for (_, refs, _) in sets]
 
-    def run_e2e(first, count, heads=False):
+    def run_e2e(first, count, heads=True, packed=True, u8=False):
         """`count` frames through the host-buffer calls a reference adaptor makes.  The engine overlaps the copies
         of frames i+1, i+2 with the kernels of frame i (its own copy streams, three submits in flight); the host
-        reads frame i's results after fme_wait_oldest, i.e. every step includes its H2D and its D2H."""
+        reads frame i's results after fme_wait_oldest, i.e. every step includes its H2D and its D2H.
+        heads: 16-byte records, the engine computes the 3x3 integer error surface itself (K0) instead of receiving
+        array_e / C; packed: 8-byte results (FME_MODE_RESULT8); u8: pictures as 8-bit planes instead of Pel."""
         acc = 0
+        mode = fme.MODE_BOTH | (fme.MODE_RESULT8 if packed else 0)
         for j in range(count):
             i = first + j
             k = i % n_sets
@@ -270,13 +275,18 @@ def run_gpu(args):
                 dist.broadcast(d_refs[k][slot], src=i % world)
                 torch.cuda.current_stream(dev).synchronize()
                 eng.upload_ref_device_u8(slot, d_refs[k][slot].data_ptr(), width)
+            elif u8:
+                eng._check(lib.fme_upload_ref_u8(hnd, slot, ctypes.c_void_p(h_ref8[k][slot].data_ptr()), width))
             else:
                 eng._check(lib.fme_upload_ref(hnd, slot, ctypes.c_void_p(h_ref16[k][slot].data_ptr()), width))
-            eng._check(lib.fme_upload_org(hnd, ctypes.c_void_p(h_org16[k].data_ptr()), width))
-            if heads:   # 16-byte records: the engine computes the 3x3 integer error surface itself (K0)
-                eng.submit_heads_async(h_heads[k].data_ptr(), len(sets[k][2]), h_outs[i % (LAG + 1)].data_ptr(), fme.MODE_BOTH)
+            if u8:
+                eng._check(lib.fme_upload_org_u8(hnd, ctypes.c_void_p(h_org8[k].data_ptr()), width))
             else:
-                eng.submit_async(h_pus[k].data_ptr(), len(sets[k][2]), h_outs[i % (LAG + 1)].data_ptr(), fme.MODE_BOTH)
+                eng._check(lib.fme_upload_org(hnd, ctypes.c_void_p(h_org16[k].data_ptr()), width))
+            if heads:
+                eng.submit_heads_async(h_heads[k].data_ptr(), len(sets[k][2]), h_outs[i % (LAG + 1)].data_ptr(), mode)
+            else:
+                eng.submit_async(h_pus[k].data_ptr(), len(sets[k][2]), h_outs[i % (LAG + 1)].data_ptr(), mode)
             if j >= LAG:
                 eng.wait_oldest()
                 acc += int(h_outs[(i - LAG) % (LAG + 1)][0, 4])   # the caller consumes frame i-LAG's results here
@@ -285,34 +295,32 @@ def run_gpu(args):
             acc += int(h_outs[(first + count - min(LAG, count) + t) % (LAG + 1)][0, 4])
         return acc
 
+    def time_e2e(**kw):
+        run_e2e(0, args.warmup, **kw)
+        eng.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        run_e2e(args.warmup, args.steps, **kw)
+        eng.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
     eng.set_stream(0)                      # the engine's own kernel + copy streams
-    run_e2e(0, args.warmup)
-    eng.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    run_e2e(args.warmup, args.steps)
-    eng.synchronize()
-    ms_e2e = (time.perf_counter() - t0) * 1e3
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
-    # the same loop with 16-byte records (no error grid on PCIe, K0 on the device instead); informational
-    run_e2e(0, args.warmup, heads=True)
-    eng.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    run_e2e(args.warmup, args.steps, heads=True)
-    eng.synchronize()
-    ms_e2e_heads = (time.perf_counter() - t0) * 1e3
-    if world > 1:
-        t = torch.tensor([ms_e2e_heads], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e_heads = float(t.item())
+    # headline e2e: 16-byte head records in, 8-byte results out, Pel pictures (what TComPicYuv holds)
+    ms_e2e = time_e2e(heads=True, packed=True, u8=False)
+    # the round-1 path for comparison: 52-byte records with the error grid, 16-byte results
+    ms_e2e_full = time_e2e(heads=False, packed=False, u8=False)
+    # callers that hold 8-bit planes (fme_upload_*_u8): half the picture bytes
+    ms_e2e_u8 = time_e2e(heads=True, packed=True, u8=True)
     eng.set_stream(stream.cuda_stream)
     e2e_value = pus_per_step_all * args.steps / (ms_e2e / 1e3)
-    h2d = width * height * 2 * (1 if banded and world > 1 else 2) + int(pus_per_step) * 52
-    d2h = int(pus_per_step) * 16
+    npu = int(pus_per_step)
+    pic_pel = width * height * 2 * (1 if banded and world > 1 else 2)
+    h2d, d2h = pic_pel + npu * 16, npu * 8
 
     # ---- per-kernel times: CUDA events on the launching stream around each pass of a step ----
     # (K2 and K3 are launched by separate submit calls here so that an event fits between them; the STD call
@@ -425,12 +433,18 @@ def run_gpu(args):
             "frames_per_sec": frames_per_step * args.steps / (ms_dev / 1e3),
             "interp_gb_s": kernels["k1_interp"]["achieved"],
             "e2e": {"value": e2e_value, "unit": "PU/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps, "frames_per_sec": frames_per_step * args.steps / (ms_e2e / 1e3)},
-            "e2e_heads": {"value": pus_per_step_all * args.steps / (ms_e2e_heads / 1e3), "unit": "PU/s",
-                          "h2d_bytes_per_step": h2d - int(pus_per_step) * 36, "d2h_bytes_per_step": d2h,
-                          "ms_per_step": ms_e2e_heads / args.steps,
-                          "note": "same loop through fme_submit_heads_async: 16-byte records, the 3x3 integer error "
-                                  "surface is computed on the device (K0) instead of being uploaded"},
+                    "ms_per_step": ms_e2e / args.steps, "frames_per_sec": frames_per_step * args.steps / (ms_e2e / 1e3),
+                    "path": "fme_set_slice + fme_upload_ref + fme_upload_org (Pel planes) + fme_submit_heads_async("
+                            "FME_MODE_BOTH | FME_MODE_RESULT8) + fme_wait_oldest per frame: 16-byte head records in (the 3x3 "
+                            "integer error surface is computed on the device, K0), 8-byte results out"},
+            "e2e_full_records": {"value": pus_per_step_all * args.steps / (ms_e2e_full / 1e3), "unit": "PU/s",
+                                 "h2d_bytes_per_step": pic_pel + npu * 52, "d2h_bytes_per_step": npu * 16,
+                                 "ms_per_step": ms_e2e_full / args.steps,
+                                 "note": "fme_submit_async: 52-byte records carrying array_e / C, 16-byte results (the round-1 e2e path)"},
+            "e2e_u8_pictures": {"value": pus_per_step_all * args.steps / (ms_e2e_u8 / 1e3), "unit": "PU/s",
+                                "h2d_bytes_per_step": pic_pel // 2 + npu * 16, "d2h_bytes_per_step": npu * 8,
+                                "ms_per_step": ms_e2e_u8 / args.steps,
+                                "note": "the headline e2e path with fme_upload_ref_u8 / fme_upload_org_u8 (callers holding 8-bit planes)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,

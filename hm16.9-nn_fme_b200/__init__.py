@@ -36,6 +36,21 @@ EXPORTS = [
 ]
 
 
+MODE_RESULT8 = 0x10   # FME_MODE_RESULT8: 8-byte results (fme_result8)
+RESULT8_DTYPE = np.dtype([("cost", "<u4"), ("mv", "<u4")])
+
+
+def unpack_result8(r8):
+    """fme_result8 records -> fme_result records (fme_result8_unpack of include/fme_b200.h)."""
+    out = np.zeros(len(r8), RESULT_DTYPE)
+    m = r8["mv"].astype(np.int64)
+    out["cost"] = r8["cost"]
+    for k, f in enumerate(("halfX", "halfY", "qterX", "qterY", "nnHalfX", "nnHalfY", "nnQterX", "nnQterY")):
+        out[f] = ((m >> (2 * k)) & 3) - 1
+    out["nnClass"] = (m >> 16) & 63
+    return out
+
+
 class FmeConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("margin", C.c_int32),
                 ("bitDepth", C.c_int32), ("numRefSlots", C.c_int32), ("maxPUs", C.c_int32), ("useHadME", C.c_int32),
@@ -204,6 +219,10 @@ class Fme:
     # ---- search ----
     def submit(self, pus, mode=MODE_BOTH):
         pus = np.ascontiguousarray(pus, dtype=PU_DTYPE)
+        if mode & MODE_RESULT8:
+            out8 = np.zeros(len(pus), RESULT8_DTYPE)
+            self._check(self.lib.fme_submit(self.h, _addr(pus), len(pus), _addr(out8), mode))
+            return unpack_result8(out8)
         out = np.zeros(len(pus), RESULT_DTYPE)
         self._check(self.lib.fme_submit(self.h, _addr(pus), len(pus), _addr(out), mode))
         return out

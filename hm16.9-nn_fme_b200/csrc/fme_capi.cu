@@ -77,6 +77,7 @@ struct fme_ctx {
   fme_pu* d_pusBuf[FME_NBUF] = {};
   fme_pu_head* d_headBuf[FME_NBUF] = {};  // allocated on the first fme_submit_heads*
   fme_result* d_resBuf[FME_NBUF] = {};
+  fme_result8* d_res8Buf[FME_NBUF] = {};  // FME_MODE_RESULT8: packed copy that travels to the host
   fme_pu* d_pus = nullptr;       // = d_pusBuf[0], used by the synchronous helpers (fme_mc)
   fme_result* d_res = nullptr;
   float* d_nn = nullptr;
@@ -317,15 +318,16 @@ int fme_create(const fme_config* cfg, fme_ctx** out) {
     CREATE_CHECK(cudaMalloc(&c->d_pelPic[b], (size_t)g.W * g.H * sizeof(int16_t)));
     CREATE_CHECK(cudaMalloc(&c->d_pusBuf[b], sizeof(fme_pu) * (size_t)cfg->maxPUs));
     CREATE_CHECK(cudaMalloc(&c->d_resBuf[b], sizeof(fme_result) * (size_t)cfg->maxPUs));
+    CREATE_CHECK(cudaMalloc(&c->d_res8Buf[b], sizeof(fme_result8) * (size_t)cfg->maxPUs));
   }
   c->d_org = c->d_orgBuf[0]; c->d_pic = c->d_picBuf[0]; c->d_pus = c->d_pusBuf[0]; c->d_res = c->d_resBuf[0];
   CREATE_CHECK(cudaMalloc(&c->d_k1Counter, 2 * sizeof(int)));
   CREATE_CHECK(cudaMemsetAsync(c->d_k1Counter, 0, 2 * sizeof(int), c->stream));
-  CREATE_CHECK(cudaMalloc(&c->k2.classCount, sizeof(int) * (4 * FME_MAX_CLASSES + 16)));
-  c->k2.classCursor = c->k2.classCount + FME_MAX_CLASSES;
-  c->k2.workCounter = c->k2.classCursor + FME_MAX_CLASSES;  // counts, cursors and the work counter are cleared together
+  CREATE_CHECK(cudaMalloc(&c->k2.classCount, sizeof(int) * (4 * FME_K2_KEYS + 16)));
+  c->k2.classCursor = c->k2.classCount + FME_K2_KEYS;
+  c->k2.workCounter = c->k2.classCursor + FME_K2_KEYS;  // counts, cursors and the work counter are cleared together
   c->k2.classOffset = c->k2.workCounter + 4;
-  c->k2.packOffset = c->k2.classOffset + FME_MAX_CLASSES + 1;
+  c->k2.packOffset = c->k2.classOffset + FME_K2_KEYS + 1;
   CREATE_CHECK(cudaMalloc(&c->k2.order, sizeof(int) * (size_t)cfg->maxPUs));
   CREATE_CHECK(cudaStreamSynchronize(c->stream));
 #undef CREATE_CHECK
@@ -339,7 +341,7 @@ void fme_destroy(fme_ctx* c) {
   cudaDeviceSynchronize();
   cudaFree(c->d_planes); cudaFree(c->d_pel); cudaFree(c->d_pel2);
   for (int b = 0; b < FME_NBUF; ++b) {
-    cudaFree(c->d_orgBuf[b]); cudaFree(c->d_picBuf[b]); cudaFree(c->d_pelPic[b]); cudaFree(c->d_pusBuf[b]); cudaFree(c->d_resBuf[b]);
+    cudaFree(c->d_orgBuf[b]); cudaFree(c->d_picBuf[b]); cudaFree(c->d_pelPic[b]); cudaFree(c->d_pusBuf[b]); cudaFree(c->d_resBuf[b]); cudaFree(c->d_res8Buf[b]);
     cudaFree(c->d_headBuf[b]);
     for (cudaEvent_t e : {c->evIn[b], c->evDone[b], c->evOut[b], c->evPicIn[b], c->evPicFree[b], c->evOrgFree[b]})
       if (e) cudaEventDestroy(e);
@@ -655,6 +657,8 @@ static bool valid_pu_size(int w, int h) { return fme_hevc_pu_shape(w, h); }
 static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, int mode, bool sync,
                          const fme_pu_head* heads = nullptr) {
   if (!c || (!pus && !heads) || !out) return fail(FME_ERR_INVALID, "null argument");
+  const bool packed = (mode & FME_MODE_RESULT8) != 0;  // `out` is an fme_result8 array
+  mode &= ~FME_MODE_RESULT8;
   if (n < 0 || n > c->cfg.maxPUs) return fail(FME_ERR_INVALID, "n=%d exceeds maxPUs=%d", n, c->cfg.maxPUs);
   if (n == 0) return FME_OK;
   CU_CHECK(cudaSetDevice(c->cfg.device));
@@ -719,11 +723,13 @@ static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, 
   }
   int rc = run_search(c, d_pus, n, d_res, mode);
   if (rc) return rc;
+  if (packed) CU_CHECK(fme_launch_pack_results(d_res, n, c->d_res8Buf[b], c->stream, &c->launches));
   CU_CHECK(cudaEventRecord(c->evDone[b], c->stream));
   CU_CHECK(cudaEventRecord(c->evOrgFree[(c->orgSeq + FME_NBUF - 1) % FME_NBUF], c->stream));  // the source buffer this submit read
   // results out
   CU_CHECK(cudaStreamWaitEvent(c->sOut, c->evDone[b], 0));
-  CU_CHECK(cudaMemcpyAsync(out, d_res, sizeof(fme_result) * (size_t)n, cudaMemcpyDeviceToHost, c->sOut));
+  if (packed) CU_CHECK(cudaMemcpyAsync(out, c->d_res8Buf[b], sizeof(fme_result8) * (size_t)n, cudaMemcpyDeviceToHost, c->sOut));
+  else CU_CHECK(cudaMemcpyAsync(out, d_res, sizeof(fme_result) * (size_t)n, cudaMemcpyDeviceToHost, c->sOut));
   CU_CHECK(cudaEventRecord(c->evOut[b], c->sOut));
   c->fifo[c->fifoCount++] = b;
   if (sync) {
@@ -753,8 +759,11 @@ int fme_submit_device(fme_ctx* c, const fme_pu* d_pus, int n, fme_result* d_out,
   if (n < 0 || n > c->cfg.maxPUs) return fail(FME_ERR_INVALID, "n=%d exceeds maxPUs=%d", n, c->cfg.maxPUs);
   if (n == 0) return FME_OK;
   CU_CHECK(cudaSetDevice(c->cfg.device));
-  int rc = run_search(c, const_cast<fme_pu*>(d_pus), n, d_out, mode);
+  const bool packed = (mode & FME_MODE_RESULT8) != 0;  // d_out is a device fme_result8 array
+  mode &= ~FME_MODE_RESULT8;
+  int rc = run_search(c, const_cast<fme_pu*>(d_pus), n, packed ? c->d_resBuf[0] : d_out, mode);
   if (rc) return rc;
+  if (packed) CU_CHECK(fme_launch_pack_results(c->d_resBuf[0], n, reinterpret_cast<fme_result8*>(d_out), c->stream, &c->launches));
   CU_CHECK(cudaEventRecord(c->evOrgFree[(c->orgSeq + FME_NBUF - 1) % FME_NBUF], c->stream));
   return FME_OK;
 }

@@ -9,6 +9,11 @@
 #define FME_NUM_PLANES 16     // P[fy][fx], fy,fx in 0..3; plane 0 = padded integer-pel copy
 #define FME_COST_LUT_SIZE 160 // MV bit counts: 2 * (1 + 2*17) = 70 max for 16-bit components, padded
 #define FME_MAX_CLASSES 64    // (w index) * 8 + (h index), w,h in {4,8,12,16,24,32,48,64}
+// K2 bins PUs by (reference slot group, shape class): key = (slot & 7) * 64 + class.  Packs are scheduled slot-major so
+// that the 16 planes of one reference picture (43 MB at 1080p) stay in the 126 MB L2 while every shape class of that
+// slot is served, instead of all slots being swept once per shape class.
+#define FME_K2_SLOT_GROUPS 8
+#define FME_K2_KEYS (FME_K2_SLOT_GROUPS * FME_MAX_CLASSES)
 
 // MV-bit cost table of one slice, cost[bits] (fme_set_slice).  It travels BY VALUE as a kernel argument of k2_refine:
 // every launch carries the table of the slice it was submitted under, so changing lambda never has to wait for
@@ -69,10 +74,10 @@ __host__ __device__ inline bool fme_hevc_pu_shape(int w, int h) {
 
 // ---- launchers implemented in the kernel translation units ----------------------------------
 struct FmeK2Scratch {
-  int* classCount;   // [FME_MAX_CLASSES]
-  int* classCursor;  // [FME_MAX_CLASSES]
-  int* classOffset;  // [FME_MAX_CLASSES + 1]
-  int* packOffset;   // [FME_MAX_CLASSES + 1] cumulative number of packs
+  int* classCount;   // [FME_K2_KEYS]
+  int* classCursor;  // [FME_K2_KEYS]
+  int* classOffset;  // [FME_K2_KEYS + 1] in schedule order v = key ^ 63
+  int* packOffset;   // [FME_K2_KEYS + 1] cumulative number of packs, schedule order
   int* order;        // [maxPUs] PU indices grouped by class
   int* workCounter;  // [1] dynamic pack scheduler
 };
@@ -99,6 +104,7 @@ cudaError_t fme_launch_dist(int kind, const int16_t* d_org, int orgStride, const
                             int64_t* launches);
 cudaError_t fme_launch_pel_to_u8(const int16_t* d_src, int srcStride, uint8_t* d_dst, int dstPitch, int w, int h,
                                  cudaStream_t s, int64_t* launches);
+cudaError_t fme_launch_pack_results(const fme_result* d_res, int n, fme_result8* d_out, cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_expand_heads(const fme_pu_head* d_heads, int n, fme_pu* d_pus, cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_mc_bi(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_cb, const uint8_t* d_cr,
                              const fme_mc_bi_pu* d_pus, int n, int16_t* d_y, int16_t* d_cbOut, int16_t* d_crOut,

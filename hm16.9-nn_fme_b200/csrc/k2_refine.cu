@@ -64,13 +64,9 @@ __host__ __device__ inline ClassInfo class_info(int cls) {
   return c;
 }
 
-// PUs per pack.  8x8-tiled classes served by k2_group_mma (mmaGroups) use "groups" of eight tiles instead of 32-lane packs.
-__host__ __device__ inline int group_pus(int w, int h) {
-  const int tpp = (w >> 3) * (h >> 3);  // 8x8 tiles per PU
-  return tpp <= 4 ? 8 / tpp : 1;
-}
-__host__ __device__ inline int pack_pus(const ClassInfo& c, int mmaGroups) {
-  return (mmaGroups && c.ts == 8) ? group_pus(c.w, c.h) : c.P;
+// PUs per pack: the binning is the same for every K2 path (k2_group_mma walks a whole pack as sub-items of eight tiles).
+__host__ __device__ inline int pack_pus(const ClassInfo& c, int /*mmaGroups*/) {
+  return c.P;  // k2_group_mma walks a whole pack as sub-items of eight tiles: the binning is the same for every path
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -83,77 +79,89 @@ __device__ __forceinline__ int k2_class_of(const fme_pu& p, int wantBi) {
   if (!fme_hevc_pu_shape(p.w, p.h)) return -1;
   return fme_dim_index(p.w) * 8 + fme_dim_index(p.h);
 }
+// binning key: (reference slot group, shape class); the schedule position of a key is key ^ 63 (slot-major, large
+// shapes first inside a slot: a 64x64 PU is a whole double-length pack, the cheap 4x8 / 8x4 packs end the slot)
+__device__ __forceinline__ int k2_key_of(const fme_pu& p, int wantBi) {
+  const int c = k2_class_of(p, wantBi);
+  return c < 0 ? -1 : ((p.refSlot & (FME_K2_SLOT_GROUPS - 1)) << 6) | c;
+}
 
 // res != nullptr (the uni-prediction pass): records no K2 pass will serve -- a shape HEVC cannot produce, or FME_PU_BI
 // on a ctx without biPred -- get the sentinel result (zero vectors, cost 0xffffffff) instead of whatever the result
 // buffer held (the unvalidated async / device entry points, include/fme_b200.h).
 __global__ void k2_count(const fme_pu* __restrict__ pus, int n, int* __restrict__ classCount, int wantBi,
                          fme_result* __restrict__ res, int biServed) {
-  __shared__ int s_cnt[FME_MAX_CLASSES];
-  for (int i = threadIdx.x; i < FME_MAX_CLASSES; i += blockDim.x) s_cnt[i] = 0;
+  __shared__ int s_cnt[FME_K2_KEYS];
+  for (int i = threadIdx.x; i < FME_K2_KEYS; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const fme_pu p = pus[i];
-    const int c = k2_class_of(p, wantBi);
+    const int c = k2_key_of(p, wantBi);
     if (c >= 0) atomicAdd(&s_cnt[c], 1);
     else if (res && (!fme_hevc_pu_shape(p.w, p.h) || ((p.flags & FME_PU_BI) && !biServed)))
       *reinterpret_cast<uint2*>(&res[i]) = make_uint2(0u, 0xffffffffu);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < FME_MAX_CLASSES; i += blockDim.x)
+  for (int i = threadIdx.x; i < FME_K2_KEYS; i += blockDim.x)
     if (s_cnt[i]) atomicAdd(&classCount[i], s_cnt[i]);
 }
 
-// Scatter PU indices into class-major order.  Every block derives the class and pack offsets itself from the 64
-// class counts (a warp scan, cheaper than a separate launch); block 0 also publishes them for k2_refine.
+// Scatter PU indices into schedule order.  Every block derives the key and pack offsets itself from the key counts
+// (one warp: 16 schedule positions per lane + a warp scan, cheaper than a separate launch); block 0 also publishes
+// them for k2_refine.
 __global__ void k2_scatter(const fme_pu* __restrict__ pus, int n, const int* __restrict__ classCount,
                            int* __restrict__ classOffset, int* __restrict__ packOffset,
                            int* __restrict__ classCursor, int* __restrict__ order, int wantBi, int mmaGroups) {
-  __shared__ int s_cnt[FME_MAX_CLASSES];
-  __shared__ int s_base[FME_MAX_CLASSES];
-  __shared__ int s_classOff[FME_MAX_CLASSES];
-  // Offsets are laid out in SCHEDULE order v = 63 - class: large shapes (one 64x64 PU is a whole, double-length pack)
-  // come first and the cheap 4x8 / 8x4 packs last, so the tail of the persistent kernel is short.
+  __shared__ int s_cnt[FME_K2_KEYS];
+  __shared__ int s_base[FME_K2_KEYS];
+  __shared__ int s_classOff[FME_K2_KEYS];
+  constexpr int PER = FME_K2_KEYS / 32;
   if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;  // two classes per lane
-    const int k0 = FME_MAX_CLASSES - 1 - 2 * lane, k1 = k0 - 1;
-    const int c0 = classCount[k0], c1 = classCount[k1];
-    const int P0 = pack_pus(class_info(k0), mmaGroups), P1 = pack_pus(class_info(k1), mmaGroups);
-    const int p0 = c0 ? (c0 + P0 - 1) / P0 : 0;
-    const int p1 = c1 ? (c1 + P1 - 1) / P1 : 0;
-    int sc = c0 + c1, sp = p0 + p1;
+    const int lane = threadIdx.x;
+    int cnt[PER], pk[PER], sc = 0, sp = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int v = lane * PER + j;  // schedule position; key = v ^ 63, class = 63 - (v & 63)
+      cnt[j] = classCount[v ^ 63];
+      const int P = pack_pus(class_info(63 - (v & 63)), mmaGroups);
+      pk[j] = cnt[j] ? (cnt[j] + P - 1) / P : 0;
+      sc += cnt[j];
+      sp += pk[j];
+    }
+    int ec = sc, ep = sp;  // inclusive warp scan of the lane totals
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const int tc = __shfl_up_sync(0xffffffffu, sc, d), tp = __shfl_up_sync(0xffffffffu, sp, d);
-      if (lane >= d) { sc += tc; sp += tp; }
+      const int tc = __shfl_up_sync(0xffffffffu, ec, d), tp = __shfl_up_sync(0xffffffffu, ep, d);
+      if (lane >= d) { ec += tc; ep += tp; }
     }
-    s_classOff[2 * lane] = sc - c0 - c1;
-    s_classOff[2 * lane + 1] = sc - c1;
-    if (blockIdx.x == 0) {
-      classOffset[2 * lane] = sc - c0 - c1;
-      classOffset[2 * lane + 1] = sc - c1;
-      packOffset[2 * lane] = sp - p0 - p1;
-      packOffset[2 * lane + 1] = sp - p1;
-      if (lane == 31) { classOffset[FME_MAX_CLASSES] = sc; packOffset[FME_MAX_CLASSES] = sp; }
+    int oc = ec - sc, op = ep - sp;  // exclusive offsets of this lane's first position
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int v = lane * PER + j;
+      s_classOff[v] = oc;
+      if (blockIdx.x == 0) { classOffset[v] = oc; packOffset[v] = op; }
+      oc += cnt[j];
+      op += pk[j];
     }
+    if (blockIdx.x == 0 && lane == 31) { classOffset[FME_K2_KEYS] = oc; packOffset[FME_K2_KEYS] = op; }
   }
   // one contiguous chunk per block so that local ranks are well defined
   int chunk = (n + gridDim.x - 1) / gridDim.x;
   int lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
-  for (int i = threadIdx.x; i < FME_MAX_CLASSES; i += blockDim.x) s_cnt[i] = 0;
+  for (int i = threadIdx.x; i < FME_K2_KEYS; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
   for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const int c = k2_class_of(pus[i], wantBi);
+    const int c = k2_key_of(pus[i], wantBi);
     if (c >= 0) atomicAdd(&s_cnt[c], 1);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < FME_MAX_CLASSES; i += blockDim.x) {
-    s_base[i] = s_cnt[i] ? s_classOff[FME_MAX_CLASSES - 1 - i] + atomicAdd(&classCursor[i], s_cnt[i]) : 0;
+  for (int i = threadIdx.x; i < FME_K2_KEYS; i += blockDim.x) {
+    s_base[i] = s_cnt[i] ? s_classOff[i ^ 63] + atomicAdd(&classCursor[i], s_cnt[i]) : 0;
     s_cnt[i] = 0;
   }
   __syncthreads();
   for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const int c = k2_class_of(pus[i], wantBi);
+    const int c = k2_key_of(pus[i], wantBi);
     if (c >= 0) order[s_base[c] + atomicAdd(&s_cnt[c], 1)] = i;
   }
 }
@@ -1028,82 +1036,128 @@ __device__ __forceinline__ unsigned satd8x8_cands_mma(const unsigned (&addr)[NC]
   }
 }
 
-// Returns false (nothing done) when the group holds a lossless PU: the caller then runs it through k2_pack.
+// One work item = one pack of k2_scatter (ci.P PUs of one shape: 32 tiles, or one PU of 48 / 64 tiles), walked as
+// SUB "sub-items" of eight tiles: C groups of P PUs (tiles per PU <= 4), C whole PUs of eight tiles, or the nStrips
+// strips of a larger PU.  Every sub-item contributes three JOBS -- H (its 4 half-pel planes, 9 candidates as 4 + 4 + 1),
+// Qa and Qb (quarter-pel candidates 1..4 and 5..8 around its PU's half-pel winner) -- and the jobs of the work item
+// form one list, H jobs first.  Job k is staged into buffer half k & 1, job k + 1 is in flight while job k is
+// evaluated and job k + 2 is issued as soon as job k has freed its half, so the global -> shared copies of a job
+// overlap the evaluation of the one before it (a Q job can only be issued once its PU's half-pel decision exists:
+// with several PUs per work item that is long before it is needed).  The 16-byte record heads of the pack are fetched
+// once, coalesced, into shared memory; per-PU half-pel decisions are parked there between the phases.
+// Returns false (nothing done) when the pack holds a lossless PU: the caller then runs it through k2_pack.
+constexpr int K2_GROUP_HEADS = K2_GROUP_BYTES;            // 32 x 4 words: record heads of the pack
+constexpr int K2_GROUP_IDX = K2_GROUP_HEADS + 32 * 16;    // 32 PU indices
+constexpr int K2_GROUP_DEC = K2_GROUP_IDX + 32 * 4;       // 32 x (half-pel winner, its cost)
+static_assert(K2_GROUP_DEC + 32 * 8 <= K2_SMEM_PER_WARP, "group scratch must fit the warp's shared-memory slice");
+
 template <int A>
 __device__ __noinline__ bool k2_group_mma(int w, int h, const int* __restrict__ order, int first, int count,
                                           const fme_pu* __restrict__ pus, fme_result* __restrict__ res,
                                           const uint8_t* __restrict__ planes, const uint8_t* __restrict__ org,
                                           const FmeGeom& g, const uint32_t* __restrict__ costLut, uint8_t* smem) {
   const int lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
+  // ---- the pack's record heads -> shared memory (one coalesced pass) ----
+  unsigned* const sHead = reinterpret_cast<unsigned*>(smem + K2_GROUP_HEADS);
+  int* const sIdx = reinterpret_cast<int*>(smem + K2_GROUP_IDX);
+  uint2* const sDec = reinterpret_cast<uint2*>(smem + K2_GROUP_DEC);
+  unsigned myFlags = 0;
+  if (lane < count) {
+    const int idx = order[first + lane];
+    const unsigned* hp = reinterpret_cast<const unsigned*>(pus + idx);
+    const unsigned h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2), h3 = __ldg(hp + 3);
+    sHead[4 * lane + 0] = h0; sHead[4 * lane + 1] = h1; sHead[4 * lane + 2] = h2; sHead[4 * lane + 3] = h3;
+    sIdx[lane] = idx;
+    myFlags = h1 >> 24;
+  }
+  if (__any_sync(0xffffffffu, (myFlags & FME_PU_LOSSLESS) != 0)) return false;
+  __syncwarp();
+
+  // ---- class geometry (uniform) ----
   const int tilesX = w >> 3, tilesY = h >> 3, tpp = tilesX * tilesY;
-  const bool small = tpp <= 4;                        // several whole PUs per group
+  const bool small = tpp <= 4;                        // several whole PUs per sub-item
   const int lt = small ? (tpp >> 1) : 0;              // log2(tpp) for 1, 2, 4
-  const int P = small ? (8 >> lt) : 1;                // PUs per group
-  const int R = small ? tilesY : 8 / tilesX;          // tile rows per strip
+  const int P = small ? (8 >> lt) : 1;                // PUs per sub-item
+  const int R = small ? tilesY : 8 / tilesX;          // tile rows per sub-item
   const int nStrips = small ? 1 : (tilesY + R - 1) / R;
+  const int nSub = small ? (count + P - 1) / P : count * nStrips;
+  const int tps = small ? tpp : 8;                    // result columns per PU
   auto tile_row = [&](int j) { return small ? j >> (tilesX >> 1) : (j >= tilesX) + (j >= 2 * tilesX) + (j >= 3 * tilesX); };
-  // feeder role: column gq
+  // lane roles inside a sub-item: feeder of column gq, holder of the result of column 2t + (gq & 1)
   const int pf = small ? gq >> lt : 0;
   const int jF = small ? gq & (tpp - 1) : gq;
   const int tyF = tile_row(jF), txF = jF - tyF * tilesX;
-  // result role: column 2t + (gq & 1)
   const int nR = 2 * t + (gq & 1);
   const int pr = small ? nR >> lt : 0;
   const int tyR = tile_row(small ? nR & (tpp - 1) : nR);
-
+  const int cq = gq >> 1;                             // this lane's candidate inside a batch of four
   const int gPitch = g.pitch, gOrgPitch = g.orgPitch, gPlaneBytes = (int)g.planeBytes;
-  // ---- records: the feeder's PU and the result holder's PU (16-byte heads; lanes past `count` reuse the last PU) ----
-  const int idxF = order[first + min(pf, count - 1)], idxR = order[first + min(pr, count - 1)];
-  const unsigned* hF = reinterpret_cast<const unsigned*>(pus + idxF);
-  const unsigned* hR = reinterpret_cast<const unsigned*>(pus + idxR);
-  const unsigned f0 = __ldg(hF), f1 = __ldg(hF + 1), f2 = __ldg(hF + 2);
-  const unsigned r1 = __ldg(hR + 1), r2 = __ldg(hR + 2), r3 = __ldg(hR + 3);
-  if (__any_sync(0xffffffffu, (((f1 | r1) >> 24) & FME_PU_LOSSLESS) != 0)) return false;
-  const int px = (short)(f0 & 0xffff), py = (short)(f0 >> 16);
-  const int X = min(max(px + (short)(f2 & 0xffff), -(g.M - 8)), g.W + g.M - 8 - w);  // as k2_pack: guards memory only
-  const int Y = min(max(py + (short)(f2 >> 16), -(g.M - 8)), g.H + g.M - 8 - h);
-  const int alignX = X + g.M;
-  const uint8_t* const slotBase = planes + (size_t)min((int)((f1 >> 16) & 0xff), g.numSlots - 1) * g.slotBytes;
-  const int ox = min(max(px, 0), g.W - w), oy = min(max(py, 0), g.H - h);
-  const int mvIntX = (short)(r2 & 0xffff), mvIntY = (short)(r2 >> 16);
-  const int predX = (short)(r3 & 0xffff), predY = (short)(r3 >> 16);
 
-  // ---- staging geometry (granule A, as in k2_pack) ----
+  // ---- staging geometry (granule A, as in k2_pack); staging lane = [pf][slot k][sub] ----
   const int RW = ((w + A + A - 1) / A) * A;
   const int G = RW / A;
   const int hsMax = small ? h : R * 8;
   const int RB = (hsMax + 1) * RW;
-  const int PRB = P * RB;                  // one plane / candidate slot: the regions of the group's PUs
+  const int PRB = P * RB;                  // one plane / candidate slot: the regions of the sub-item's PUs
   const int HALF = (4 * PRB + 15) & ~15;
-  const int LPI = small ? tpp : 8;         // lanes per (plane, PU) item
+  const int LPI = small ? tpp : 8;         // lanes per (slot, PU) item
   const int lpiShift = small ? lt : 3;
   const int kS = (lane >> lpiShift) & 3, subS = lane & (LPI - 1);
   int gpShift = 0;
   while ((1 << gpShift) < G && (1 << gpShift) < LPI) ++gpShift;
   const int stGi = subS & ((1 << gpShift) - 1), stRow0 = subS >> gpShift, stRowStep = LPI >> gpShift;
   const bool stSecond = (1 << gpShift) < G;  // single-lane items (8x8 PUs): both granules of a row
-  const bool stOn = pf < count && stGi < G;
   const unsigned bufSA = (unsigned)__cvta_generic_to_shared(smem);
   const unsigned stDst = bufSA + (kS * P + pf) * RB + stRow0 * RW + stGi * A;
   const int stSrcOff = stRow0 * gPitch + stGi * A;
+  const int feedTile = pf * RB + (tyF * 8 + 2 * t) * RW + txF * 8;
 
   unsigned afrag[4];
   had16_afrag(lane, afrag);
 
-  // feeder address parts that do not depend on the candidate
-  const int feedTile = pf * RB + (tyF * 8 + 2 * t) * RW + txF * 8;
-  const unsigned feedH = bufSA + feedTile + RW + ((alignX - 1) & (A - 1)) + 1;  // half-pel regions start at (X-1, Y-1)
-
-  unsigned o[8];
-  auto load_org = [&](int y0) {  // source rows 2t, 2t+1 of the fed tile (idle columns read the PU's first tile rows)
-    const uint8_t* src = org + (size_t)(oy + min(y0 + tyF * 8, h - 8) + 2 * t) * gOrgPitch + ox + txF * 8;
-    unsigned lo0, hi0, lo1, hi1;
-    ldg_row8(src, lo0, hi0);
-    ldg_row8(src + gOrgPitch, lo1, hi1);
-    f16_rows(lo0, hi0, lo1, hi1, o);
+  // A job is addressed by a cursor (no divisions): H or Q phase, group-or-PU index `u` (small shapes: sub-item = group u of
+  // P PUs; large shapes: PU u, strip `strip`), batch b of the Q phase.  PU slot of the pack in a lane role p: pu_of(u, p).
+  struct Cursor {
+    int k, u, strip, b;
+    bool isH;
   };
-  // PU sums of the result columns: tiles of one PU sit in columns [pr * tps, (pr + 1) * tps)
-  const int tps = small ? tpp : 8;
+  auto pu_of = [&](int u, int p) { return small ? u * P + p : u; };
+  auto advance = [&](Cursor& c) {
+    ++c.k;
+    if (c.isH || c.b == 1) {
+      c.b = 0;
+      if (++c.strip == nStrips) { c.strip = 0; ++c.u; }
+      if (c.isH && c.k == nSub) { c.isH = false; c.u = 0; c.strip = 0; }
+    } else {
+      c.b = 1;
+    }
+  };
+  struct Feeder {  // what the feeder / staging role needs of its PU
+    int X, Y, alignX, ox, oy;
+    const uint8_t* slotBase;
+    bool on;
+  };
+  auto feeder = [&](int u) {
+    Feeder f;
+    const int pc = pu_of(u, pf);
+    f.on = pc < count;
+    const unsigned* hd = sHead + 4 * min(pc, count - 1);
+    const unsigned h0 = hd[0], h1 = hd[1], h2 = hd[2];
+    const int px = (short)(h0 & 0xffff), py = (short)(h0 >> 16);
+    f.X = min(max(px + (short)(h2 & 0xffff), -(g.M - 8)), g.W + g.M - 8 - w);  // as k2_pack: guards memory only
+    f.Y = min(max(py + (short)(h2 >> 16), -(g.M - 8)), g.H + g.M - 8 - h);
+    f.alignX = f.X + g.M;
+    f.slotBase = planes + (size_t)min((int)((h1 >> 16) & 0xff), g.numSlots - 1) * g.slotBytes;
+    f.ox = min(max(px, 0), g.W - w);
+    f.oy = min(max(py, 0), g.H - h);
+    return f;
+  };
+  // source rows 2t, 2t+1 of the fed tile: fetched one job ahead as aligned words, turned into f16 pairs at use
+  auto org_fetch = [&](const Feeder& f, int strip, unsigned (&r)[4]) {
+    const uint8_t* src = org + (size_t)(f.oy + min(strip * R * 8 + tyF * 8, h - 8) + 2 * t) * gOrgPitch + f.ox + txF * 8;
+    ldg_row8(src, r[0], r[1]);
+    ldg_row8(src + gOrgPitch, r[2], r[3]);
+  };
   auto pu_sum = [&](unsigned v, bool on) {
     v = on ? v : 0u;
     if (tps >= 2) v += __shfl_xor_sync(0xffffffffu, v, 4);   // column bit 0 = g & 1
@@ -1112,141 +1166,171 @@ __device__ __noinline__ bool k2_group_mma(int w, int h, const int* __restrict__ 
     return v;
   };
 
-  // ================= half-pel phase =================
-  // staging slot k: plane (fx = 2 (k & 1), fy = 2 (k >> 1)), rows Y - 1 .. Y + hs of the strip
-  auto stage_half = [&](int strip, int half) {
-    if (stOn) {
-      const int y0 = strip * R * 8;
-      const int rows = (small ? h : min(R, tilesY - strip * R) * 8) + 1;
-      const int plane = (kS & 1) * 2 + (kS >> 1) * 8;
-      const int off = plane * gPlaneBytes + (Y + g.M + y0 - 1) * gPitch + ((alignX - 1) & ~(A - 1));
-      stage_rows<A>(stDst + half * HALF, slotBase + off + stSrcOff, stRow0, stRowStep, rows, RW, gPitch, stSecond);
+  // ---- the job list: H jobs of all sub-items, then (Qa, Qb) per sub-item ----
+  const int nJobs = 3 * nSub;
+  auto issue = [&](const Cursor& c) {
+    const int half = c.k & 1;
+    const Feeder f = feeder(c.u);
+#ifdef FME_K2_EXPERIMENT_NO_STAGING
+    // measurement only (profiles/r2_k2_paths.txt): every instruction of the kernel except the global -> shared copies;
+    // the candidates read are whatever the buffer holds, so the results are meaningless
+    if (false) {
+#else
+    if (f.on && stGi < G) {
+#endif
+      int rows = small ? h : min(R, tilesY - c.strip * R) * 8, plane, dy = 0, ax;
+      if (c.isH) {  // slot kS = plane (fx = 2 (kS & 1), fy = 2 (kS >> 1)), rows Y - 1 .. Y + hs of the strip
+        rows += 1;
+        plane = (kS & 1) * 2 + (kS >> 1) * 8;
+        dy = -1;
+        ax = f.alignX - 1;
+      } else {      // slot kS = candidate q = 4 b + 1 + kS of s_acMvRefineQ around the PU's half-pel winner
+        const unsigned dec = sDec[min(pu_of(c.u, pf), count - 1)].x;
+        const int bhx = (int)(signed char)(dec & 0xff), bhy = (int)(signed char)((dec >> 8) & 0xff);
+        const int q = 4 * c.b + 1 + kS;
+        const int qx = 2 * bhx + c_refineQ[q][0], qy = 2 * bhy + c_refineQ[q][1];
+        plane = (qy & 3) * 4 + (qx & 3);
+        dy = qy >> 2;
+        ax = f.alignX + (qx >> 2);
+      }
+      const int off = plane * gPlaneBytes + (f.Y + g.M + c.strip * R * 8 + dy) * gPitch + (ax & ~(A - 1));
+      stage_rows<A>(stDst + half * HALF, f.slotBase + off + stSrcOff, stRow0, stRowStep, rows, RW, gPitch, stSecond);
     }
     cp_async_commit();
   };
-  unsigned hAcc[3] = {0, 0, 0};
-  stage_half(0, 0);
-#pragma unroll 1
-  for (int s = 0; s < nStrips; ++s) {
-    const int rowsIn = small ? tilesY : min(R, tilesY - s * R);
-    if (s + 1 < nStrips) { stage_half(s + 1, (s + 1) & 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    load_org(s * R * 8);
-    __syncwarp();
-    const bool onR = pr < count && tyR < rowsIn;
-    const unsigned base = feedH + (s & 1) * HALF;
-    // candidate i of s_acMvRefineH: slot k_i, (dx, dy) = ((2hx)>>2, (2hy)>>2)
-    //   i:  0      1       2      3       4      5        6       7       8
-    //  hx,hy (0,0) (0,-1) (0,1) (-1,0)  (1,0) (-1,-1)  (1,-1)  (-1,1)  (1,1)
-    {
-      const unsigned a[4] = {base, base + 2 * PRB - RW, base + 2 * PRB, base + PRB - 1};
-      hAcc[0] += pu_sum(satd8x8_cands_mma<4>(a, RW, o, afrag, lane), onR);
+  Cursor ic = {0, 0, 0, 0, true};  // next job to issue
+  // issue every job below `lim` whose dependency is satisfied: a Q job needs the half-pel decision of its PU(s), made
+  // by the H job of its last strip, i.e. job (u + 1) * nStrips - 1 (small shapes: nStrips == 1), which must be <= done
+  auto issue_ready = [&](int lim, int done) {
+    while (ic.k < lim && ic.k < nJobs && (ic.isH || (ic.u + 1) * nStrips - 1 <= done)) {
+      issue(ic);
+      advance(ic);
     }
-    {
-      const unsigned a[4] = {base + PRB, base + 3 * PRB - RW - 1, base + 3 * PRB - RW, base + 3 * PRB - 1};
-      hAcc[1] += pu_sum(satd8x8_cands_mma<4>(a, RW, o, afrag, lane), onR);
-    }
-    {
-      const unsigned a[1] = {base + 3 * PRB};
-      hAcc[2] += pu_sum(satd8x8_cands_mma<1>(a, RW, o, afrag, lane), onR);
-    }
-    __syncwarp();  // the buffer half is free for strip s + 2
-  }
-  // ---- half-pel decision (TEncSearch.cpp:1634 strict <, first minimum in table order) ----
-  // MV bits, cost scale 1 (TEncSearch.cpp:4531): ((int << 1) + h) << 1 against the predictor
-  const int cq = gq >> 1;  // this lane's candidate inside a batch
-  auto half_cost = [&](int i, unsigned dist) {
-    const int hx = c_refineH[i][0], hy = c_refineH[i][1];
-    const int bits = golomb_bits((((mvIntX << 1) + hx) << 1) - predX) + golomb_bits((((mvIntY << 1) + hy) << 1) - predY);
-    return dist + costLut[bits];
   };
-  unsigned bestC = half_cost(cq, hAcc[0]);
-  int bestI = cq;
-  {
-    const unsigned c1 = half_cost(4 + cq, hAcc[1]);
-    if (c1 < bestC) { bestC = c1; bestI = 4 + cq; }
-    const unsigned c2 = half_cost(8, hAcc[2]);
-    if (c2 < bestC) { bestC = c2; bestI = 8; }
-  }
-#pragma unroll
-  for (int d = 8; d <= 16; d <<= 1) {  // across the four candidate lanes of a batch
-    const unsigned oc = __shfl_xor_sync(0xffffffffu, bestC, d);
-    const int oi = __shfl_xor_sync(0xffffffffu, bestI, d);
-    if (oc < bestC || (oc == bestC && oi < bestI)) { bestC = oc; bestI = oi; }
-  }
-  const int bhxR = c_refineH[bestI][0], bhyR = c_refineH[bestI][1];
-  // the feeder needs the winner of ITS PU: held by the lane with result column pf * tps (candidate bits 0)
-  const int colF = pf * tps;
-  const int bhPackF = __shfl_sync(0xffffffffu, (bhxR & 0xff) | ((bhyR & 0xff) << 8), 4 * (colF & 1) + (colF >> 1));
-  const int bhxF = (int)(signed char)(bhPackF & 0xff), bhyF = (int)(signed char)((bhPackF >> 8) & 0xff);
 
-  // ================= quarter-pel phase =================
-  // candidate q = 1..8 of s_acMvRefineQ around the winner; batch b holds q = 4b + 1 + k in slot k of half b
-  auto stage_qter = [&](int strip, int b) {
-    if (stOn) {
-      const int y0 = strip * R * 8;
-      const int rows = small ? h : min(R, tilesY - strip * R) * 8;
-      const int q = 4 * b + 1 + kS;
-      const int qx = 2 * bhxF + c_refineQ[q][0], qy = 2 * bhyF + c_refineQ[q][1];
-      const int plane = (qy & 3) * 4 + (qx & 3);
-      const int off = plane * gPlaneBytes + (Y + g.M + y0 + (qy >> 2)) * gPitch + ((alignX + (qx >> 2)) & ~(A - 1));
-      stage_rows<A>(stDst + b * HALF, slotBase + off + stSrcOff, stRow0, stRowStep, rows, RW, gPitch, stSecond);
-    }
-    cp_async_commit();
-  };
-  // feeder addresses for x offsets -1, 0, +1 of the quarter stage (rows are handled by the staging origin)
-  unsigned feedQ[3];
-#pragma unroll
-  for (int e = 0; e < 3; ++e) feedQ[e] = bufSA + feedTile + ((alignX + ((2 * bhxF + e - 1) >> 2)) & (A - 1));
-  unsigned qAcc[2] = {0, 0};
-  const int nJobs = 2 * nStrips;  // job j = (strip j >> 1, batch j & 1) uses buffer half j & 1
-  stage_qter(0, 0);
-  stage_qter(0, 1);
+  unsigned hAcc[3] = {0, 0, 0}, qAcc[2] = {0, 0};
+  unsigned oraw[4];
+  {
+    const Feeder f0 = feeder(0);
+    org_fetch(f0, 0, oraw);
+  }
+  issue_ready(2, -1);
+  Cursor ec = {0, 0, 0, 0, true};  // the job being evaluated
 #pragma unroll 1
-  for (int j = 0; j < nJobs; ++j) {
-    const int s = j >> 1, b = j & 1;
-    const int rowsIn = small ? tilesY : min(R, tilesY - s * R);
-    if (j + 1 < nJobs) cp_async_wait<1>(); else cp_async_wait<0>();
-    if (b == 0 && nStrips > 1) load_org(s * R * 8);
+  for (int k = 0; k < nJobs; ++k) {
+    const bool isH = ec.isH;
+    const int u = ec.u, b = ec.b, strip = ec.strip;
+    const int rowsIn = small ? tilesY : min(R, tilesY - strip * R);
+    const Feeder f = feeder(u);
+    if (ic.k <= k) issue_ready(k + 1, k - 1);          // (a Q job whose decision only just became available)
+    if (ic.k > k + 1) cp_async_wait<1>(); else cp_async_wait<0>();
+    unsigned o[8];
+    f16_rows(oraw[0], oraw[1], oraw[2], oraw[3], o);
+    // the next job's source rows (another sub-item unless this is Qa -> Qb of the same one)
+    advance(ec);
+    if (ec.k < nJobs && (ec.u != u || ec.strip != strip)) {
+      const Feeder fn = feeder(ec.u);
+      org_fetch(fn, ec.strip, oraw);
+    }
     __syncwarp();
-    const bool onR = pr < count && tyR < rowsIn;
-    const unsigned hb = b * HALF;
-    // q:    1      2       3       4       5      6      7      8
-    // ox:   0      0      -1       1      -1      1     -1      1
-    if (b == 0) {
-      const unsigned a[4] = {feedQ[1] + hb, feedQ[1] + hb + PRB, feedQ[0] + hb + 2 * PRB, feedQ[2] + hb + 3 * PRB};
-      qAcc[0] += pu_sum(satd8x8_cands_mma<4>(a, RW, o, afrag, lane), onR);
+    const int pcR = pu_of(u, pr);
+    const bool onR = pcR < count && tyR < rowsIn;
+    const unsigned hb = bufSA + (k & 1) * HALF;
+    if (isH) {
+      // candidate c of s_acMvRefineH: slot k_c, (dx, dy) = ((2hx)>>2, (2hy)>>2); regions start at (X-1, Y-1)
+      //   c:   0      1       2      3       4      5        6       7       8
+      //  hx,hy (0,0) (0,-1) (0,1) (-1,0)  (1,0) (-1,-1)  (1,-1)  (-1,1)  (1,1)
+      const unsigned base = hb + feedTile + RW + ((f.alignX - 1) & (A - 1)) + 1;
+      if (strip == 0) hAcc[0] = hAcc[1] = hAcc[2] = 0;
+      {
+        const unsigned a[4] = {base, base + 2 * PRB - RW, base + 2 * PRB, base + PRB - 1};
+        hAcc[0] += pu_sum(satd8x8_cands_mma<4>(a, RW, o, afrag, lane), onR);
+      }
+      {
+        const unsigned a[4] = {base + PRB, base + 3 * PRB - RW - 1, base + 3 * PRB - RW, base + 3 * PRB - 1};
+        hAcc[1] += pu_sum(satd8x8_cands_mma<4>(a, RW, o, afrag, lane), onR);
+      }
+      {
+        const unsigned a[1] = {base + 3 * PRB};
+        hAcc[2] += pu_sum(satd8x8_cands_mma<1>(a, RW, o, afrag, lane), onR);
+      }
+      if (strip == nStrips - 1) {
+        // ---- half-pel decision (TEncSearch.cpp:1634 strict <, first minimum in table order) ----
+        // MV bits, cost scale 1 (TEncSearch.cpp:4531): ((int << 1) + h) << 1 against the predictor
+        const unsigned* hd = sHead + 4 * min(pcR, count - 1);
+        const unsigned r2 = hd[2], r3 = hd[3];
+        const int mvIntX = (short)(r2 & 0xffff), mvIntY = (short)(r2 >> 16);
+        const int predX = (short)(r3 & 0xffff), predY = (short)(r3 >> 16);
+        auto half_cost = [&](int c, unsigned dist) {
+          const int hx = c_refineH[c][0], hy = c_refineH[c][1];
+          return dist + costLut[golomb_bits((((mvIntX << 1) + hx) << 1) - predX) + golomb_bits((((mvIntY << 1) + hy) << 1) - predY)];
+        };
+        unsigned bestC = half_cost(cq, hAcc[0]);
+        int bestI = cq;
+        const unsigned c1 = half_cost(4 + cq, hAcc[1]);
+        if (c1 < bestC) { bestC = c1; bestI = 4 + cq; }
+        const unsigned c2 = half_cost(8, hAcc[2]);
+        if (c2 < bestC) { bestC = c2; bestI = 8; }
+#pragma unroll
+        for (int d = 8; d <= 16; d <<= 1) {  // across the four candidate lanes of a batch
+          const unsigned oc = __shfl_xor_sync(0xffffffffu, bestC, d);
+          const int oi = __shfl_xor_sync(0xffffffffu, bestI, d);
+          if (oc < bestC || (oc == bestC && oi < bestI)) { bestC = oc; bestI = oi; }
+        }
+        if (pcR < count && nR == pr * tps && cq == 0)
+          sDec[pcR] = make_uint2((unsigned)(c_refineH[bestI][0] & 0xff) | ((unsigned)(c_refineH[bestI][1] & 0xff) << 8), bestC);
+      }
     } else {
-      const unsigned a[4] = {feedQ[0] + hb, feedQ[2] + hb + PRB, feedQ[0] + hb + 2 * PRB, feedQ[2] + hb + 3 * PRB};
-      qAcc[1] += pu_sum(satd8x8_cands_mma<4>(a, RW, o, afrag, lane), onR);
-    }
-    __syncwarp();
-    if (j + 2 < nJobs) stage_qter((j + 2) >> 1, b);
-  }
-  // ---- quarter-pel decision: candidate 0 is the half-pel winner itself (same block, same bits) ----
-  // cost scale 0 (TEncSearch.cpp:5260): (((int << 1) + half) << 1) + q against the predictor
-  auto qter_cost = [&](int q, unsigned dist) {
-    const int bx = (((mvIntX << 1) + bhxR) << 1) + c_refineQ[q][0], by = (((mvIntY << 1) + bhyR) << 1) + c_refineQ[q][1];
-    return dist + costLut[golomb_bits(bx - predX) + golomb_bits(by - predY)];
-  };
-  unsigned qC = qter_cost(1 + cq, qAcc[0]);
-  int qI = 1 + cq;
-  {
-    const unsigned c1 = qter_cost(5 + cq, qAcc[1]);
-    if (c1 < qC) { qC = c1; qI = 5 + cq; }
-  }
+      // quarter-pel: the staged regions start at the candidate's integer origin; x offsets (2 bhx + ox) >> 2
+      //   q:    1      2       3       4       5      6      7      8
+      //   ox:   0      0      -1       1      -1      1     -1      1
+      const int bhxF = (int)(signed char)(sDec[min(pu_of(u, pf), count - 1)].x & 0xff);
+      const unsigned fq = hb + feedTile;
+      const unsigned qm = fq + ((f.alignX + ((2 * bhxF - 1) >> 2)) & (A - 1));
+      const unsigned q0 = fq + ((f.alignX + ((2 * bhxF) >> 2)) & (A - 1));
+      const unsigned qp = fq + ((f.alignX + ((2 * bhxF + 1) >> 2)) & (A - 1));
+      if (strip == 0 && b == 0) qAcc[0] = qAcc[1] = 0;
+      if (b == 0) {
+        const unsigned a[4] = {q0, q0 + PRB, qm + 2 * PRB, qp + 3 * PRB};
+        qAcc[0] += pu_sum(satd8x8_cands_mma<4>(a, RW, o, afrag, lane), onR);
+      } else {
+        const unsigned a[4] = {qm, qp + PRB, qm + 2 * PRB, qp + 3 * PRB};
+        qAcc[1] += pu_sum(satd8x8_cands_mma<4>(a, RW, o, afrag, lane), onR);
+      }
+      if (strip == nStrips - 1 && b == 1) {
+        // ---- quarter-pel decision: candidate 0 is the half-pel winner itself (same block, same bits) ----
+        // cost scale 0 (TEncSearch.cpp:5260): (((int << 1) + half) << 1) + q against the predictor
+        const unsigned* hd = sHead + 4 * min(pcR, count - 1);
+        const unsigned r2 = hd[2], r3 = hd[3];
+        const int mvIntX = (short)(r2 & 0xffff), mvIntY = (short)(r2 >> 16);
+        const int predX = (short)(r3 & 0xffff), predY = (short)(r3 >> 16);
+        const uint2 dec = sDec[min(pcR, count - 1)];
+        const int bhx = (int)(signed char)(dec.x & 0xff), bhy = (int)(signed char)((dec.x >> 8) & 0xff);
+        auto qter_cost = [&](int q, unsigned dist) {
+          const int bx = (((mvIntX << 1) + bhx) << 1) + c_refineQ[q][0], by = (((mvIntY << 1) + bhy) << 1) + c_refineQ[q][1];
+          return dist + costLut[golomb_bits(bx - predX) + golomb_bits(by - predY)];
+        };
+        unsigned qC = qter_cost(1 + cq, qAcc[0]);
+        int qI = 1 + cq;
+        const unsigned c1 = qter_cost(5 + cq, qAcc[1]);
+        if (c1 < qC) { qC = c1; qI = 5 + cq; }
 #pragma unroll
-  for (int d = 8; d <= 16; d <<= 1) {
-    const unsigned oc = __shfl_xor_sync(0xffffffffu, qC, d);
-    const int oi = __shfl_xor_sync(0xffffffffu, qI, d);
-    if (oc < qC || (oc == qC && oi < qI)) { qC = oc; qI = oi; }
-  }
-  if (bestC <= qC) { qC = bestC; qI = 0; }  // strict < against the running best that starts at candidate 0
-
-  if (pr < count && nR == pr * tps && cq == 0) {
-    fme_result* r = &res[idxR];
-    r->halfX = (int8_t)bhxR; r->halfY = (int8_t)bhyR;
-    r->qterX = c_refineQ[qI][0]; r->qterY = c_refineQ[qI][1];
-    r->cost = qC;
+        for (int d = 8; d <= 16; d <<= 1) {
+          const unsigned oc = __shfl_xor_sync(0xffffffffu, qC, d);
+          const int oi = __shfl_xor_sync(0xffffffffu, qI, d);
+          if (oc < qC || (oc == qC && oi < qI)) { qC = oc; qI = oi; }
+        }
+        if (dec.y <= qC) { qC = dec.y; qI = 0; }  // strict < against the running best that starts at candidate 0
+        if (pcR < count && nR == pr * tps && cq == 0) {
+          fme_result* r = &res[sIdx[pcR]];
+          r->halfX = (int8_t)bhx; r->halfY = (int8_t)bhy;
+          r->qterX = c_refineQ[qI][0]; r->qterY = c_refineQ[qI][1];
+          r->cost = qC;
+        }
+      }
+    }
+    __syncwarp();  // this job's buffer half is free, and any decision it made is visible
+    issue_ready(k + 3, k);
   }
   __syncwarp();
   return true;
@@ -1268,11 +1352,11 @@ k2_refine(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, const ui
   constexpr int mmaGroups = PATH == 2 ? 1 : 0;
   extern __shared__ __align__(16) uint8_t dynSmem[];
   __shared__ uint32_t s_lut[FME_COST_LUT_SIZE];
-  __shared__ int s_packOff[FME_MAX_CLASSES + 1];
-  __shared__ int s_classOff[FME_MAX_CLASSES + 1];
+  __shared__ int s_packOff[FME_K2_KEYS + 1];
+  __shared__ int s_classOff[FME_K2_KEYS + 1];
 
   for (int i = threadIdx.x; i < FME_COST_LUT_SIZE; i += blockDim.x) s_lut[i] = costLutG.v[i];
-  for (int i = threadIdx.x; i <= FME_MAX_CLASSES; i += blockDim.x) {
+  for (int i = threadIdx.x; i <= FME_K2_KEYS; i += blockDim.x) {
     s_packOff[i] = packOffset[i];
     s_classOff[i] = classOffset[i];
   }
@@ -1280,7 +1364,7 @@ k2_refine(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, const ui
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* smem = dynSmem + warp * K2_SMEM_PER_WARP;
-  const int totalPacks = s_packOff[FME_MAX_CLASSES];
+  const int totalPacks = s_packOff[FME_K2_KEYS];
 
   // dynamic pack scheduler; the next pack index is requested while the current pack is processed
   int nextPack = 0;
@@ -1289,12 +1373,17 @@ k2_refine(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, const ui
     const int pack = __shfl_sync(0xffffffffu, nextPack, 0);
     if (pack >= totalPacks) break;
     if (lane == 0) nextPack = atomicAdd(workCounter, 1);
-    // schedule slot of this pack: the v with packOff[v] <= pack < packOff[v+1] (two lanes cover the 64 slots);
-    // slot v holds class 63 - v (k2_scatter)
-    unsigned hit = __ballot_sync(0xffffffffu, s_packOff[lane] <= pack && s_packOff[lane + 1] > pack);
-    unsigned hit2 = __ballot_sync(0xffffffffu, s_packOff[lane + 32] <= pack && s_packOff[lane + 33] > pack);
-    const int v = hit ? (__ffs(hit) - 1) : (32 + __ffs(hit2) - 1);
-    ClassInfo ci = class_info(FME_MAX_CLASSES - 1 - v);
+    // schedule position of this pack: the last v with packOff[v] <= pack (binary search, uniform across the warp);
+    // position v holds shape class 63 - (v & 63) of slot group v >> 6 (k2_scatter)
+    int v = 0;
+    {
+      int hi = FME_K2_KEYS;
+      while (hi - v > 1) {
+        const int mid = (v + hi) >> 1;
+        if (s_packOff[mid] <= pack) v = mid; else hi = mid;
+      }
+    }
+    ClassInfo ci = class_info(63 - (v & 63));
     int inClass = s_classOff[v + 1] - s_classOff[v];
     const int packP = pack_pus(ci, mmaGroups);
     int first = (pack - s_packOff[v]) * packP;
@@ -1403,7 +1492,7 @@ static cudaError_t launch_k2_pass(const FmeGeom& g, const uint8_t* d_planes, con
                                   fme_result* d_res, const FmeCostLut& costLut, int useHad, int biServed, const FmeK2Scratch& sc,
                                   int numSMs, cudaStream_t s, int64_t* launches) {
   // classCount[64], classCursor[64] and the work counter are adjacent (fme_create)
-  cudaError_t e = cudaMemsetAsync(sc.classCount, 0, sizeof(int) * (2 * FME_MAX_CLASSES + 1), s);
+  cudaError_t e = cudaMemsetAsync(sc.classCount, 0, sizeof(int) * (2 * FME_K2_KEYS + 1), s);
   if (e != cudaSuccess) return e;
   int blocks = min(numSMs * 4, (n + 255) / 256);
   k2_count<<<blocks, 256, 0, s>>>(d_pus, n, sc.classCount, BI ? 1 : 0, BI ? nullptr : d_res, biServed);

@@ -458,6 +458,25 @@ cudaError_t fme_launch_dist(int kind, const int16_t* d_org, int orgStride, const
   return cudaGetLastError();
 }
 
+// fme_result (16 bytes) -> fme_result8 (include/fme_b200.h): every field of the MV group is in {-1, 0, 1}
+__global__ void k_pack_results(const fme_result* __restrict__ res, int n, fme_result8* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4 v = *reinterpret_cast<const uint4*>(&res[i]);  // x: half/qter bytes, y: cost, z: nn bytes, w: class
+  auto two = [](unsigned bytes, int k) { return (unsigned)((int)(signed char)(bytes >> (8 * k)) + 1) & 3u; };
+  unsigned m = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) m |= two(v.x, k) << (2 * k) | two(v.z, k) << (8 + 2 * k);
+  m |= (v.w & 63u) << 16;
+  *reinterpret_cast<uint2*>(&out[i]) = make_uint2(v.y, m);
+}
+cudaError_t fme_launch_pack_results(const fme_result* d_res, int n, fme_result8* d_out, cudaStream_t s, int64_t* launches) {
+  if (n <= 0) return cudaSuccess;
+  k_pack_results<<<(n + 255) / 256, 256, 0, s>>>(d_res, n, d_out);
+  ++*launches;
+  return cudaGetLastError();
+}
+
 cudaError_t fme_launch_expand_heads(const fme_pu_head* d_heads, int n, fme_pu* d_pus, cudaStream_t s, int64_t* launches) {
   if (n <= 0) return cudaSuccess;
   k_expand_heads<<<(n + 255) / 256, 256, 0, s>>>(d_heads, n, d_pus);

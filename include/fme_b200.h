@@ -114,6 +114,26 @@ typedef struct fme_result {
   uint8_t pad[3];
 } fme_result; /* 16 bytes */
 
+/* Compact result, 8 bytes instead of 16: OR FME_MODE_RESULT8 into the mode of any fme_submit* call and pass an
+ * fme_result8 array as `out`.  Halves the device->host traffic of a batch (the end-to-end path is PCIe / host-fabric
+ * bound when several GPUs share one host).  Fields hold value + 1 in two bits each; fme_result8_unpack() expands. */
+#define FME_MODE_RESULT8 0x10
+typedef struct fme_result8 {
+  uint32_t cost; /* ruiCost */
+  uint32_t mv;   /* bits 0-1 halfX+1, 2-3 halfY+1, 4-5 qterX+1, 6-7 qterY+1, 8-9 nnHalfX+1, 10-11 nnHalfY+1,
+                    12-13 nnQterX+1, 14-15 nnQterY+1, 16-21 nnClass */
+} fme_result8; /* 8 bytes */
+static inline void fme_result8_unpack(const fme_result8* p, fme_result* r) {
+  const uint32_t m = p->mv;
+  r->halfX = (int8_t)((m & 3) - 1); r->halfY = (int8_t)(((m >> 2) & 3) - 1);
+  r->qterX = (int8_t)(((m >> 4) & 3) - 1); r->qterY = (int8_t)(((m >> 6) & 3) - 1);
+  r->cost = p->cost;
+  r->nnHalfX = (int8_t)(((m >> 8) & 3) - 1); r->nnHalfY = (int8_t)(((m >> 10) & 3) - 1);
+  r->nnQterX = (int8_t)(((m >> 12) & 3) - 1); r->nnQterY = (int8_t)(((m >> 14) & 3) - 1);
+  r->nnClass = (uint8_t)((m >> 16) & 63);
+  r->pad[0] = r->pad[1] = r->pad[2] = 0;
+}
+
 /* ---- lifetime -------------------------------------------------------------------------- */
 int fme_create(const fme_config* cfg, fme_ctx** out);
 void fme_destroy(fme_ctx* ctx);

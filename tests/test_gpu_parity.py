@@ -928,3 +928,34 @@ def test_k3_references_own_three_layer_network(orc):
     want48 = np.array([orc.nn_pred(blob48, e, 16, 16)[0] for e in recs["err"][:3000]])
     np.testing.assert_array_equal(got48["nnClass"][:3000], want48)
     eng.close()
+
+
+@pytest.mark.gpu
+def test_packed_result8_equals_full_results(small):
+    """FME_MODE_RESULT8: the 8-byte result carries exactly the fields of fme_result (synchronous, async heads and
+    device-resident entry points)."""
+    import torch
+    eng0, g, recs = small
+    eng = fme.Fme(128, 96, num_ref_slots=2, max_pus=len(recs))
+    eng.set_nn_weights(fme.nn_weights.load_blob(27))
+    eng.set_slice(float(g["small_lambda"][0]))
+    eng.upload_org(g["small_org"])
+    for s in range(2):
+        eng.upload_ref(s, g["small_refs"][s])
+    fields = ("halfX", "halfY", "qterX", "qterY", "cost", "nnHalfX", "nnHalfY", "nnQterX", "nnQterY", "nnClass")
+
+    def same(a, b):
+        for f in fields:
+            np.testing.assert_array_equal(a[f], b[f], err_msg=f)
+    want = eng.submit(recs, fme.MODE_BOTH)
+    got = eng.submit(recs, fme.MODE_BOTH | fme.MODE_RESULT8)
+    same(got, want)
+    assert len(set(want["nnClass"].tolist())) > 3 and want["halfX"].min() == -1 and want["qterY"].max() == 1
+    d_in = torch.from_numpy(recs.view(np.uint8).reshape(len(recs), -1).copy()).cuda()
+    d_out = torch.zeros((len(recs), 8), dtype=torch.uint8, device="cuda")
+    eng.submit_device(d_in.data_ptr(), len(recs), d_out.data_ptr(), fme.MODE_BOTH | fme.MODE_RESULT8)
+    eng.synchronize()
+    torch.cuda.synchronize()
+    got_d = fme.unpack_result8(d_out.cpu().numpy().copy().view(fme.RESULT8_DTYPE).reshape(-1))
+    same(got_d, want)
+    eng.close()
