@@ -31,7 +31,7 @@ EXPORTS = [
     "fme_set_nn_weights", "fme_load_nn_csv_dir", "fme_set_slice", "fme_upload_ref", "fme_upload_ref_u8",
     "fme_upload_org", "fme_upload_org_u8", "fme_submit", "fme_submit_async", "fme_submit_heads", "fme_submit_heads_async", "fme_wait_oldest", "fme_submit_device", "fme_interp_slot",
     "fme_upload_ref_device_u8", "fme_upload_org_device_u8", "fme_int_surface_device", "fme_filter_hor",
-    "fme_filter_ver", "fme_dist", "fme_mv_cost", "fme_upload_ref_chroma", "fme_mc", "fme_mc_bi", "fme_pred_error", "fme_download_plane",
+    "fme_filter_ver", "fme_dist", "fme_mv_cost", "fme_upload_ref_chroma", "fme_upload_ref_chroma_u8", "fme_upload_ref_yuv420_u8", "fme_upload_org_yuv420_u8", "fme_mc", "fme_mc_bi", "fme_pred_error", "fme_download_plane",
     "fme_last_kernel_ms", "fme_launch_count", "fme_set_profiling",
 ]
 
@@ -89,6 +89,8 @@ def load_library():
     lib.fme_set_slice.argtypes = [vp, C.c_double]
     lib.fme_upload_ref.argtypes = [vp, i32, vp, i32]
     lib.fme_upload_ref_u8.argtypes = [vp, i32, vp, i32]
+    lib.fme_upload_ref_yuv420_u8.argtypes = [vp, i32, vp, i32]
+    lib.fme_upload_org_yuv420_u8.argtypes = [vp, vp]
     lib.fme_upload_org.argtypes = [vp, vp, i32]
     lib.fme_upload_org_u8.argtypes = [vp, vp, i32]
     lib.fme_submit.argtypes = [vp, vp, i32, vp, i32]
@@ -209,6 +211,17 @@ class Fme:
         cb, cr = np.ascontiguousarray(cb, np.int16), np.ascontiguousarray(cr, np.int16)
         assert cb.shape == cr.shape == (self.height // 2, self.width // 2)
         self._check(self.lib.fme_upload_ref_chroma(self.h, slot, _addr(cb), _addr(cr), cb.shape[1]))
+
+    def upload_ref_yuv420(self, slot, frame, with_chroma=True):
+        """frame: one raw 8-bit 4:2:0 frame (uint8, W*H*3/2 bytes) exactly as read from a .yuv file."""
+        frame = np.ascontiguousarray(frame, np.uint8).reshape(-1)
+        assert frame.size == self.width * self.height * 3 // 2
+        self._check(self.lib.fme_upload_ref_yuv420_u8(self.h, slot, _addr(frame), int(with_chroma)))
+
+    def upload_org_yuv420(self, frame):
+        frame = np.ascontiguousarray(frame, np.uint8).reshape(-1)
+        assert frame.size >= self.width * self.height
+        self._check(self.lib.fme_upload_org_yuv420_u8(self.h, _addr(frame)))
 
     def download_plane(self, slot, fy, fx):
         wp, hp = self.width + 2 * self.margin, self.height + 2 * self.margin

@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges cost nothing unless a profiler is attached
+
 #include "fme_common.cuh"
 
 namespace {
@@ -162,8 +164,20 @@ struct StageTimer {
       for (float& m : c->lastMs) m = -1.f;
     }
   }
-  StageTimer(fme_ctx* c_, int i) : c(c_), idx(i) { rec(2 * idx); }
-  ~StageTimer() { rec(2 * idx + 1); }
+  // every pass is also an NVTX range ("fme:K1 interp", ...) for Nsight Systems / Compute timelines
+  StageTimer(fme_ctx* c_, int i) : c(c_), idx(i) {
+    static const char* const names[4] = {"fme:K1 interp", "fme:K2 refine", "fme:K3 nn_pred", "fme:K0 int surface"};
+    nvtxRangePushA(names[idx & 3]);
+    rec(2 * idx);
+  }
+  ~StageTimer() {
+    rec(2 * idx + 1);
+    nvtxRangePop();
+  }
+};
+struct NvtxRange {  // host-side span of an ABI call (copies + launches it issues)
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
 };
 
 int run_k1(fme_ctx* c, int slot, const uint8_t* d_pic = nullptr, int picPitch = 0) {
@@ -542,6 +556,7 @@ int fme_mv_cost(fme_ctx* c, int x, int y, int scale, int predX, int predY, uint3
 extern "C++" {
 template <typename T>
 static int upload_ref_host(fme_ctx* c, int slot, const T* y, int stride) {
+  NvtxRange nvtxSpan("fme_upload_ref");
   int rc = check_slot(c, slot);
   if (rc) return rc;
   CU_CHECK(cudaSetDevice(c->cfg.device));
@@ -627,7 +642,9 @@ int fme_upload_org_device_u8(fme_ctx* c, const uint8_t* d_y, int pitch) {
   return FME_OK;
 }
 
-int fme_upload_ref_chroma(fme_ctx* c, int slot, const int16_t* cb, const int16_t* cr, int stride) {
+extern "C++" {
+template <typename T>
+static int upload_ref_chroma_host(fme_ctx* c, int slot, const T* cb, const T* cr, int stride) {
   int rc = check_slot(c, slot);
   if (rc) return rc;
   if (!cb || !cr) return fail(FME_ERR_INVALID, "null chroma plane");
@@ -648,6 +665,28 @@ int fme_upload_ref_chroma(fme_ctx* c, int slot, const int16_t* cb, const int16_t
   }
   return FME_OK;
 }
+}  // extern "C++"
+int fme_upload_ref_chroma(fme_ctx* c, int slot, const int16_t* cb, const int16_t* cr, int stride) {
+  return upload_ref_chroma_host(c, slot, cb, cr, stride);
+}
+int fme_upload_ref_chroma_u8(fme_ctx* c, int slot, const uint8_t* cb, const uint8_t* cr, int stride) {
+  return upload_ref_chroma_host(c, slot, cb, cr, stride);
+}
+
+// One frame of a raw planar 8-bit 4:2:0 file (TVideoIOYuv layout: Y, then Cb, then Cr, no padding) straight into the
+// padded device planes of a reference slot: three DMAs from the caller's frame buffer, no host pass over the samples.
+int fme_upload_ref_yuv420_u8(fme_ctx* c, int slot, const uint8_t* frame, int withChroma) {
+  if (!c || !frame) return fail(FME_ERR_INVALID, "null argument");
+  const int W = c->cfg.width, H = c->cfg.height;
+  int rc = fme_upload_ref_u8(c, slot, frame, W);
+  if (rc || !withChroma) return rc;
+  const uint8_t* cb = frame + (size_t)W * H;
+  return fme_upload_ref_chroma_u8(c, slot, cb, cb + (size_t)(W / 2) * (H / 2), W / 2);
+}
+int fme_upload_org_yuv420_u8(fme_ctx* c, const uint8_t* frame) {
+  if (!c || !frame) return fail(FME_ERR_INVALID, "null argument");
+  return fme_upload_org_u8(c, frame, c->cfg.width);  // fractional ME searches on luma only (TEncSearch.cpp:4474-4479)
+}
 
 // Inter PU shapes of HEVC (fme_hevc_pu_shape): K2's lane units are 8x8 tiles or PAIRS of 4x4 tiles, and every HEVC
 // shape that is 4x4-tiled has an even tile count.
@@ -657,6 +696,7 @@ static bool valid_pu_size(int w, int h) { return fme_hevc_pu_shape(w, h); }
 static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, int mode, bool sync,
                          const fme_pu_head* heads = nullptr) {
   if (!c || (!pus && !heads) || !out) return fail(FME_ERR_INVALID, "null argument");
+  NvtxRange nvtxSpan(heads ? "fme_submit_heads" : "fme_submit");
   const bool packed = (mode & FME_MODE_RESULT8) != 0;  // `out` is an fme_result8 array
   mode &= ~FME_MODE_RESULT8;
   if (n < 0 || n > c->cfg.maxPUs) return fail(FME_ERR_INVALID, "n=%d exceeds maxPUs=%d", n, c->cfg.maxPUs);

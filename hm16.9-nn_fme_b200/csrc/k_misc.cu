@@ -57,6 +57,52 @@ __device__ __forceinline__ void k0_accumulate(unsigned (&acc)[9], const uint8_t*
   }
 }
 
+// SSE widths 4 / 8 / 16 / 32 / 64 (the common case): a lane owns a strip of NW words (4 NW samples) and a block of
+// consecutive source rows, and slides a three-row window down the reference: every reference row is loaded and aligned
+// ONCE (NW + 2 words) and serves the three vertical offsets of three source rows -- 2 NW + 2 loads per 4 NW samples instead
+// of 11 per 4 samples in the per-item form above (K0 was bound by L1 wavefronts, not by arithmetic).
+template <int NW>
+__device__ __forceinline__ void k0_sse_strip(unsigned (&acc)[9], const uint8_t* __restrict__ src, int orgPitch,
+                                             const uint8_t* __restrict__ ref, int pitch, int nrows) {
+  const uint8_t* rp = ref - pitch - 1;  // row -1, byte -1 of the strip
+  const unsigned a8 = (unsigned)((size_t)rp & 3) * 8u;
+  const unsigned* rw = reinterpret_cast<const unsigned*>((size_t)rp & ~(size_t)3);
+  const unsigned* sw = reinterpret_cast<const unsigned*>(src);  // 4-byte aligned (checked by the caller)
+  const int pitchW = pitch >> 2, orgPitchW = orgPitch >> 2;
+  unsigned A[NW + 1], B[NW + 1], C[NW + 1];
+  auto load_row = [&](const unsigned* p, unsigned (&x)[NW + 1]) {
+    unsigned w[NW + 2];
+#pragma unroll
+    for (int j = 0; j < NW + 2; ++j) w[j] = __ldg(p + j);
+#pragma unroll
+    for (int j = 0; j <= NW; ++j) x[j] = __funnelshift_r(w[j], w[j + 1], a8);  // bytes 4j-1 .. 4j+2 of the row
+  };
+  auto row_sse = [&](const unsigned (&o)[NW], const unsigned (&x)[NW + 1], int dy) {
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+      for (int j = 0; j < NW; ++j) {
+        const unsigned v = dx == 0 ? x[j] : __funnelshift_r(x[j], x[j + 1], 8 * dx);
+        const unsigned d = __vabsdiffu4(o[j], v);
+        acc[dy * 3 + dx] = __dp4a(d, d, acc[dy * 3 + dx]);
+      }
+  };
+  load_row(rw, A);
+  load_row(rw + pitchW, B);
+#pragma unroll 1
+  for (int r = 0; r < nrows; ++r) {
+    load_row(rw + (r + 2) * pitchW, C);
+    unsigned o[NW];
+#pragma unroll
+    for (int j = 0; j < NW; ++j) o[j] = __ldg(sw + r * orgPitchW + j);
+    row_sse(o, A, 0);
+    row_sse(o, B, 1);
+    row_sse(o, C, 2);
+#pragma unroll
+    for (int j = 0; j <= NW; ++j) { A[j] = B[j]; B[j] = C[j]; }
+  }
+}
+
 __global__ void __launch_bounds__(256) k0_int_surface(fme_pu* __restrict__ pus, int n, const uint8_t* __restrict__ planes,
                                                       const uint8_t* __restrict__ org, const FmeGeom g, int fen) {
   const int sub = threadIdx.x & 7;                                      // lane within the PU's 8-lane group
@@ -89,8 +135,27 @@ __global__ void __launch_bounds__(256) k0_int_surface(fme_pu* __restrict__ pus, 
       const uint8_t* ref = planes + (size_t)min(slot, g.numSlots - 1) * g.slotBytes +
                            (size_t)((Y + g.M) * g.pitch + (X + g.M));
       const uint8_t* src = org + (size_t)(oy * g.orgPitch + ox);
-      if (useSad) k0_accumulate<true>(acc, src, g.orgPitch, ref, g.pitch, w, step == 2 ? h >> 1 : h, step, sub);
-      else k0_accumulate<false>(acc, src, g.orgPitch, ref, g.pitch, w, h, 1, sub);
+      if (useSad) {
+        k0_accumulate<true>(acc, src, g.orgPitch, ref, g.pitch, w, step == 2 ? h >> 1 : h, step, sub);
+      } else if (((size_t)src & 3) == 0) {
+        // 8 lanes = strips x row blocks: strips of 16 samples (w >= 16), else one strip of w samples
+        const int strips = w >= 16 ? w >> 4 : 1;                 // 1, 2, 4
+        const int sShift = strips >> 1;                          // log2
+        const int lanesY = 8 >> sShift;
+        const int strip = sub & (strips - 1), rb = sub >> sShift;
+        const int rowsPer = (h + lanesY - 1) >> (3 - sShift);
+        const int r0 = rb * rowsPer;
+        const int nrows = min(rowsPer, h - r0);
+        if (nrows > 0) {
+          const uint8_t* s2 = src + (size_t)r0 * g.orgPitch + strip * 16;
+          const uint8_t* f2 = ref + (size_t)r0 * g.pitch + strip * 16;
+          if (w >= 16) k0_sse_strip<4>(acc, s2, g.orgPitch, f2, g.pitch, nrows);
+          else if (w == 8) k0_sse_strip<2>(acc, s2, g.orgPitch, f2, g.pitch, nrows);
+          else k0_sse_strip<1>(acc, s2, g.orgPitch, f2, g.pitch, nrows);
+        }
+      } else {
+        k0_accumulate<false>(acc, src, g.orgPitch, ref, g.pitch, w, h, 1, sub);  // out-of-contract (unaligned) source position
+      }
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k) {

@@ -31,6 +31,16 @@ def read_yuv420_frame(path, width, height, index):
     return y.copy(), cb.copy(), cr.copy()
 
 
+def read_yuv420_raw(path, width, height, index):
+    """Frame `index` as the flat byte buffer of the file (Y, Cb, Cr back to back): what fme_upload_ref_yuv420_u8 /
+    fme_upload_org_yuv420_u8 take -- no per-plane copies on the host."""
+    n = yuv420_frame_bytes(width, height)
+    a = np.fromfile(path, np.uint8, count=n, offset=n * index)
+    if a.size != n:
+        raise EOFError("frame %d is beyond the end of %s" % (index, path))
+    return a
+
+
 def write_yuv420_frame(f, y, cb=None, cr=None):
     """Append one frame to an open binary file; missing chroma is written as mid-grey."""
     h, w = y.shape

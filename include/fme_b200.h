@@ -227,6 +227,13 @@ int fme_mv_cost(fme_ctx* ctx, int x, int y, int scale, int predX, int predY, uin
 /* ---- motion compensation ("next" row f2) ------------------------------------ */
 /* Chroma reference planes for MC (Pel, picture sample (0,0), chroma stride; 4:2:0). */
 int fme_upload_ref_chroma(fme_ctx* ctx, int slot, const int16_t* cb, const int16_t* cr, int stride);
+int fme_upload_ref_chroma_u8(fme_ctx* ctx, int slot, const uint8_t* cb, const uint8_t* cr, int stride);
+/* Raw planar 8-bit 4:2:0 frames as TVideoIOYuv reads and writes them (TLibVideoIO/TVideoIOYuv.cpp; Y, Cb, Cr back to
+ * back, no padding; SURVEY.md "next" row f4): the frame buffer goes straight into the padded device planes (luma: K1 on
+ * all 16 planes; chroma, if withChroma: the two padded planes fme_mc reads).  fme_upload_org_yuv420_u8 takes the luma
+ * plane of a source frame. */
+int fme_upload_ref_yuv420_u8(fme_ctx* ctx, int slot, const uint8_t* frame, int withChroma);
+int fme_upload_org_yuv420_u8(fme_ctx* ctx, const uint8_t* frame);
 /* xPredInterBlk, uni-prediction (TComPrediction.cpp:643-681) for n PUs: mv = quarter-pel luma MV.
  * dstY: n blocks back to back, each 64x64 Pel (stride 64); dstCb/dstCr: each 32x32 (stride 32). */
 typedef struct fme_mc_pu {

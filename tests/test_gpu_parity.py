@@ -959,3 +959,46 @@ def test_packed_result8_equals_full_results(small):
     got_d = fme.unpack_result8(d_out.cpu().numpy().copy().view(fme.RESULT8_DTYPE).reshape(-1))
     same(got_d, want)
     eng.close()
+
+
+@pytest.mark.gpu
+def test_raw_yuv420_frames_go_straight_into_device_planes(tmp_path, small):
+    """SURVEY.md "next" row f4 on the device: frames of a raw 8-bit 4:2:0 file (TVideoIOYuv layout) uploaded with
+    fme_upload_ref_yuv420_u8 / fme_upload_org_yuv420_u8 give the planes, the search results and the chroma motion
+    compensation of the per-plane Pel uploads."""
+    eng0, g, recs = small
+    W, H = 128, 96
+    rng = np.random.default_rng(12)
+    cbs = [rng.integers(0, 256, (H // 2, W // 2)).astype(np.uint8) for _ in range(3)]
+    crs = [rng.integers(0, 256, (H // 2, W // 2)).astype(np.uint8) for _ in range(3)]
+    ys = [g["small_org"].astype(np.uint8), g["small_refs"][0].astype(np.uint8), g["small_refs"][1].astype(np.uint8)]
+    path = str(tmp_path / "clip_128x96.yuv")
+    with open(path, "wb") as f:
+        for y, cb, cr in zip(ys, cbs, crs):
+            fme.formats.write_yuv420_frame(f, y, cb, cr)
+    lam = float(g["small_lambda"][0])
+    a = fme.Fme(W, H, num_ref_slots=2, max_pus=len(recs))      # per-plane Pel uploads
+    b = fme.Fme(W, H, num_ref_slots=2, max_pus=len(recs))      # raw frames
+    for e in (a, b):
+        e.set_slice(lam)
+    a.upload_org(ys[0])
+    b.upload_org_yuv420(fme.formats.read_yuv420_raw(path, W, H, 0))
+    for s in range(2):
+        a.upload_ref(s, ys[1 + s])
+        a.upload_ref_chroma(s, cbs[1 + s].astype(np.int16), crs[1 + s].astype(np.int16))
+        b.upload_ref_yuv420(s, fme.formats.read_yuv420_raw(path, W, H, 1 + s))
+    for s in range(2):
+        for k in (0, 5, 10, 15):
+            np.testing.assert_array_equal(a.download_plane(s, k // 4, k % 4), b.download_plane(s, k // 4, k % 4))
+    ra, rb = a.submit(recs, fme.MODE_STD), b.submit(recs, fme.MODE_STD)
+    np.testing.assert_array_equal(ra["cost"], rb["cost"])
+    mc = np.zeros(64, fme.MC_PU_DTYPE)
+    mc["x"], mc["y"] = (np.arange(64) % 8) * 16, (np.arange(64) // 8) * 8
+    mc["w"], mc["h"], mc["refSlot"] = 16, 8, np.arange(64) % 2
+    mc["mvX"], mc["mvY"] = rng.integers(-20, 21, 64), rng.integers(-20, 21, 64)
+    for u, v in zip(a.mc(mc), b.mc(mc)):
+        np.testing.assert_array_equal(u, v)
+    with pytest.raises(EOFError):
+        fme.formats.read_yuv420_raw(path, W, H, 3)
+    a.close()
+    b.close()
