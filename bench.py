@@ -373,6 +373,56 @@ def run_gpu(args):
         k3_fma_ms = f0.elapsed_time(f1) / 8
         fast.close()
 
+    # ---- "next" rows f2 / f3 as batched operators: candidate costs (AMVP template / merge) and compact luma MC ----
+    ops = {}
+    if not banded:
+        rc0 = h_recs[0]
+        nc = len(rc0)
+        rng = np.random.default_rng(5)
+        cands = np.zeros(nc, fme.CAND_DTYPE)
+        for f in ("x", "y", "w", "h", "refSlot"):
+            cands[f] = rc0[f]
+        cands["mvX"] = rc0["mvIntX"] * 4 + rng.integers(-3, 4, nc)
+        cands["mvY"] = rc0["mvIntY"] * 4 + rng.integers(-3, 4, nc)
+        cands["bits"] = rng.integers(1, 6, nc)
+        cands["groupStart"] = (np.arange(nc) % 3 == 0)
+        mcp = np.zeros(nc, fme.MC_PU_DTYPE)
+        for f in ("x", "y", "w", "h", "refSlot", "mvX", "mvY"):
+            mcp[f] = cands[f]
+        sizes = mcp["w"].astype(np.int64) * mcp["h"]
+        offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint32)
+        d_c = torch.from_numpy(cands.view(np.uint8).reshape(nc, -1).copy()).to(dev)
+        d_m = torch.from_numpy(mcp.view(np.uint8).reshape(nc, -1).copy()).to(dev)
+        d_off = torch.from_numpy(offs.view(np.int32)).to(dev)
+        d_cost = torch.zeros(nc, dtype=torch.int32, device=dev)
+        d_best = torch.zeros(nc, dtype=torch.int32, device=dev)
+        d_blk = torch.zeros(int(sizes.sum()), dtype=torch.uint8, device=dev)
+        eng.upload_org_device_u8(d_org[0].data_ptr(), width)
+        for s_ in range(N_REFS):
+            eng.upload_ref_device_u8(s_, d_refs[0][s_].data_ptr(), width)
+
+        def time_op(fn, reps=6):
+            for _ in range(2):
+                fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                fn()
+            b.record(stream)
+            torch.cuda.synchronize(dev)
+            return a.elapsed_time(b) / reps
+        px = float(sizes.sum())
+        ms_c = time_op(lambda: eng.cand_cost_device(d_c.data_ptr(), nc, d_cost.data_ptr(), d_best.data_ptr()))
+        ms_m = time_op(lambda: eng.mc_luma_compact_device(d_m.data_ptr(), nc, d_off.data_ptr(), d_blk.data_ptr()))
+        ops = {"cand_cost": {"ms": ms_c, "candidates": nc, "candidates_per_s": nc / (ms_c * 1e-3), "alg_bytes": 2.0 * px,
+                             "achieved": 2.0 * px / (ms_c * 1e-3) / 1e9, "unit": "GB/s",
+                             "note": "fme_cand_cost_device: one candidate per PU of the frame's list (MC block + HADs + "
+                                     "index-bit cost, first minimum per group of 3); bytes = candidate block + source block"},
+               "mc_luma_compact": {"ms": ms_m, "pus": nc, "pus_per_s": nc / (ms_m * 1e-3), "alg_bytes": 2.0 * px,
+                                   "achieved": 2.0 * px / (ms_m * 1e-3) / 1e9, "unit": "GB/s",
+                                   "note": "fme_mc_luma_compact_device: w*h bytes read from the sub-pel plane and written compactly per PU"}}
+        del d_c, d_m, d_off, d_cost, d_best, d_blk
+
     out = None
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -449,6 +499,7 @@ def run_gpu(args):
             "clocks": clocks,
             "roofline": roofline,
             "kernels": kernels,
+            "operators": {k: dict(v, frac_of_hbm_peak=v["achieved"] / peak) for k, v in ops.items()},
         }
         if world == 1:
             out["cpu_baseline"] = cpu_baseline_single(fme, sets[0], h_recs[0], lam, blob)

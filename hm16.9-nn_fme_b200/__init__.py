@@ -15,7 +15,7 @@ import numpy as np
 
 from . import nn_weights  # noqa: F401  (re-export)
 from . import formats  # noqa: F401
-from .pu_list import PU_DTYPE, HEAD_DTYPE, RESULT_DTYPE, MC_PU_DTYPE, MC_BI_PU_DTYPE  # noqa: F401
+from .pu_list import PU_DTYPE, HEAD_DTYPE, RESULT_DTYPE, MC_PU_DTYPE, MC_BI_PU_DTYPE, CAND_DTYPE  # noqa: F401
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 # FME_B200_LIB selects another build of the same library (A/B builds for profiling, e.g. variants/libfme_swar8.so)
@@ -24,6 +24,7 @@ LIB_PATH = os.environ.get("FME_B200_LIB") or os.path.join(PKG_DIR, "libfme_b200.
 MODE_STD, MODE_NN, MODE_BOTH = 1, 2, 3
 K2_PATH_AUTO, K2_PATH_SWAR, K2_PATH_MMA_PACK, K2_PATH_MMA_GROUP = 0, 1, 2, 3
 PU_LOSSLESS, PU_ERR_ON_GPU, PU_BI = 0x01, 0x02, 0x04
+CAND_SAD = 0x08
 
 # every symbol include/fme_b200.h declares (checked by tests/test_abi.py against the header)
 EXPORTS = [
@@ -31,7 +32,8 @@ EXPORTS = [
     "fme_set_nn_weights", "fme_load_nn_csv_dir", "fme_set_slice", "fme_upload_ref", "fme_upload_ref_u8",
     "fme_upload_org", "fme_upload_org_u8", "fme_submit", "fme_submit_async", "fme_submit_heads", "fme_submit_heads_async", "fme_wait_oldest", "fme_submit_device", "fme_interp_slot",
     "fme_upload_ref_device_u8", "fme_upload_org_device_u8", "fme_int_surface_device", "fme_filter_hor",
-    "fme_filter_ver", "fme_dist", "fme_mv_cost", "fme_upload_ref_chroma", "fme_upload_ref_chroma_u8", "fme_upload_ref_yuv420_u8", "fme_upload_org_yuv420_u8", "fme_mc", "fme_mc_bi", "fme_pred_error", "fme_download_plane",
+    "fme_filter_ver", "fme_dist", "fme_mv_cost", "fme_upload_ref_chroma", "fme_upload_ref_chroma_u8", "fme_upload_ref_yuv420_u8", "fme_upload_org_yuv420_u8", "fme_mc", "fme_mc_bi", "fme_pred_error", "fme_cand_cost", "fme_cand_cost_device", "fme_mc_luma_compact",
+    "fme_mc_luma_compact_device", "fme_download_plane",
     "fme_last_kernel_ms", "fme_launch_count", "fme_set_profiling",
 ]
 
@@ -98,6 +100,10 @@ def load_library():
     lib.fme_submit_heads.argtypes = [vp, vp, i32, vp, i32]
     lib.fme_submit_heads_async.argtypes = [vp, vp, i32, vp, i32]
     lib.fme_submit_device.argtypes = [vp, vp, i32, vp, i32]
+    lib.fme_cand_cost.argtypes = [vp, vp, i32, vp, vp]
+    lib.fme_cand_cost_device.argtypes = [vp, vp, i32, vp, vp]
+    lib.fme_mc_luma_compact.argtypes = [vp, vp, i32, vp, vp, C.c_size_t]
+    lib.fme_mc_luma_compact_device.argtypes = [vp, vp, i32, vp, vp]
     lib.fme_wait_oldest.argtypes = [vp]
     lib.fme_interp_slot.argtypes = [vp, i32]
     lib.fme_upload_ref_device_u8.argtypes = [vp, i32, vp, i32]
@@ -316,6 +322,31 @@ class Fme:
         out = np.zeros(len(pus), np.uint32)
         self._check(self.lib.fme_pred_error(self.h, _addr(pus), len(pus), _addr(out)))
         return out
+
+    def cand_cost(self, cands, want_best=True):
+        """fme_cand_cost: (cost[n], bestIndex[n] or None) for AMVP-template / merge candidates."""
+        cands = np.ascontiguousarray(cands, dtype=CAND_DTYPE)
+        cost = np.zeros(len(cands), np.uint32)
+        best = np.zeros(len(cands), np.int32) if want_best else None
+        self._check(self.lib.fme_cand_cost(self.h, _addr(cands), len(cands), _addr(cost), _addr(best) if want_best else None))
+        return cost, best
+
+    def cand_cost_device(self, d_cands_ptr, n, d_cost_ptr, d_best_ptr=0):
+        self._check(self.lib.fme_cand_cost_device(self.h, C.c_void_p(d_cands_ptr), n, C.c_void_p(d_cost_ptr),
+                                                  C.c_void_p(d_best_ptr) if d_best_ptr else None))
+
+    def mc_luma_compact(self, pus):
+        """fme_mc_luma_compact: (flat uint8 output, offsets); block i = out[offsets[i] : offsets[i] + w*h].reshape(h, w)."""
+        pus = np.ascontiguousarray(pus, dtype=MC_PU_DTYPE)
+        sizes = pus["w"].astype(np.int64) * pus["h"]
+        offsets = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint32)
+        out = np.zeros(int(sizes.sum()), np.uint8)
+        self._check(self.lib.fme_mc_luma_compact(self.h, _addr(pus), len(pus), _addr(offsets), _addr(out), C.c_size_t(out.size)))
+        return out, offsets
+
+    def mc_luma_compact_device(self, d_pus_ptr, n, d_offsets_ptr, d_out_ptr):
+        self._check(self.lib.fme_mc_luma_compact_device(self.h, C.c_void_p(d_pus_ptr), n, C.c_void_p(d_offsets_ptr),
+                                                        C.c_void_p(d_out_ptr)))
 
     # ---- introspection ----
     def last_kernel_ms(self):

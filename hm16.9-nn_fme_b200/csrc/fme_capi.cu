@@ -88,6 +88,8 @@ struct fme_ctx {
   int* d_k1Counter = nullptr;    // K1's dynamic tile hand-out (2 ints, re-armed by the kernel)
   uint32_t* d_scratchU32 = nullptr;
   size_t scratchU32Capacity = 0;
+  void* d_opBuf = nullptr;       // staging of the synchronous batched operators (fme_cand_cost, fme_mc_luma_compact)
+  size_t opBufCap = 0;
   FmeK2Scratch k2{};
   // state
   std::vector<char> refValid;
@@ -360,7 +362,7 @@ void fme_destroy(fme_ctx* c) {
     for (cudaEvent_t e : {c->evIn[b], c->evDone[b], c->evOut[b], c->evPicIn[b], c->evPicFree[b], c->evOrgFree[b]})
       if (e) cudaEventDestroy(e);
   }
-  cudaFree(c->d_cb); cudaFree(c->d_cr); cudaFree(c->d_nn);
+  cudaFree(c->d_cb); cudaFree(c->d_cr); cudaFree(c->d_nn); cudaFree(c->d_opBuf);
   cudaFree(c->d_k1Counter); cudaFree(c->d_scratchU32); cudaFree(c->k2.classCount); cudaFree(c->k2.order);
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
@@ -976,6 +978,90 @@ int fme_pred_error(fme_ctx* c, const fme_mc_pu* pus, int n, uint32_t* out) {
   CU_CHECK(fme_launch_pred_error(c->g, c->d_planes, c->d_org, reinterpret_cast<const fme_mc_pu*>(c->d_pus), n,
                                  c->cfg.useHadME, c->d_scratchU32, c->stream, &c->launches));
   CU_CHECK(cudaMemcpyAsync(out, c->d_scratchU32, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(cudaStreamSynchronize(c->stream));
+  return FME_OK;
+}
+
+// ---- batched candidate costs / compact MC ---------------------------------------------------------------
+static int ensure_bytes(void** p, size_t* cap, size_t bytes) {
+  if (*cap >= bytes) return FME_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  CU_CHECK(cudaMalloc(p, bytes));
+  *cap = bytes;
+  return FME_OK;
+}
+
+int fme_cand_cost_device(fme_ctx* c, const fme_cand_pu* d_cands, int n, uint32_t* d_cost, int32_t* d_best) {
+  if (!c || !d_cands || !d_cost) return fail(FME_ERR_INVALID, "null argument");
+  if (n < 0) return fail(FME_ERR_INVALID, "n out of range");
+  if (!c->orgValid || !c->sliceValid) return fail(FME_ERR_STATE, "fme_cand_cost needs fme_upload_org and fme_set_slice first");
+  if (n == 0) return FME_OK;
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  CU_CHECK(fme_launch_cand_cost(c->g, c->d_planes, c->d_org, d_cands, n, c->costLut, c->cfg.useHadME, d_cost, d_best, c->stream,
+                                &c->launches));
+  CU_CHECK(cudaEventRecord(c->evOrgFree[(c->orgSeq + FME_NBUF - 1) % FME_NBUF], c->stream));
+  return FME_OK;
+}
+
+int fme_cand_cost(fme_ctx* c, const fme_cand_pu* cands, int n, uint32_t* cost, int32_t* best) {
+  if (!c || !cands || !cost) return fail(FME_ERR_INVALID, "null argument");
+  if (n < 0) return fail(FME_ERR_INVALID, "n out of range");
+  if (n == 0) return FME_OK;
+  for (int i = 0; i < n; ++i) {
+    if (cands[i].refSlot >= c->cfg.numRefSlots || !c->refValid[cands[i].refSlot])
+      return fail(FME_ERR_STATE, "candidate %d references slot %d which holds no picture", i, cands[i].refSlot);
+    if (!fme_hevc_pu_shape(cands[i].w, cands[i].h)) return fail(FME_ERR_INVALID, "candidate %d: %dx%d is not an HEVC PU size", i, cands[i].w, cands[i].h);
+    if (cands[i].bits >= FME_COST_LUT_SIZE) return fail(FME_ERR_INVALID, "candidate %d: bits out of range", i);
+  }
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  const size_t inB = sizeof(fme_cand_pu) * (size_t)n, outB = 4 * (size_t)n;
+  int rc = ensure_bytes(&c->d_opBuf, &c->opBufCap, inB + 2 * outB);
+  if (rc) return rc;
+  fme_cand_pu* d_c = static_cast<fme_cand_pu*>(c->d_opBuf);
+  uint32_t* d_cost = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(c->d_opBuf) + inB);
+  int32_t* d_best = reinterpret_cast<int32_t*>(d_cost + n);
+  // stream-ordered on the kernel stream; only this call's own copies are waited for (no pipeline drain)
+  CU_CHECK(cudaMemcpyAsync(d_c, cands, inB, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = fme_cand_cost_device(c, d_c, n, d_cost, best ? d_best : nullptr))) return rc;
+  CU_CHECK(cudaMemcpyAsync(cost, d_cost, outB, cudaMemcpyDeviceToHost, c->stream));
+  if (best) CU_CHECK(cudaMemcpyAsync(best, d_best, outB, cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(cudaStreamSynchronize(c->stream));
+  return FME_OK;
+}
+
+int fme_mc_luma_compact_device(fme_ctx* c, const fme_mc_pu* d_pus, int n, const uint32_t* d_offsets, uint8_t* d_out) {
+  if (!c || !d_pus || !d_offsets || !d_out) return fail(FME_ERR_INVALID, "null argument");
+  if (n < 0) return fail(FME_ERR_INVALID, "n out of range");
+  if (n == 0) return FME_OK;
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  CU_CHECK(fme_launch_mc_luma_compact(c->g, c->d_planes, d_pus, n, d_offsets, d_out, c->stream, &c->launches));
+  return FME_OK;
+}
+
+int fme_mc_luma_compact(fme_ctx* c, const fme_mc_pu* pus, int n, const uint32_t* offsets, uint8_t* out, size_t outBytes) {
+  if (!c || !pus || !offsets || !out) return fail(FME_ERR_INVALID, "null argument");
+  if (n < 0) return fail(FME_ERR_INVALID, "n out of range");
+  if (n == 0) return FME_OK;
+  for (int i = 0; i < n; ++i) {
+    if (pus[i].refSlot >= c->cfg.numRefSlots || !c->refValid[pus[i].refSlot])
+      return fail(FME_ERR_STATE, "PU %d references slot %d which holds no picture", i, pus[i].refSlot);
+    if (pus[i].w > 64 || pus[i].h > 64 || pus[i].w < 4 || pus[i].h < 4 || (pus[i].w & 3)) return fail(FME_ERR_INVALID, "PU %d: bad size", i);
+    if ((offsets[i] & 3) || (size_t)offsets[i] + (size_t)pus[i].w * pus[i].h > outBytes)
+      return fail(FME_ERR_INVALID, "PU %d: offset %u misaligned or block beyond outBytes", i, offsets[i]);
+  }
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  const size_t inB = (sizeof(fme_mc_pu) * (size_t)n + 15) & ~(size_t)15, offB = (4 * (size_t)n + 15) & ~(size_t)15;
+  int rc = ensure_bytes(&c->d_opBuf, &c->opBufCap, inB + offB + outBytes);
+  if (rc) return rc;
+  uint8_t* base = static_cast<uint8_t*>(c->d_opBuf);
+  CU_CHECK(cudaMemcpyAsync(base, pus, sizeof(fme_mc_pu) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CU_CHECK(cudaMemcpyAsync(base + inB, offsets, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = fme_mc_luma_compact_device(c, reinterpret_cast<const fme_mc_pu*>(base), n, reinterpret_cast<const uint32_t*>(base + inB),
+                                       base + inB + offB)))
+    return rc;
+  CU_CHECK(cudaMemcpyAsync(out, base + inB + offB, outBytes, cudaMemcpyDeviceToHost, c->stream));
   CU_CHECK(cudaStreamSynchronize(c->stream));
   return FME_OK;
 }

@@ -112,5 +112,10 @@ cudaError_t fme_launch_mc_bi(const FmeGeom& g, const uint8_t* d_planes, const ui
 cudaError_t fme_launch_mc(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_cb, const uint8_t* d_cr,
                           const fme_mc_pu* d_pus, int n, int16_t* d_y, int16_t* d_cbOut, int16_t* d_crOut,
                           cudaStream_t s, int64_t* launches);
+cudaError_t fme_launch_cand_cost(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_cand_pu* d_cands,
+                                 int n, const FmeCostLut& lut, int useHad, uint32_t* d_cost, int32_t* d_best, cudaStream_t s,
+                                 int64_t* launches);
+cudaError_t fme_launch_mc_luma_compact(const FmeGeom& g, const uint8_t* d_planes, const fme_mc_pu* d_pus, int n,
+                                       const uint32_t* d_offsets, uint8_t* d_out, cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_pred_error(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_mc_pu* d_pus,
                                   int n, int useHad, uint32_t* d_out, cudaStream_t s, int64_t* launches);

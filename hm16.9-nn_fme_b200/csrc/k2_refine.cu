@@ -1470,6 +1470,95 @@ __global__ void __launch_bounds__(PE_WARPS * 32) k_pred_error(const fme_mc_pu* _
   }
 }
 
+// Batched candidate costs (fme_cand_cost): k_pred_error's distortion + the bit cost of the candidate's side information,
+// one warp per candidate; a second pass picks the first minimum of every group.
+__global__ void __launch_bounds__(PE_WARPS * 32) k_cand_cost(const fme_cand_pu* __restrict__ cands, int n,
+                                                             const uint8_t* __restrict__ planes,
+                                                             const uint8_t* __restrict__ org, const FmeGeom g,
+                                                             const FmeCostLut lut, int useHad, uint32_t* __restrict__ out) {
+  __shared__ __align__(16) uint8_t s_buf[PE_WARPS][PE_SMEM_PER_WARP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* buf = s_buf[warp];
+  for (int i = blockIdx.x * PE_WARPS + warp; i < n; i += gridDim.x * PE_WARPS) {
+    const fme_cand_pu p = cands[i];
+    const int w = p.w, h = p.h;
+    if (!fme_hevc_pu_shape(w, h)) {
+      if (lane == 0) out[i] = 0xffffffffu;
+      continue;
+    }
+    const int fx = p.mvX & 3, fy = p.mvY & 3;
+    const int X = min(max(p.x + (p.mvX >> 2), -(g.M - 8)), g.W + g.M - 8 - w);
+    const int Y = min(max(p.y + (p.mvY >> 2), -(g.M - 8)), g.H + g.M - 8 - h);
+    const int ox = min(max((int)p.x, 0), g.W - w), oy = min(max((int)p.y, 0), g.H - h);
+    const uint8_t* src = planes + (size_t)min((int)p.refSlot, g.numSlots - 1) * g.slotBytes +
+                         (size_t)(fy * 4 + fx) * g.planeBytes + (size_t)(Y + g.M) * g.pitch + ((X + g.M) & ~3);
+    const int al = (X + g.M) & 3;
+    const int RW = w + 4, wpr = RW >> 2;
+    __syncwarp();
+    for (int t = lane; t < h * wpr; t += 32) {
+      const int r = t / wpr, c = t - r * wpr;
+      reinterpret_cast<unsigned*>(buf + r * RW)[c] = __ldg(reinterpret_cast<const unsigned*>(src + (size_t)r * g.pitch) + c);
+    }
+    __syncwarp();
+    const bool had = useHad && !(p.flags & (FME_PU_LOSSLESS | FME_CAND_SAD));
+    const int ts = ((w & 7) == 0 && (h & 7) == 0) ? 8 : 4;
+    const int tilesX = w / ts, tiles = tilesX * (h / ts);
+    unsigned dist = 0;
+    for (int t = lane; t < tiles; t += 32) {
+      const int ty = t / tilesX, tx = t - ty * tilesX;
+      const uint8_t* o = org + (size_t)(oy + ty * ts) * g.orgPitch + ox + tx * ts;
+      const uint8_t* c = buf + ty * ts * RW + al + tx * ts;
+      if (ts == 8) {
+        auto row = [&](int r, unsigned& lo, unsigned& hi) { ldg_row8(o + (size_t)r * g.orgPitch, lo, hi); };
+        dist += had ? satd8x8(row, c, RW) : sad8x8(row, c, RW);
+      } else {
+        unsigned oo[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) oo[r] = ldg_row4(o + (size_t)r * g.orgPitch);
+        dist += had ? satd4x4(oo, c, RW) : sad4x4(oo, c, RW);
+      }
+    }
+    dist = __reduce_add_sync(0xffffffffu, dist);
+    if (lane == 0) out[i] = dist + lut.v[min((int)p.bits, FME_COST_LUT_SIZE - 1)];
+  }
+}
+__global__ void k_cand_best(const fme_cand_pu* __restrict__ cands, int n, const uint32_t* __restrict__ cost,
+                            int32_t* __restrict__ best) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (!cands[i].groupStart && i != 0) { best[i] = -1; return; }
+  unsigned bc = cost[i];
+  int bi = i;
+  for (int j = i + 1; j < n && !cands[j].groupStart; ++j)  // groups are a handful of candidates (<= 5 merge, <= 3 AMVP)
+    if (cost[j] < bc) { bc = cost[j]; bi = j; }              // strict <: the first minimum wins
+  best[i] = bi;
+}
+
+// Compact luma motion compensation (fme_mc_luma_compact): one warp per PU; the block is plane P[my & 3][mx & 3] at the
+// integer part of the MV, copied 4 samples per lane step through an aligned-load funnel.
+__global__ void __launch_bounds__(256) k_mc_luma_compact(const fme_mc_pu* __restrict__ pus, int n,
+                                                         const uint32_t* __restrict__ offsets,
+                                                         const uint8_t* __restrict__ planes, const FmeGeom g,
+                                                         uint8_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warpsPerGrid) {
+    const fme_mc_pu p = pus[i];
+    const int w = p.w, h = p.h;
+    if (w < 4 || h < 4 || w > 64 || h > 64 || (w & 3)) continue;
+    const int X = min(max(p.x + (p.mvX >> 2), -(g.M - 8)), g.W + g.M - 8 - w);
+    const int Y = min(max(p.y + (p.mvY >> 2), -(g.M - 8)), g.H + g.M - 8 - h);
+    const uint8_t* src = planes + (size_t)min((int)p.refSlot, g.numSlots - 1) * g.slotBytes +
+                         (size_t)((p.mvY & 3) * 4 + (p.mvX & 3)) * g.planeBytes + (size_t)(Y + g.M) * g.pitch + (X + g.M);
+    unsigned* dst = reinterpret_cast<unsigned*>(out + (offsets[i] & ~3u));
+    const int wq = w >> 2, items = wq * h;
+    for (int t = lane; t < items; t += 32) {
+      const int r = t / wq, c = t - r * wq;
+      dst[t] = ldg_row4(src + (size_t)r * g.pitch + 4 * c);
+    }
+  }
+}
+
 __global__ void k_clear_results(fme_result* res, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
@@ -1528,6 +1617,31 @@ cudaError_t fme_launch_k2(const FmeGeom& g, const uint8_t* d_planes, const uint8
 #undef K2_UNI
   if (e != cudaSuccess || !biPred) return e;
   return launch_k2_pass<true, 0>(g, d_planes, d_org, d_pus, n, d_res, costLut, useHad, biPred, sc, numSMs, s, launches);
+}
+
+cudaError_t fme_launch_cand_cost(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_cand_pu* d_cands,
+                                 int n, const FmeCostLut& lut, int useHad, uint32_t* d_cost, int32_t* d_best, cudaStream_t s,
+                                 int64_t* launches) {
+  if (n <= 0) return cudaSuccess;
+  int blocks = (n + PE_WARPS - 1) / PE_WARPS;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_cand_cost<<<blocks, PE_WARPS * 32, 0, s>>>(d_cands, n, d_planes, d_org, g, lut, useHad, d_cost);
+  ++*launches;
+  if (d_best) {
+    k_cand_best<<<(n + 255) / 256, 256, 0, s>>>(d_cands, n, d_cost, d_best);
+    ++*launches;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t fme_launch_mc_luma_compact(const FmeGeom& g, const uint8_t* d_planes, const fme_mc_pu* d_pus, int n,
+                                       const uint32_t* d_offsets, uint8_t* d_out, cudaStream_t s, int64_t* launches) {
+  if (n <= 0) return cudaSuccess;
+  int blocks = (n + 7) / 8;  // 8 warps per CTA, one PU per warp step
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_mc_luma_compact<<<blocks, 256, 0, s>>>(d_pus, n, d_offsets, d_planes, g, d_out);
+  ++*launches;
+  return cudaGetLastError();
 }
 
 cudaError_t fme_launch_pred_error(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_mc_pu* d_pus,

@@ -37,6 +37,10 @@ MC_BI_PU_DTYPE = np.dtype(
     [("x", "<i2"), ("y", "<i2"), ("w", "u1"), ("h", "u1"), ("refSlot0", "u1"), ("refSlot1", "u1"),
      ("mv0X", "<i2"), ("mv0Y", "<i2"), ("mv1X", "<i2"), ("mv1Y", "<i2")])
 assert MC_BI_PU_DTYPE.itemsize == 16
+CAND_DTYPE = np.dtype(   # fme_cand_pu: one AMVP-template / merge candidate
+    [("x", "<i2"), ("y", "<i2"), ("w", "u1"), ("h", "u1"), ("refSlot", "u1"), ("flags", "u1"),
+     ("mvX", "<i2"), ("mvY", "<i2"), ("bits", "<u2"), ("groupStart", "<u2")])
+assert CAND_DTYPE.itemsize == 16
 assert PU_DTYPE.itemsize == 52 and RESULT_DTYPE.itemsize == 16 and MC_PU_DTYPE.itemsize == 12
 
 # lowdelay_P GOP entry QP offsets / factors (cfg/encoder_lowdelay_P_main.cfg:24-27)

@@ -260,6 +260,36 @@ int fme_mc_bi(fme_ctx* ctx, const fme_mc_bi_pu* pus, int n, int16_t* dstY, int16
  * useHadME = 0).  SURVEY.md "next" row f3. */
 int fme_pred_error(fme_ctx* ctx, const fme_mc_pu* pus, int n, uint32_t* out);
 
+/* ---- batched candidate costs and compact prediction output (SURVEY.md "next" rows f2 / f3) -------- */
+/* One candidate of AMVP template matching or merge estimation: a uni-predicted PU at a quarter-pel MV (already clipped
+ * by the caller as TComDataCU::clipMv does) plus the side-information bits the reference adds:
+ *   xGetTemplateCost (TEncSearch.cpp:4397-4436): SAD of the MC block against the source + the cost of
+ *     m_auiMVPIdxCost[iMVPIdx][iMVPNum] bits (xGetMvpIdxBits, :4258-4284) -> flags |= FME_CAND_SAD;
+ *   xMergeEstimation (TEncSearch.cpp:3599-3655): xGetInterPredictionError (HADs when HadamardME is on, :3576-3596) +
+ *     getCost(uiMergeCand + 1, one less for the last candidate), uni-predictive candidates.
+ * cost = distortion + uint32((m_dLambdaMotionSAD[0] * bits) / 65536.0): TComRdCost::calcRdCost(bits, dist, DF_SAD) in
+ * the standard lossy mode (TComRdCost.cpp:80-89) and getCost (TComRdCost.h:165) are the same expression, the table
+ * of fme_set_slice.  The candidates of one PU are consecutive; groupStart = 1 on the first of them.  bestIndex[i]
+ * (optional), at every group start i, is the index of the group's first minimum -- the candidate the reference's
+ * strict-< loops keep (:3646, :4343-4349). */
+#define FME_CAND_SAD 0x08 /* SAD distortion whatever HadamardME says (template matching) */
+typedef struct fme_cand_pu {
+  int16_t x, y;
+  uint8_t w, h, refSlot, flags; /* FME_CAND_SAD, FME_PU_LOSSLESS (-> SAD) */
+  int16_t mvX, mvY;             /* quarter-pel luma MV */
+  uint16_t bits;                /* MVP-index / merge-index bits of this candidate */
+  uint16_t groupStart;          /* 1: first candidate of a PU */
+} fme_cand_pu; /* 16 bytes */
+int fme_cand_cost(fme_ctx* ctx, const fme_cand_pu* cands, int n, uint32_t* cost, int32_t* bestIndex);
+/* The same on device-resident arrays, stream-ordered on the ctx stream, no synchronisation. */
+int fme_cand_cost_device(fme_ctx* ctx, const fme_cand_pu* d_cands, int n, uint32_t* d_cost, int32_t* d_bestIndex);
+/* Luma motion compensation with compact output: block i is written as w*h 8-bit samples (row-major, pitch w) at byte
+ * offset offsets[i] of out (offsets are multiples of 4; normally the running sum of w*h).  The uni-prediction of
+ * xPredInterBlk (TComPrediction.cpp:643-681) at 8 bit IS an 8-bit block: nothing is lost against fme_mc, which pads
+ * every block to 64x64 Pel.  Host (synchronous) and device-resident (stream-ordered) forms. */
+int fme_mc_luma_compact(fme_ctx* ctx, const fme_mc_pu* pus, int n, const uint32_t* offsets, uint8_t* out, size_t outBytes);
+int fme_mc_luma_compact_device(fme_ctx* ctx, const fme_mc_pu* d_pus, int n, const uint32_t* d_offsets, uint8_t* d_out);
+
 /* ---- introspection (parity tests, profiling) ------------------------------------------------ */
 /* Copy padded sub-pel plane P[fy][fx] of `slot` to host: (height+2*margin) rows of (width+2*margin) bytes. */
 int fme_download_plane(fme_ctx* ctx, int slot, int fy, int fx, uint8_t* dst, int dstStride);

@@ -1002,3 +1002,65 @@ def test_raw_yuv420_frames_go_straight_into_device_planes(tmp_path, small):
         fme.formats.read_yuv420_raw(path, W, H, 3)
     a.close()
     b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_had", [True, False])
+def test_candidate_costs_and_compact_mc(use_had, small):
+    """f2 / f3 as batched operators: fme_cand_cost = prediction error (fme_pred_error, itself checked against the oracle)
+    + the bit cost of the candidate's MVP / merge index with the slice's table, SAD forced by FME_CAND_SAD (template
+    matching, xGetTemplateCost TEncSearch.cpp:4397-4436), first minimum per group (xMergeEstimation :3646); device and
+    host forms agree; fme_mc_luma_compact returns the luma blocks of fme_mc without the 64x64 padding."""
+    import torch
+    eng0, g, recs = small
+    lam = float(g["small_lambda"][0])
+    eng = fme.Fme(128, 96, num_ref_slots=2, max_pus=8192, use_had=use_had)
+    sad = fme.Fme(128, 96, num_ref_slots=2, max_pus=8192, use_had=False)
+    for e in (eng, sad):
+        e.set_slice(lam)
+        e.upload_org(g["small_org"])
+        for s in range(2):
+            e.upload_ref(s, g["small_refs"][s])
+    rng = np.random.default_rng(21)
+    pick = recs[rng.choice(len(recs), 1200, replace=False)]
+    n_c = rng.integers(1, 6, len(pick))                       # 1..5 candidates per PU (merge: <= MaxNumMergeCand = 5)
+    n = int(n_c.sum())
+    cands = np.zeros(n, fme.CAND_DTYPE)
+    owner = np.repeat(np.arange(len(pick)), n_c)
+    for f in ("x", "y", "w", "h", "refSlot"):
+        cands[f] = pick[f][owner]
+    cands["mvX"] = pick["mvIntX"][owner] * 4 + rng.integers(-9, 10, n)
+    cands["mvY"] = pick["mvIntY"][owner] * 4 + rng.integers(-9, 10, n)
+    starts = np.concatenate([[0], np.cumsum(n_c)[:-1]])
+    cands["groupStart"][starts] = 1
+    cands["bits"] = rng.integers(0, 7, n)
+    tmpl = rng.random(n) < 0.4                                # AMVP template candidates: SAD whatever HadamardME says
+    cands["flags"][tmpl] = fme.CAND_SAD
+    mc = np.zeros(n, fme.MC_PU_DTYPE)
+    for f in ("x", "y", "w", "h", "refSlot", "mvX", "mvY"):
+        mc[f] = cands[f]
+    dist = np.where(tmpl, sad.pred_error(mc), eng.pred_error(mc)).astype(np.uint64)
+    motion_lambda = 65536.0 * np.sqrt(lam)
+    lut = np.array([int((motion_lambda * b) / 65536.0) for b in range(8)], np.uint64)   # TComRdCost.h:165
+    want = (dist + lut[cands["bits"]]).astype(np.uint32)
+    cost, best = eng.cand_cost(cands)
+    np.testing.assert_array_equal(cost, want)
+    for s0, k in zip(starts, n_c):
+        assert best[s0] == s0 + int(np.argmin(want[s0:s0 + k])), (s0, k)      # np.argmin: first minimum
+    assert (best[np.setdiff1d(np.arange(n), starts)] == -1).all()
+    d_c = torch.from_numpy(cands.view(np.uint8).reshape(n, -1).copy()).cuda()
+    d_cost = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_best = torch.zeros(n, dtype=torch.int32, device="cuda")
+    eng.cand_cost_device(d_c.data_ptr(), n, d_cost.data_ptr(), d_best.data_ptr())
+    eng.synchronize()
+    np.testing.assert_array_equal(d_cost.cpu().numpy().view(np.uint32), want)
+    np.testing.assert_array_equal(d_best.cpu().numpy(), best)
+    # compact luma MC against the padded fme_mc output
+    sub = mc[:400]
+    flat, offs = eng.mc_luma_compact(sub)
+    y, _, _ = eng.mc(sub, chroma=False)
+    for i, p in enumerate(sub):
+        blk = flat[offs[i]:offs[i] + int(p["w"]) * int(p["h"])].reshape(int(p["h"]), int(p["w"]))
+        np.testing.assert_array_equal(blk, y[i, :p["h"], :p["w"]].astype(np.uint8), err_msg=str(i))
+    eng.close()
+    sad.close()
