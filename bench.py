@@ -524,8 +524,9 @@ def run_gpu(args):
 def banded_leg(fme, torch, dist, dev, stream, rank, world, local, steps, warmup):
     """One 2160p frame per step, the PU list cut into `world` pixel-balanced CTU bands (pu_list.band_mask_balanced).
     The rank that "reconstructed" the new reference broadcasts the 8-bit picture with NCCL; the broadcast of frame
-    i+1 is issued on a side stream while frame i's kernels run, every rank then interpolates the full picture (K1,
-    redundant: cheaper than gathering 15 planes) and searches its own band.  Strong scaling: the same frame on one GPU
+    i+1 is issued on a side stream while frame i's kernels run; every rank then interpolates the plane rows its own
+    PUs can reference (K1 on a row range derived from the band's records -- no fixed halo, so it stays exact) and
+    searches its band.  Strong scaling: the same frame on one GPU
     (no broadcast) is timed in the same run on every rank, efficiency = t1 / (world * tN), device-timed, max over ranks."""
     n_sets = 2
     sets = build_workload(fme, W4K, H4K, n_sets, 3000)
@@ -544,13 +545,14 @@ def banded_leg(fme, torch, dist, dev, stream, rank, world, local, steps, warmup)
             eng.upload_ref_device_u8(s_, d_refs[i][s_].data_ptr(), W4K)
         eng.int_surface_device(d_full[i].data_ptr(), n_full)
     torch.cuda.synchronize(dev)
-    d_band, n_band = [], []
+    d_band, n_band, rows_band = [], [], []
     for i, (_, _, rc) in enumerate(sets):
         full = d_full[i].cpu().numpy().view(fme.PU_DTYPE).reshape(-1).copy()
         full["flags"] = 0
         d_full[i].copy_(torch.from_numpy(full.view(np.uint8).reshape(len(full), -1)))
         mine = np.ascontiguousarray(full[fme.pu_list.band_mask_balanced(full, rank, world, W4K)])
         n_band.append(len(mine))
+        rows_band.append(fme.pu_list.referenced_rows(mine))   # the plane rows this rank's PUs can read (from its records)
         d_band.append(torch.from_numpy(mine.view(np.uint8).reshape(len(mine), -1).copy()).to(dev))
     d_res = torch.zeros((n_full, 16), dtype=torch.uint8, device=dev)
     torch.cuda.synchronize(dev)
@@ -567,7 +569,8 @@ def banded_leg(fme, torch, dist, dev, stream, rank, world, local, steps, warmup)
         k, slot = i % n_sets, i % N_REFS
         if world > 1:
             pending.pop(i).wait()           # compute stream waits for frame i's reference (issued a step ago)
-        eng.upload_ref_device_u8(slot, d_refs[k][slot].data_ptr(), W4K)       # K1 on the full picture
+        # K1 only on the plane rows this band's PUs reference (exact: the range comes from the band's own records)
+        eng.upload_ref_device_u8_rows(slot, d_refs[k][slot].data_ptr(), W4K, rows_band[k][0], rows_band[k][1])
         eng.upload_org_device_u8(d_org[k].data_ptr(), W4K)
         issue_bcast(i + 1)                  # next frame's reference travels while this band is searched
         eng.submit_device(d_band[k].data_ptr(), n_band[k], d_res.data_ptr(), fme.MODE_BOTH)
@@ -624,7 +627,8 @@ def banded_leg(fme, torch, dist, dev, stream, rank, world, local, steps, warmup)
                     "broadcast_us_blocking": tb * 1e3, "broadcast_bytes": W4K * H4K,
                     "band_pus": sizes, "band_split": "pixel-balanced contiguous CTU runs (boundaries may fall mid-row)",
                     "parallelism": "ctu bands x%d, ncclBroadcast of the new reference one frame ahead on a side stream, "
-                                   "K1 redundant on every rank" % world})
+                                   "K1 per rank on the plane rows its band references" % world,
+                    "k1_rows_this_rank": [int(rows_band[0][0]), int(rows_band[0][1])]})
     else:
         rec.update({"ms_per_step": t1, "value": n_full / (t1 * 1e-3), "unit": "PU/s", "frames_per_sec": 1e3 / t1})
     eng.close()

@@ -182,11 +182,11 @@ struct NvtxRange {  // host-side span of an ABI call (copies + launches it issue
   ~NvtxRange() { nvtxRangePop(); }
 };
 
-int run_k1(fme_ctx* c, int slot, const uint8_t* d_pic = nullptr, int picPitch = 0) {
+int run_k1(fme_ctx* c, int slot, const uint8_t* d_pic = nullptr, int picPitch = 0, int rowBegin = 0, int rowEnd = 1 << 30) {
   StageTimer t(c, 0);
   if (!d_pic) { d_pic = c->d_pic; picPitch = c->picPitch; }
   CU_CHECK(fme_launch_k1(c->g, d_pic, picPitch, c->d_planes + (size_t)slot * c->g.slotBytes, c->d_k1Counter, c->numSMs,
-                         c->stream, &c->launches));
+                         rowBegin, rowEnd, c->stream, &c->launches));
   c->refValid[slot] = 1;
   return FME_OK;
 }
@@ -588,6 +588,19 @@ int fme_upload_ref_device_u8(fme_ctx* c, int slot, const uint8_t* d_y, int pitch
   CU_CHECK(cudaMemcpy2DAsync(c->d_pic, c->picPitch, d_y, pitch, c->g.W, c->g.H, cudaMemcpyDeviceToDevice, c->stream));
   if ((rc = run_k1(c, slot))) return rc;
   return release_picture(c, idx);
+}
+
+// Banded multi-GPU mode: a rank interpolates only the rows its own PUs can reference.  picRowBegin / picRowEnd are PICTURE
+// rows (may lie outside [0, H): the margin); the sub-pel planes are produced for these rows, every other row of the slot
+// keeps whatever it held.  The caller derives the range from its band's records: a PU at row y with integer MV my and
+// height h reads plane rows y + my - 1 .. y + my + h (quarter-pel candidates one row up / down, TEncSearch.cpp:1613-1623).
+int fme_upload_ref_device_u8_rows(fme_ctx* c, int slot, const uint8_t* d_y, int pitch, int picRowBegin, int picRowEnd) {
+  int rc = check_slot(c, slot);
+  if (rc) return rc;
+  if (!d_y || pitch < c->g.W || ((size_t)d_y & 3) || (pitch & 3)) return fail(FME_ERR_INVALID, "bad device picture (4-byte aligned base and pitch required)");
+  if (picRowEnd <= picRowBegin) return fail(FME_ERR_INVALID, "empty row range");
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  return run_k1(c, slot, d_y, pitch, picRowBegin + c->g.M, picRowEnd + c->g.M);
 }
 
 int fme_interp_slot(fme_ctx* c, int slot) {

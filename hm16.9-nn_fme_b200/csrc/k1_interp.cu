@@ -83,14 +83,16 @@ constexpr int K1_PREF = (K1_IN_WORDS + K1_THREADS - 1) / K1_THREADS;  // input w
 #endif
 __global__ void __launch_bounds__(K1_THREADS, FME_K1_CTAS)
 k1_interp_planes(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int M, int Wp, int Hp, int pitch,
-                 size_t planeBytes, uint8_t* __restrict__ planes, int tilesX, unsigned tilesXRcp, int nTiles, int* __restrict__ tileCounter) {
+                 size_t planeBytes, uint8_t* __restrict__ planes, int tilesX, unsigned tilesXRcp, int nTiles, int* __restrict__ tileCounter,
+                 int tyBegin) {  // first tile row to produce (row-range launches of the banded multi-GPU mode)
   __shared__ __align__(16) uint8_t s_in[IN_H][IN_W];
   __shared__ __align__(16) int16_t s_t[4][IN_H][TW];
 
   const int tid = threadIdx.x;
   unsigned pref[K1_PREF];
   auto fetch = [&](int tile) {
-    const int ty = (int)__umulhi((unsigned)tile, tilesXRcp), tx = tile - ty * tilesX;  // tilesXRcp = ceil(2^32 / tilesX)
+    const int tr = (int)__umulhi((unsigned)tile, tilesXRcp), tx = tile - tr * tilesX;  // tilesXRcp = ceil(2^32 / tilesX)
+    const int ty = tr + tyBegin;
     const int pxBase = tx * TW - M - 4, pyBase = ty * TH - M - 3;  // picture coords of input (0,0); pxBase % 4 == 0
 #pragma unroll
     for (int k = 0; k < K1_PREF; ++k) {
@@ -113,8 +115,8 @@ k1_interp_planes(const uint8_t* __restrict__ pic, int picPitch, int W, int H, in
   int tile = blockIdx.x;
   if (tile < nTiles) fetch(tile);
   while (tile < nTiles) {
-    const int tyI = (int)__umulhi((unsigned)tile, tilesXRcp), txI = tile - tyI * tilesX;
-    const int x0 = txI * TW, y0 = tyI * TH;  // padded-plane coordinates of the tile
+    const int trI = (int)__umulhi((unsigned)tile, tilesXRcp), txI = tile - trI * tilesX;
+    const int x0 = txI * TW, y0 = (trI + tyBegin) * TH;  // padded-plane coordinates of the tile
     if (tid == 0) s_next = (int)gridDim.x + atomicAdd(&tileCounter[0], 1);
     __syncthreads();  // every thread is done with s_in / s_t of the previous tile; s_next is published
     park();
@@ -254,15 +256,18 @@ __global__ void k_pel_to_u8(const int16_t* __restrict__ src, int srcStride, uint
 
 }  // namespace
 
+// rowBegin / rowEnd: padded-plane rows [rowBegin, rowEnd) to produce (whole 16-row tiles covering them); 0 / Hp = all
 cudaError_t fme_launch_k1(const FmeGeom& g, const uint8_t* d_pic, int picPitch, uint8_t* d_planes, int* d_tileCounter,
-                          int numSMs, cudaStream_t s, int64_t* launches) {
-  const int tilesX = (g.Wp + TW - 1) / TW, tilesY = (g.Hp + TH - 1) / TH;
-  const int nTiles = tilesX * tilesY;
+                          int numSMs, int rowBegin, int rowEnd, cudaStream_t s, int64_t* launches) {
+  const int tilesX = (g.Wp + TW - 1) / TW;
+  const int tyBegin = max(rowBegin, 0) / TH, tyEnd = (min(rowEnd, g.Hp) + TH - 1) / TH;
+  if (tyEnd <= tyBegin) return cudaSuccess;
+  const int nTiles = tilesX * (tyEnd - tyBegin);
   const int grid = nTiles < numSMs * FME_K1_CTAS ? nTiles : numSMs * FME_K1_CTAS;
   // ceil(2^32 / tilesX): __umulhi(tile, rcp) == tile / tilesX for every tile < 2^32 / tilesX (tiles are < 2^17 at 8K)
   const unsigned tilesXRcp = (unsigned)((0x100000000ull + tilesX - 1) / tilesX);
   k1_interp_planes<<<grid, K1_THREADS, 0, s>>>(d_pic, picPitch, g.W, g.H, g.M, g.Wp, g.Hp, g.pitch, g.planeBytes,
-                                                d_planes, tilesX, tilesXRcp, nTiles, d_tileCounter);
+                                                d_planes, tilesX, tilesXRcp, nTiles, d_tileCounter, tyBegin);
   ++*launches;
   return cudaGetLastError();
 }

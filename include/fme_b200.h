@@ -204,6 +204,11 @@ int fme_interp_slot(fme_ctx* ctx, int slot);
  * stream --, anything else is staged through a device copy.  Used with torch/NCCL buffers in the banded mode. */
 int fme_upload_ref_device_u8(fme_ctx* ctx, int slot, const uint8_t* d_y, int pitch);
 int fme_upload_org_device_u8(fme_ctx* ctx, const uint8_t* d_y, int pitch);
+/* The same for a ROW RANGE of the picture (banded multi-GPU mode): only the sub-pel plane rows [picRowBegin, picRowEnd)
+ * (picture rows; the range may reach into the margin) are produced, whole 16-row tiles covering it; the rest of the slot
+ * keeps its previous content.  Exact as long as the range covers every row the submitted PUs reference: a PU at row y with
+ * integer MV my and height h reads plane rows y + my - 1 .. y + my + h.  d_y must be 4-byte aligned, read in place. */
+int fme_upload_ref_device_u8_rows(fme_ctx* ctx, int slot, const uint8_t* d_y, int pitch, int picRowBegin, int picRowEnd);
 /* K0: fill fme_pu.err[] of device-resident records from the 3x3 integer error surface
  * (xTZ8PointSquareSearch(save=true) metric, TEncSearch.cpp:1085-1166, 5037-5050). */
 int fme_int_surface_device(fme_ctx* ctx, fme_pu* d_pus, int n);

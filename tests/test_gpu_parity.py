@@ -1064,3 +1064,39 @@ def test_candidate_costs_and_compact_mc(use_had, small):
         np.testing.assert_array_equal(blk, y[i, :p["h"], :p["w"]].astype(np.uint8), err_msg=str(i))
     eng.close()
     sad.close()
+
+
+@pytest.mark.gpu
+def test_row_range_interpolation_serves_a_band_exactly():
+    """Banded mode: a rank that interpolates only the plane rows its band's records reference (fme_upload_ref_device_u8_rows
+    with pu_list.referenced_rows) gets the results of full-picture interpolation for that band -- also when the slot held
+    another picture before, i.e. nothing outside the range is read."""
+    import torch
+    W, H = 416, 240
+    org, refs, motions = fme.pu_list.synth_frames(W, H, n_refs=2, seed=51)
+    other = fme.pu_list.synth_frames(W, H, n_refs=2, seed=52)[1]
+    recs = fme.pu_list.make_records(W, H, motions, seed=6, amp=True, err_on_gpu=True)
+    lam = fme.pu_list.slice_lambda(22)
+    full = fme.Fme(W, H, num_ref_slots=2, max_pus=len(recs))
+    part = fme.Fme(W, H, num_ref_slots=2, max_pus=len(recs))
+    for e in (full, part):
+        e.set_nn_weights(fme.nn_weights.load_blob(22))
+        e.set_slice(lam)
+        e.upload_org(org)
+    d_refs = [torch.from_numpy(r).cuda() for r in refs]
+    for s in range(2):
+        full.upload_ref(s, refs[s])
+        part.upload_ref(s, other[s])           # stale content everywhere
+    for band in range(3):
+        mine = np.ascontiguousarray(recs[fme.pu_list.band_mask_balanced(recs, band, 3, W)])
+        lo, hi = fme.pu_list.referenced_rows(mine)
+        assert hi - lo < H                    # really a sub-range
+        for s in range(2):
+            part.upload_ref(s, other[s])
+            part.upload_ref_device_u8_rows(s, d_refs[s].data_ptr(), W, lo, hi)
+        want = full.submit(mine, fme.MODE_BOTH)
+        got = part.submit(mine, fme.MODE_BOTH)
+        for f in ("halfX", "halfY", "qterX", "qterY", "cost", "nnClass"):
+            np.testing.assert_array_equal(got[f], want[f], err_msg="band %d %s" % (band, f))
+    full.close()
+    part.close()

@@ -125,9 +125,9 @@ def test_balanced_bands_partition_the_list_and_even_out_the_work():
         recs = fme.pu_list.make_records(W, H, motions[:1], seed=2)
         masks = [fme.pu_list.band_mask_balanced(recs, b, nb, W) for b in range(nb)]
         assert np.array_equal(np.sum(masks, axis=0), np.ones(len(recs), np.int64))       # disjoint cover
-        px = recs["w"].astype(np.int64) * recs["h"]
+        px = recs["w"].astype(np.int64) * recs["h"] + fme.pu_list.PER_PU_WORK
         work = np.array([px[m].sum() for m in masks], np.float64)
-        ctu_work = 12.0 * 64 * 64                                                        # 12 coverings of a CTU's pixels
+        ctu_work = 12.0 * 64 * 64 * 1.5                                                  # 12 coverings of a CTU's pixels + per-PU work
         assert work.max() - work.min() <= 2 * ctu_work, (W, H, work)
         ctus_x = (W + 63) // 64
         cid = (recs["y"] // 64).astype(np.int64) * ctus_x + recs["x"] // 64
