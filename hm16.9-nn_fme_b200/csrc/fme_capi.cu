@@ -345,6 +345,7 @@ int fme_create(const fme_config* cfg, fme_ctx** out) {
   c->k2.classOffset = c->k2.workCounter + 4;
   c->k2.packOffset = c->k2.classOffset + FME_K2_KEYS + 1;
   CREATE_CHECK(cudaMalloc(&c->k2.order, sizeof(int) * (size_t)cfg->maxPUs));
+  CREATE_CHECK(cudaMalloc(&c->k2.keys, sizeof(short) * (size_t)cfg->maxPUs));
   CREATE_CHECK(cudaStreamSynchronize(c->stream));
 #undef CREATE_CHECK
   *out = c;
@@ -363,7 +364,7 @@ void fme_destroy(fme_ctx* c) {
       if (e) cudaEventDestroy(e);
   }
   cudaFree(c->d_cb); cudaFree(c->d_cr); cudaFree(c->d_nn); cudaFree(c->d_opBuf);
-  cudaFree(c->d_k1Counter); cudaFree(c->d_scratchU32); cudaFree(c->k2.classCount); cudaFree(c->k2.order);
+  cudaFree(c->d_k1Counter); cudaFree(c->d_scratchU32); cudaFree(c->k2.classCount); cudaFree(c->k2.order); cudaFree(c->k2.keys);
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
   if (c->ownStream) cudaStreamDestroy(c->ownStream);

@@ -79,6 +79,8 @@ struct FmeK2Scratch {
   int* classOffset;  // [FME_K2_KEYS + 1] in schedule order v = key ^ 63
   int* packOffset;   // [FME_K2_KEYS + 1] cumulative number of packs, schedule order
   int* order;        // [maxPUs] PU indices grouped by class
+  short* keys;       // [maxPUs] binning key of every record (-1: not served by this pass), written by k2_count so that
+                     // k2_scatter reads 2 bytes per record instead of striding through the 52-byte records twice more
   int* workCounter;  // [1] dynamic pack scheduler
 };
 

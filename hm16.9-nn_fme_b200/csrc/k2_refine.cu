@@ -90,13 +90,14 @@ __device__ __forceinline__ int k2_key_of(const fme_pu& p, int wantBi) {
 // on a ctx without biPred -- get the sentinel result (zero vectors, cost 0xffffffff) instead of whatever the result
 // buffer held (the unvalidated async / device entry points, include/fme_b200.h).
 __global__ void k2_count(const fme_pu* __restrict__ pus, int n, int* __restrict__ classCount, int wantBi,
-                         fme_result* __restrict__ res, int biServed) {
+                         fme_result* __restrict__ res, int biServed, short* __restrict__ keys) {
   __shared__ int s_cnt[FME_K2_KEYS];
   for (int i = threadIdx.x; i < FME_K2_KEYS; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const fme_pu p = pus[i];
     const int c = k2_key_of(p, wantBi);
+    keys[i] = (short)c;
     if (c >= 0) atomicAdd(&s_cnt[c], 1);
     else if (res && (!fme_hevc_pu_shape(p.w, p.h) || ((p.flags & FME_PU_BI) && !biServed)))
       *reinterpret_cast<uint2*>(&res[i]) = make_uint2(0u, 0xffffffffu);
@@ -109,9 +110,9 @@ __global__ void k2_count(const fme_pu* __restrict__ pus, int n, int* __restrict_
 // Scatter PU indices into schedule order.  Every block derives the key and pack offsets itself from the key counts
 // (one warp: 16 schedule positions per lane + a warp scan, cheaper than a separate launch); block 0 also publishes
 // them for k2_refine.
-__global__ void k2_scatter(const fme_pu* __restrict__ pus, int n, const int* __restrict__ classCount,
+__global__ void k2_scatter(const short* __restrict__ keys, int n, const int* __restrict__ classCount,
                            int* __restrict__ classOffset, int* __restrict__ packOffset,
-                           int* __restrict__ classCursor, int* __restrict__ order, int wantBi, int mmaGroups) {
+                           int* __restrict__ classCursor, int* __restrict__ order, int mmaGroups) {
   __shared__ int s_cnt[FME_K2_KEYS];
   __shared__ int s_base[FME_K2_KEYS];
   __shared__ int s_classOff[FME_K2_KEYS];
@@ -151,7 +152,7 @@ __global__ void k2_scatter(const fme_pu* __restrict__ pus, int n, const int* __r
   for (int i = threadIdx.x; i < FME_K2_KEYS; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
   for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const int c = k2_key_of(pus[i], wantBi);
+    const int c = keys[i];
     if (c >= 0) atomicAdd(&s_cnt[c], 1);
   }
   __syncthreads();
@@ -161,7 +162,7 @@ __global__ void k2_scatter(const fme_pu* __restrict__ pus, int n, const int* __r
   }
   __syncthreads();
   for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const int c = k2_key_of(pus[i], wantBi);
+    const int c = keys[i];
     if (c >= 0) order[s_base[c] + atomicAdd(&s_cnt[c], 1)] = i;
   }
 }
@@ -1584,9 +1585,9 @@ static cudaError_t launch_k2_pass(const FmeGeom& g, const uint8_t* d_planes, con
   cudaError_t e = cudaMemsetAsync(sc.classCount, 0, sizeof(int) * (2 * FME_K2_KEYS + 1), s);
   if (e != cudaSuccess) return e;
   int blocks = min(numSMs * 4, (n + 255) / 256);
-  k2_count<<<blocks, 256, 0, s>>>(d_pus, n, sc.classCount, BI ? 1 : 0, BI ? nullptr : d_res, biServed);
-  k2_scatter<<<blocks, 256, 0, s>>>(d_pus, n, sc.classCount, sc.classOffset, sc.packOffset, sc.classCursor, sc.order,
-                                    BI ? 1 : 0, PATH == 2 ? 1 : 0);
+  k2_count<<<blocks, 256, 0, s>>>(d_pus, n, sc.classCount, BI ? 1 : 0, BI ? nullptr : d_res, biServed, sc.keys);
+  k2_scatter<<<blocks, 256, 0, s>>>(sc.keys, n, sc.classCount, sc.classOffset, sc.packOffset, sc.classCursor, sc.order,
+                                    PATH == 2 ? 1 : 0);
   *launches += 2;
   const int smemBytes = k2_warps<PATH>() * K2_SMEM_PER_WARP;
   // the opt-in to > 48 KB dynamic shared memory is a per-device, per-function attribute; setting it is cheap and
