@@ -1100,3 +1100,59 @@ def test_row_range_interpolation_serves_a_band_exactly():
             np.testing.assert_array_equal(got[f], want[f], err_msg="band %d %s" % (band, f))
     full.close()
     part.close()
+
+
+@pytest.mark.gpu
+def test_error_behaviour_of_the_round2_entry_points(small):
+    """Status codes instead of faults: bad arguments and call-order violations of the entry points added in round 2,
+    and an unaligned device picture taking the staging-copy branch of fme_upload_ref_device_u8."""
+    import ctypes
+    import torch
+    eng0, g, recs = small
+    W, H = 128, 96
+    eng = fme.Fme(W, H, num_ref_slots=2, max_pus=64)
+    c = np.zeros(2, fme.CAND_DTYPE)
+    c["w"], c["h"] = 8, 8
+    with pytest.raises(fme.FmeError):
+        eng.cand_cost(c)                                     # no source picture / slice yet
+    eng.set_slice(4.0)
+    eng.upload_org(g["small_org"])
+    with pytest.raises(fme.FmeError):
+        eng.cand_cost(c)                                     # slot 0 holds no picture
+    eng.upload_ref(0, g["small_refs"][0])
+    c["w"][1] = 12                                           # 12x8 is not an HEVC PU
+    with pytest.raises(fme.FmeError):
+        eng.cand_cost(c)
+    c["w"][1] = 8
+    c["bits"][1] = 4000
+    with pytest.raises(fme.FmeError):
+        eng.cand_cost(c)
+    c["bits"][1] = 3
+    cost, best = eng.cand_cost(c)
+    assert best[0] == 0 and cost[1] == cost[0] + int((65536.0 * 2.0 * 3) / 65536.0)   # same block, 3 bits more
+    mc = np.zeros(2, fme.MC_PU_DTYPE)
+    mc["w"], mc["h"] = 8, 8
+    offs = np.array([0, 62], np.uint32)                      # not a multiple of 4
+    out = np.zeros(128, np.uint8)
+    rc = eng.lib.fme_mc_luma_compact(eng.h, ctypes.c_void_p(mc.ctypes.data), 2, ctypes.c_void_p(offs.ctypes.data),
+                                     ctypes.c_void_p(out.ctypes.data), ctypes.c_size_t(out.size))
+    assert rc == -1 and b"offset" in eng.lib.fme_last_error()
+    offs[1] = 96                                             # second block would end beyond outBytes
+    rc = eng.lib.fme_mc_luma_compact(eng.h, ctypes.c_void_p(mc.ctypes.data), 2, ctypes.c_void_p(offs.ctypes.data),
+                                     ctypes.c_void_p(out.ctypes.data), ctypes.c_size_t(out.size))
+    assert rc == -1
+    d = torch.from_numpy(g["small_refs"][1].astype(np.uint8)).cuda()
+    with pytest.raises(fme.FmeError):
+        eng.upload_ref_device_u8_rows(1, d.data_ptr(), W, 10, 10)          # empty range
+    with pytest.raises(fme.FmeError):
+        eng.upload_ref_device_u8_rows(1, d.data_ptr() + 1, W, 0, 16)       # unaligned base
+    with pytest.raises(fme.FmeError):
+        fme.Fme(W, H, k2_path=7)
+    # unaligned device picture: the staging-copy branch must give the planes of the aligned (in-place) branch
+    pad = torch.zeros(W * H + 8, dtype=torch.uint8, device="cuda")
+    pad[1:1 + W * H] = d.reshape(-1)
+    eng.upload_ref_device_u8(0, d.data_ptr(), W)
+    eng.upload_ref_device_u8(1, pad.data_ptr() + 1, W)
+    for k in (0, 6, 15):
+        np.testing.assert_array_equal(eng.download_plane(0, k // 4, k % 4), eng.download_plane(1, k // 4, k % 4))
+    eng.close()
