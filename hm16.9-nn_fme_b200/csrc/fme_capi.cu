@@ -44,6 +44,9 @@ inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 constexpr int FME_NBUF = 3;
 
 // What FME_K2_PATH_AUTO resolves to: the fastest measured path (profiles/r2_k2_paths.txt).
+#ifndef FME_K1_PATH_DEFAULT
+#define FME_K1_PATH_DEFAULT FME_K1_PATH_DP4A
+#endif
 #ifndef FME_K2_PATH_DEFAULT
 #define FME_K2_PATH_DEFAULT FME_K2_PATH_SWAR
 #endif
@@ -186,7 +189,8 @@ int run_k1(fme_ctx* c, int slot, const uint8_t* d_pic = nullptr, int picPitch = 
   StageTimer t(c, 0);
   if (!d_pic) { d_pic = c->d_pic; picPitch = c->picPitch; }
   CU_CHECK(fme_launch_k1(c->g, d_pic, picPitch, c->d_planes + (size_t)slot * c->g.slotBytes, c->d_k1Counter, c->numSMs,
-                         rowBegin, rowEnd, c->stream, &c->launches));
+                         rowBegin, rowEnd, c->cfg.k1Path == FME_K1_PATH_AUTO ? FME_K1_PATH_DEFAULT : c->cfg.k1Path, c->stream,
+                         &c->launches));
   c->refValid[slot] = 1;
   return FME_OK;
 }
@@ -268,6 +272,7 @@ int fme_create(const fme_config* cfg, fme_ctx** out) {
   if (cfg->numRefSlots < 1 || cfg->numRefSlots > 64) return fail(FME_ERR_INVALID, "numRefSlots out of range");
   if (cfg->maxPUs < 1) return fail(FME_ERR_INVALID, "maxPUs must be positive");
   if (cfg->k2Path < FME_K2_PATH_AUTO || cfg->k2Path > FME_K2_PATH_MMA_GROUP) return fail(FME_ERR_INVALID, "k2Path out of range");
+  if (cfg->k1Path < FME_K1_PATH_AUTO || cfg->k1Path > FME_K1_PATH_MMA) return fail(FME_ERR_INVALID, "k1Path out of range");
 
   int nDev = 0;
   if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) {

@@ -86,7 +86,7 @@ struct FmeK2Scratch {
 
 // d_tileCounter: two zero-initialised ints owned by the ctx (dynamic tile hand-out; the kernel re-arms them itself)
 cudaError_t fme_launch_k1(const FmeGeom& g, const uint8_t* d_pic, int picPitch, uint8_t* d_planes, int* d_tileCounter,
-                          int numSMs, int rowBegin, int rowEnd, cudaStream_t s, int64_t* launches);
+                          int numSMs, int rowBegin, int rowEnd, int path, cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_pad_chroma(const FmeGeom& g, const uint8_t* d_pic, int picPitch, uint8_t* d_plane,
                                   cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_k2(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_pu* d_pus, int n,

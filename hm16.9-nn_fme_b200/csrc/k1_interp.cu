@@ -16,6 +16,7 @@
 //            shift; cvt.pack.sat (I2IP) narrowing, u8x4 stores
 // Algorithmic HBM bytes: 1 B read + 16 B written per padded sample (plane 0 is the padded copy).
 #include "fme_common.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -229,6 +230,271 @@ k1_interp_planes(const uint8_t* __restrict__ pic, int picPitch, int W, int H, in
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// K1 on the tensor pipe (FME_K1_PATH_MMA).  At 8 bit the first filter stage has shift 0 (IF.cpp:197-218), so a plane is
+// the EXACT 2-D form  P[fy][fx] = clip255(floor((sum_ky sum_kx c_fy[ky] c_fx[kx] R(x+kx-3, y+ky-3) + 2048) / 4096))
+// (the -8192 first-stage offset and the 8192<<6 second-stage offset cancel; fy = 0 is the tap row (0,0,0,64,0,0,0,0)),
+// and both stages are small GEMMs against constant Toeplitz tap matrices:
+//   H:  T[x][y]      = A1_fx[x][xin] * R[xin][y]      IMMA m16n8k32 u8 x s8 -> s32: 16 output columns x 8 rows from a
+//                                                     32-column window; the B fragment is the two words a lane loaded
+//   V:  P[(fy,r)][x] = A2[(fy,r)][yT] * T[yT][x]      HMMA m16n8k16 f16 -> f32: 2 phases x 8 rows, 8 columns, 15 T rows
+// T (15 bits) enters V as two exact f16 operands scaled so that ONE tap matrix (the taps themselves) serves both: the
+// IMMA accumulator starts from 0x54342000, so that one PRMT per pair builds the f16x2 words 0x3400|low byte =
+// 0.25 + lo/4096 and 0x5400|high byte = 64 + hi/16 (the 64 is subtracted, the 0.25 folded into V's start value: the
+// sum of the two is (T + 8192)/4096 + 0.25).  The D fragment of H *is*
+// the B fragment of V (same lanes, same element order) when H puts columns on M and rows on N, so T never leaves the
+// register file; a warp slides down a 16-column strip 8 rows at a time and keeps the previous T tile.  All f32 sums are
+// multiples of 2^-12 below 2^10: exact.  f32 -> u8 without the XU pipe (F2I runs at 16 lanes/clk/SM and was the limit
+// of the first version): y = sat(D/256 + 2^-22), z = floor(y * (256 - 2^-15)) by FFMA.RM onto 2^23 -- the low mantissa
+// byte is clip255(floor(D)).  Eight warps stage 128-byte plane rows in shared memory (16-byte chunks XOR-swizzled by
+// row, conflict-free both ways) and the CTA writes whole lines with 16-byte stores.
+namespace k1m {
+
+constexpr int kTap[4][8] = {{0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1},
+                            {0, 1, -5, 17, 58, -10, 4, -1}};  // TComInterpolationFilter.cpp:57-63
+
+// f16 bit pattern of c * 2^-s (|c| <= 64: exact, normal for s <= 14)
+constexpr uint32_t f16_of(int c, int s) {
+  if (c == 0) return 0;
+  const uint32_t sign = c < 0 ? 0x8000u : 0u;
+  const int a = c < 0 ? -c : c;
+  int e = 0;
+  while ((a >> (e + 1)) != 0) ++e;
+  return sign | ((uint32_t)(e - s + 15) << 10) | (((uint32_t)a << (10 - e)) & 0x3ffu);
+}
+// H: A1 row m computes output column colOfRow(m) of the strip, chosen so that after V a lane owns 4 adjacent columns.
+constexpr int colOfRow(int m) { return m < 8 ? 4 * (m / 2) + (m % 2) : 4 * ((m - 8) / 2) + 2 + (m % 2); }
+// H: K index k is window column 8t + {0..7} of the lane t = (k % 16) / 4 that loaded it (word 0: k < 16, word 1: k >= 16)
+constexpr int inColOfK(int k) { return 8 * ((k % 16) / 4) + 4 * (k / 16) + (k % 4); }
+constexpr uint32_t a1_elem(int fx, int m, int k) {
+  const int idx = inColOfK(k) - colOfRow(m) - 5;  // window column 0 is strip column -8; taps reach x-3 .. x+4
+  return idx >= 0 && idx < 8 ? (uint32_t)(kTap[fx][idx] & 0xff) : 0u;
+}
+constexpr uint32_t a2_elem(int mt, int m, int kk) {  // row m = (phase 2mt + m/8, output row m%8); T row kk is y-3+kk
+  const int idx = kk - (m % 8);
+  return idx >= 0 && idx < 8 ? f16_of(kTap[2 * mt + m / 8][idx], 0) : 0u;
+}
+struct Tables {
+  uint32_t a1[4][32][4];     // [fx][lane] -> the lane's A fragment (m16n8k32 s8, row-major A)
+  uint32_t a2[2][2][32][4];  // [K halves exchanged?][m-tile][lane] (m16n8k16 f16, the taps themselves)
+};
+constexpr Tables make_tables() {
+  Tables t{};
+  for (int lane = 0; lane < 32; ++lane) {
+    const int g = lane >> 2, q = lane & 3;
+    for (int r = 0; r < 4; ++r) {
+      const int m = g + (r & 1) * 8;
+      for (int fx = 0; fx < 4; ++fx) {
+        uint32_t v = 0;
+        for (int j = 0; j < 4; ++j) v |= a1_elem(fx, m, 4 * q + (r >> 1) * 16 + j) << (8 * j);
+        t.a1[fx][lane][r] = v;
+      }
+      const int k0 = 2 * q + (r >> 1) * 8;
+      for (int mt = 0; mt < 2; ++mt) {
+        t.a2[0][mt][lane][r] = a2_elem(mt, m, k0) | (a2_elem(mt, m, k0 + 1) << 16);
+        t.a2[1][mt][lane][r] = a2_elem(mt, m, k0 ^ 8) | (a2_elem(mt, m, (k0 ^ 8) + 1) << 16);  // T rows 8..15 first
+      }
+    }
+  }
+  return t;
+}
+__device__ const Tables d_tables = make_tables();
+
+__device__ __forceinline__ void imma(int (&d)[4], const uint4& a, unsigned b0, unsigned b1) {
+  asm("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void hmma(float (&d)[4], const uint4& a, unsigned b0, unsigned b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+// first product of a chain: every accumulator element starts from the same constant (no per-chain register copies)
+__device__ __forceinline__ void hmma_c(float (&d)[4], const uint4& a, unsigned b0, unsigned b1, float c) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1), "f"(c));
+}
+__device__ __forceinline__ void imma_c(int (&d)[4], const uint4& a, unsigned b0, unsigned b1, int c) {
+  asm("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1), "r"(c));
+}
+__device__ __forceinline__ unsigned hsub2u(unsigned a, unsigned b) {
+  unsigned d;
+  asm("sub.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+// clip255(floor(v)) in the low byte (upper bytes hold 0x4b0000), v a multiple of 2^-12 with |v| < 2^10
+__device__ __forceinline__ unsigned floor_clip_u8(float v) {
+  float y, z;
+  asm("fma.rn.sat.f32 %0, %1, 0f3B800000, 0f34800000;" : "=f"(y) : "f"(v));           // sat(v / 256 + 2^-22)
+  asm("fma.rm.f32 %0, %1, 0f437FFFFF, 0f4B000000;" : "=f"(z) : "f"(y));                // floor(y * (256 - 2^-15)) + 2^23
+  return __float_as_uint(z);
+}
+
+#ifndef FME_K1M_WARPS
+#define FME_K1M_WARPS 8
+#endif
+#ifndef FME_K1M_CTAS
+#define FME_K1M_CTAS 3
+#endif
+constexpr int WARPS = FME_K1M_WARPS, THREADS = 32 * WARPS;
+constexpr int BW = 16 * WARPS;            // CTA block: 128 (64) plane columns = one (half a) line per plane row
+constexpr int SLAB = 16 * 8 * BW;         // one iteration's output: 16 planes x 8 rows x BW bytes
+constexpr int CHUNKS = BW / 16;           // 16-byte chunks per slab row
+// slab rows are XOR-swizzled by 16-byte chunk so that both the per-warp 4-byte writes (8 rows x one chunk) and the
+// 16-byte read-back (whole rows) touch every bank once
+__device__ __forceinline__ int swz(int chunk, int row) { return chunk ^ (WARPS == 8 ? row : WARPS == 4 ? (row >> 1) : (row >> 2)); }
+
+struct TTile { unsigned lo[4][2], hi[4][2]; };  // per fx: B fragments of V for the strip's two 8-column halves
+
+__global__ void __launch_bounds__(THREADS, FME_K1M_CTAS)
+k1_interp_mma(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int M, int Wp, int Hp, int pitch,
+              size_t planeBytes, uint8_t* __restrict__ planes, int itBegin, int itersPerBlock, int totalUnits) {
+  __shared__ __align__(128) uint8_t s_out[2 * SLAB];
+  __shared__ __align__(16) uint32_t s_tab[4][32][4];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+
+  // V's tap fragments stay in registers; H's four (one per fx) are re-read from shared memory at each use
+  for (int i = tid; i < (int)(sizeof(d_tables.a1) / 16); i += THREADS)
+    reinterpret_cast<uint4*>(&s_tab)[i] = reinterpret_cast<const uint4*>(&d_tables.a1)[i];
+  __syncthreads();
+  const unsigned tabBase = (unsigned)__cvta_generic_to_shared(&s_tab) + lane * 16;
+  auto A1 = [&](int fx) {  // volatile: not hoisted out of the loop into 16 registers
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(tabBase + fx * 512));
+    return v;
+  };
+  uint4 A2[2][2];
+#pragma unroll
+  for (int sw = 0; sw < 2; ++sw)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) A2[sw][mt] = *reinterpret_cast<const uint4*>(d_tables.a2[sw][mt][lane]);
+
+  // H for all four fx: T + 8192 (15 bits, positive) as (0.25 + low byte / 4096, high byte / 16) f16 pairs in V's
+  // B-fragment order.  The four products are independent: issued back to back, converted afterwards.
+  auto h_stage = [&](unsigned w0, unsigned w1, TTile& T) {
+    int d[4][4];
+#pragma unroll
+    for (int fx = 0; fx < 4; ++fx) imma_c(d[fx], A1(fx), w0, w1, 0x54342000);
+#pragma unroll
+    for (int fx = 0; fx < 4; ++fx) {
+      T.lo[fx][0] = __byte_perm(d[fx][0], d[fx][1], 0x6420); T.lo[fx][1] = __byte_perm(d[fx][2], d[fx][3], 0x6420);
+      T.hi[fx][0] = hsub2u(__byte_perm(d[fx][0], d[fx][1], 0x7531), 0x54005400u);
+      T.hi[fx][1] = hsub2u(__byte_perm(d[fx][2], d[fx][3], 0x7531), 0x54005400u);
+    }
+  };
+  // One 8-row iteration: a new T tile from (w0, w1), 16 planes x 8 rows x 16 columns into the slab.  The two tiles
+  // alternate roles; the B operand of V is always the register pair (ta, tb), and when ta holds the NEWER rows the
+  // K halves of the tap matrix are exchanged instead (a second fragment set), so no tile is ever copied.
+  // V of fx+1 is issued before the f32 -> u8 epilogue of fx, so that the tensor pipe and the FMA pipe overlap in a warp.
+  auto iteration = [&](auto swapTag, TTile& ta, TTile& tb, unsigned w0, unsigned w1, uint8_t* so) {
+    constexpr bool SWAP = decltype(swapTag)::value;
+    h_stage(w0, w1, SWAP ? ta : tb);
+    float acc[2][2][2][4];  // [fx parity][8-column half][m-tile][fragment]
+    auto v_stage = [&](int fx) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {  // start: + 2048 for the rounding, - 64 * (8192 + 1024) for the operand offsets, all / 4096
+          hmma_c(acc[fx & 1][nt][mt], A2[SWAP ? 1 : 0][mt], ta.hi[fx][nt], tb.hi[fx][nt], 0.5f - 144.0f);
+          hmma(acc[fx & 1][nt][mt], A2[SWAP ? 1 : 0][mt], ta.lo[fx][nt], tb.lo[fx][nt]);
+        }
+    };
+    auto epilogue = [&](int fx) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {  // fragment rows g (phase 2mt) and g+8 (phase 2mt+1)
+          const float(&a0)[4] = acc[fx & 1][0][mt], (&a1)[4] = acc[fx & 1][1][mt];
+          const unsigned z0 = floor_clip_u8(a0[2 * half]), z1 = floor_clip_u8(a0[2 * half + 1]);
+          const unsigned z2 = floor_clip_u8(a1[2 * half]), z3 = floor_clip_u8(a1[2 * half + 1]);
+          // 0x4b000000 << 8 vanishes mod 2^32: the low halves of z1*256+z0 and z3*256+z2 are the four bytes
+          const unsigned word = __byte_perm(z1 * 256u + z0, z3 * 256u + z2, 0x5410);
+          const int p = (2 * mt + half) * 4 + fx;
+          *reinterpret_cast<unsigned*>(so + p * (8 * BW)) = word;
+        }
+    };
+    v_stage(0);
+#pragma unroll
+    for (int fx = 1; fx < 4; ++fx) {
+      v_stage(fx);
+      epilogue(fx - 1);
+    }
+    epilogue(3);
+  };
+
+  // this CTA's share of the (column block, 8-row iteration) sequence, contiguous so that T tiles are reused
+  int u = (int)((long long)blockIdx.x * totalUnits / gridDim.x);
+  const int uEnd = (int)((long long)(blockIdx.x + 1) * totalUnits / gridDim.x);
+  int buf = 0;
+  // slab: this lane writes row g, chunk w; in the store phase it moves chunk sc of row sr, planes sp0 + k * THREADS/64
+  const int sOff = g * BW + (swz(w, g) << 4) + 4 * t;
+  const int sc = tid % CHUNKS, sr = (tid / CHUNKS) & 7, sp0 = tid / (8 * CHUNKS);
+  constexpr int PSTEP = THREADS / (8 * CHUNKS), NST = 16 / PSTEP;  // planes per pass, passes
+  const uint8_t* sread = s_out + (sp0 * 8 + sr) * BW + (swz(sc, sr) << 4);
+
+  while (u < uEnd) {
+    const int cb = u / itersPerBlock, it0 = u - cb * itersPerBlock;
+    const int n = min(itersPerBlock - it0, uEnd - u);
+    u += n;
+    const int x0 = cb * BW + w * 16;       // padded-plane column of the strip
+    const bool active = x0 < Wp;
+    // this lane's 8 input bytes: picture columns px0 .. px0+7.  W, M and px0 are multiples of 8, so the group lies
+    // inside the picture or entirely in the replicated margin: there it is 8 copies of the row's first / last sample,
+    // taken from the nearest inside group with a per-lane byte selector.
+    const int px0 = x0 - 8 - M + 8 * t;
+    const int pxl = min(max(px0, 0), W - 8);
+    const unsigned selA = px0 < 0 ? 0x0000u : px0 >= W ? 0x7777u : 0x3210u, selB = px0 < 0 ? 0x0000u : px0 >= W ? 0x7777u : 0x7654u;
+    const uint8_t* colp = pic + pxl;
+    int yIn = 8 * (itBegin + it0) - 3 + g - M;  // picture row of this lane's input row in T tile k (advances by 8)
+    auto load_rows = [&](unsigned& a, unsigned& b) {  // raw words; the selectors are applied at use (fix_cols)
+      const uint8_t* row = colp + (size_t)min(max(yIn, 0), H - 1) * picPitch;
+      a = *reinterpret_cast<const unsigned*>(row);
+      b = *reinterpret_cast<const unsigned*>(row + 4);
+      yIn += 8;
+    };
+    auto fix_cols = [&](unsigned a, unsigned b, unsigned& w0, unsigned& w1) {
+      w0 = __byte_perm(a, b, selA);
+      w1 = __byte_perm(a, b, selB);
+    };
+
+    TTile ta, tb;
+    unsigned w0 = 0, w1 = 0, n0 = 0, n1 = 0;
+    if (active) {
+      load_rows(n0, n1);
+      fix_cols(n0, n1, w0, w1);
+      load_rows(n0, n1);
+      h_stage(w0, w1, ta);
+    }
+    int y = 8 * (itBegin + it0) + sr;
+    uint8_t* gdst = planes + (size_t)sp0 * planeBytes + (size_t)y * pitch + cb * BW + sc * 16;
+    const bool colOk = cb * BW + sc * 16 < Wp;
+    for (int i = 0; i < n; ++i) {
+      if (active) {
+        fix_cols(n0, n1, w0, w1);
+        load_rows(n0, n1);  // in flight during this iteration's filtering
+        uint8_t* so = s_out + buf * SLAB + sOff;
+        if (i & 1) iteration(std::true_type{}, ta, tb, w0, w1, so); else iteration(std::false_type{}, ta, tb, w0, w1, so);
+      }
+      __syncthreads();  // the 16 x 8 x BW-byte slab of this iteration is complete
+      if (colOk && y < Hp) {
+#pragma unroll
+        for (int k = 0; k < NST; ++k)
+          *reinterpret_cast<uint4*>(gdst + (size_t)(PSTEP * k) * planeBytes) =
+              *reinterpret_cast<const uint4*>(sread + buf * SLAB + k * (PSTEP * 8 * BW));
+      }
+      gdst += (size_t)8 * pitch;
+      y += 8;
+      buf ^= 1;  // the slab written two iterations ago was read before the previous barrier
+    }
+  }
+}
+
+}  // namespace k1m
+
 // Edge-replicating copy of a chroma picture into its padded plane (used by MC only).
 __global__ void k_pad_plane(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int M, int Wp, int Hp,
                             int pitch, uint8_t* __restrict__ dst) {
@@ -258,7 +524,17 @@ __global__ void k_pel_to_u8(const int16_t* __restrict__ src, int srcStride, uint
 
 // rowBegin / rowEnd: padded-plane rows [rowBegin, rowEnd) to produce (whole 16-row tiles covering them); 0 / Hp = all
 cudaError_t fme_launch_k1(const FmeGeom& g, const uint8_t* d_pic, int picPitch, uint8_t* d_planes, int* d_tileCounter,
-                          int numSMs, int rowBegin, int rowEnd, cudaStream_t s, int64_t* launches) {
+                          int numSMs, int rowBegin, int rowEnd, int path, cudaStream_t s, int64_t* launches) {
+  if (path == 2 && g.W % 8 == 0 && g.M % 8 == 0) {  // FME_K1_PATH_MMA (its input groups of 8 columns must not straddle the picture edge): 8-row iterations of 128-column blocks, split evenly over two CTAs per SM
+    const int itBegin = max(rowBegin, 0) / 8, itEnd = (min(rowEnd, g.Hp) + 7) / 8;
+    if (itEnd <= itBegin) return cudaSuccess;
+    const int iters = itEnd - itBegin, units = ((g.Wp + k1m::BW - 1) / k1m::BW) * iters;
+    const int grid = max(1, min(numSMs * FME_K1M_CTAS, units / 4));
+    k1m::k1_interp_mma<<<grid, k1m::THREADS, 0, s>>>(d_pic, picPitch, g.W, g.H, g.M, g.Wp, g.Hp, g.pitch, g.planeBytes,
+                                                     d_planes, itBegin, iters, units);
+    ++*launches;
+    return cudaGetLastError();
+  }
   const int tilesX = (g.Wp + TW - 1) / TW;
   const int tyBegin = max(rowBegin, 0) / TH, tyEnd = (min(rowEnd, g.Hp) + TH - 1) / TH;
   if (tyEnd <= tyBegin) return cudaSuccess;

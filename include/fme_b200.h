@@ -75,8 +75,14 @@ typedef struct fme_config {
                            access configurations); 0 (default): such records are rejected / left untouched */
   int32_t k2Path;       /* how K2 computes the 8x8 SATD of uni-prediction Hadamard PUs; all paths are bit-identical:
                            FME_K2_PATH_AUTO (0, the fastest measured), _SWAR, _MMA_PACK, _MMA_GROUP */
-  int32_t reserved[4];
+  int32_t k1Path;       /* how K1 builds the 16 sub-pel planes; both paths are bit-identical: FME_K1_PATH_AUTO (0, the
+                           fastest measured), _DP4A (integer dot products on the CUDA cores), _MMA (both filter stages
+                           as exact fp16-in / fp32-accumulate mma.sync products against Toeplitz tap matrices) */
+  int32_t reserved[3];
 } fme_config;
+#define FME_K1_PATH_AUTO 0
+#define FME_K1_PATH_DP4A 1
+#define FME_K1_PATH_MMA 2
 #define FME_K2_PATH_AUTO 0
 #define FME_K2_PATH_SWAR 1      /* carry-tolerant 16-bit SWAR Hadamard in registers */
 #define FME_K2_PATH_MMA_PACK 2  /* fp16-in / fp32-accumulate mma.sync Hadamard inside the 32-lane packs */
