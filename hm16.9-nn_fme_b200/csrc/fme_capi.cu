@@ -44,9 +44,6 @@ inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 constexpr int FME_NBUF = 3;
 
 // What FME_K2_PATH_AUTO resolves to: the fastest measured path (profiles/r2_k2_paths.txt).
-#ifndef FME_K1_PATH_DEFAULT
-#define FME_K1_PATH_DEFAULT FME_K1_PATH_DP4A
-#endif
 #ifndef FME_K2_PATH_DEFAULT
 #define FME_K2_PATH_DEFAULT FME_K2_PATH_SWAR
 #endif
@@ -189,7 +186,7 @@ int run_k1(fme_ctx* c, int slot, const uint8_t* d_pic = nullptr, int picPitch = 
   StageTimer t(c, 0);
   if (!d_pic) { d_pic = c->d_pic; picPitch = c->picPitch; }
   CU_CHECK(fme_launch_k1(c->g, d_pic, picPitch, c->d_planes + (size_t)slot * c->g.slotBytes, c->d_k1Counter, c->numSMs,
-                         rowBegin, rowEnd, c->cfg.k1Path == FME_K1_PATH_AUTO ? FME_K1_PATH_DEFAULT : c->cfg.k1Path, c->stream,
+                         rowBegin, rowEnd, c->cfg.k1Path, c->stream,
                          &c->launches));
   c->refValid[slot] = 1;
   return FME_OK;

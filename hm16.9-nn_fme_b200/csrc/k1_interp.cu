@@ -335,15 +335,16 @@ __device__ __forceinline__ unsigned floor_clip_u8(float v) {
 }
 
 #ifndef FME_K1M_WARPS
-#define FME_K1M_WARPS 8
+#define FME_K1M_WARPS 4
 #endif
 #ifndef FME_K1M_CTAS
-#define FME_K1M_CTAS 3
+#define FME_K1M_CTAS 4
 #endif
 constexpr int WARPS = FME_K1M_WARPS, THREADS = 32 * WARPS;
 constexpr int BW = 16 * WARPS;            // CTA block: 128 (64) plane columns = one (half a) line per plane row
 constexpr int SLAB = 16 * 8 * BW;         // one iteration's output: 16 planes x 8 rows x BW bytes
 constexpr int CHUNKS = BW / 16;           // 16-byte chunks per slab row
+constexpr int RING = 4;                   // slabs in flight (see the main loop)
 // slab rows are XOR-swizzled by 16-byte chunk so that both the per-warp 4-byte writes (8 rows x one chunk) and the
 // 16-byte read-back (whole rows) touch every bank once
 __device__ __forceinline__ int swz(int chunk, int row) { return chunk ^ (WARPS == 8 ? row : WARPS == 4 ? (row >> 1) : (row >> 2)); }
@@ -353,13 +354,16 @@ struct TTile { unsigned lo[4][2], hi[4][2]; };  // per fx: B fragments of V for 
 __global__ void __launch_bounds__(THREADS, FME_K1M_CTAS)
 k1_interp_mma(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int M, int Wp, int Hp, int pitch,
               size_t planeBytes, uint8_t* __restrict__ planes, int itBegin, int itersPerBlock, int totalUnits) {
-  __shared__ __align__(128) uint8_t s_out[2 * SLAB];
+  __shared__ __align__(128) uint8_t s_out[RING * SLAB];
+  __shared__ __align__(8) unsigned long long s_full[RING];  // mbarrier per slab: all WARPS warps have written it
   __shared__ __align__(16) uint32_t s_tab[4][32][4];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
 
   // V's tap fragments stay in registers; H's four (one per fx) are re-read from shared memory at each use
   for (int i = tid; i < (int)(sizeof(d_tables.a1) / 16); i += THREADS)
     reinterpret_cast<uint4*>(&s_tab)[i] = reinterpret_cast<const uint4*>(&d_tables.a1)[i];
+  const unsigned barBase = (unsigned)__cvta_generic_to_shared(s_full);
+  if (tid < RING) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barBase + tid * 8), "r"(WARPS));
   __syncthreads();
   const unsigned tabBase = (unsigned)__cvta_generic_to_shared(&s_tab) + lane * 16;
   auto A1 = [&](int fx) {  // volatile: not hoisted out of the loop into 16 registers
@@ -429,12 +433,39 @@ k1_interp_mma(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int M
   // this CTA's share of the (column block, 8-row iteration) sequence, contiguous so that T tiles are reused
   int u = (int)((long long)blockIdx.x * totalUnits / gridDim.x);
   const int uEnd = (int)((long long)(blockIdx.x + 1) * totalUnits / gridDim.x);
-  int buf = 0;
   // slab: this lane writes row g, chunk w; in the store phase it moves chunk sc of row sr, planes sp0 + k * THREADS/64
   const int sOff = g * BW + (swz(w, g) << 4) + 4 * t;
   const int sc = tid % CHUNKS, sr = (tid / CHUNKS) & 7, sp0 = tid / (8 * CHUNKS);
   constexpr int PSTEP = THREADS / (8 * CHUNKS), NST = 16 / PSTEP;  // planes per pass, passes
   const uint8_t* sread = s_out + (sp0 * 8 + sr) * BW + (swz(sc, sr) << 4);
+
+  // The warps of a CTA meet only through the slabs.  Slab k of the ring is "full" when all warps have arrived on its
+  // mbarrier; a warp stores slab i-1 to the planes AFTER filtering iteration i, so it practically never waits, and the
+  // warps drift apart by up to an iteration (their tensor / FMA / store phases interleave instead of coinciding).
+  // Ring of 4: before writing slab i+4 (same buffer as i) a warp has waited for "full(i+2)", and every warp stores
+  // slab i before it filters i+2.
+  unsigned seq = 0;  // slabs produced so far by this CTA: buffer seq % RING, phase parity (seq / RING) & 1
+  auto arrive = [&](unsigned s) {
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(barBase + (s % RING) * 8) : "memory");
+  };
+  auto wait_full = [&](unsigned s) {
+    const unsigned bar = barBase + (s % RING) * 8, parity = (s / RING) & 1;
+    unsigned done;
+    do {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+  };
+  auto store_slab = [&](unsigned s, uint8_t* gdst, bool ok) {
+    wait_full(s);
+    if (ok) {
+      const uint8_t* src = sread + (s % RING) * SLAB;
+#pragma unroll
+      for (int k = 0; k < NST; ++k)
+        *reinterpret_cast<uint4*>(gdst + (size_t)(PSTEP * k) * planeBytes) = *reinterpret_cast<const uint4*>(src + k * (PSTEP * 8 * BW));
+    }
+  };
 
   while (u < uEnd) {
     const int cb = u / itersPerBlock, it0 = u - cb * itersPerBlock;
@@ -476,20 +507,18 @@ k1_interp_mma(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int M
       if (active) {
         fix_cols(n0, n1, w0, w1);
         load_rows(n0, n1);  // in flight during this iteration's filtering
-        uint8_t* so = s_out + buf * SLAB + sOff;
+        uint8_t* so = s_out + (seq % RING) * SLAB + sOff;
         if (i & 1) iteration(std::true_type{}, ta, tb, w0, w1, so); else iteration(std::false_type{}, ta, tb, w0, w1, so);
       }
-      __syncthreads();  // the 16 x 8 x BW-byte slab of this iteration is complete
-      if (colOk && y < Hp) {
-#pragma unroll
-        for (int k = 0; k < NST; ++k)
-          *reinterpret_cast<uint4*>(gdst + (size_t)(PSTEP * k) * planeBytes) =
-              *reinterpret_cast<const uint4*>(sread + buf * SLAB + k * (PSTEP * 8 * BW));
+      arrive(seq);
+      if (i > 0) {
+        store_slab(seq - 1, gdst, colOk && y < Hp);
+        gdst += (size_t)8 * pitch;
+        y += 8;
       }
-      gdst += (size_t)8 * pitch;
-      y += 8;
-      buf ^= 1;  // the slab written two iterations ago was read before the previous barrier
+      ++seq;
     }
+    store_slab(seq - 1, gdst, colOk && y < Hp);  // the segment's last slab
   }
 }
 
@@ -525,7 +554,11 @@ __global__ void k_pel_to_u8(const int16_t* __restrict__ src, int srcStride, uint
 // rowBegin / rowEnd: padded-plane rows [rowBegin, rowEnd) to produce (whole 16-row tiles covering them); 0 / Hp = all
 cudaError_t fme_launch_k1(const FmeGeom& g, const uint8_t* d_pic, int picPitch, uint8_t* d_planes, int* d_tileCounter,
                           int numSMs, int rowBegin, int rowEnd, int path, cudaStream_t s, int64_t* launches) {
-  if (path == 2 && g.W % 8 == 0 && g.M % 8 == 0) {  // FME_K1_PATH_MMA (its input groups of 8 columns must not straddle the picture edge): 8-row iterations of 128-column blocks, split evenly over two CTAs per SM
+  // FME_K1_PATH_AUTO: measured on B200 (tools/k1_probe.py, us per launch, dp4a | mma): 720p 16.4 | 12.5, 1080p 21.5 | 16.7,
+  // 1440p 33.2 | 26.8, 2160p 61.2 | 65.2 -- the tensor path up to ~6.5 M padded samples per launch, dp4a above.
+  const long long samples = (long long)g.Wp * (min(rowEnd, g.Hp) - max(rowBegin, 0));
+  if (path == 0) path = samples <= 6500000ll ? 2 : 1;
+  if (path == 2 && g.W % 8 == 0 && g.M % 8 == 0) {  // FME_K1_PATH_MMA (its input groups of 8 columns must not straddle the picture edge)
     const int itBegin = max(rowBegin, 0) / 8, itEnd = (min(rowEnd, g.Hp) + 7) / 8;
     if (itEnd <= itBegin) return cudaSuccess;
     const int iters = itEnd - itBegin, units = ((g.Wp + k1m::BW - 1) / k1m::BW) * iters;

@@ -3,7 +3,8 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, fme_loader
 fme = fme_loader.load()
-W, H = (3840, 2160) if len(sys.argv) > 1 and sys.argv[1] == "4k" else (1920, 1080)
+arg = sys.argv[1] if len(sys.argv) > 1 else "1920x1080"
+W, H = (3840, 2160) if arg == "4k" else tuple(int(v) for v in arg.split("x"))
 eng = fme.Fme(W, H, num_ref_slots=4, max_pus=16)
 st = torch.cuda.Stream(); torch.cuda.set_stream(st); eng.set_stream(st.cuda_stream)
 pic = np.random.default_rng(0).integers(0, 256, (H, W)).astype(np.uint8)
