@@ -92,7 +92,8 @@ k1_interp_planes(const uint8_t* __restrict__ pic, int picPitch, int W, int H, in
   const int tid = threadIdx.x;
   unsigned pref[K1_PREF];
   auto fetch = [&](int tile) {
-    const int tr = (int)__umulhi((unsigned)tile, tilesXRcp), tx = tile - tr * tilesX;  // tilesXRcp = ceil(2^32 / tilesX)
+    // tilesXRcp = ceil(2^32 / tilesX); 0 stands for tilesX == 1 (2^32 does not fit)
+    const int tr = tilesXRcp ? (int)__umulhi((unsigned)tile, tilesXRcp) : tile, tx = tile - tr * tilesX;
     const int ty = tr + tyBegin;
     const int pxBase = tx * TW - M - 4, pyBase = ty * TH - M - 3;  // picture coords of input (0,0); pxBase % 4 == 0
 #pragma unroll
@@ -116,7 +117,7 @@ k1_interp_planes(const uint8_t* __restrict__ pic, int picPitch, int W, int H, in
   int tile = blockIdx.x;
   if (tile < nTiles) fetch(tile);
   while (tile < nTiles) {
-    const int trI = (int)__umulhi((unsigned)tile, tilesXRcp), txI = tile - trI * tilesX;
+    const int trI = tilesXRcp ? (int)__umulhi((unsigned)tile, tilesXRcp) : tile, txI = tile - trI * tilesX;
     const int x0 = txI * TW, y0 = (trI + tyBegin) * TH;  // padded-plane coordinates of the tile
     if (tid == 0) s_next = (int)gridDim.x + atomicAdd(&tileCounter[0], 1);
     __syncthreads();  // every thread is done with s_in / s_t of the previous tile; s_next is published
@@ -457,13 +458,14 @@ k1_interp_mma(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int M
                    : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);
   };
-  auto store_slab = [&](unsigned s, uint8_t* gdst, bool ok) {
+  const unsigned planeStep = (unsigned)planeBytes * PSTEP;  // a slot (16 planes) is below 2^31 bytes: 32-bit offsets
+  auto store_slab = [&](unsigned s, unsigned goff, bool ok) {
     wait_full(s);
     if (ok) {
       const uint8_t* src = sread + (s % RING) * SLAB;
 #pragma unroll
       for (int k = 0; k < NST; ++k)
-        *reinterpret_cast<uint4*>(gdst + (size_t)(PSTEP * k) * planeBytes) = *reinterpret_cast<const uint4*>(src + k * (PSTEP * 8 * BW));
+        *reinterpret_cast<uint4*>(planes + (goff + k * planeStep)) = *reinterpret_cast<const uint4*>(src + k * (PSTEP * 8 * BW));
     }
   };
 
@@ -501,7 +503,7 @@ k1_interp_mma(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int M
       h_stage(w0, w1, ta);
     }
     int y = 8 * (itBegin + it0) + sr;
-    uint8_t* gdst = planes + (size_t)sp0 * planeBytes + (size_t)y * pitch + cb * BW + sc * 16;
+    unsigned goff = sp0 * (unsigned)planeBytes + y * pitch + cb * BW + sc * 16;
     const bool colOk = cb * BW + sc * 16 < Wp;
     for (int i = 0; i < n; ++i) {
       if (active) {
@@ -512,13 +514,13 @@ k1_interp_mma(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int M
       }
       arrive(seq);
       if (i > 0) {
-        store_slab(seq - 1, gdst, colOk && y < Hp);
-        gdst += (size_t)8 * pitch;
+        store_slab(seq - 1, goff, colOk && y < Hp);
+        goff += 8 * pitch;
         y += 8;
       }
       ++seq;
     }
-    store_slab(seq - 1, gdst, colOk && y < Hp);  // the segment's last slab
+    store_slab(seq - 1, goff, colOk && y < Hp);  // the segment's last slab
   }
 }
 

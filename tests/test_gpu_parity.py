@@ -1156,3 +1156,57 @@ def test_error_behaviour_of_the_round2_entry_points(small):
     for k in (0, 6, 15):
         np.testing.assert_array_equal(eng.download_plane(0, k // 4, k % 4), eng.download_plane(1, k // 4, k % 4))
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size,margin", [((424, 248), 80), ((136, 72), 16), ((1920, 1080), 80), ((72, 64), 32), ((64, 64), 16)])
+def test_k1_tensor_path_equals_dp4a_path(size, margin, orc):
+    """The two plane builders behind fme_config.k1Path (dp4a on the CUDA cores; IMMA + HMMA Toeplitz products with the
+    FFMA floor/clip epilogue) must give the same 16 planes byte for byte -- on content that saturates the clip and the
+    15-bit intermediate, on widths whose padded row ends in half a 16-byte chunk (424 + 160, 72 + 64), on the smallest
+    picture; three planes are also checked against the oracle."""
+    W, H = size
+    rng = np.random.default_rng(W * 7 + H)
+    pic = rng.integers(0, 256, (H, W)).astype(np.uint8)
+    pic[: H // 3] = np.where(rng.integers(0, 2, (H // 3, W)) > 0, 255, 0)          # full-swing noise: overshoot both ways
+    pic[H // 3: H // 2, : W // 2] = (np.indices((H // 2 - H // 3, W // 2)).sum(0) % 2 * 255)
+    planes = {}
+    for path in (fme.K1_PATH_DP4A, fme.K1_PATH_MMA):
+        eng = fme.Fme(W, H, num_ref_slots=1, max_pus=16, margin=margin, k1_path=path)
+        eng.upload_ref(0, pic)
+        planes[path] = [eng.download_plane(0, k // 4, k % 4) for k in range(16)]
+        eng.close()
+    for k in range(16):
+        np.testing.assert_array_equal(planes[fme.K1_PATH_DP4A][k], planes[fme.K1_PATH_MMA][k], err_msg="plane %d" % k)
+    if W * H <= 424 * 248:
+        padded = ob.pad_plane(pic, margin + 8)
+        S = padded.shape[1]
+        for fy, fx in ((2, 2), (3, 1), (0, 3)):
+            want = orc.subpel_plane(padded, (margin + 8) * S + (margin + 8), S, -margin, -margin, W + 2 * margin,
+                                    H + 2 * margin, fy, fx)
+            assert np.array_equal(planes[fme.K1_PATH_MMA][fy * 4 + fx].astype(np.int16), want), (fy, fx)
+
+
+@pytest.mark.gpu
+def test_k1_tensor_path_row_ranges_and_bad_path():
+    """Row-range launches (banded multi-GPU mode) on the tensor path produce exactly the rows of the full launch, whatever
+    the alignment of the range to its 8-row iterations; an out-of-range k1Path is refused by fme_create."""
+    import torch
+    W, H, M = 416, 240, 80
+    rng = np.random.default_rng(3)
+    pic = rng.integers(0, 256, (H, W)).astype(np.uint8)
+    d = torch.from_numpy(pic).cuda()
+    full = fme.Fme(W, H, num_ref_slots=1, max_pus=16, k1_path=fme.K1_PATH_MMA)
+    full.upload_ref_device_u8(0, d.data_ptr(), W)
+    want = [full.download_plane(0, k // 4, k % 4) for k in (0, 5, 10, 15)]
+    full.close()
+    for r0, r1 in ((0, H), (37, 101), (-M, 3), (H - 5, H + M)):
+        eng = fme.Fme(W, H, num_ref_slots=1, max_pus=16, k1_path=fme.K1_PATH_MMA)
+        eng.upload_ref_device_u8_rows(0, d.data_ptr(), W, r0, r1)
+        lo, hi = max(r0 + M, 0), min(r1 + M, H + 2 * M)
+        for j, k in enumerate((0, 5, 10, 15)):
+            got = eng.download_plane(0, k // 4, k % 4)
+            np.testing.assert_array_equal(got[lo:hi], want[j][lo:hi], err_msg="rows %d..%d plane %d" % (r0, r1, k))
+        eng.close()
+    with pytest.raises(fme.FmeError):
+        fme.Fme(W, H, k1_path=3)
