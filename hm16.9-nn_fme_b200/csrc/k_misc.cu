@@ -399,6 +399,20 @@ __global__ void k_expand_heads(const fme_pu_head* __restrict__ heads, int n, fme
   d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
 }
 
+// Host-supplied error grids for some of the expanded heads: err[] filled, FME_PU_ERR_ON_GPU cleared (K0 skips them).
+static_assert(sizeof(fme_err_grid) == 40, "grid layout");
+__global__ void k_apply_grids(const fme_err_grid* __restrict__ grids, int nGrids, fme_pu* __restrict__ pus, int n) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nGrids) return;
+  const unsigned* gw = reinterpret_cast<const unsigned*>(&grids[j]);  // 40-byte entries are 4-byte aligned
+  const int i = (int)gw[0];
+  if (i < 0 || i >= n) return;
+  unsigned* d = reinterpret_cast<unsigned*>(&pus[i]);
+  d[1] &= ~((unsigned)FME_PU_ERR_ON_GPU << 24);  // flags is byte 7 of the record
+#pragma unroll
+  for (int k = 0; k < 9; ++k) d[4 + k] = gw[1 + k];
+}
+
 // ------------------------------------------------------------------------------------------------
 // Motion compensation, bi-prediction: xPredInterBi with both lists valid (TComPrediction.cpp:575-621) =
 // two xPredInterUni(bi = true) blocks of 14-bit intermediates (xPredInterBlk with isLast = !bi = false,
@@ -545,6 +559,14 @@ cudaError_t fme_launch_pack_results(const fme_result* d_res, int n, fme_result8*
 cudaError_t fme_launch_expand_heads(const fme_pu_head* d_heads, int n, fme_pu* d_pus, cudaStream_t s, int64_t* launches) {
   if (n <= 0) return cudaSuccess;
   k_expand_heads<<<(n + 255) / 256, 256, 0, s>>>(d_heads, n, d_pus);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t fme_launch_apply_grids(const fme_err_grid* d_grids, int nGrids, fme_pu* d_pus, int n, cudaStream_t s,
+                                   int64_t* launches) {
+  if (nGrids <= 0) return cudaSuccess;
+  k_apply_grids<<<(nGrids + 255) / 256, 256, 0, s>>>(d_grids, nGrids, d_pus, n);
   ++*launches;
   return cudaGetLastError();
 }

@@ -25,6 +25,20 @@ def heads_of(recs):
     return h
 
 
+GRID_DTYPE = np.dtype([("pu", "<i4"), ("err", "<u4", (9,))])   # fme_err_grid: a host error grid for heads[pu]
+assert GRID_DTYPE.itemsize == 40
+
+
+def grids_of(recs, min_area):
+    """fme_err_grid entries for the records of at least `min_area` luma samples (the caller's array_e / C): the split
+    a caller makes between bus bytes and K0 time (fme_submit_heads_grids*)."""
+    idx = np.nonzero(recs["w"].astype(np.int32) * recs["h"].astype(np.int32) >= min_area)[0]
+    g = np.zeros(len(idx), GRID_DTYPE)
+    g["pu"] = idx
+    g["err"] = recs["err"][idx]
+    return g
+
+
 RESULT_DTYPE = np.dtype(
     [("halfX", "i1"), ("halfY", "i1"), ("qterX", "i1"), ("qterY", "i1"), ("cost", "<u4"),
      ("nnHalfX", "i1"), ("nnHalfY", "i1"), ("nnQterX", "i1"), ("nnQterY", "i1"), ("nnClass", "u1"),

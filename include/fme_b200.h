@@ -196,6 +196,21 @@ int fme_submit_async(fme_ctx* ctx, const fme_pu* pus, int n, fme_result* out, in
  * FME_PU_ERR_ON_GPU (the 3x3 surface of TEncSearch.cpp:5037-5050 is computed on the device before K2 / K3). */
 int fme_submit_heads(fme_ctx* ctx, const fme_pu_head* heads, int n, fme_result* out, int mode);
 int fme_submit_heads_async(fme_ctx* ctx, const fme_pu_head* heads, int n, fme_result* out, int mode);
+/* Head records plus the caller's own error grids for SOME of them.  The integer search has array_e / C in hand for
+ * every PU (TEncSearch.cpp:88, 1341-1376, 5049-5050); sending them costs 40 bytes per PU over the bus, computing them on
+ * the device costs K0 time that is dominated by per-PU overhead, not by PU area.  The caller picks the split that its
+ * bus allows (bench.py: grids for the PUs of 128 samples and more on one or two GPUs -- K0 0.173 -> 0.088 ms per 858 000
+ * PUs for +8.4 MB per frame -- none on eight GPUs sharing one host fabric).  grids[j].pu indexes heads[]; a head named by
+ * a grid is served exactly like a full record carrying that err[]; entries with pu outside [0, n) are ignored on the
+ * asynchronous path and rejected on the synchronous one. */
+typedef struct fme_err_grid {
+  int32_t pu;      /* index into heads[] */
+  uint32_t err[9]; /* raster 3x3 grid as in fme_pu.err */
+} fme_err_grid; /* 40 bytes */
+int fme_submit_heads_grids(fme_ctx* ctx, const fme_pu_head* heads, int n, const fme_err_grid* grids, int nGrids,
+                           fme_result* out, int mode);
+int fme_submit_heads_grids_async(fme_ctx* ctx, const fme_pu_head* heads, int n, const fme_err_grid* grids, int nGrids,
+                                 fme_result* out, int mode);
 /* With the ctx's own streams the copies of fme_upload_* / fme_submit_async run on dedicated copy streams and
  * overlap the kernels of neighbouring frames (staging rings of three, at most three submits in flight).
  * fme_wait_oldest blocks until the results of the oldest outstanding fme_submit_async are in `out`. */

@@ -1210,3 +1210,50 @@ def test_k1_tensor_path_row_ranges_and_bad_path():
         eng.close()
     with pytest.raises(fme.FmeError):
         fme.Fme(W, H, k1_path=3)
+
+
+@pytest.mark.gpu
+def test_heads_with_host_error_grids_for_some_pus(small):
+    """fme_submit_heads_grids: heads named by a host grid behave like full records carrying that err[] (NN_pred sees the
+    caller's array_e / C), the others get the device surface (K0); the standard search is the same for all.  Checked
+    with grids that differ from the true surface so that the source of each PU's err[] is visible; through the
+    asynchronous entry point too, where out-of-range grid indices are ignored (the synchronous one rejects them)."""
+    import torch
+    eng, g, recs = small
+    eng.set_nn_weights(fme.nn_weights.load_blob(22))
+    heads = fme.pu_list.heads_of(recs)
+    on_dev = eng.submit_heads(heads, fme.MODE_BOTH)                 # every err[] from K0
+    rng = np.random.default_rng(5)
+    host = recs.copy()
+    host["flags"] &= ~np.uint8(fme.PU_ERR_ON_GPU)
+    host["err"] = rng.integers(1, 1 << 20, host["err"].shape).astype(np.uint32)   # "the caller's" grids
+    from_host = eng.submit(host, fme.MODE_BOTH)                      # every err[] from the record
+    grids = fme.pu_list.grids_of(host, 128)
+    assert 0 < len(grids) < len(recs)
+    named = np.zeros(len(recs), bool)
+    named[grids["pu"]] = True
+    got = eng.submit_heads_grids(heads, grids, fme.MODE_BOTH)
+    for f in ("halfX", "halfY", "qterX", "qterY", "cost"):
+        np.testing.assert_array_equal(got[f], on_dev[f], err_msg=f)
+    for f in ("nnHalfX", "nnHalfY", "nnQterX", "nnQterY", "nnClass"):
+        np.testing.assert_array_equal(got[f][named], from_host[f][named], err_msg=f + " (host grid)")
+        np.testing.assert_array_equal(got[f][~named], on_dev[f][~named], err_msg=f + " (device surface)")
+    assert (from_host["nnClass"][named] != on_dev["nnClass"][named]).any()    # the two sources are distinguishable
+    # asynchronous, with two entries that name no PU
+    extra = np.zeros(2, fme.GRID_DTYPE)
+    extra["pu"] = (-7, len(recs) + 5)
+    ga = np.concatenate([grids, extra])
+    h_in = torch.from_numpy(heads.view(np.uint8).reshape(len(heads), -1).copy()).pin_memory()
+    h_gr = torch.from_numpy(ga.view(np.uint8).reshape(len(ga), -1).copy()).pin_memory()
+    h_out = torch.zeros((len(heads), 16), dtype=torch.uint8).pin_memory()
+    for _ in range(4):
+        eng.submit_heads_grids_async(h_in.data_ptr(), len(heads), h_gr.data_ptr(), len(ga), h_out.data_ptr(), fme.MODE_BOTH)
+    eng.synchronize()
+    back = h_out.numpy().reshape(-1).view(fme.RESULT_DTYPE)
+    for f in ("cost", "nnClass", "nnHalfX", "nnQterY"):
+        np.testing.assert_array_equal(back[f], got[f], err_msg=f)
+    with pytest.raises(fme.FmeError):
+        eng.submit_heads_grids(heads, ga, fme.MODE_BOTH)
+    # heads-only submits afterwards are untouched by the grid buffers
+    again = eng.submit_heads(heads, fme.MODE_BOTH)
+    assert np.array_equal(again.view(np.uint8), on_dev.view(np.uint8))
