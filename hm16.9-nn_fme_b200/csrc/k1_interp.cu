@@ -242,13 +242,15 @@ k1_interp_planes(const uint8_t* __restrict__ pic, int picPitch, int W, int H, in
 // T (15 bits) enters V as two exact f16 operands scaled so that ONE tap matrix (the taps themselves) serves both: the
 // IMMA accumulator starts from 0x54342000, so that one PRMT per pair builds the f16x2 words 0x3400|low byte =
 // 0.25 + lo/4096 and 0x5400|high byte = 64 + hi/16 (the 64 is subtracted, the 0.25 folded into V's start value: the
-// sum of the two is (T + 8192)/4096 + 0.25).  The D fragment of H *is*
-// the B fragment of V (same lanes, same element order) when H puts columns on M and rows on N, so T never leaves the
-// register file; a warp slides down a 16-column strip 8 rows at a time and keeps the previous T tile.  All f32 sums are
-// multiples of 2^-12 below 2^10: exact.  f32 -> u8 without the XU pipe (F2I runs at 16 lanes/clk/SM and was the limit
-// of the first version): y = sat(D/256 + 2^-22), z = floor(y * (256 - 2^-15)) by FFMA.RM onto 2^23 -- the low mantissa
-// byte is clip255(floor(D)).  Eight warps stage 128-byte plane rows in shared memory (16-byte chunks XOR-swizzled by
-// row, conflict-free both ways) and the CTA writes whole lines with 16-byte stores.
+// sum of the two is (T + 8192)/4096 + 0.25).  The D fragment of H *is* the B fragment of V (same lanes, same element
+// order) when H puts columns on M and rows on N, so T never leaves the register file; a warp slides down a 16-column
+// strip 8 rows at a time and keeps the previous T tile.  All f32 sums are multiples of 2^-12 below 2^10: exact.
+// f32 -> u8 without the XU pipe (F2I runs at 16 lanes/clk/SM and was the limit of the first version):
+// y = sat(D/256 + 2^-22), z = floor(y * (256 - 2^-15)) by FFMA.RM onto 2^23 -- the low mantissa byte is
+// clip255(floor(D)): with u = D/256 a multiple of 2^-20, y*(256 - 2^-15) = 256u + e with 2^-15 < e <= 2^-14 < 2^-12 for
+// 0 <= u < 1 (same floor as 256u), y = 0 for u < 0, and y = 1 gives 255.99997 for u >= 1.
+// The warps of a CTA stage 64-byte plane rows in shared memory (16-byte chunks XOR-swizzled by row, conflict-free both
+// ways) and write them out with 16-byte stores.
 namespace k1m {
 
 constexpr int kTap[4][8] = {{0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1},
@@ -301,11 +303,6 @@ constexpr Tables make_tables() {
 }
 __device__ const Tables d_tables = make_tables();
 
-__device__ __forceinline__ void imma(int (&d)[4], const uint4& a, unsigned b0, unsigned b1) {
-  asm("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
-      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
-}
 __device__ __forceinline__ void hmma(float (&d)[4], const uint4& a, unsigned b0, unsigned b1) {
   asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
