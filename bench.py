@@ -600,6 +600,12 @@ def banded_leg(fme, torch, dist, dev, stream, rank, world, local, steps, warmup)
         issue_bcast(i + 1)                  # next frame's reference travels while this band is searched
         eng.submit_device(d_band[k].data_ptr(), n_band[k], d_res.data_ptr(), fme.MODE_BOTH)
 
+    def step_compute(i):                     # the band's kernels alone (no broadcast): per-rank balance
+        k, slot = i % n_sets, i % N_REFS
+        eng.upload_ref_device_u8_rows(slot, d_refs[k][slot].data_ptr(), W4K, rows_band[k][0], rows_band[k][1])
+        eng.upload_org_device_u8(d_org[k].data_ptr(), W4K)
+        eng.submit_device(d_band[k].data_ptr(), n_band[k], d_res.data_ptr(), fme.MODE_BOTH)
+
     def step_full(i):
         k, slot = i % n_sets, i % N_REFS
         eng.upload_ref_device_u8(slot, d_refs[k][slot].data_ptr(), W4K)
@@ -623,6 +629,7 @@ def banded_leg(fme, torch, dist, dev, stream, rank, world, local, steps, warmup)
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
+        timed.local_ms = ms / n        # this rank's own device time (the step time is the max over ranks)
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -641,6 +648,11 @@ def banded_leg(fme, torch, dist, dev, stream, rank, world, local, steps, warmup)
         pending.pop(warmup).wait()
         torch.cuda.synchronize(dev)
         tn = timed(step_band, warmup, steps, pre=lambda: issue_bcast(warmup))
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, round(timed.local_ms, 4))
+        timed(step_compute, warmup, steps)
+        compute_rank = [None] * world
+        dist.all_gather_object(compute_rank, round(timed.local_ms, 4))
         if (warmup + steps) in pending:
             pending.pop(warmup + steps).wait()
         # the broadcast alone, blocking, for reference (it is off the critical path above)
@@ -650,7 +662,8 @@ def banded_leg(fme, torch, dist, dev, stream, rank, world, local, steps, warmup)
         rec.update({"ms_per_step": tn, "value": n_full / (tn * 1e-3), "unit": "PU/s", "frames_per_sec": 1e3 / tn,
                     "scaling": "strong", "efficiency_vs_1gpu_same_run": t1 / (world * tn),
                     "broadcast_us_blocking": tb * 1e3, "broadcast_bytes": W4K * H4K,
-                    "band_pus": sizes, "band_split": "pixel-balanced contiguous CTU runs (boundaries may fall mid-row)",
+                    "band_pus": sizes, "ms_per_rank": per_rank, "compute_ms_per_rank_without_broadcast": compute_rank,
+                    "band_split": "pixel-balanced contiguous CTU runs (boundaries may fall mid-row)",
                     "parallelism": "ctu bands x%d, ncclBroadcast of the new reference one frame ahead on a side stream, "
                                    "K1 per rank on the plane rows its band references" % world,
                     "k1_rows_this_rank": [int(rows_band[0][0]), int(rows_band[0][1])]})
