@@ -85,6 +85,17 @@ struct FmeK2Scratch {
 };
 
 // d_tileCounter: two zero-initialised ints owned by the ctx (dynamic tile hand-out; the kernel re-arms them itself)
+// Grid of a grid-striding kernel: at most one resident wave (numSMs x the CTAs of this kernel an SM holds).  More CTAs
+// than that run after the wave at a fraction of the occupancy (K3: 6 per SM against 5 resident cost 4 %).
+template <typename Kernel>
+inline int fme_one_wave(Kernel kernel, int threads, size_t smemBytes, int wanted) {
+  int dev = 0, sms = 148, perSM = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, threads, smemBytes) != cudaSuccess || perSM < 1) perSM = 4;
+  return wanted < sms * perSM ? wanted : sms * perSM;
+}
+
 cudaError_t fme_launch_k1(const FmeGeom& g, const uint8_t* d_pic, int picPitch, uint8_t* d_planes, int* d_tileCounter,
                           int numSMs, int rowBegin, int rowEnd, int path, cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_pad_chroma(const FmeGeom& g, const uint8_t* d_pic, int picPitch, uint8_t* d_plane,

@@ -1624,8 +1624,7 @@ cudaError_t fme_launch_cand_cost(const FmeGeom& g, const uint8_t* d_planes, cons
                                  int n, const FmeCostLut& lut, int useHad, uint32_t* d_cost, int32_t* d_best, cudaStream_t s,
                                  int64_t* launches) {
   if (n <= 0) return cudaSuccess;
-  int blocks = (n + PE_WARPS - 1) / PE_WARPS;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  const int blocks = fme_one_wave(k_cand_cost, PE_WARPS * 32, 0, (n + PE_WARPS - 1) / PE_WARPS);
   k_cand_cost<<<blocks, PE_WARPS * 32, 0, s>>>(d_cands, n, d_planes, d_org, g, lut, useHad, d_cost);
   ++*launches;
   if (d_best) {
@@ -1638,8 +1637,7 @@ cudaError_t fme_launch_cand_cost(const FmeGeom& g, const uint8_t* d_planes, cons
 cudaError_t fme_launch_mc_luma_compact(const FmeGeom& g, const uint8_t* d_planes, const fme_mc_pu* d_pus, int n,
                                        const uint32_t* d_offsets, uint8_t* d_out, cudaStream_t s, int64_t* launches) {
   if (n <= 0) return cudaSuccess;
-  int blocks = (n + 7) / 8;  // 8 warps per CTA, one PU per warp step
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  const int blocks = fme_one_wave(k_mc_luma_compact, 256, 0, (n + 7) / 8);  // 8 warps per CTA, one PU per warp step
   k_mc_luma_compact<<<blocks, 256, 0, s>>>(d_pus, n, d_offsets, d_planes, g, d_out);
   ++*launches;
   return cudaGetLastError();
@@ -1648,8 +1646,7 @@ cudaError_t fme_launch_mc_luma_compact(const FmeGeom& g, const uint8_t* d_planes
 cudaError_t fme_launch_pred_error(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_mc_pu* d_pus,
                                   int n, int useHad, uint32_t* d_out, cudaStream_t s, int64_t* launches) {
   if (n <= 0) return cudaSuccess;
-  int blocks = (n + PE_WARPS - 1) / PE_WARPS;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  const int blocks = fme_one_wave(k_pred_error, PE_WARPS * 32, 0, (n + PE_WARPS - 1) / PE_WARPS);
   k_pred_error<<<blocks, PE_WARPS * 32, 0, s>>>(d_pus, n, d_planes, d_org, g, useHad, d_out);
   ++*launches;
   return cudaGetLastError();

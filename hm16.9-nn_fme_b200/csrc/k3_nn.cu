@@ -324,15 +324,8 @@ cudaError_t launch_fixed(const fme_pu* d_pus, int n, fme_result* d_res, const fl
     if (e != cudaSuccess) return e;
   }
   int blocks = (n + K3F_NPU * K3F_THREADS - 1) / (K3F_NPU * K3F_THREADS);
-  // exactly one resident wave of grid-striding CTAs: with more (it was 6 per SM against 5 resident at 90 registers) the
-  // extra CTAs run alone after the wave, at a fifth of the occupancy (measured 0.144 -> 0.140 ms per 858 000 PUs)
-  int dev = 0, numSMs = 148, perSM = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k3_nn_fixed<NEMB, H1, H2, H3, NOUT, FMA>, K3F_THREADS, smem) != cudaSuccess ||
-      perSM < 1)
-    perSM = 4;
-  if (blocks > numSMs * perSM) blocks = numSMs * perSM;
+  // one resident wave of grid-striding CTAs (it was 6 per SM against 5 resident at 90 registers: 0.144 -> 0.138 ms)
+  blocks = fme_one_wave(k3_nn_fixed<NEMB, H1, H2, H3, NOUT, FMA>, K3F_THREADS, smem, blocks);
   k3_nn_fixed<NEMB, H1, H2, H3, NOUT, FMA><<<blocks, K3F_THREADS, smem, s>>>(d_pus, n, d_res, d_nn,
                                                                              outSigmoid ? 36.7368f : 3.0e38f);
   return cudaGetLastError();
