@@ -269,8 +269,8 @@ constexpr uint32_t f16_of(int c, int s) {
 constexpr int colOfRow(int m) { return m < 8 ? 4 * (m / 2) + (m % 2) : 4 * ((m - 8) / 2) + 2 + (m % 2); }
 // H: K index k is window column 8t + {0..7} of the lane t = (k % 16) / 4 that loaded it (word 0: k < 16, word 1: k >= 16)
 constexpr int inColOfK(int k) { return 8 * ((k % 16) / 4) + 4 * (k / 16) + (k % 4); }
-constexpr uint32_t a1_elem(int fx, int m, int k) {
-  const int idx = inColOfK(k) - colOfRow(m) - 5;  // window column 0 is strip column -8; taps reach x-3 .. x+4
+constexpr uint32_t a1_elem(int fx, int m, int k, bool natural = false) {
+  const int idx = inColOfK(k) - (natural ? m : colOfRow(m)) - 5;  // window column 0 is strip column -8; taps reach x-3 .. x+4
   return idx >= 0 && idx < 8 ? (uint32_t)(kTap[fx][idx] & 0xff) : 0u;
 }
 constexpr uint32_t a2_elem(int mt, int m, int kk) {  // row m = (phase 2mt + m/8, output row m%8); T row kk is y-3+kk
@@ -279,6 +279,7 @@ constexpr uint32_t a2_elem(int mt, int m, int kk) {  // row m = (phase 2mt + m/8
 }
 struct Tables {
   uint32_t a1[4][32][4];     // [fx][lane] -> the lane's A fragment (m16n8k32 s8, row-major A)
+  uint32_t a1n[4][32][4];    // the same with row m = column m (the UMMA path wants N in column order)
   uint32_t a2[2][2][32][4];  // [K halves exchanged?][m-tile][lane] (m16n8k16 f16, the taps themselves)
 };
 constexpr Tables make_tables() {
@@ -288,9 +289,13 @@ constexpr Tables make_tables() {
     for (int r = 0; r < 4; ++r) {
       const int m = g + (r & 1) * 8;
       for (int fx = 0; fx < 4; ++fx) {
-        uint32_t v = 0;
-        for (int j = 0; j < 4; ++j) v |= a1_elem(fx, m, 4 * q + (r >> 1) * 16 + j) << (8 * j);
+        uint32_t v = 0, vn = 0;
+        for (int j = 0; j < 4; ++j) {
+          v |= a1_elem(fx, m, 4 * q + (r >> 1) * 16 + j) << (8 * j);
+          vn |= a1_elem(fx, m, 4 * q + (r >> 1) * 16 + j, true) << (8 * j);
+        }
         t.a1[fx][lane][r] = v;
+        t.a1n[fx][lane][r] = vn;
       }
       const int k0 = 2 * q + (r >> 1) * 8;
       for (int mt = 0; mt < 2; ++mt) {
@@ -523,6 +528,211 @@ k1_interp_mma(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int M
 
 }  // namespace k1m
 
+// ---------------------------------------------------------------------------------------------------------------
+// K1 with the vertical stage on the asynchronous tensor path (FME_K1_PATH_UMMA): the horizontal stage is the IMMA of
+// k1_interp_mma, but the T tiles go to shared memory in the canonical K-major UMMA layout (a warp's B fragment IS one
+// 8 x 8 core matrix: 128 contiguous bytes per STS.32) and V is tcgen05.mma kind::f16 issued by one thread:
+//   D[M = 4 phases x 32 rows][N = 4 fx x 64 columns] = A[M][K = 48 T rows] x B[K][N],   K-steps of 16, hi and lo parts
+// with the accumulator in TMEM (256 columns per CTA, two CTAs per SM).  No warp waits on an mma.sync any more, and the
+// 32 HMMA per 16 x 8 step leave the issue stream.  TMEM lane = (phase, row): tcgen05.ld hands a thread 64 adjacent
+// pixels of one plane row, converted with the same FFMA.SAT / FFMA.RM pair and staged through the swizzled slab.
+namespace k1u {
+
+using k1m::kTap;
+using k1m::f16_of;
+constexpr int THREADS = 128, BWU = 64;       // 4 warps x 16 columns
+constexpr int BR = 32;                       // output rows per block
+constexpr int KBS = 8;                       // T ring: k-blocks of 8 rows
+constexpr int NCOL = 4 * BWU;                // UMMA N
+constexpr int T_KB_BYTES = NCOL * 16;        // one k-block: 256 n x (8 k x 2 B)
+constexpr int T_BYTES = KBS * T_KB_BYTES;    // per half (hi / lo)
+constexpr int A_CHUNK_BYTES = 128 * 16;      // one 8-wide K chunk of the tap matrix: 128 m x 16 B
+constexpr int A_BYTES = 6 * A_CHUNK_BYTES;
+constexpr int SLAB_BYTES = 16 * BR * BWU;
+constexpr int SMEM_BYTES = 2 * T_BYTES + A_BYTES + SLAB_BYTES;
+constexpr int TMEM_COLS = NCOL;
+
+struct TapA { uint16_t v[6][16][8][8]; };    // [k chunk][m group][m % 8][k % 8], m = phase * 32 + row, T row k = row + tap
+constexpr TapA make_tapA() {
+  TapA t{};
+  for (int m = 0; m < 128; ++m)
+    for (int k = 0; k < 48; ++k) {
+      const int idx = k - (m % 32);
+      t.v[k / 8][m / 8][m % 8][k % 8] = idx >= 0 && idx < 8 ? (uint16_t)f16_of(kTap[m / 32][idx], 0) : (uint16_t)0;
+    }
+  return t;
+}
+__device__ const TapA d_tapA = make_tapA();
+static_assert(sizeof(TapA) == A_BYTES, "tap matrix size");
+
+__device__ __forceinline__ uint64_t smem_desc(unsigned addr, unsigned lboBytes, unsigned sboBytes) {
+  // SWIZZLE_NONE, K-major: 8 x 16-byte core matrices; LBO = distance between the two K chunks of a K = 16 step,
+  // SBO = distance between 8-row groups along M / N; descriptor version 1 (bits 46-47)
+  return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lboBytes >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)((sboBytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_f16(unsigned tmemD, uint64_t descA, uint64_t descB, unsigned idesc, unsigned accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmemD), "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&v)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                 "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                 "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                 "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// clip255(floor(D - 143.5)) in the low byte: D carries + 128 + 16 of the operand offsets, the rounding needs + 0.5
+__device__ __forceinline__ unsigned floor_clip_u8(unsigned dBits) {
+  float y, z;
+  asm("fma.rn.sat.f32 %0, %1, 0f3B800000, 0fBF0F7FFC;" : "=f"(y) : "f"(__uint_as_float(dBits)));  // sat((D - 143.5) / 256 + 2^-22)
+  asm("fma.rm.f32 %0, %1, 0f437FFFFF, 0f4B000000;" : "=f"(z) : "f"(y));
+  return __float_as_uint(z);
+}
+
+__global__ void __launch_bounds__(THREADS, 2)
+k1_interp_umma(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int M, int Wp, int Hp, int pitch,
+               size_t planeBytes, uint8_t* __restrict__ planes, int blkBegin, int blocksPerCol, int totalUnits) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* const sThi = smem;
+  uint8_t* const sTlo = smem + T_BYTES;
+  uint8_t* const sA = smem + 2 * T_BYTES;
+  uint8_t* const sSlab = sA + A_BYTES;
+  __shared__ __align__(8) unsigned long long s_mbar;
+  __shared__ unsigned s_tmem;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+
+  for (int i = tid; i < A_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sA)[i] = reinterpret_cast<const uint4*>(&d_tapA)[i];
+  uint4 A1[4];
+#pragma unroll
+  for (int fx = 0; fx < 4; ++fx) A1[fx] = *reinterpret_cast<const uint4*>(k1m::d_tables.a1n[fx][lane]);
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(&s_mbar);
+  if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+  if (w == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_tmem)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tap matrix (generic-proxy stores) is read by the tensor pipe
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem = s_tmem;
+  const unsigned aAddr = (unsigned)__cvta_generic_to_shared(sA), hiAddr = (unsigned)__cvta_generic_to_shared(sThi),
+                 loAddr = (unsigned)__cvta_generic_to_shared(sTlo);
+  constexpr unsigned IDESC = (1u << 4) | ((unsigned)(NCOL >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major, M 128, N 256
+  unsigned parity = 0;
+
+  int u = (int)((long long)blockIdx.x * totalUnits / gridDim.x);
+  const int uEnd = (int)((long long)(blockIdx.x + 1) * totalUnits / gridDim.x);
+  while (u < uEnd) {
+    const int cb = u / blocksPerCol, b0 = u - cb * blocksPerCol;
+    const int n = min(blocksPerCol - b0, uEnd - u);
+    u += n;
+    const int x0 = cb * BWU + w * 16;
+    const int px0 = x0 - 8 - M + 8 * t;
+    const int pxl = min(max(px0, 0), W - 8);
+    const unsigned selA = px0 < 0 ? 0x0000u : px0 >= W ? 0x7777u : 0x3210u, selB = px0 < 0 ? 0x0000u : px0 >= W ? 0x7777u : 0x7654u;
+    const uint8_t* colp = pic + pxl;
+    int kbNext = 4 * (blkBegin + b0);                 // next T k-block to produce: plane rows 8 kb - 3 .. 8 kb + 4
+    int yIn = 8 * kbNext - 3 + g - M;
+    unsigned n0, n1;
+    auto load_rows = [&]() {
+      const uint8_t* row = colp + (size_t)min(max(yIn, 0), H - 1) * picPitch;
+      n0 = *reinterpret_cast<const unsigned*>(row);
+      n1 = *reinterpret_cast<const unsigned*>(row + 4);
+      yIn += 8;
+    };
+    load_rows();
+    const unsigned tOff = (unsigned)((2 * w) * 128 + g * 16 + 4 * t);   // + fx * 1024 + nt * 128 + slot * T_KB_BYTES
+    for (int bi = 0; bi < n; ++bi) {
+      const int b = blkBegin + b0 + bi;
+      while (kbNext <= 4 * b + 5) {                   // six tiles for the first block of a segment, four afterwards
+        const unsigned w0 = __byte_perm(n0, n1, selA), w1 = __byte_perm(n0, n1, selB);
+        load_rows();
+        const unsigned slotOff = (unsigned)(kbNext & (KBS - 1)) * T_KB_BYTES + tOff;
+#pragma unroll
+        for (int fx = 0; fx < 4; ++fx) {
+          int d[4];
+          k1m::imma_c(d, A1[fx], w0, w1, 0x54342000);
+          const unsigned o = slotOff + fx * 1024;
+          *reinterpret_cast<unsigned*>(sTlo + o) = __byte_perm(d[0], d[1], 0x6420);
+          *reinterpret_cast<unsigned*>(sTlo + o + 128) = __byte_perm(d[2], d[3], 0x6420);
+          *reinterpret_cast<unsigned*>(sThi + o) = k1m::hsub2u(__byte_perm(d[0], d[1], 0x7531), 0x54005400u);
+          *reinterpret_cast<unsigned*>(sThi + o + 128) = k1m::hsub2u(__byte_perm(d[2], d[3], 0x7531), 0x54005400u);
+        }
+        ++kbNext;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();   // T tiles of this block are in shared memory; the previous block's slab has been stored
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+          for (int ks = 0; ks < 3; ++ks) {
+            const unsigned slot = (unsigned)((4 * b + 2 * ks) & (KBS - 1));
+            umma_f16(tmem, smem_desc(aAddr + 2 * ks * A_CHUNK_BYTES, A_CHUNK_BYTES, 128),
+                     smem_desc((hl ? loAddr : hiAddr) + slot * T_KB_BYTES, T_KB_BYTES, 128), IDESC, (hl | ks) != 0);
+          }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+      }
+      {
+        unsigned done = 0;
+        for (int spin = 0; !done; ++spin) {
+          asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                       : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+          if (spin > (1 << 22)) __trap();   // a lost completion must not hang the device
+        }
+        parity ^= 1;
+      }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // epilogue: TMEM lane = phase w, row `lane`; columns fx * 64 + x
+#pragma unroll 1
+      for (int q = 0; q < 8; ++q) {   // q = fx * 2 + half: 32 adjacent pixels of plane (w, fx), row lane
+        unsigned v[32];
+        tmem_ld32(tmem + ((unsigned)(32 * w) << 16) + q * 32, v);
+        const int p = w * 4 + (q >> 1);
+        uint8_t* row = sSlab + (p * BR + lane) * BWU;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint4 o;
+          unsigned* ow = reinterpret_cast<unsigned*>(&o);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const unsigned* s4 = &v[c * 16 + k * 4];
+            const unsigned z0 = floor_clip_u8(s4[0]), z1 = floor_clip_u8(s4[1]), z2 = floor_clip_u8(s4[2]), z3 = floor_clip_u8(s4[3]);
+            ow[k] = __byte_perm(z1 * 256u + z0, z3 * 256u + z2, 0x5410);
+          }
+          const int chunk = (q & 1) * 2 + c;
+          *reinterpret_cast<uint4*>(row + ((chunk ^ ((lane >> 1) & 3)) << 4)) = o;
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();   // slab complete, TMEM drained
+      {
+        const int c = tid & 3, r = (tid >> 2) & 31;
+        const int y = BR * b + r, x = cb * BWU + c * 16;
+        if (y < Hp && x < Wp) {
+          const uint8_t* src = sSlab + r * BWU + ((c ^ ((r >> 1) & 3)) << 4);
+          uint8_t* dst = planes + (size_t)y * pitch + x;
+#pragma unroll 4
+          for (int pl = 0; pl < 16; ++pl)
+            *reinterpret_cast<uint4*>(dst + pl * planeBytes) = *reinterpret_cast<const uint4*>(src + pl * (BR * BWU));
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+}
+
+}  // namespace k1u
+
 // Edge-replicating copy of a chroma picture into its padded plane (used by MC only).
 __global__ void k_pad_plane(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int M, int Wp, int Hp,
                             int pitch, uint8_t* __restrict__ dst) {
@@ -557,6 +767,18 @@ cudaError_t fme_launch_k1(const FmeGeom& g, const uint8_t* d_pic, int picPitch, 
   // 1440p 33.2 | 26.8, 2160p 61.2 | 65.2 -- the tensor path up to ~6.5 M padded samples per launch, dp4a above.
   const long long samples = (long long)g.Wp * (min(rowEnd, g.Hp) - max(rowBegin, 0));
   if (path == 0) path = samples <= 6500000ll ? 2 : 1;
+  if (path == 3 && g.W % 8 == 0 && g.M % 8 == 0) {  // FME_K1_PATH_UMMA: (64-column block, 32-row block) units over two CTAs per SM
+    const int bBegin = max(rowBegin, 0) / k1u::BR, bEnd = (min(rowEnd, g.Hp) + k1u::BR - 1) / k1u::BR;
+    if (bEnd <= bBegin) return cudaSuccess;
+    const int nb = bEnd - bBegin, units = ((g.Wp + k1u::BWU - 1) / k1u::BWU) * nb;
+    cudaError_t e = cudaFuncSetAttribute(k1u::k1_interp_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, k1u::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    const int grid = max(1, min(numSMs * 2, units));
+    k1u::k1_interp_umma<<<grid, k1u::THREADS, k1u::SMEM_BYTES, s>>>(d_pic, picPitch, g.W, g.H, g.M, g.Wp, g.Hp, g.pitch,
+                                                                   g.planeBytes, d_planes, bBegin, nb, units);
+    ++*launches;
+    return cudaGetLastError();
+  }
   if (path == 2 && g.W % 8 == 0 && g.M % 8 == 0) {  // FME_K1_PATH_MMA (its input groups of 8 columns must not straddle the picture edge)
     const int itBegin = max(rowBegin, 0) / 8, itEnd = (min(rowEnd, g.Hp) + 7) / 8;
     if (itEnd <= itBegin) return cudaSuccess;

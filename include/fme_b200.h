@@ -83,6 +83,7 @@ typedef struct fme_config {
 #define FME_K1_PATH_AUTO 0
 #define FME_K1_PATH_DP4A 1
 #define FME_K1_PATH_MMA 2
+#define FME_K1_PATH_UMMA 3 /* experimental: vertical stage on tcgen05.mma / TMEM */
 #define FME_K2_PATH_AUTO 0
 #define FME_K2_PATH_SWAR 1      /* carry-tolerant 16-bit SWAR Hadamard in registers */
 #define FME_K2_PATH_MMA_PACK 2  /* fp16-in / fp32-accumulate mma.sync Hadamard inside the 32-lane packs */
