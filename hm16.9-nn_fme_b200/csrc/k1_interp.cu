@@ -540,7 +540,7 @@ namespace k1u {
 
 using k1m::kTap;
 using k1m::f16_of;
-constexpr int THREADS = 128, BWU = 64;       // 4 warps x 16 columns
+constexpr int THREADS = 256, BWU = 64;       // 8 warps: 4 strips of 16 columns x 2
 constexpr int BR = 32;                       // output rows per block
 constexpr int KBS = 8;                       // T ring: k-blocks of 8 rows
 constexpr int NCOL = 4 * BWU;                // UMMA N
@@ -604,7 +604,9 @@ k1_interp_umma(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int 
   uint8_t* const sSlab = sA + A_BYTES;
   __shared__ __align__(8) unsigned long long s_mbar;
   __shared__ unsigned s_tmem;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+  // eight warps: warp w and w + 4 share strip (w & 3) in the horizontal stage (even / odd k-blocks) and TMEM lane quarter
+  // (w & 3) = vertical phase in the epilogue (fx 0-1 / fx 2-3)
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, ws = w & 3, wh = w >> 2, g = lane >> 2, t = lane & 3;
 
   for (int i = tid; i < A_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sA)[i] = reinterpret_cast<const uint4*>(&d_tapA)[i];
   uint4 A1[4];
@@ -616,11 +618,7 @@ k1_interp_umma(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_tmem)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tap matrix (generic-proxy stores) is read by the tensor pipe
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const unsigned tmem = s_tmem;
+  // no barrier here: the first block's barrier publishes the tap matrix, the mbarrier and the TMEM address
   const unsigned aAddr = (unsigned)__cvta_generic_to_shared(sA), hiAddr = (unsigned)__cvta_generic_to_shared(sThi),
                  loAddr = (unsigned)__cvta_generic_to_shared(sTlo);
   constexpr unsigned IDESC = (1u << 4) | ((unsigned)(NCOL >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major, M 128, N 256
@@ -632,43 +630,52 @@ k1_interp_umma(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int 
     const int cb = u / blocksPerCol, b0 = u - cb * blocksPerCol;
     const int n = min(blocksPerCol - b0, uEnd - u);
     u += n;
-    const int x0 = cb * BWU + w * 16;
+    const int x0 = cb * BWU + ws * 16;
     const int px0 = x0 - 8 - M + 8 * t;
     const int pxl = min(max(px0, 0), W - 8);
     const unsigned selA = px0 < 0 ? 0x0000u : px0 >= W ? 0x7777u : 0x3210u, selB = px0 < 0 ? 0x0000u : px0 >= W ? 0x7777u : 0x7654u;
     const uint8_t* colp = pic + pxl;
+    const unsigned tOff = (unsigned)((2 * ws) * 128 + g * 16 + 4 * t);   // + fx * 1024 + nt * 128 + slot * T_KB_BYTES
     int kbNext = 4 * (blkBegin + b0);                 // next T k-block to produce: plane rows 8 kb - 3 .. 8 kb + 4
-    int yIn = 8 * kbNext - 3 + g - M;
-    unsigned n0, n1;
-    auto load_rows = [&]() {
-      const uint8_t* row = colp + (size_t)min(max(yIn, 0), H - 1) * picPitch;
-      n0 = *reinterpret_cast<const unsigned*>(row);
-      n1 = *reinterpret_cast<const unsigned*>(row + 4);
-      yIn += 8;
-    };
-    load_rows();
-    const unsigned tOff = (unsigned)((2 * w) * 128 + g * 16 + 4 * t);   // + fx * 1024 + nt * 128 + slot * T_KB_BYTES
     for (int bi = 0; bi < n; ++bi) {
       const int b = blkBegin + b0 + bi;
-      while (kbNext <= 4 * b + 5) {                   // six tiles for the first block of a segment, four afterwards
-        const unsigned w0 = __byte_perm(n0, n1, selA), w1 = __byte_perm(n0, n1, selB);
-        load_rows();
-        const unsigned slotOff = (unsigned)(kbNext & (KBS - 1)) * T_KB_BYTES + tOff;
+      // horizontal stage: k-blocks kbNext .. 4b+5 (six for the first block of a segment, four afterwards), this warp the
+      // ones of its parity; all their rows are requested before the first is used
+      const int kbEnd = 4 * b + 6;
+      const int kb0 = kbNext + ((kbNext ^ wh) & 1);   // first k-block of this warp's parity
+      unsigned ra[3], rb[3];
 #pragma unroll
-        for (int fx = 0; fx < 4; ++fx) {
-          int d[4];
-          k1m::imma_c(d, A1[fx], w0, w1, 0x54342000);
-          const unsigned o = slotOff + fx * 1024;
-          *reinterpret_cast<unsigned*>(sTlo + o) = __byte_perm(d[0], d[1], 0x6420);
-          *reinterpret_cast<unsigned*>(sTlo + o + 128) = __byte_perm(d[2], d[3], 0x6420);
-          *reinterpret_cast<unsigned*>(sThi + o) = k1m::hsub2u(__byte_perm(d[0], d[1], 0x7531), 0x54005400u);
-          *reinterpret_cast<unsigned*>(sThi + o + 128) = k1m::hsub2u(__byte_perm(d[2], d[3], 0x7531), 0x54005400u);
+      for (int j = 0; j < 3; ++j) {
+        const int kb = kb0 + 2 * j;
+        if (kb < kbEnd) {
+          const uint8_t* row = colp + (size_t)min(max(8 * kb - 3 + g - M, 0), H - 1) * picPitch;
+          ra[j] = *reinterpret_cast<const unsigned*>(row);
+          rb[j] = *reinterpret_cast<const unsigned*>(row + 4);
         }
-        ++kbNext;
       }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int kb = kb0 + 2 * j;
+        if (kb < kbEnd) {
+          const unsigned w0 = __byte_perm(ra[j], rb[j], selA), w1 = __byte_perm(ra[j], rb[j], selB);
+          const unsigned slotOff = (unsigned)(kb & (KBS - 1)) * T_KB_BYTES + tOff;
+#pragma unroll
+          for (int fx = 0; fx < 4; ++fx) {
+            int d[4];
+            k1m::imma_c(d, A1[fx], w0, w1, 0x54342000);
+            const unsigned o = slotOff + fx * 1024;
+            *reinterpret_cast<unsigned*>(sTlo + o) = __byte_perm(d[0], d[1], 0x6420);
+            *reinterpret_cast<unsigned*>(sTlo + o + 128) = __byte_perm(d[2], d[3], 0x6420);
+            *reinterpret_cast<unsigned*>(sThi + o) = k1m::hsub2u(__byte_perm(d[0], d[1], 0x7531), 0x54005400u);
+            *reinterpret_cast<unsigned*>(sThi + o + 128) = k1m::hsub2u(__byte_perm(d[2], d[3], 0x7531), 0x54005400u);
+          }
+        }
+      }
+      kbNext = kbEnd;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();   // T tiles of this block are in shared memory; the previous block's slab has been stored
+      const unsigned tmem = s_tmem;
       if (tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -691,12 +698,13 @@ k1_interp_umma(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int 
         parity ^= 1;
       }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // epilogue: TMEM lane = phase w, row `lane`; columns fx * 64 + x
+      // epilogue: TMEM lane = (phase ws, row `lane`); columns fx * 64 + x; this warp takes fx = 2 wh, 2 wh + 1
 #pragma unroll 1
-      for (int q = 0; q < 8; ++q) {   // q = fx * 2 + half: 32 adjacent pixels of plane (w, fx), row lane
+      for (int qq = 0; qq < 4; ++qq) {   // q = fx * 2 + half: 32 adjacent pixels of plane (ws, fx), row lane
+        const int q = 4 * wh + qq;
         unsigned v[32];
-        tmem_ld32(tmem + ((unsigned)(32 * w) << 16) + q * 32, v);
-        const int p = w * 4 + (q >> 1);
+        tmem_ld32(tmem + ((unsigned)(32 * ws) << 16) + q * 32, v);
+        const int p = ws * 4 + (q >> 1);
         uint8_t* row = sSlab + (p * BR + lane) * BWU;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -715,20 +723,26 @@ k1_interp_umma(const uint8_t* __restrict__ pic, int picPitch, int W, int H, int 
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();   // slab complete, TMEM drained
       {
-        const int c = tid & 3, r = (tid >> 2) & 31;
+        const int c = tid & 3, r = (tid >> 2) & 31, ph = tid >> 7;   // 256 threads: planes ph, ph + 2, ...
         const int y = BR * b + r, x = cb * BWU + c * 16;
         if (y < Hp && x < Wp) {
-          const uint8_t* src = sSlab + r * BWU + ((c ^ ((r >> 1) & 3)) << 4);
-          uint8_t* dst = planes + (size_t)y * pitch + x;
-#pragma unroll 4
-          for (int pl = 0; pl < 16; ++pl)
-            *reinterpret_cast<uint4*>(dst + pl * planeBytes) = *reinterpret_cast<const uint4*>(src + pl * (BR * BWU));
+          const uint8_t* src = sSlab + (ph * BR + r) * BWU + ((c ^ ((r >> 1) & 3)) << 4);
+          uint8_t* dst = planes + ph * planeBytes + (size_t)y * pitch + x;
+          uint4 vv[8];
+#pragma unroll
+          for (int pl = 0; pl < 8; ++pl) vv[pl] = *reinterpret_cast<const uint4*>(src + pl * (2 * BR * BWU));
+#pragma unroll
+          for (int pl = 0; pl < 8; ++pl) *reinterpret_cast<uint4*>(dst + (size_t)(2 * pl) * planeBytes) = vv[pl];
         }
       }
     }
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+  if (w == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(TMEM_COLS));
+  }
 }
 
 }  // namespace k1u

@@ -77,7 +77,8 @@ typedef struct fme_config {
                            FME_K2_PATH_AUTO (0, the fastest measured), _SWAR, _MMA_PACK, _MMA_GROUP */
   int32_t k1Path;       /* how K1 builds the 16 sub-pel planes; both paths are bit-identical: FME_K1_PATH_AUTO (0, the
                            fastest measured), _DP4A (integer dot products on the CUDA cores), _MMA (both filter stages
-                           as exact fp16-in / fp32-accumulate mma.sync products against Toeplitz tap matrices) */
+                           as exact mma.sync products against Toeplitz tap matrices), _UMMA (experimental: the vertical
+                           stage on tcgen05.mma with the accumulator in TMEM; never picked by AUTO) */
   int32_t reserved[3];
 } fme_config;
 #define FME_K1_PATH_AUTO 0

@@ -1161,8 +1161,8 @@ def test_error_behaviour_of_the_round2_entry_points(small):
 @pytest.mark.gpu
 @pytest.mark.parametrize("size,margin", [((424, 248), 80), ((136, 72), 16), ((1920, 1080), 80), ((72, 64), 32), ((64, 64), 16)])
 def test_k1_tensor_path_equals_dp4a_path(size, margin, orc):
-    """The two plane builders behind fme_config.k1Path (dp4a on the CUDA cores; IMMA + HMMA Toeplitz products with the
-    FFMA floor/clip epilogue) must give the same 16 planes byte for byte -- on content that saturates the clip and the
+    """The plane builders behind fme_config.k1Path (dp4a on the CUDA cores; IMMA + HMMA Toeplitz products with the
+    FFMA floor/clip epilogue; the same with the vertical stage on tcgen05.mma / TMEM) must give the same 16 planes byte for byte -- on content that saturates the clip and the
     15-bit intermediate, on widths whose padded row ends in half a 16-byte chunk (424 + 160, 72 + 64), on the smallest
     picture; three planes are also checked against the oracle."""
     W, H = size
@@ -1171,13 +1171,14 @@ def test_k1_tensor_path_equals_dp4a_path(size, margin, orc):
     pic[: H // 3] = np.where(rng.integers(0, 2, (H // 3, W)) > 0, 255, 0)          # full-swing noise: overshoot both ways
     pic[H // 3: H // 2, : W // 2] = (np.indices((H // 2 - H // 3, W // 2)).sum(0) % 2 * 255)
     planes = {}
-    for path in (fme.K1_PATH_DP4A, fme.K1_PATH_MMA):
+    for path in (fme.K1_PATH_DP4A, fme.K1_PATH_MMA, fme.K1_PATH_UMMA):
         eng = fme.Fme(W, H, num_ref_slots=1, max_pus=16, margin=margin, k1_path=path)
         eng.upload_ref(0, pic)
         planes[path] = [eng.download_plane(0, k // 4, k % 4) for k in range(16)]
         eng.close()
     for k in range(16):
         np.testing.assert_array_equal(planes[fme.K1_PATH_DP4A][k], planes[fme.K1_PATH_MMA][k], err_msg="plane %d" % k)
+        np.testing.assert_array_equal(planes[fme.K1_PATH_DP4A][k], planes[fme.K1_PATH_UMMA][k], err_msg="plane %d (tcgen05)" % k)
     if W * H <= 424 * 248:
         padded = ob.pad_plane(pic, margin + 8)
         S = padded.shape[1]
@@ -1200,8 +1201,9 @@ def test_k1_tensor_path_row_ranges_and_bad_path():
     full.upload_ref_device_u8(0, d.data_ptr(), W)
     want = [full.download_plane(0, k // 4, k % 4) for k in (0, 5, 10, 15)]
     full.close()
-    for r0, r1 in ((0, H), (37, 101), (-M, 3), (H - 5, H + M)):
-        eng = fme.Fme(W, H, num_ref_slots=1, max_pus=16, k1_path=fme.K1_PATH_MMA)
+    for path, (r0, r1) in [(fme.K1_PATH_MMA, rr) for rr in ((0, H), (37, 101), (-M, 3), (H - 5, H + M))] + \
+                          [(fme.K1_PATH_UMMA, rr) for rr in ((37, 101), (H - 5, H + M))]:
+        eng = fme.Fme(W, H, num_ref_slots=1, max_pus=16, k1_path=path)
         eng.upload_ref_device_u8_rows(0, d.data_ptr(), W, r0, r1)
         lo, hi = max(r0 + M, 0), min(r1 + M, H + 2 * M)
         for j, k in enumerate((0, 5, 10, 15)):
@@ -1209,7 +1211,7 @@ def test_k1_tensor_path_row_ranges_and_bad_path():
             np.testing.assert_array_equal(got[lo:hi], want[j][lo:hi], err_msg="rows %d..%d plane %d" % (r0, r1, k))
         eng.close()
     with pytest.raises(fme.FmeError):
-        fme.Fme(W, H, k1_path=3)
+        fme.Fme(W, H, k1_path=4)
 
 
 @pytest.mark.gpu
