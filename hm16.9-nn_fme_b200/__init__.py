@@ -22,7 +22,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FME_B200_LIB") or os.path.join(PKG_DIR, "libfme_b200.so")
 
 MODE_STD, MODE_NN, MODE_BOTH = 1, 2, 3
-K2_PATH_AUTO, K2_PATH_SWAR, K2_PATH_MMA_PACK, K2_PATH_MMA_GROUP = 0, 1, 2, 3
+K2_PATH_AUTO, K2_PATH_SWAR, K2_PATH_MMA_PACK, K2_PATH_MMA_GROUP, K2_PATH_UMMA = 0, 1, 2, 3, 4
 K1_PATH_AUTO, K1_PATH_DP4A, K1_PATH_MMA, K1_PATH_UMMA = 0, 1, 2, 3
 PU_LOSSLESS, PU_ERR_ON_GPU, PU_BI = 0x01, 0x02, 0x04
 CAND_SAD = 0x08

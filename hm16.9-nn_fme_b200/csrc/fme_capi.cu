@@ -269,7 +269,7 @@ int fme_create(const fme_config* cfg, fme_ctx** out) {
   if (cfg->bitDepth != 8) return fail(FME_ERR_INVALID, "frame-level passes support bitDepth 8 only");
   if (cfg->numRefSlots < 1 || cfg->numRefSlots > 64) return fail(FME_ERR_INVALID, "numRefSlots out of range");
   if (cfg->maxPUs < 1) return fail(FME_ERR_INVALID, "maxPUs must be positive");
-  if (cfg->k2Path < FME_K2_PATH_AUTO || cfg->k2Path > FME_K2_PATH_MMA_GROUP) return fail(FME_ERR_INVALID, "k2Path out of range");
+  if (cfg->k2Path < FME_K2_PATH_AUTO || cfg->k2Path > FME_K2_PATH_UMMA) return fail(FME_ERR_INVALID, "k2Path out of range");
   if (cfg->k1Path < FME_K1_PATH_AUTO || cfg->k1Path > FME_K1_PATH_UMMA) return fail(FME_ERR_INVALID, "k1Path out of range");
 
   int nDev = 0;

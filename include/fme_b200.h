@@ -74,7 +74,7 @@ typedef struct fme_config {
   int32_t biPred;       /* 1: serve FME_PU_BI records with a second binning + refinement pass per submit (random
                            access configurations); 0 (default): such records are rejected / left untouched */
   int32_t k2Path;       /* how K2 computes the 8x8 SATD of uni-prediction Hadamard PUs; all paths are bit-identical:
-                           FME_K2_PATH_AUTO (0, the fastest measured), _SWAR, _MMA_PACK, _MMA_GROUP */
+                           FME_K2_PATH_AUTO (0, the fastest measured), _SWAR, _MMA_PACK, _MMA_GROUP, _UMMA */
   int32_t k1Path;       /* how K1 builds the 16 sub-pel planes; both paths are bit-identical: FME_K1_PATH_AUTO (0, the
                            fastest measured), _DP4A (integer dot products on the CUDA cores), _MMA (both filter stages
                            as exact mma.sync products against Toeplitz tap matrices), _UMMA (experimental: the vertical
@@ -89,6 +89,7 @@ typedef struct fme_config {
 #define FME_K2_PATH_SWAR 1      /* carry-tolerant 16-bit SWAR Hadamard in registers */
 #define FME_K2_PATH_MMA_PACK 2  /* fp16-in / fp32-accumulate mma.sync Hadamard inside the 32-lane packs */
 #define FME_K2_PATH_MMA_GROUP 3 /* the same on eight-tile groups x four candidates per evaluation */
+#define FME_K2_PATH_UMMA 4      /* tcgen05.mma kind::i8 (u8 pixels x +-1 Hadamard matrix -> s32 in TMEM), one row per tile-candidate */
 
 /* One PU's integer-ME hand-off: what xMotionEstimation has in hand at
  * TEncSearch.cpp:4534 / 4541.  err[] is the raster 3x3 integer error grid [TL,T,TR,L,C,R,BL,B,BR]:

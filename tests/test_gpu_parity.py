@@ -266,7 +266,7 @@ def test_full_416x240_list_vs_oracle(use_had):
         eng.close()
 
 
-@pytest.mark.parametrize("k2_path", [fme.K2_PATH_SWAR, fme.K2_PATH_MMA_PACK, fme.K2_PATH_MMA_GROUP])
+@pytest.mark.parametrize("k2_path", [fme.K2_PATH_SWAR, fme.K2_PATH_MMA_PACK, fme.K2_PATH_MMA_GROUP, fme.K2_PATH_UMMA])
 def test_k2_paths_bit_identical_vs_oracle(k2_path):
     """fme_config.k2Path: the SWAR integer Hadamard and the two fp16-in / fp32-accumulate tensor-pipe formulations must
     give the reference's costs and vectors bit for bit (TComRdCost.cpp:1330-1425), on every HEVC PU shape (AMP

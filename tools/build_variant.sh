@@ -10,7 +10,7 @@ src=$root/hm16.9-nn_fme_b200/csrc
 out=$root/variants; obj=$root/variants/obj_$name
 mkdir -p "$obj"
 arch="-gencode arch=compute_100a,code=sm_100a"
-for f in fme_capi k1_interp k2_refine k3_nn k_misc; do
+for f in fme_capi k1_interp k2_refine k2_umma k3_nn k_misc; do
   nvcc $arch -O3 -std=c++17 -lineinfo -Xcompiler -fPIC $extra -c $src/$f.cu -o $obj/$f.o &
 done
 wait
