@@ -10,7 +10,7 @@ namespace {
 #define FME_K2_WARPS 12
 #endif
 constexpr int K2_WARPS = FME_K2_WARPS;
-constexpr int K2_STAGE_BYTES = 10496;  // two staging buffers of max P*(h+1)*RW + 16 bytes (64x64: 65*80 = 5200)
+constexpr int K2_STAGE_BYTES = 10496;  // two staging buffers of max P*(h+1)*RW + 16 bytes (64x64: 65*80 = 5200; 8x8: 32*152 = 4864)
 constexpr int K2_ORG2_BYTES = 2048;    // second source tile of every lane for PUs with more than 32 tiles (8 rows x 32 lanes x 8 B)
 constexpr int K2_SMEM_PER_WARP = K2_STAGE_BYTES + K2_ORG2_BYTES;
 

@@ -29,12 +29,32 @@ constexpr int UM_THREADS = (UM_WORKERS + 1) * 32;   // + the issuer warp
 constexpr int UM_A_BYTES = 128 * 64;                // one operand buffer: 128 rows x 64 bytes
 constexpr int UM_OFF_B8 = 0;                        // H8 (x) H8, 64 x 64 s8
 constexpr int UM_OFF_B4 = 4096;                     // diag(H4 (x) H4, H4 (x) H4), 32 x 32 s8
-constexpr int UM_OFF_A = 5120;                      // two candidate buffers (rounds alternate)
-constexpr int UM_OFF_ORG = UM_OFF_A + 2 * UM_A_BYTES;      // complemented source tiles: slot 0, slot 1 (units 32.. of big PUs)
-constexpr int UM_OFF_STAGE = UM_OFF_ORG + 2 * UM_A_BYTES;  // per worker warp: the two staging buffers of k2_pack
+#ifndef FME_UM_DEPTH
+#define FME_UM_DEPTH 2
+#endif
+constexpr int UM_DEPTH = FME_UM_DEPTH;              // rounds in flight per CTA: candidate buffers, accumulators, mbarrier pairs
+static_assert(UM_DEPTH == 2 || UM_DEPTH == 4, "UM_DEPTH must be 2 or 4 (TMEM allocations are powers of two)");
+constexpr int UM_OFF_A = 5120;                      // UM_DEPTH candidate buffers (round r uses buffer r % UM_DEPTH)
+constexpr int UM_OFF_ORG = UM_OFF_A + UM_DEPTH * UM_A_BYTES;  // complemented source tiles (units 0..31 of every PU)
+// The second source tile of the PUs with more than 32 units (64x64, 64x48, 48x64) is parked in candidate buffer 1; packs of
+// those shapes run one round at a time through candidate buffer 0 (the other CTAs of the SM cover the latency).
+constexpr int UM_OFF_STAGE = UM_OFF_ORG + UM_A_BYTES;      // per worker warp: the two staging buffers of k2_pack
 constexpr int UM_SMEM = UM_OFF_STAGE + UM_WORKERS * K2_STAGE_BYTES;
-constexpr int UM_TMEM_COLS = 128;                   // two accumulators of 64 columns
-constexpr unsigned UM_CMD_QUIT = 1u, UM_CMD_TS4 = 2u, UM_CMD_SLOT1 = 4u;
+constexpr int UM_CTAS_PER_SM = UM_DEPTH == 2 ? 3 : 2;   // by shared memory (3 x 77 KB) and TMEM columns
+constexpr int UM_TMEM_COLS = 64 * UM_DEPTH;         // UM_DEPTH accumulators of 64 columns
+// round command: what the issuing thread multiplies (candidate buffer = round % UM_DEPTH unless _BUF0; source rows from
+// the source area unless _ORG_IN_BUF1)
+constexpr unsigned UM_CMD_QUIT = 1u, UM_CMD_TS4 = 2u, UM_CMD_BUF0 = 4u, UM_CMD_ORG_IN_BUF1 = 8u;
+// table index of the q-th candidate a pack evaluates: the half-pel candidates in staging order (c_stepFirst / c_stepCount:
+// H0 | H3 H4 | H1 H2 | H5..H8), then Q1..Q8
+__constant__ int8_t c_seqI[17] = {0, 3, 4, 1, 2, 5, 6, 7, 8, 1, 2, 3, 4, 5, 6, 7, 8};
+// the q-th candidate's offset (ox, oy) in {-1, 0, 1}^2 (c_refineH for q < 9, c_refineQ afterwards), as the two PRMT
+// selectors that pick byte ox + 1 of bitsX and byte oy + 1 of bitsY: 0x444b | 0x444b << 16
+#define UM_SEL(ox, oy) (0x4440u | (unsigned)((ox) + 1) | ((0x4440u | (unsigned)((oy) + 1)) << 16))
+__constant__ unsigned c_seqSel[17] = {
+    UM_SEL(0, 0), UM_SEL(-1, 0), UM_SEL(1, 0), UM_SEL(0, -1), UM_SEL(0, 1), UM_SEL(-1, -1), UM_SEL(1, -1), UM_SEL(-1, 1), UM_SEL(1, 1),
+    UM_SEL(0, -1), UM_SEL(0, 1), UM_SEL(-1, -1), UM_SEL(1, -1), UM_SEL(-1, 0), UM_SEL(1, 0), UM_SEL(-1, 1), UM_SEL(1, 1)};
+#undef UM_SEL
 
 __device__ __forceinline__ uint64_t um_desc(unsigned addr, unsigned lboBytes, unsigned sboBytes) {
   // SWIZZLE_NONE, K-major: core matrix = 8 rows x 16 bytes, stored as 128 contiguous bytes; LBO = distance between the
@@ -73,37 +93,54 @@ __device__ __forceinline__ unsigned lds32(unsigned sa) {
   return v;
 }
 
+// Optional phase timers (-DFME_UM_PROF, tools/um_prof.py): clock64 deltas of lane 0 of every worker warp, summed per phase.
+#ifdef FME_UM_PROF
+__device__ unsigned long long g_umProf[16];
+#define UM_PROF_DECL long long umT = clock64();
+#define UM_PROF(k) { const long long umN = clock64(); um.prof[k] += umN - umT; umT = umN; }
+#else
+#define UM_PROF_DECL
+#define UM_PROF(k)
+#endif
+enum { UMP_SETUP, UMP_STAGE_ISSUE, UMP_STAGE_WAIT, UMP_DONE_WAIT, UMP_COLLECT, UMP_BOOK, UMP_REPACK, UMP_SUBMIT, UMP_SCHED, UMP_TOTAL, UMP_N };
+
 // What a worker warp needs of its CTA's tensor-path state.
 struct UmCtx {
   unsigned aAddr;     // shared address of candidate buffer 0 (+ UM_A_BYTES: buffer 1)
-  unsigned orgAddr;   // shared address of source slot 0 (+ UM_A_BYTES: slot 1)
-  unsigned full0;     // mbarrier "rows of round r written" (one arrival per worker warp), + 8: odd rounds
-  unsigned done0;     // mbarrier "MMAs of round r complete" (tcgen05.commit), + 8: odd rounds
+  unsigned orgAddr;   // shared address of the source rows
+  unsigned full0;     // mbarrier "rows of round r written" (one arrival per worker warp), + 8 * (r % UM_DEPTH)
+  unsigned done0;     // mbarrier "MMAs of round r complete" (tcgen05.commit), + 8 * (r % UM_DEPTH)
   unsigned tmem;      // TMEM base address of the CTA's 128 columns
-  volatile unsigned* cmd;  // [2] what the issuer runs for an even / odd round (written by warp 0)
+  volatile unsigned* cmd;  // [UM_DEPTH] what the issuer runs for round r % UM_DEPTH (written by warp 0)
   unsigned round;     // rounds submitted so far (identical in all worker warps and in the issuer)
+  unsigned* sadFifo;  // [UM_DEPTH][128] per-thread SAD of the rounds in flight (lossless PUs)
+#ifdef FME_UM_PROF
+  long long prof[UMP_N];
+#endif
 };
 
 // This thread's operand rows of the current round are in shared memory: make them visible to the async proxy and count
-// the warp in.  Returns the round's index.
-__device__ __forceinline__ unsigned um_submit(UmCtx& um, unsigned cmd, int warp, int lane) {
+// the warp in (the issuer warp's lane 0 waits for the four arrivals).  A dedicated issuer beats lane 0 of warp 0 doing
+// the issue itself (1.21 against 1.31 ms per 1080p frame): the worker goes straight on to the next candidate.
+__device__ __forceinline__ void um_submit(UmCtx& um, unsigned cmd, int warp, int lane) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncwarp();
   const unsigned r = um.round++;
   if (lane == 0) {
-    if (warp == 0) um.cmd[r & 1] = cmd;
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(um.full0 + 8 * (r & 1)) : "memory");
+    if (warp == 0) um.cmd[r % UM_DEPTH] = cmd;
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(um.full0 + 8 * (r % UM_DEPTH)) : "memory");
   }
-  return r;
 }
 
 // Rounded SATD of this thread's row of round r: (sum |coef| + 2) >> 2 for an 8x8 tile (TComRdCost.cpp:1421),
 // (sum + 1) >> 1 per 4x4 tile (:1325), summed over the pair.
 template <int TS>
-__device__ __forceinline__ unsigned um_collect(const UmCtx& um, unsigned r, int warp) {
-  um_mbar_wait(um.done0 + 8 * (r & 1), (r >> 1) & 1);
+__device__ __forceinline__ unsigned um_collect(UmCtx& um, unsigned r, int warp) {
+  UM_PROF_DECL
+  um_mbar_wait(um.done0 + 8 * (r % UM_DEPTH), (r / UM_DEPTH) & 1);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const unsigned ta = um.tmem + ((unsigned)(32 * warp) << 16) + (r & 1) * 64;
+  UM_PROF(UMP_DONE_WAIT)
+  const unsigned ta = um.tmem + ((unsigned)(32 * warp) << 16) + (r % UM_DEPTH) * 64;
   unsigned s = 0;
   if constexpr (TS == 8) {
     int v0[32], v1[32];
@@ -126,26 +163,37 @@ __device__ __forceinline__ unsigned um_collect(const UmCtx& um, unsigned r, int 
     for (int j = 0; j < 16; ++j) { s += (unsigned)abs(v[j]); s1 += (unsigned)abs(v[16 + j]); }
     s = ((s + 1) >> 1) + ((s1 + 1) >> 1);
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // D[r & 1] is free once every warp has counted in again
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // this accumulator is free once every warp has counted in again
+  UM_PROF(UMP_COLLECT)
   return s;
 }
 
-// One 8x8 candidate tile from a staged region into this thread's operand row (chunk kc = tile rows 2 kc, 2 kc + 1).
-__device__ __forceinline__ void um_repack8(const uint8_t* cand, int pitch, unsigned dst) {
-  const CandTile ct = cand_tile(cand, pitch);
+// One 8x8 candidate tile from a staged region (shared address of its first byte, row pitch a multiple of 4) into this
+// thread's operand row: chunk kc = tile rows 2 kc, 2 kc + 1.  Rows are read as aligned words and funnel-shifted.
+__device__ __forceinline__ void um_repack8(unsigned cand, int pitch, unsigned dst) {
+  const unsigned sh = (cand & 3u) * 8u;
+  unsigned p = cand & ~3u;
 #pragma unroll
   for (int kc = 0; kc < 4; ++kc) {
-    unsigned a0, a1, b0, b1;
-    cand_row8(ct, 2 * kc, a0, a1);
-    cand_row8(ct, 2 * kc + 1, b0, b1);
-    sts128(dst + kc * 2048, a0, a1, b0, b1);
+    const unsigned w0 = lds32(p), w1 = lds32(p + 4), w2 = lds32(p + 8);
+    p += pitch;
+    const unsigned x0 = lds32(p), x1 = lds32(p + 4), x2 = lds32(p + 8);
+    p += pitch;
+    sts128(dst + kc * 2048, __funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(x0, x1, sh),
+           __funnelshift_r(x1, x2, sh));
   }
 }
-// A pair of 4x4 candidate tiles: chunk 0 = first tile, chunk 1 = second tile.
-__device__ __forceinline__ void um_repack4(const uint8_t* cand, int pitch, int tile1Off, unsigned dst) {
-  const CandTile c0 = cand_tile(cand, pitch), c1 = cand_tile(cand + tile1Off, pitch);
-  sts128(dst, cand_row4(c0, 0), cand_row4(c0, 1), cand_row4(c0, 2), cand_row4(c0, 3));
-  sts128(dst + 2048, cand_row4(c1, 0), cand_row4(c1, 1), cand_row4(c1, 2), cand_row4(c1, 3));
+// A 4x4 candidate tile -> one 16-byte chunk.
+__device__ __forceinline__ void um_repack4(unsigned cand, int pitch, unsigned dst) {
+  const unsigned sh = (cand & 3u) * 8u;
+  unsigned p = cand & ~3u;
+  unsigned v[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    v[r] = __funnelshift_r(lds32(p), lds32(p + 4), sh);
+    p += pitch;
+  }
+  sts128(dst, v[0], v[1], v[2], v[3]);
 }
 
 // One pack on worker warp `warp` (count <= 0: the warp has no PUs in this CTA pack and only keeps the rounds in step).
@@ -155,6 +203,7 @@ __device__ __noinline__ void k2_pack_umma(const ClassInfo ci, const int* __restr
                                           const uint8_t* __restrict__ planes, const uint8_t* __restrict__ org,
                                           const FmeGeom& g, const uint32_t* __restrict__ costLut, uint8_t* smem, UmCtx& um,
                                           int warp) {
+  UM_PROF_DECL
   const int lane = threadIdx.x & 31;
   const int w = ci.w, h = ci.h;
   const int U = ci.units;
@@ -263,7 +312,7 @@ __device__ __noinline__ void k2_pack_umma(const ClassInfo ci, const int* __restr
         const int ty = u / ci.tilesX, tx = u - ty * ci.tilesX;
         uOff2 = ty * 8 * sg.RW + tx * 8;
         const uint8_t* src = org + (size_t)(oy + ty * 8) * gOrgPitch + ox + tx * 8;
-        const unsigned dst = um.orgAddr + UM_A_BYTES + rowOff;
+        const unsigned dst = um.aAddr + UM_A_BYTES + rowOff;
 #pragma unroll
         for (int kc = 0; kc < 4; ++kc) {
           unsigned a0, a1, b0, b1;
@@ -287,7 +336,7 @@ __device__ __noinline__ void k2_pack_umma(const ClassInfo ci, const int* __restr
         d = sad8x8(row, regionCand + uOff, sg.RW);
       }
       if (uOn2) {
-        const unsigned so = um.orgAddr + UM_A_BYTES + rowOff;
+        const unsigned so = um.aAddr + UM_A_BYTES + rowOff;
         auto row = [&](int r, unsigned& lo, unsigned& hi) {
           lo = ~lds32(so + (r >> 1) * 2048 + (r & 1) * 8);
           hi = ~lds32(so + (r >> 1) * 2048 + (r & 1) * 8 + 4);
@@ -313,88 +362,122 @@ __device__ __noinline__ void k2_pack_umma(const ClassInfo ci, const int* __restr
     bitsX |= (unsigned)golomb_bits((((mvIntX << 1) + (t - 1)) << 1) - predX) << (8 * t);
     bitsY |= (unsigned)golomb_bits((((mvIntY << 1) + (t - 1)) << 1) - predY) << (8 * t);
   }
-  // the round in flight: 0 none, 1 a whole candidate, 2 first unit of a big PU's candidate, 3 its second unit
-  int pKind = 0, pI = 0, pBits = 0;
-  bool pHalf = false;
-  unsigned pRound = 0, pPartial = 0, pSad = 0;
+  // Rounds are retired in submission order, up to UM_DEPTH - 1 rounds after their submission.  What a retiring round was
+  // follows from its sequence number in the pack: candidate q (half-pel candidates in staging order, then Q1..Q8), and for
+  // the big PUs the unit (even rounds: units 0..31, odd rounds: units 32..).  The MV bits are recomputed at retirement
+  // (the per-axis bit counts of the half-pel stage are replaced only after the stage has drained).
+  int sub = 0, ret = 0;                 // rounds of this pack submitted / retired
+  const unsigned round0 = um.round;     // CTA round index of the pack's first round
+  unsigned pPartial = 0;
+  unsigned* const sadFifo = um.sadFifo + (warp * 32 + lane);   // [UM_DEPTH][128]: SAD of lossless PUs' units per round
   auto retire = [&]() {
-    if (pKind == 0) return;
-    const unsigned d = um_collect<TS>(um, pRound, warp);
-    if (pKind == 2) {
+    const int q = twoUnits ? ret >> 1 : ret;
+    const bool second = twoUnits && (ret & 1);
+    const unsigned d = um_collect<TS>(um, round0 + ret, warp);
+#ifdef FME_UM_PROF
+    umT = clock64();
+#endif
+    const int slot = ret % UM_DEPTH;
+    ++ret;
+    if (twoUnits && !second) {
       pPartial = uOn ? d : 0u;
-      pKind = 0;
       return;
     }
-    unsigned dist = pKind == 3 ? pPartial + (uOn2 ? d : 0u) : (uOn ? d : 0u);
-    if (anyLossless && !had) dist = pSad;   // lossless PUs: SAD (TEncSearch.cpp:5258)
+    const bool half = q < 9;
+    const int i = c_seqI[q];
+    const unsigned sel = c_seqSel[q];
+    const int bits = (int)(__byte_perm(bitsX, 0, sel) + __byte_perm(bitsY, 0, sel >> 16));
+    unsigned dist = second ? pPartial + (uOn2 ? d : 0u) : (uOn ? d : 0u);
+    if (anyLossless && !had) dist = sadFifo[slot * 128];   // lossless PUs: SAD (TEncSearch.cpp:5258)
     if (lanesPerPu == 32) dist = __reduce_add_sync(0xffffffffu, dist);
     else for (int dd = lanesPerPu >> 1; dd > 0; dd >>= 1) dist += __shfl_xor_sync(0xffffffffu, dist, dd);
     if (laneActive) {
-      dist += costLut[pBits];
-      if (pHalf) {
-        if (dist < hBest || (dist == hBest && pI < hBestI)) { hBest = dist; hBestI = pI; }
+      dist += costLut[bits];
+      if (half) {
+        if (dist < hBest || (dist == hBest && i < hBestI)) { hBest = dist; hBestI = i; }
       } else if (dist < qBest) {
         qBest = dist;
-        qBestI = pI;
+        qBestI = i;
       }
     }
-    pKind = 0;
+    UM_PROF(UMP_BOOK)
+  };
+  // submit the rows this thread has just written as the pack's next round
+  auto submit = [&](unsigned cmd, unsigned sadNow) {
+    if (anyLossless) sadFifo[(sub % UM_DEPTH) * 128] = sadNow;   // read back by this thread only
+    UM_PROF(UMP_REPACK)
+    um_submit(um, cmd, warp, lane);
+    ++sub;
+    UM_PROF(UMP_SUBMIT)
+  };
+  // before writing the rows of a new round: its buffer's previous round (UM_DEPTH rounds ago) must have been retired
+  const int depth = twoUnits ? 1 : UM_DEPTH;
+  auto makeRoom = [&]() {
+    UM_PROF(UMP_BOOK)
+    if (sub - ret == depth) retire();
   };
 
+  // shared address of this lane's unit inside its PU's region of staging buffer A; half-pel candidates sit at (1, 1) of
+  // the region (origin X - 1, Y - 1), minus one sample / one row for the offsets -1
+  const unsigned regionSA0 = (unsigned)__cvta_generic_to_shared(smem) + myPu * sg.RB + uOff;
+  const int halfOff = sg.RW + ((alignX - 1) & (A - 1)) + 1;
+  int cq = 0;   // sequence number of the next candidate
+  UM_PROF(UMP_SETUP)
 #pragma unroll 1
   for (int s = 0; s < 12; ++s) {
     const bool prefetch = (s != 3) && (s != 11);
     if (prefetch) {
       stage(s + 1);
+      UM_PROF(UMP_STAGE_ISSUE)
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
     __syncwarp();
-    const uint8_t* region = ((s & 1) ? bufB : bufA) + myPu * sg.RB;
-    const int iFirst = c_stepFirst[s], iCount = c_stepCount[s];
+    UM_PROF(UMP_STAGE_WAIT)
+    const unsigned regionSA = regionSA0 + ((s & 1) ? bufBytes : 0);   // shared address of this lane's unit in the region
+    const int iCount = c_stepCount[s];
 #pragma unroll 1
-    for (int c = 0; c < iCount; ++c) {
-      const int i = iFirst + c;
-      int candOff, ox3, oy3;
+    for (int c = 0; c < iCount; ++c, ++cq) {
+      int candOff;   // candidate's first byte relative to the region's
       if (s < 4) {
-        ox3 = c_refineH[i][0]; oy3 = c_refineH[i][1];
-        candOff = (1 + ((2 * oy3) >> 2)) * sg.RW + ((alignX - 1) & (A - 1)) + 1 + ((2 * ox3) >> 2);
+        const unsigned sel = c_seqSel[cq];   // ox + 1 in bits 0-1, oy + 1 in bits 16-17; offsets -1 reach one sample back
+        candOff = halfOff - ((sel & 3u) == 0 ? 1 : 0) - ((sel & 0x30000u) == 0 ? sg.RW : 0);
       } else {
-        ox3 = c_refineQ[i][0]; oy3 = c_refineQ[i][1];
-        const int qx = 2 * bhx + ox3;
+        const int qx = 2 * bhx + (int)(c_seqSel[cq] & 3u) - 1;
         candOff = (alignX + (qx >> 2)) & (A - 1);
       }
-      const int bits = (int)(((bitsX >> (8 * ox3 + 8)) & 0xffu) + ((bitsY >> (8 * oy3 + 8)) & 0xffu));
-      const uint8_t* rc = region + candOff;
+      makeRoom();
       if (uOn) {
-        const unsigned dst = um.aAddr + (um.round & 1) * UM_A_BYTES + rowOff;
-        if constexpr (TS == 8) um_repack8(rc + uOff, sg.RW, dst);
-        else um_repack4(rc + uOff, sg.RW, u1Off, dst);
+        const unsigned dst = um.aAddr + (twoUnits ? 0u : (um.round % UM_DEPTH) * UM_A_BYTES) + rowOff;
+        if constexpr (TS == 8) um_repack8(regionSA + candOff, sg.RW, dst);
+        else {
+          um_repack4(regionSA + candOff, sg.RW, dst);
+          um_repack4(regionSA + candOff + u1Off, sg.RW, dst + 2048);
+        }
       }
       unsigned sadNow = 0;
-      if (anyLossless && laneActive && !had) sadNow = laneSad(rc);
-      const unsigned r0 = um_submit(um, TS == 4 ? UM_CMD_TS4 : 0u, warp, lane);
-      retire();
-      pKind = twoUnits ? 2 : 1; pI = i; pBits = bits; pHalf = s < 4; pRound = r0; pSad = sadNow;
+      if (anyLossless && laneActive && !had) sadNow = laneSad(((s & 1) ? bufB : bufA) + myPu * sg.RB + candOff);
+      submit(TS == 4 ? UM_CMD_TS4 : twoUnits ? UM_CMD_BUF0 : 0u, sadNow);
       if constexpr (TS == 8 && A == 16) {
         if (twoUnits) {
-          if (uOn2) um_repack8(rc + uOff2, sg.RW, um.aAddr + (um.round & 1) * UM_A_BYTES + rowOff);
-          const unsigned r1 = um_submit(um, UM_CMD_SLOT1, warp, lane);
-          retire();   // first unit -> pPartial
-          pKind = 3; pRound = r1;
+          makeRoom();
+          if (uOn2) um_repack8(regionSA + candOff + (uOff2 - uOff), sg.RW, um.aAddr + rowOff);
+          submit(UM_CMD_BUF0 | UM_CMD_ORG_IN_BUF1, sadNow);
         }
       }
     }
     __syncwarp();  // all lanes are done with this buffer before step s+2 overwrites it
+    UM_PROF(UMP_BOOK)
     if (s == 3) {
-      retire();    // the half-pel winner needs every half-pel candidate
+      while (ret < sub) retire();   // the half-pel winner needs every half-pel candidate
       const int bestI = hBestI < 9 ? hBestI : 0;
       bhx = c_refineH[bestI][0];
       bhy = c_refineH[bestI][1];
       qBest = hBest;
       qBestI = 0;
       stage(4);
+      UM_PROF(UMP_STAGE_ISSUE)
       bitsX = bitsY = 0;
 #pragma unroll
       for (int t = 0; t < 3; ++t) {
@@ -403,7 +486,7 @@ __device__ __noinline__ void k2_pack_umma(const ClassInfo ci, const int* __restr
       }
     }
   }
-  retire();
+  while (ret < sub) retire();
 
   if (laneActive && unit0 == 0) {
     fme_result* r = &res[puIdx];
@@ -412,27 +495,25 @@ __device__ __noinline__ void k2_pack_umma(const ClassInfo ci, const int* __restr
     r->cost = qBest;
   }
   __syncwarp();
+  UM_PROF(UMP_BOOK)
 }
 
-__global__ void __launch_bounds__(UM_THREADS, 2)
+__global__ void __launch_bounds__(UM_THREADS, UM_CTAS_PER_SM)
 k2_refine_umma(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, const uint8_t* __restrict__ planes,
                const uint8_t* __restrict__ org, const FmeGeom g, const FmeCostLut costLutG, const int* __restrict__ order,
                const int* __restrict__ classOffset, const int* __restrict__ packOffset, int* __restrict__ workCounter) {
   extern __shared__ __align__(128) uint8_t dynSmem[];
   __shared__ uint32_t s_lut[FME_COST_LUT_SIZE];
   __shared__ int s_packOff[FME_K2_KEYS + 1];
-  __shared__ int s_classOff[FME_K2_KEYS + 1];
-  __shared__ __align__(8) unsigned long long s_full[2], s_done[2];
-  __shared__ unsigned s_cmd[2];
+  __shared__ __align__(8) unsigned long long s_full[UM_DEPTH], s_done[UM_DEPTH];
+  __shared__ unsigned s_cmd[UM_DEPTH];
+  __shared__ unsigned s_sad[UM_DEPTH * 128];
   __shared__ unsigned s_tmem;
   __shared__ int s_next[2];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   for (int i = tid; i < FME_COST_LUT_SIZE; i += UM_THREADS) s_lut[i] = costLutG.v[i];
-  for (int i = tid; i <= FME_K2_KEYS; i += UM_THREADS) {
-    s_packOff[i] = packOffset[i];
-    s_classOff[i] = classOffset[i];
-  }
+  for (int i = tid; i <= FME_K2_KEYS; i += UM_THREADS) s_packOff[i] = packOffset[i];
   // transform matrices in the canonical layout: byte i -> (n, k)
   for (int i = tid; i < 4096; i += UM_THREADS) {
     const int kc = i >> 10, n = ((i & 1023) >> 7) * 8 + ((i & 127) >> 4), k = kc * 16 + (i & 15);
@@ -447,7 +528,7 @@ k2_refine_umma(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, con
   const unsigned full0 = (unsigned)__cvta_generic_to_shared(&s_full[0]), done0 = (unsigned)__cvta_generic_to_shared(&s_done[0]);
   if (tid == 0) {
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < UM_DEPTH; ++b) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8 * b), "r"(UM_WORKERS));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(done0 + 8 * b));
     }
@@ -472,14 +553,14 @@ k2_refine_umma(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, con
       const uint64_t b8lo = um_desc(base + UM_OFF_B8, 1024, 128), b8hi = um_desc(base + UM_OFF_B8 + 2048, 1024, 128);
       const uint64_t b4 = um_desc(base + UM_OFF_B4, 512, 128);
       for (unsigned r = 0;; ++r) {
-        const unsigned b = r & 1;
-        um_mbar_wait(full0 + 8 * b, (r >> 1) & 1);
+        const unsigned b = r % UM_DEPTH;
+        um_mbar_wait(full0 + 8 * b, (r / UM_DEPTH) & 1);
         const unsigned cmd = *reinterpret_cast<volatile unsigned*>(&s_cmd[b]);
         if (cmd & UM_CMD_QUIT) break;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const unsigned d = tmem + b * 64;
-        const unsigned a = base + UM_OFF_A + b * UM_A_BYTES;
-        const unsigned o = base + UM_OFF_ORG + ((cmd & UM_CMD_SLOT1) ? UM_A_BYTES : 0);
+        const unsigned a = base + UM_OFF_A + ((cmd & UM_CMD_BUF0) ? 0u : b * UM_A_BYTES);
+        const unsigned o = (cmd & UM_CMD_ORG_IN_BUF1) ? base + UM_OFF_A + UM_A_BYTES : base + UM_OFF_ORG;
         if (!(cmd & UM_CMD_TS4)) {
           umma_i8(d, um_desc(a, 2048, 128), b8lo, IDESC8, 0);
           umma_i8(d, um_desc(a + 4096, 2048, 128), b8hi, IDESC8, 1);
@@ -502,6 +583,12 @@ k2_refine_umma(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, con
     um.tmem = tmem;
     um.cmd = s_cmd;
     um.round = 0;
+    um.sadFifo = s_sad;
+#ifdef FME_UM_PROF
+    for (int k = 0; k < UMP_N; ++k) um.prof[k] = 0;
+    const long long umStart = clock64();
+    long long umT = umStart;
+#endif
     uint8_t* const smem = dynSmem + UM_OFF_STAGE + warp * K2_STAGE_BYTES;
     const int totalPacks = s_packOff[FME_K2_KEYS];
     for (int it = 0;; ++it) {
@@ -518,10 +605,12 @@ k2_refine_umma(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, con
         }
       }
       const ClassInfo ci = class_info(63 - (v & 63));
-      const int inClass = s_classOff[v + 1] - s_classOff[v];
+      const int classOff = __ldg(classOffset + v);   // (two loads per pack: the table stays out of shared memory)
+      const int inClass = __ldg(classOffset + v + 1) - classOff;
       const int ctaFirst = (pack - s_packOff[v]) * 4 * ci.P;
-      const int first = s_classOff[v] + ctaFirst + warp * ci.P;
+      const int first = classOff + ctaFirst + warp * ci.P;
       const int count = min(ci.P, inClass - ctaFirst - warp * ci.P);   // <= 0: nothing for this warp
+      UM_PROF(UMP_SCHED)
 #define K2U_ARGS ci, order, first, count, pus, res, planes, org, g, s_lut, smem, um, warp
       if (ci.ts == 8) {
         if (ci.w >= 16) k2_pack_umma<8, 16>(K2U_ARGS);
@@ -532,8 +621,15 @@ k2_refine_umma(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, con
         else k2_pack_umma<4, 4>(K2U_ARGS);
       }
 #undef K2U_ARGS
+#ifdef FME_UM_PROF
+      umT = clock64();
+#endif
     }
     um_submit(um, UM_CMD_QUIT, warp, lane);
+#ifdef FME_UM_PROF
+    um.prof[UMP_TOTAL] = clock64() - umStart;
+    if (lane == 0) for (int k = 0; k < UMP_N; ++k) atomicAdd(&g_umProf[k], (unsigned long long)um.prof[k]);
+#endif
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -552,11 +648,24 @@ cudaError_t fme_launch_k2_umma(const FmeGeom& g, const uint8_t* d_planes, const 
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k2_refine_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM);
   if (e != cudaSuccess) return e;
-  int perSM = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k2_refine_umma, UM_THREADS, UM_SMEM) != cudaSuccess || perSM < 1) perSM = 1;
-  if (perSM > 512 / UM_TMEM_COLS) perSM = 512 / UM_TMEM_COLS;   // TMEM columns of an SM
+  e = cudaFuncSetAttribute(k2_refine_umma, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  // UM_CTAS_PER_SM CTAs per SM; the pack hand-out is dynamic, so a CTA that starts late just finds less work
+  const int perSM = UM_CTAS_PER_SM;
   k2_refine_umma<<<numSMs * perSM, UM_THREADS, UM_SMEM, s>>>(d_pus, d_res, d_planes, d_org, g, costLut, sc.order, sc.classOffset,
                                                              sc.packOffset, sc.workCounter);
   ++*launches;
   return cudaGetLastError();
 }
+
+#ifdef FME_UM_PROF
+// Debug build only: phase timers of k2_refine_umma summed over the worker warps since the last call (then reset).
+extern "C" int fme_debug_um_prof(unsigned long long* out, int n) {
+  unsigned long long h[16] = {0}, z[16] = {0};
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(h, g_umProf, sizeof(h)) != cudaSuccess) return -1;
+  cudaMemcpyToSymbol(g_umProf, z, sizeof(z));
+  for (int i = 0; i < n && i < 16; ++i) out[i] = h[i];
+  return UMP_N;
+}
+#endif
