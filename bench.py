@@ -401,6 +401,30 @@ def run_gpu(args):
         k3_fma_ms = f0.elapsed_time(f1) / 8
         fast.close()
 
+    # informational: the same K2 pass on every selectable transform path (fme_config.k2Path; all bit-identical, the headline
+    # uses FME_K2_PATH_AUTO = the fastest measured): SWAR integer, two mma.sync fp16/fp32 formulations, tcgen05 kind::i8
+    k2_paths_ms = None
+    if rank == 0 and world == 1 and not banded and not args.no_k2_paths:
+        k2_paths_ms = {}
+        for pname_, pid in (("swar", fme.K2_PATH_SWAR), ("mma_pack", fme.K2_PATH_MMA_PACK), ("mma_group", fme.K2_PATH_MMA_GROUP),
+                            ("umma_i8", fme.K2_PATH_UMMA)):
+            alt = fme.Fme(width, height, num_ref_slots=N_REFS, max_pus=n_pus, device=local, k2_path=pid)
+            alt.set_stream(stream.cuda_stream)
+            alt.set_slice(lam)
+            alt.upload_org_device_u8(d_org[0].data_ptr(), width)
+            for s_ in range(N_REFS):
+                alt.upload_ref_device_u8(s_, d_refs[0][s_].data_ptr(), width)
+            for _ in range(2):
+                alt.submit_device(d_recs[0].data_ptr(), len(sets[0][2]), d_res.data_ptr(), fme.MODE_STD)
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record(stream)
+            for _ in range(6):
+                alt.submit_device(d_recs[0].data_ptr(), len(sets[0][2]), d_res.data_ptr(), fme.MODE_STD)
+            p1.record(stream)
+            torch.cuda.synchronize(dev)
+            k2_paths_ms[pname_] = p0.elapsed_time(p1) / 6
+            alt.close()
+
     # ---- "next" rows f2 / f3 as batched operators: candidate costs (AMVP template / merge) and compact luma MC ----
     ops = {}
     if not banded:
@@ -470,7 +494,9 @@ def run_gpu(args):
                           "peak": peak, "unit": "GB/s", "frac": gbs(k2_bytes, kavg["k2_refine"]) / peak,
                           "alg_bytes": k2_bytes, "int_ops_per_s": 144.0 * pu_px / (kavg["k2_refine"] * 1e-3) if kavg["k2_refine"] > 0 else 0,
                           "int_lane_rate_frac": (144.0 * pu_px / (kavg["k2_refine"] * 1e-3)) / (148 * 128 * 1.965e9) if kavg["k2_refine"] > 0 else 0,
-                          "note": "issue-bound integer SATD; HBM fraction reported because the contract asks for it"},
+                          "paths_ms": k2_paths_ms,
+                          "note": "issue-bound integer SATD; HBM fraction reported because the contract asks for it; paths_ms = the "
+                                  "same pass (binning included) per fme_config.k2Path, one PU list repeated (warm L2)"},
             "k3_nn": {"ms": kavg["k3_nn"], "bound": "fp32", "achieved": k3_flops / (kavg["k3_nn"] * 1e-3) / 1e12 if kavg["k3_nn"] > 0 else 0,
                       "unit": "TFLOP/s", "ms_opt_in_fma_mode": k3_fma_ms},
         }
@@ -791,6 +817,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="replica", choices=["replica", "banded"])
     ap.add_argument("--no-banded", action="store_true", help="skip the 2160p banded_4k sub-record of the replica run")
+    ap.add_argument("--no-k2-paths", action="store_true", help="skip the informational per-k2Path timing (kernels.k2_refine.paths_ms)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
