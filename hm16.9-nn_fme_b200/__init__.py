@@ -15,7 +15,7 @@ import numpy as np
 
 from . import nn_weights  # noqa: F401  (re-export)
 from . import formats  # noqa: F401
-from .pu_list import PU_DTYPE, HEAD_DTYPE, GRID_DTYPE, RESULT_DTYPE, MC_PU_DTYPE, MC_BI_PU_DTYPE, CAND_DTYPE  # noqa: F401
+from .pu_list import PU_DTYPE, HEAD_DTYPE, GRID_DTYPE, COMPACT_DTYPE, RESULT_DTYPE, MC_PU_DTYPE, MC_BI_PU_DTYPE, CAND_DTYPE  # noqa: F401
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 # FME_B200_LIB selects another build of the same library (A/B builds for profiling, e.g. variants/libfme_swar8.so)
@@ -31,7 +31,7 @@ CAND_SAD = 0x08
 EXPORTS = [
     "fme_create", "fme_destroy", "fme_last_error", "fme_version", "fme_set_stream", "fme_synchronize",
     "fme_set_nn_weights", "fme_load_nn_csv_dir", "fme_set_slice", "fme_upload_ref", "fme_upload_ref_u8",
-    "fme_upload_org", "fme_upload_org_u8", "fme_submit", "fme_submit_async", "fme_submit_heads", "fme_submit_heads_async", "fme_submit_heads_grids", "fme_submit_heads_grids_async", "fme_wait_oldest", "fme_submit_device", "fme_interp_slot",
+    "fme_upload_org", "fme_upload_org_u8", "fme_submit", "fme_submit_async", "fme_submit_heads", "fme_submit_heads_async", "fme_submit_heads_grids", "fme_submit_heads_grids_async", "fme_submit_compact", "fme_submit_compact_async", "fme_wait_oldest", "fme_submit_device", "fme_interp_slot",
     "fme_upload_ref_device_u8", "fme_upload_ref_device_u8_rows", "fme_upload_org_device_u8", "fme_int_surface_device", "fme_filter_hor",
     "fme_filter_ver", "fme_dist", "fme_mv_cost", "fme_upload_ref_chroma", "fme_upload_ref_chroma_u8", "fme_upload_ref_yuv420_u8", "fme_upload_org_yuv420_u8", "fme_mc", "fme_mc_bi", "fme_pred_error", "fme_cand_cost", "fme_cand_cost_device", "fme_mc_luma_compact",
     "fme_mc_luma_compact_device", "fme_download_plane",
@@ -102,6 +102,8 @@ def load_library():
     lib.fme_submit_heads_async.argtypes = [vp, vp, i32, vp, i32]
     lib.fme_submit_heads_grids.argtypes = [vp, vp, i32, vp, i32, vp, i32]
     lib.fme_submit_heads_grids_async.argtypes = [vp, vp, i32, vp, i32, vp, i32]
+    lib.fme_submit_compact.argtypes = [vp, vp, i32, vp, i32, vp, i32]
+    lib.fme_submit_compact_async.argtypes = [vp, vp, i32, vp, i32, vp, i32]
     lib.fme_submit_device.argtypes = [vp, vp, i32, vp, i32]
     lib.fme_cand_cost.argtypes = [vp, vp, i32, vp, vp]
     lib.fme_cand_cost_device.argtypes = [vp, vp, i32, vp, vp]
@@ -269,6 +271,19 @@ class Fme:
         out = np.zeros(len(heads), RESULT_DTYPE)
         self._check(self.lib.fme_submit_heads_grids(self.h, _addr(heads), len(heads), _addr(grids), len(grids), _addr(out), mode))
         return out
+
+    def submit_compact(self, recs, big=None, mode=MODE_BOTH):
+        """44-byte records (COMPACT_DTYPE: head + nine 24-bit grid values) plus full grids for the PUs that need 32 bits."""
+        recs = np.ascontiguousarray(recs, dtype=COMPACT_DTYPE)
+        big = np.ascontiguousarray(big if big is not None else np.zeros(0, GRID_DTYPE), dtype=GRID_DTYPE)
+        out = np.zeros(len(recs), RESULT_DTYPE)
+        self._check(self.lib.fme_submit_compact(self.h, _addr(recs), len(recs), _addr(big) if len(big) else None, len(big),
+                                                _addr(out), mode))
+        return out
+
+    def submit_compact_async(self, recs_ptr, n, big_ptr, n_big, out_ptr, mode=MODE_BOTH):
+        self._check(self.lib.fme_submit_compact_async(self.h, C.c_void_p(recs_ptr), n, C.c_void_p(big_ptr) if n_big else None, n_big,
+                                                      C.c_void_p(out_ptr), mode))
 
     def submit_heads_grids_async(self, heads_ptr, n, grids_ptr, n_grids, out_ptr, mode=MODE_BOTH):
         self._check(self.lib.fme_submit_heads_grids_async(self.h, C.c_void_p(heads_ptr), n, C.c_void_p(grids_ptr), n_grids,

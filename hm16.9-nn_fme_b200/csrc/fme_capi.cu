@@ -79,6 +79,7 @@ struct fme_ctx {
   fme_pu* d_pusBuf[FME_NBUF] = {};
   fme_pu_head* d_headBuf[FME_NBUF] = {};  // allocated on the first fme_submit_heads*
   fme_err_grid* d_gridBuf[FME_NBUF] = {};  // allocated on the first fme_submit_heads_grids*
+  fme_pu_compact* d_compactBuf[FME_NBUF] = {};  // allocated on the first fme_submit_compact*
   fme_result* d_resBuf[FME_NBUF] = {};
   fme_result8* d_res8Buf[FME_NBUF] = {};  // FME_MODE_RESULT8: packed copy that travels to the host
   fme_pu* d_pus = nullptr;       // = d_pusBuf[0], used by the synchronous helpers (fme_mc)
@@ -362,7 +363,7 @@ void fme_destroy(fme_ctx* c) {
   cudaFree(c->d_planes); cudaFree(c->d_pel); cudaFree(c->d_pel2);
   for (int b = 0; b < FME_NBUF; ++b) {
     cudaFree(c->d_orgBuf[b]); cudaFree(c->d_picBuf[b]); cudaFree(c->d_pelPic[b]); cudaFree(c->d_pusBuf[b]); cudaFree(c->d_resBuf[b]); cudaFree(c->d_res8Buf[b]);
-    cudaFree(c->d_headBuf[b]); cudaFree(c->d_gridBuf[b]);
+    cudaFree(c->d_headBuf[b]); cudaFree(c->d_gridBuf[b]); cudaFree(c->d_compactBuf[b]);
     for (cudaEvent_t e : {c->evIn[b], c->evDone[b], c->evOut[b], c->evPicIn[b], c->evPicFree[b], c->evOrgFree[b]})
       if (e) cudaEventDestroy(e);
   }
@@ -713,11 +714,12 @@ static bool valid_pu_size(int w, int h) { return fme_hevc_pu_shape(w, h); }
 
 // ---- the batched search ------------------------------------------------------------------------
 static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, int mode, bool sync,
-                         const fme_pu_head* heads = nullptr, const fme_err_grid* grids = nullptr, int nGrids = 0) {
-  if (!c || (!pus && !heads) || !out) return fail(FME_ERR_INVALID, "null argument");
-  if (nGrids < 0 || (nGrids > 0 && (!grids || !heads))) return fail(FME_ERR_INVALID, "bad error-grid list");
+                         const fme_pu_head* heads = nullptr, const fme_err_grid* grids = nullptr, int nGrids = 0,
+                         const fme_pu_compact* compact = nullptr) {
+  if (!c || (!pus && !heads && !compact) || !out) return fail(FME_ERR_INVALID, "null argument");
+  if (nGrids < 0 || (nGrids > 0 && (!grids || (!heads && !compact)))) return fail(FME_ERR_INVALID, "bad error-grid list");
   if (nGrids > c->cfg.maxPUs) return fail(FME_ERR_INVALID, "nGrids=%d exceeds maxPUs=%d", nGrids, c->cfg.maxPUs);
-  NvtxRange nvtxSpan(heads ? "fme_submit_heads" : "fme_submit");
+  NvtxRange nvtxSpan(heads ? "fme_submit_heads" : compact ? "fme_submit_compact" : "fme_submit");
   const bool packed = (mode & FME_MODE_RESULT8) != 0;  // `out` is an fme_result8 array
   mode &= ~FME_MODE_RESULT8;
   if (n < 0 || n > c->cfg.maxPUs) return fail(FME_ERR_INVALID, "n=%d exceeds maxPUs=%d", n, c->cfg.maxPUs);
@@ -740,6 +742,24 @@ static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, 
     }
     for (int b = 0; b < FME_NBUF; ++b)
       if (!c->d_headBuf[b]) CU_CHECK(cudaMalloc(&c->d_headBuf[b], sizeof(fme_pu_head) * (size_t)c->cfg.maxPUs));
+    for (int b = 0; b < FME_NBUF && nGrids > 0; ++b)
+      if (!c->d_gridBuf[b]) CU_CHECK(cudaMalloc(&c->d_gridBuf[b], sizeof(fme_err_grid) * (size_t)c->cfg.maxPUs));
+  } else if (compact) {   // grids travel with the records (or in the big list): no K0 pass
+    if (sync) {
+      for (int i = 0; i < n; ++i) {
+        const fme_pu_head& h = compact[i].head;
+        if ((mode & FME_MODE_STD) && (h.refSlot >= c->cfg.numRefSlots || !c->refValid[h.refSlot]))
+          return fail(FME_ERR_STATE, "PU %d references slot %d which holds no picture", i, h.refSlot);
+        if ((mode & FME_MODE_STD) && !valid_pu_size(h.w, h.h))
+          return fail(FME_ERR_INVALID, "PU %d: %dx%d is not an HEVC PU size", i, h.w, h.h);
+        if (h.flags & FME_PU_BI)
+          return fail(FME_ERR_INVALID, "PU %d: FME_PU_BI needs a full record (the other list's slot and MV live in err[])", i);
+      }
+      for (int j = 0; j < nGrids; ++j)
+        if (grids[j].pu < 0 || grids[j].pu >= n) return fail(FME_ERR_INVALID, "error grid %d names PU %d of %d", j, grids[j].pu, n);
+    }
+    for (int b = 0; b < FME_NBUF; ++b)
+      if (!c->d_compactBuf[b]) CU_CHECK(cudaMalloc(&c->d_compactBuf[b], sizeof(fme_pu_compact) * (size_t)c->cfg.maxPUs));
     for (int b = 0; b < FME_NBUF && nGrids > 0; ++b)
       if (!c->d_gridBuf[b]) CU_CHECK(cudaMalloc(&c->d_gridBuf[b], sizeof(fme_err_grid) * (size_t)c->cfg.maxPUs));
   } else if (sync) {  // full validation on the synchronous path
@@ -776,6 +796,7 @@ static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, 
   // records in: the kernels that read d_pus[b] FME_NBUF submits ago must be done
   CU_CHECK(cudaStreamWaitEvent(c->sIn, c->evDone[b], 0));
   if (heads) CU_CHECK(cudaMemcpyAsync(c->d_headBuf[b], heads, sizeof(fme_pu_head) * (size_t)n, cudaMemcpyHostToDevice, c->sIn));
+  else if (compact) CU_CHECK(cudaMemcpyAsync(c->d_compactBuf[b], compact, sizeof(fme_pu_compact) * (size_t)n, cudaMemcpyHostToDevice, c->sIn));
   else CU_CHECK(cudaMemcpyAsync(d_pus, pus, sizeof(fme_pu) * (size_t)n, cudaMemcpyHostToDevice, c->sIn));
   if (nGrids > 0)
     CU_CHECK(cudaMemcpyAsync(c->d_gridBuf[b], grids, sizeof(fme_err_grid) * (size_t)nGrids, cudaMemcpyHostToDevice, c->sIn));
@@ -784,6 +805,7 @@ static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, 
   CU_CHECK(cudaStreamWaitEvent(c->stream, c->evIn[b], 0));
   CU_CHECK(cudaStreamWaitEvent(c->stream, c->evOut[b], 0));
   if (heads) CU_CHECK(fme_launch_expand_heads(c->d_headBuf[b], n, d_pus, c->stream, &c->launches));
+  if (compact) CU_CHECK(fme_launch_expand_compact(c->d_compactBuf[b], n, d_pus, c->stream, &c->launches));
   if (nGrids > 0) CU_CHECK(fme_launch_apply_grids(c->d_gridBuf[b], nGrids, d_pus, n, c->stream, &c->launches));
   if (needK0) {
     StageTimer t(c, 3);
@@ -829,6 +851,15 @@ int fme_submit_heads_grids(fme_ctx* c, const fme_pu_head* heads, int n, const fm
 int fme_submit_heads_grids_async(fme_ctx* c, const fme_pu_head* heads, int n, const fme_err_grid* grids, int nGrids,
                                  fme_result* out, int mode) {
   return submit_common(c, nullptr, n, out, mode, false, heads, grids, nGrids);
+}
+
+int fme_submit_compact(fme_ctx* c, const fme_pu_compact* recs, int n, const fme_err_grid* big, int nBig, fme_result* out,
+                       int mode) {
+  return submit_common(c, nullptr, n, out, mode, true, nullptr, big, nBig, recs);
+}
+int fme_submit_compact_async(fme_ctx* c, const fme_pu_compact* recs, int n, const fme_err_grid* big, int nBig,
+                             fme_result* out, int mode) {
+  return submit_common(c, nullptr, n, out, mode, false, nullptr, big, nBig, recs);
 }
 
 int fme_submit_device(fme_ctx* c, const fme_pu* d_pus, int n, fme_result* d_out, int mode) {

@@ -119,6 +119,7 @@ cudaError_t fme_launch_pel_to_u8(const int16_t* d_src, int srcStride, uint8_t* d
                                  cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_pack_results(const fme_result* d_res, int n, fme_result8* d_out, cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_expand_heads(const fme_pu_head* d_heads, int n, fme_pu* d_pus, cudaStream_t s, int64_t* launches);
+cudaError_t fme_launch_expand_compact(const fme_pu_compact* d_recs, int n, fme_pu* d_pus, cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_apply_grids(const fme_err_grid* d_grids, int nGrids, fme_pu* d_pus, int n, cudaStream_t s,
                                    int64_t* launches);
 cudaError_t fme_launch_mc_bi(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_cb, const uint8_t* d_cr,

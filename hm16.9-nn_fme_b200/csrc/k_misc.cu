@@ -399,6 +399,28 @@ __global__ void k_expand_heads(const fme_pu_head* __restrict__ heads, int n, fme
   d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
 }
 
+// Compact records (head + nine 24-bit grid values) -> full records; no K0 flag, no FME_PU_BI (see fme_b200.h).
+static_assert(sizeof(fme_pu_compact) == 44, "compact record layout");
+__global__ void k_expand_compact(const fme_pu_compact* __restrict__ recs, int n, fme_pu* __restrict__ pus) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned* s = reinterpret_cast<const unsigned*>(recs) + (size_t)i * 11;  // 44-byte records are 4-byte aligned
+  unsigned w[11];
+#pragma unroll
+  for (int k = 0; k < 11; ++k) w[k] = __ldg(s + k);
+  unsigned* d = reinterpret_cast<unsigned*>(&pus[i]);
+  d[0] = w[0];
+  d[1] = w[1] & ~((unsigned)(FME_PU_BI | FME_PU_ERR_ON_GPU) << 24);  // flags is byte 7 of the record
+  d[2] = w[2];
+  d[3] = w[3];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {   // value k = bytes 3k .. 3k+2 of the 28-byte tail
+    const int b = 3 * k, q = b >> 2, r = b & 3;
+    const unsigned lo = w[4 + q], hi = q + 1 < 7 ? w[5 + q] : 0u;
+    d[4 + k] = __funnelshift_r(lo, hi, 8 * r) & 0xffffffu;
+  }
+}
+
 // Host-supplied error grids for some of the expanded heads: err[] filled, FME_PU_ERR_ON_GPU cleared (K0 skips them).
 static_assert(sizeof(fme_err_grid) == 40, "grid layout");
 __global__ void k_apply_grids(const fme_err_grid* __restrict__ grids, int nGrids, fme_pu* __restrict__ pus, int n) {
@@ -559,6 +581,13 @@ cudaError_t fme_launch_pack_results(const fme_result* d_res, int n, fme_result8*
 cudaError_t fme_launch_expand_heads(const fme_pu_head* d_heads, int n, fme_pu* d_pus, cudaStream_t s, int64_t* launches) {
   if (n <= 0) return cudaSuccess;
   k_expand_heads<<<(n + 255) / 256, 256, 0, s>>>(d_heads, n, d_pus);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t fme_launch_expand_compact(const fme_pu_compact* d_recs, int n, fme_pu* d_pus, cudaStream_t s, int64_t* launches) {
+  if (n <= 0) return cudaSuccess;
+  k_expand_compact<<<(n + 255) / 256, 256, 0, s>>>(d_recs, n, d_pus);
   ++*launches;
   return cudaGetLastError();
 }

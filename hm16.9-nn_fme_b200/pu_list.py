@@ -39,6 +39,31 @@ def grids_of(recs, min_area):
     return g
 
 
+COMPACT_DTYPE = np.dtype(   # fme_pu_compact: head + nine 24-bit little-endian grid values + one reserved byte
+    [("x", "<i2"), ("y", "<i2"), ("w", "u1"), ("h", "u1"), ("refSlot", "u1"), ("flags", "u1"),
+     ("mvIntX", "<i2"), ("mvIntY", "<i2"), ("mvPredX", "<i2"), ("mvPredY", "<i2"), ("err24", "u1", (27,)), ("reserved", "u1")])
+assert COMPACT_DTYPE.itemsize == 44
+
+
+def compact_of(recs):
+    """fme_pu records -> (fme_pu_compact records, fme_err_grid entries for the PUs with a grid value of 2^24 or more):
+    what fme_pu_compact_pack does per record (include/fme_b200.h)."""
+    c = np.zeros(len(recs), COMPACT_DTYPE)
+    for f in HEAD_DTYPE.names:
+        c[f] = recs[f]
+    e = recs["err"].astype(np.uint32)
+    b = np.empty((len(recs), 9, 3), np.uint8)
+    b[:, :, 0] = e & 0xff
+    b[:, :, 1] = (e >> 8) & 0xff
+    b[:, :, 2] = (e >> 16) & 0xff
+    c["err24"] = b.reshape(len(recs), 27)
+    idx = np.nonzero((e >> 24).any(axis=1))[0]
+    g = np.zeros(len(idx), GRID_DTYPE)
+    g["pu"] = idx
+    g["err"] = recs["err"][idx]
+    return c, g
+
+
 RESULT_DTYPE = np.dtype(
     [("halfX", "i1"), ("halfY", "i1"), ("qterX", "i1"), ("qterY", "i1"), ("cost", "<u4"),
      ("nnHalfX", "i1"), ("nnHalfY", "i1"), ("nnQterX", "i1"), ("nnQterY", "i1"), ("nnClass", "u1"),

@@ -214,6 +214,38 @@ int fme_submit_heads_grids(fme_ctx* ctx, const fme_pu_head* heads, int n, const 
                            fme_result* out, int mode);
 int fme_submit_heads_grids_async(fme_ctx* ctx, const fme_pu_head* heads, int n, const fme_err_grid* grids, int nGrids,
                                  fme_result* out, int mode);
+/* Compact records: the head plus the caller's 3x3 error grid as nine 24-bit little-endian values, 44 bytes instead of 52.
+ * The integer metric of this fork is the SSE (TComRdCost.cpp:212), so a grid value is below w*h*255^2: every PU of at most
+ * 256 luma samples fits 24 bits exactly (256 * 65025 < 2^24) -- 94 % of the records of a 1080p list -- and so does almost
+ * every larger one in practice; a PU with a value of 2^24 or more gets its grid through the fme_err_grid list instead
+ * (big[j].pu indexes recs[]; its err24 bytes are then ignored).  No K0 pass runs: served exactly like full records
+ * carrying the same err[].  One GPU moves full records at the PCIe limit (52.9 MB per 1080p frame at ~51 GB/s = 1.03 ms
+ * against a 0.93 ms device step); 44-byte records put the end-to-end path back on the device step.  FME_PU_BI and
+ * FME_PU_ERR_ON_GPU are ignored on compact records (a bi-predictive record needs the full err[] words). */
+typedef struct fme_pu_compact {
+  fme_pu_head head;
+  uint8_t err24[27]; /* err[k] = err24[3k] | err24[3k+1] << 8 | err24[3k+2] << 16, raster order as fme_pu.err */
+  uint8_t reserved;
+} fme_pu_compact; /* 44 bytes */
+/* Packs one full record; returns 1 when a grid value needs more than 24 bits (send that PU's grid in the big list). */
+static inline int fme_pu_compact_pack(const fme_pu* p, fme_pu_compact* c) {
+  int k, big = 0;
+  const uint8_t* src = (const uint8_t*)p;
+  uint8_t* dst = (uint8_t*)&c->head;
+  for (k = 0; k < 16; ++k) dst[k] = src[k];
+  for (k = 0; k < 9; ++k) {
+    big |= p->err[k] >> 24 ? 1 : 0;
+    c->err24[3 * k] = (uint8_t)p->err[k];
+    c->err24[3 * k + 1] = (uint8_t)(p->err[k] >> 8);
+    c->err24[3 * k + 2] = (uint8_t)(p->err[k] >> 16);
+  }
+  c->reserved = 0;
+  return big;
+}
+int fme_submit_compact(fme_ctx* ctx, const fme_pu_compact* recs, int n, const fme_err_grid* big, int nBig, fme_result* out,
+                       int mode);
+int fme_submit_compact_async(fme_ctx* ctx, const fme_pu_compact* recs, int n, const fme_err_grid* big, int nBig,
+                             fme_result* out, int mode);
 /* With the ctx's own streams the copies of fme_upload_* / fme_submit_async run on dedicated copy streams and
  * overlap the kernels of neighbouring frames (staging rings of three, at most three submits in flight).
  * fme_wait_oldest blocks until the results of the oldest outstanding fme_submit_async are in `out`. */

@@ -86,3 +86,38 @@ def test_hm_adaptor_compiles_against_reference_headers():
         open(src, "w").write('#include "fme_hm_adaptor.h"\nint main() { FmeHmAdaptor a; (void)a; return 0; }\n')
         subprocess.check_call(["g++", "-std=gnu++11", "-fsyntax-only", "-w", "-I", ref, "-I", os.path.join(ROOT, "include"),
                                "-I", os.path.join(ROOT, "hm16.9-nn_fme_b200", "adaptor"), src])
+
+
+def test_compact_record_pack_helper_matches_python_mirror():
+    """fme_pu_compact_pack (header-only, what an adaptor calls per PU) == pu_list.compact_of: 44-byte layout, 24-bit
+    little-endian grid values, return value 1 exactly for the records that need the fme_err_grid list."""
+    rng = np.random.default_rng(11)
+    recs = np.zeros(64, fme.PU_DTYPE)
+    for f in ("x", "y", "mvIntX", "mvIntY", "mvPredX", "mvPredY"):
+        recs[f] = rng.integers(-2000, 2000, len(recs))
+    recs["w"], recs["h"], recs["refSlot"], recs["flags"] = 16, 8, rng.integers(0, 4, len(recs)), rng.integers(0, 2, len(recs))
+    recs["err"] = rng.integers(0, 1 << 24, recs["err"].shape).astype(np.uint32)
+    recs["err"][::7, 3] = rng.integers(1 << 24, 1 << 32, len(recs[::7]), dtype=np.uint64).astype(np.uint32)
+    src = r'''
+#include <stdio.h>
+#include "fme_b200.h"
+int main(void) {
+  fme_pu p; fme_pu_compact c;
+  if (sizeof(fme_pu_compact) != 44) return 2;
+  while (fread(&p, sizeof p, 1, stdin) == 1) {
+    unsigned char big = (unsigned char)fme_pu_compact_pack(&p, &c);
+    fwrite(&c, sizeof c, 1, stdout);
+    fwrite(&big, 1, 1, stdout);
+  }
+  return 0;
+}'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+        out = subprocess.run([os.path.join(d, "t")], input=recs.tobytes(), stdout=subprocess.PIPE, check=True).stdout
+    got = np.frombuffer(out, np.uint8).reshape(len(recs), 45)
+    comp, big = fme.pu_list.compact_of(recs)
+    assert np.array_equal(got[:, :44], comp.view(np.uint8).reshape(len(recs), 44))
+    flag = np.zeros(len(recs), np.uint8); flag[big["pu"]] = 1
+    assert np.array_equal(got[:, 44], flag) and len(big) == len(recs[::7])
+    assert np.array_equal(big["err"], recs["err"][big["pu"]])

@@ -1259,3 +1259,96 @@ def test_heads_with_host_error_grids_for_some_pus(small):
     # heads-only submits afterwards are untouched by the grid buffers
     again = eng.submit_heads(heads, fme.MODE_BOTH)
     assert np.array_equal(again.view(np.uint8), on_dev.view(np.uint8))
+
+
+@pytest.mark.gpu
+def test_k2_tcgen05_path_equals_default_at_1080p_and_2160p():
+    """FME_K2_PATH_UMMA (tcgen05.mma kind::i8, TMEM accumulators, csrc/k2_umma.cu) at BASELINE's full sizes: every vector and
+    cost of the 858 000-PU 1080p frame and of a 2160p frame equals the default (SWAR) path's bit for bit, lossless PUs and a
+    ragged tail included; SAD mode and bi-predictive records on a UMMA ctx fall through to the integer kernels."""
+    for (W, H, seed) in ((1920, 1080, 2022), (3840, 2160, 4)):
+        org, refs, motions = fme.pu_list.synth_frames(W, H, n_refs=4, seed=seed)
+        recs = fme.pu_list.make_records(W, H, motions, seed=2, amp=(W == 3840))
+        recs["flags"][::97] |= fme.PU_LOSSLESS
+        recs = np.ascontiguousarray(recs[:len(recs) - 5])
+        lam = fme.pu_list.slice_lambda(22)
+        got = {}
+        for path in (fme.K2_PATH_SWAR, fme.K2_PATH_UMMA):
+            eng = fme.Fme(W, H, num_ref_slots=4, max_pus=len(recs), k2_path=path)
+            eng.set_slice(lam)
+            eng.upload_org(org)
+            for s in range(4):
+                eng.upload_ref(s, refs[s])
+            got[path] = eng.submit(recs, fme.MODE_STD)
+            eng.close()
+        for f in ("halfX", "halfY", "qterX", "qterY", "cost"):
+            bad = np.nonzero(got[fme.K2_PATH_SWAR][f] != got[fme.K2_PATH_UMMA][f])[0]
+            assert len(bad) == 0, (W, f, len(bad), recs[bad[:4]])
+    # SAD mode on a UMMA ctx: served by the integer kernel, same answers as a SWAR ctx
+    W, H = 416, 240
+    org, refs, motions = fme.pu_list.synth_frames(W, H, n_refs=2, seed=9)
+    recs = fme.pu_list.make_records(W, H, motions, seed=1, amp=True)
+    lam = fme.pu_list.slice_lambda(27, had_me=False)
+    res = []
+    for path in (fme.K2_PATH_SWAR, fme.K2_PATH_UMMA):
+        eng = fme.Fme(W, H, num_ref_slots=2, max_pus=len(recs), use_had=False, k2_path=path)
+        eng.set_slice(lam)
+        eng.upload_org(org)
+        for s in range(2):
+            eng.upload_ref(s, refs[s])
+        res.append(eng.submit(recs, fme.MODE_STD))
+        eng.close()
+    assert np.array_equal(res[0].view(np.uint8), res[1].view(np.uint8))
+
+
+@pytest.mark.gpu
+def test_compact_44_byte_records_equal_full_records(small):
+    """fme_submit_compact / _async: 44-byte records (head + nine 24-bit grid values) with full grids for the PUs whose
+    surface needs 32 bits are served exactly like 52-byte records carrying the same err[] (TEncSearch.cpp:88, 5049-5050:
+    array_e / C of the integer search) -- all three modes, 8-byte results, the asynchronous ring, and the error behaviour."""
+    eng, g, recs = small
+    eng.set_nn_weights(fme.nn_weights.load_blob(22))
+    rng = np.random.default_rng(3)
+    recs = recs.copy()
+    recs["flags"] &= ~np.uint8(fme.PU_ERR_ON_GPU)
+    recs["err"] = rng.integers(0, 1 << 24, recs["err"].shape).astype(np.uint32)
+    big_rows = rng.choice(len(recs), 300, replace=False)
+    recs["err"][big_rows, rng.integers(0, 9, 300)] = rng.integers(1 << 24, 1 << 32, 300, dtype=np.uint64).astype(np.uint32)
+    recs["err"][big_rows[0]] = 0xffffffff
+    comp, big = fme.pu_list.compact_of(recs)
+    assert comp.dtype.itemsize == 44 and len(big) == 300
+    for mode in (fme.MODE_STD, fme.MODE_NN, fme.MODE_BOTH):
+        want = eng.submit(recs, mode)
+        got = eng.submit_compact(comp, big, mode)
+        assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), mode
+    # without the big list the oversized grids are truncated to 24 bits: only those PUs' NN fields may differ
+    trunc = eng.submit_compact(comp, None, fme.MODE_BOTH)
+    want = eng.submit(recs, fme.MODE_BOTH)
+    keep = np.ones(len(recs), bool); keep[big_rows] = False
+    assert np.array_equal(trunc[keep].view(np.uint8), want[keep].view(np.uint8))
+    for f in ("halfX", "halfY", "qterX", "qterY", "cost"):
+        assert np.array_equal(trunc[f], want[f])
+    # asynchronous ring with 8-byte results, four submits through three buffers
+    import torch
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(len(a), -1)).pin_memory()
+    h_c, h_b = pin(comp), pin(big)
+    outs = [torch.zeros((len(recs), 8), dtype=torch.uint8).pin_memory() for _ in range(4)]
+    for o in outs:
+        eng.submit_compact_async(h_c.data_ptr(), len(comp), h_b.data_ptr(), len(big), o.data_ptr(), fme.MODE_BOTH | fme.MODE_RESULT8)
+    eng.synchronize()
+    ref8 = torch.zeros((len(recs), 8), dtype=torch.uint8).pin_memory()
+    h_p = pin(recs)
+    eng.submit_async(h_p.data_ptr(), len(recs), ref8.data_ptr(), fme.MODE_BOTH | fme.MODE_RESULT8)
+    eng.synchronize()
+    for o in outs:
+        assert torch.equal(o, ref8)
+    # error behaviour of the synchronous entry point
+    bad = comp.copy(); bad["w"][5] = 12
+    with pytest.raises(fme.FmeError):
+        eng.submit_compact(bad, big, fme.MODE_BOTH)
+    bad = comp.copy(); bad["flags"][7] |= fme.PU_BI
+    with pytest.raises(fme.FmeError):
+        eng.submit_compact(bad, big, fme.MODE_BOTH)
+    badg = big.copy(); badg["pu"][0] = len(recs)
+    with pytest.raises(fme.FmeError):
+        eng.submit_compact(comp, badg, fme.MODE_BOTH)
