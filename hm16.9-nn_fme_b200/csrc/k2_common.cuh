@@ -21,6 +21,17 @@ __constant__ int8_t c_stepFirst[12] = {0, 3, 1, 5, 1, 2, 3, 4, 5, 6, 7, 8};
 __constant__ int8_t c_stepCount[12] = {1, 2, 2, 4, 1, 1, 1, 1, 1, 1, 1, 1};
 __constant__ int8_t c_refineQ[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {1, 1}};
 
+// table index of the q-th candidate a pack evaluates: the half-pel candidates in staging order (c_stepFirst / c_stepCount:
+// H0 | H3 H4 | H1 H2 | H5..H8), then Q1..Q8
+__constant__ int8_t c_seqI[17] = {0, 3, 4, 1, 2, 5, 6, 7, 8, 1, 2, 3, 4, 5, 6, 7, 8};
+// the q-th candidate's offset (ox, oy) in {-1, 0, 1}^2 (c_refineH for q < 9, c_refineQ afterwards), as the two PRMT
+// selectors that pick byte ox + 1 of bitsX and byte oy + 1 of bitsY: 0x444b | 0x444b << 16
+#define K2_SEL(ox, oy) (0x4440u | (unsigned)((ox) + 1) | ((0x4440u | (unsigned)((oy) + 1)) << 16))
+__constant__ unsigned c_seqSel[17] = {
+    K2_SEL(0, 0), K2_SEL(-1, 0), K2_SEL(1, 0), K2_SEL(0, -1), K2_SEL(0, 1), K2_SEL(-1, -1), K2_SEL(1, -1), K2_SEL(-1, 1), K2_SEL(1, 1),
+    K2_SEL(0, -1), K2_SEL(0, 1), K2_SEL(-1, -1), K2_SEL(1, -1), K2_SEL(-1, 0), K2_SEL(1, 0), K2_SEL(-1, 1), K2_SEL(1, 1)};
+#undef K2_SEL
+
 struct ClassInfo {
   int w, h;
   int ts;        // tile size 8 or 4

@@ -670,6 +670,8 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
     bitsX |= (unsigned)golomb_bits((((mvIntX << 1) + (t - 1)) << 1) - predX) << (8 * t);
     bitsY |= (unsigned)golomb_bits((((mvIntY << 1) + (t - 1)) << 1) - predY) << (8 * t);
   }
+  const int halfOff = sg.RW + ((alignX - 1) & (A - 1)) + 1;   // half-pel candidate (0, 0) inside a region
+  int cq = 0;                                                 // sequence number of the next candidate
 #pragma unroll 1
   for (int s = 0; s < 12; ++s) {
     const bool prefetch = (s != 3) && (s != 11);  // step 4 depends on the half-pel winner found after step 3
@@ -683,22 +685,24 @@ __device__ __noinline__ void k2_pack(const ClassInfo ci, const int* __restrict__
     const uint8_t* region = ((s & 1) ? bufB : bufA) + myPu * sg.RB;
     // candidates served by this step, in table order (TEncSearch.cpp:212-236):
     // s=0: H0 | s=1 (fx=2): H3 (-1,0), H4 (1,0) | s=2 (fy=2): H1 (0,-1), H2 (0,1) | s=3: H5..H8 | s>=4: Q(s-3)
-    const int iFirst = c_stepFirst[s], iCount = c_stepCount[s];
+    const int iCount = c_stepCount[s];
 #pragma unroll 1
-    for (int c = 0; c < iCount; ++c) {
-      const int i = iFirst + c;
-      int candOff, ox3, oy3;  // ox3/oy3: candidate offset -1/0/1 per axis in units of the current stage
+    for (int c = 0; c < iCount; ++c, ++cq) {
+      // candidate cq of the pack's sequence: table index i, offset (ox, oy) in {-1, 0, 1}^2 in units of the current stage,
+      // held as the PRMT selectors of byte ox + 1 / oy + 1 (k2_common.cuh)
+      const int i = c_seqI[cq];
+      const unsigned sel = c_seqSel[cq];
+      int candOff;
       if (s < 4) {
-        ox3 = c_refineH[i][0]; oy3 = c_refineH[i][1];
-        // inside the region (origin X-1, Y-1): x offset 1 + ((2hx)>>2), y offset 1 + ((2hy)>>2)
-        candOff = (1 + ((2 * oy3) >> 2)) * sg.RW + ((alignX - 1) & (A - 1)) + 1 + ((2 * ox3) >> 2);
+        // inside the region (origin X-1, Y-1): x offset 1 + ((2hx)>>2), y offset 1 + ((2hy)>>2), i.e. one sample / one row
+        // back for the offsets -1
+        candOff = halfOff - ((sel & 3u) == 0 ? 1 : 0) - ((sel & 0x30000u) == 0 ? sg.RW : 0);
       } else {
-        ox3 = c_refineQ[i][0]; oy3 = c_refineQ[i][1];
-        const int qx = 2 * bhx + ox3;
+        const int qx = 2 * bhx + (int)(sel & 3u) - 1;
         candOff = (alignX + (qx >> 2)) & (A - 1);
       }
       // exp-Golomb bit counts of the three possible vector components per axis were computed once per stage
-      const int bits = (int)(((bitsX >> (8 * ox3 + 8)) & 0xffu) + ((bitsY >> (8 * oy3 + 8)) & 0xffu));
+      const int bits = (int)(__byte_perm(bitsX, 0, sel) + __byte_perm(bitsY, 0, sel >> 16));
       unsigned dist = 0;
       bool swar = true;
       if constexpr (kMma) {

@@ -45,16 +45,6 @@ constexpr int UM_TMEM_COLS = 64 * UM_DEPTH;         // UM_DEPTH accumulators of 
 // round command: what the issuing thread multiplies (candidate buffer = round % UM_DEPTH unless _BUF0; source rows from
 // the source area unless _ORG_IN_BUF1)
 constexpr unsigned UM_CMD_QUIT = 1u, UM_CMD_TS4 = 2u, UM_CMD_BUF0 = 4u, UM_CMD_ORG_IN_BUF1 = 8u;
-// table index of the q-th candidate a pack evaluates: the half-pel candidates in staging order (c_stepFirst / c_stepCount:
-// H0 | H3 H4 | H1 H2 | H5..H8), then Q1..Q8
-__constant__ int8_t c_seqI[17] = {0, 3, 4, 1, 2, 5, 6, 7, 8, 1, 2, 3, 4, 5, 6, 7, 8};
-// the q-th candidate's offset (ox, oy) in {-1, 0, 1}^2 (c_refineH for q < 9, c_refineQ afterwards), as the two PRMT
-// selectors that pick byte ox + 1 of bitsX and byte oy + 1 of bitsY: 0x444b | 0x444b << 16
-#define UM_SEL(ox, oy) (0x4440u | (unsigned)((ox) + 1) | ((0x4440u | (unsigned)((oy) + 1)) << 16))
-__constant__ unsigned c_seqSel[17] = {
-    UM_SEL(0, 0), UM_SEL(-1, 0), UM_SEL(1, 0), UM_SEL(0, -1), UM_SEL(0, 1), UM_SEL(-1, -1), UM_SEL(1, -1), UM_SEL(-1, 1), UM_SEL(1, 1),
-    UM_SEL(0, -1), UM_SEL(0, 1), UM_SEL(-1, -1), UM_SEL(1, -1), UM_SEL(-1, 0), UM_SEL(1, 0), UM_SEL(-1, 1), UM_SEL(1, 1)};
-#undef UM_SEL
 
 __device__ __forceinline__ uint64_t um_desc(unsigned addr, unsigned lboBytes, unsigned sboBytes) {
   // SWIZZLE_NONE, K-major: core matrix = 8 rows x 16 bytes, stored as 128 contiguous bytes; LBO = distance between the
