@@ -184,12 +184,32 @@ struct NvtxRange {  // host-side span of an ABI call (copies + launches it issue
   ~NvtxRange() { nvtxRangePop(); }
 };
 
+// Debug build only (-DFME_STAMPS, tools/e2e_timeline.py): %globaltimer stamps on the kernel stream around the passes of a
+// frame, to see where the kernel stream is busy and where it waits for copies.
+#ifdef FME_STAMPS
+__global__ void k_stamp(unsigned long long* buf, int idx, int tag) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  buf[idx] = (t << 4) | (unsigned long long)tag;
+}
+static unsigned long long* g_stamps = nullptr;
+static int g_stampN = 0;
+static void dbg_stamp(fme_ctx* c, int tag) {
+  if (!g_stamps) cudaMalloc(&g_stamps, 8 * 65536);
+  if (g_stampN < 65536) k_stamp<<<1, 1, 0, c->stream>>>(g_stamps, g_stampN++, tag);
+}
+#else
+static inline void dbg_stamp(fme_ctx*, int) {}
+#endif
+
 int run_k1(fme_ctx* c, int slot, const uint8_t* d_pic = nullptr, int picPitch = 0, int rowBegin = 0, int rowEnd = 1 << 30) {
+  dbg_stamp(c, 1);
   StageTimer t(c, 0);
   if (!d_pic) { d_pic = c->d_pic; picPitch = c->picPitch; }
   CU_CHECK(fme_launch_k1(c->g, d_pic, picPitch, c->d_planes + (size_t)slot * c->g.slotBytes, c->d_k1Counter, c->numSMs,
                          rowBegin, rowEnd, c->cfg.k1Path, c->stream,
                          &c->launches));
+  dbg_stamp(c, 2);
   c->refValid[slot] = 1;
   return FME_OK;
 }
@@ -215,7 +235,10 @@ int release_picture(fme_ctx* c, int idx) {
   return FME_OK;
 }
 
-int run_search(fme_ctx* c, fme_pu* d_pus, int n, fme_result* d_out, int mode) {
+// k0BehindK2: the unvalidated path may carry FME_PU_ERR_ON_GPU records (K3 needs their err[]); K2's binning pass counts
+// them while it reads the records anyway, and the K0 pass launched behind K2 returns at once when there are none (a K0
+// launched ahead of K2 has to scan every record to find that out: 0.05 ms per 858 000 records).
+int run_search(fme_ctx* c, fme_pu* d_pus, int n, fme_result* d_out, int mode, bool k0BehindK2 = false) {
   if (mode < 1 || mode > 3) return fail(FME_ERR_INVALID, "mode must be FME_MODE_STD|NN|BOTH");
   if ((mode & FME_MODE_STD) && (!c->orgValid || !c->sliceValid))
     return fail(FME_ERR_STATE, "fme_submit(STD) needs fme_upload_org and fme_set_slice first");
@@ -227,10 +250,16 @@ int run_search(fme_ctx* c, fme_pu* d_pus, int n, fme_result* d_out, int mode) {
                            c->cfg.k2Path == FME_K2_PATH_AUTO ? FME_K2_PATH_DEFAULT : c->cfg.k2Path, c->k2, c->numSMs, c->stream,
                            &c->launches));
   }
+  if (k0BehindK2) {
+    StageTimer t(c, 3);
+    CU_CHECK(fme_launch_k0(c->g, c->d_planes, c->d_org, d_pus, n, c->cfg.fen, c->stream, &c->launches, c->k2.workCounter + 1));
+  }
+  dbg_stamp(c, 5);
   if (mode & FME_MODE_NN) {
     StageTimer t(c, 2);
     CU_CHECK(fme_launch_k3(d_pus, n, d_out, c->d_nn, c->nnBytes, c->nnHeader, c->cfg.nnFma, c->stream, &c->launches));
   }
+  dbg_stamp(c, 6);
   return FME_OK;
 }
 
@@ -252,6 +281,16 @@ void collect_ms(fme_ctx* c) {
 }
 
 }  // namespace
+
+#ifdef FME_STAMPS
+extern "C" int fme_debug_stamps(unsigned long long* out, int max) {
+  cudaDeviceSynchronize();
+  const int n = g_stampN < max ? g_stampN : max;
+  if (n > 0) cudaMemcpy(out, g_stamps, 8 * (size_t)n, cudaMemcpyDeviceToHost);
+  g_stampN = 0;
+  return n;
+}
+#endif
 
 extern "C" {
 
@@ -804,16 +843,21 @@ static int submit_common(fme_ctx* c, const fme_pu* pus, int n, fme_result* out, 
   // kernels: need the records, and the previous read-out of d_res[b] must be done
   CU_CHECK(cudaStreamWaitEvent(c->stream, c->evIn[b], 0));
   CU_CHECK(cudaStreamWaitEvent(c->stream, c->evOut[b], 0));
+  dbg_stamp(c, 3);
   if (heads) CU_CHECK(fme_launch_expand_heads(c->d_headBuf[b], n, d_pus, c->stream, &c->launches));
   if (compact) CU_CHECK(fme_launch_expand_compact(c->d_compactBuf[b], n, d_pus, c->stream, &c->launches));
   if (nGrids > 0) CU_CHECK(fme_launch_apply_grids(c->d_gridBuf[b], nGrids, d_pus, n, c->stream, &c->launches));
-  if (needK0) {
+  // full records on the unvalidated path with both passes: K0 goes behind K2's record count (see run_search)
+  const bool k0BehindK2 = needK0 && !sync && !heads && !compact && mode == FME_MODE_BOTH;
+  if (needK0 && !k0BehindK2) {
     StageTimer t(c, 3);
     CU_CHECK(fme_launch_k0(c->g, c->d_planes, c->d_org, d_pus, n, c->cfg.fen, c->stream, &c->launches));
   }
-  int rc = run_search(c, d_pus, n, d_res, mode);
+  dbg_stamp(c, 4);
+  int rc = run_search(c, d_pus, n, d_res, mode, k0BehindK2);
   if (rc) return rc;
   if (packed) CU_CHECK(fme_launch_pack_results(d_res, n, c->d_res8Buf[b], c->stream, &c->launches));
+  dbg_stamp(c, 7);
   CU_CHECK(cudaEventRecord(c->evDone[b], c->stream));
   CU_CHECK(cudaEventRecord(c->evOrgFree[(c->orgSeq + FME_NBUF - 1) % FME_NBUF], c->stream));  // the source buffer this submit read
   // results out

@@ -106,7 +106,7 @@ cudaError_t fme_launch_k2(const FmeGeom& g, const uint8_t* d_planes, const uint8
 cudaError_t fme_launch_k3(const fme_pu* d_pus, int n, fme_result* d_res, const float* d_nn, size_t nnBytes,
                           const FmeNnHeader& h, int fma, cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_k0(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, fme_pu* d_pus, int n,
-                          int fen, cudaStream_t s, int64_t* launches);
+                          int fen, cudaStream_t s, int64_t* launches, const int* d_runIf = nullptr);
 cudaError_t fme_launch_clear_results(fme_result* d_res, int n, cudaStream_t s, int64_t* launches);
 
 cudaError_t fme_launch_filter(int isVertical, int ntaps, int isFirst, int isLast, int bitDepth, const int16_t* d_src,

@@ -45,15 +45,20 @@ __device__ __forceinline__ int k2_key_of(const fme_pu& p, int wantBi) {
 // res != nullptr (the uni-prediction pass): records no K2 pass will serve -- a shape HEVC cannot produce, or FME_PU_BI
 // on a ctx without biPred -- get the sentinel result (zero vectors, cost 0xffffffff) instead of whatever the result
 // buffer held (the unvalidated async / device entry points, include/fme_b200.h).
+// errOnGpuCount != nullptr (the uni-prediction pass): += the number of records flagged FME_PU_ERR_ON_GPU, so that a K0 pass
+// launched behind K2 on the unvalidated path can return at once when no record asks for it.
 __global__ void k2_count(const fme_pu* __restrict__ pus, int n, int* __restrict__ classCount, int wantBi,
-                         fme_result* __restrict__ res, int biServed, short* __restrict__ keys) {
+                         fme_result* __restrict__ res, int biServed, short* __restrict__ keys, int* __restrict__ errOnGpuCount) {
   __shared__ int s_cnt[FME_K2_KEYS];
+  __shared__ int s_flagged;
   for (int i = threadIdx.x; i < FME_K2_KEYS; i += blockDim.x) s_cnt[i] = 0;
+  if (threadIdx.x == 0) s_flagged = 0;
   __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const fme_pu p = pus[i];
     const int c = k2_key_of(p, wantBi);
     keys[i] = (short)c;
+    if (errOnGpuCount && (p.flags & FME_PU_ERR_ON_GPU)) atomicAdd(&s_flagged, 1);
     if (c >= 0) atomicAdd(&s_cnt[c], 1);
     else if (res && (!fme_hevc_pu_shape(p.w, p.h) || ((p.flags & FME_PU_BI) && !biServed)))
       *reinterpret_cast<uint2*>(&res[i]) = make_uint2(0u, 0xffffffffu);
@@ -61,6 +66,7 @@ __global__ void k2_count(const fme_pu* __restrict__ pus, int n, int* __restrict_
   __syncthreads();
   for (int i = threadIdx.x; i < FME_K2_KEYS; i += blockDim.x)
     if (s_cnt[i]) atomicAdd(&classCount[i], s_cnt[i]);
+  if (errOnGpuCount && threadIdx.x == 0 && s_flagged) atomicAdd(errOnGpuCount, s_flagged);
 }
 
 // Scatter PU indices into schedule order.  Every block derives the key and pack offsets itself from the key counts
@@ -1427,11 +1433,12 @@ cudaError_t fme_launch_clear_results(fme_result* d_res, int n, cudaStream_t s, i
 
 cudaError_t fme_k2_bin(const fme_pu* d_pus, int n, fme_result* d_res, int wantBi, int biServed, const FmeK2Scratch& sc,
                        int packMode, int numSMs, cudaStream_t s, int64_t* launches) {
-  // classCount[64], classCursor[64] and the work counter are adjacent (fme_create)
-  cudaError_t e = cudaMemsetAsync(sc.classCount, 0, sizeof(int) * (2 * FME_K2_KEYS + 1), s);
+  // classCount[64], classCursor[64], the work counter and (behind it) the FME_PU_ERR_ON_GPU count are adjacent (fme_create);
+  // the bi-predictive pass leaves the count of the uni-prediction pass alone
+  cudaError_t e = cudaMemsetAsync(sc.classCount, 0, sizeof(int) * (2 * FME_K2_KEYS + (wantBi ? 1 : 2)), s);
   if (e != cudaSuccess) return e;
   int blocks = min(numSMs * 4, (n + 255) / 256);
-  k2_count<<<blocks, 256, 0, s>>>(d_pus, n, sc.classCount, wantBi, d_res, biServed, sc.keys);
+  k2_count<<<blocks, 256, 0, s>>>(d_pus, n, sc.classCount, wantBi, d_res, biServed, sc.keys, wantBi ? nullptr : sc.workCounter + 1);
   k2_scatter<<<blocks, 256, 0, s>>>(sc.keys, n, sc.classCount, sc.classOffset, sc.packOffset, sc.classCursor, sc.order, packMode);
   *launches += 2;
   return cudaGetLastError();

@@ -103,8 +103,11 @@ __device__ __forceinline__ void k0_sse_strip(unsigned (&acc)[9], const uint8_t* 
   }
 }
 
+// runIf != nullptr: the number of flagged records counted by k2_count earlier on the stream; zero -> nothing to do.
 __global__ void __launch_bounds__(256) k0_int_surface(fme_pu* __restrict__ pus, int n, const uint8_t* __restrict__ planes,
-                                                      const uint8_t* __restrict__ org, const FmeGeom g, int fen) {
+                                                      const uint8_t* __restrict__ org, const FmeGeom g, int fen,
+                                                      const int* __restrict__ runIf) {
+  if (runIf && *runIf == 0) return;
   const int sub = threadIdx.x & 7;                                      // lane within the PU's 8-lane group
   const int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;        // PU group index
   const int nGrp = (gridDim.x * blockDim.x) >> 3;
@@ -401,24 +404,33 @@ __global__ void k_expand_heads(const fme_pu_head* __restrict__ heads, int n, fme
 
 // Compact records (head + nine 24-bit grid values) -> full records; no K0 flag, no FME_PU_BI (see fme_b200.h).
 static_assert(sizeof(fme_pu_compact) == 44, "compact record layout");
-__global__ void k_expand_compact(const fme_pu_compact* __restrict__ recs, int n, fme_pu* __restrict__ pus) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const unsigned* s = reinterpret_cast<const unsigned*>(recs) + (size_t)i * 11;  // 44-byte records are 4-byte aligned
-  unsigned w[11];
+// A block serves 256 records: their 11 x 256 words come in and their 13 x 256 words go out as coalesced streams through
+// shared memory (a thread reading its own 44-byte record and writing its own 52-byte one touches 4x the sectors: 0.064 ms
+// per 858 000 records against 0.02 ms).
+__global__ void __launch_bounds__(256) k_expand_compact(const fme_pu_compact* __restrict__ recs, int n, fme_pu* __restrict__ pus) {
+  __shared__ unsigned s_in[256 * 11];
+  __shared__ unsigned s_out[256 * 13];
+  const int first = blockIdx.x * 256, cnt = min(256, n - first);
+  const unsigned* src = reinterpret_cast<const unsigned*>(recs) + (size_t)first * 11;  // 44-byte records are 4-byte aligned
+  for (int k = threadIdx.x; k < cnt * 11; k += 256) s_in[k] = __ldg(src + k);
+  __syncthreads();
+  if ((int)threadIdx.x < cnt) {
+    const unsigned* w = s_in + threadIdx.x * 11;   // 11 is odd: conflict-free
+    unsigned* d = s_out + threadIdx.x * 13;        // 13 is odd: conflict-free
+    d[0] = w[0];
+    d[1] = w[1] & ~((unsigned)(FME_PU_BI | FME_PU_ERR_ON_GPU) << 24);  // flags is byte 7 of the record
+    d[2] = w[2];
+    d[3] = w[3];
 #pragma unroll
-  for (int k = 0; k < 11; ++k) w[k] = __ldg(s + k);
-  unsigned* d = reinterpret_cast<unsigned*>(&pus[i]);
-  d[0] = w[0];
-  d[1] = w[1] & ~((unsigned)(FME_PU_BI | FME_PU_ERR_ON_GPU) << 24);  // flags is byte 7 of the record
-  d[2] = w[2];
-  d[3] = w[3];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {   // value k = bytes 3k .. 3k+2 of the 28-byte tail
-    const int b = 3 * k, q = b >> 2, r = b & 3;
-    const unsigned lo = w[4 + q], hi = q + 1 < 7 ? w[5 + q] : 0u;
-    d[4 + k] = __funnelshift_r(lo, hi, 8 * r) & 0xffffffu;
+    for (int k = 0; k < 9; ++k) {   // value k = bytes 3k .. 3k+2 of the 28-byte tail
+      const int b = 3 * k, q = b >> 2, r = b & 3;
+      const unsigned lo = w[4 + q], hi = q + 1 < 7 ? w[5 + q] : 0u;
+      d[4 + k] = __funnelshift_r(lo, hi, 8 * r) & 0xffffffu;
+    }
   }
+  __syncthreads();
+  unsigned* dst = reinterpret_cast<unsigned*>(pus) + (size_t)first * 13;   // 52-byte records are 4-byte aligned
+  for (int k = threadIdx.x; k < cnt * 13; k += 256) dst[k] = s_out[k];
 }
 
 // Host-supplied error grids for some of the expanded heads: err[] filled, FME_PU_ERR_ON_GPU cleared (K0 skips them).
@@ -530,11 +542,11 @@ __global__ void __launch_bounds__(256) k_mc_bi(const fme_mc_bi_pu* __restrict__ 
 }  // namespace
 
 cudaError_t fme_launch_k0(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, fme_pu* d_pus, int n,
-                          int fen, cudaStream_t s, int64_t* launches) {
+                          int fen, cudaStream_t s, int64_t* launches, const int* d_runIf) {
   if (n <= 0) return cudaSuccess;
   int blocks = (n + 31) / 32;  // 32 PUs per 256-thread CTA
   if (blocks > 148 * 16) blocks = 148 * 16;
-  k0_int_surface<<<blocks, 256, 0, s>>>(d_pus, n, d_planes, d_org, g, fen);
+  k0_int_surface<<<blocks, 256, 0, s>>>(d_pus, n, d_planes, d_org, g, fen, d_runIf);
   ++*launches;
   return cudaGetLastError();
 }
