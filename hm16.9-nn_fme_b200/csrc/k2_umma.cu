@@ -9,14 +9,19 @@
 // Hk = diag(H4 (x) H4, H4 (x) H4) (one step).  kind::i8 takes the pixels as they are (u8) and accumulates in s32: exact.
 // The residual needs no subtraction pass: the source tile is parked once per pack as its one's complement and accumulated
 // into the same D with the same Hk,  Hk (c + 255 - o) = Hk (c - o) + 255 * K * e0,  and the constant leaves coefficient 0
-// in the epilogue.  A CTA is four worker warps -- warp w owns rows 32 w .. 32 w + 31 of A and the same TMEM lanes of D, one
-// pack each, lane = unit exactly as in k2_pack -- plus an issuer warp whose lane 0 waits for the four warps' rows
-// (mbarrier), issues the MMAs and commits them onto a second mbarrier.  Per candidate a worker lane copies its tile's 64
-// bytes from the staged region into the canonical K-major operand layout (row m, 16-byte chunk kc at 16 m + 2048 kc:
-// SWIZZLE_NONE core matrices of 8 rows x 16 bytes, SBO 128, LBO 2048), and ONE round later -- while the next candidate's
-// MMAs run -- reads its row of D with tcgen05.ld and sums the 64 |coefficients|.  ~45 + ~100 instructions per
-// tile-candidate instead of the ~410 of the SWAR transform; the tensor pipe does 4 x 32 cycles of work per 128
-// tile-candidates.  Layout, descriptors and arithmetic were pinned first in tools/proto_umma_satd.cu.
+// in the epilogue.  A CTA is four worker warps -- warp w owns rows 32 w .. 32 w + 31 of A and the same TMEM lanes of D (a
+// warp can only read its own 32 TMEM lanes, which is what ties four packs into one CTA), one pack each, lane = unit exactly
+// as in k2_pack -- plus an issuer warp whose lane 0 waits for the four warps' rows (mbarrier), issues the MMAs and commits
+// them onto a second mbarrier.  Per candidate a worker lane copies its tile's 64 bytes from the staged region into the
+// canonical K-major operand layout (row m, 16-byte chunk kc at 16 m + 2048 kc: SWIZZLE_NONE core matrices of 8 rows x 16
+// bytes, SBO 128, LBO 2048), and one round later -- while the next candidate's MMAs run -- reads its row of D with
+// tcgen05.ld and sums the 64 |coefficients|.  UM_DEPTH candidate buffers / accumulators / mbarrier pairs per CTA, three
+// CTAs per SM.  Layout, descriptors and arithmetic were pinned first in tools/proto_umma_satd.cu.
+//
+// Measured (profiles/r2_k2_umma.txt): bit-exact over the whole GPU suite, 1.20 ms per 1080p frame against 0.74 ms for the
+// SWAR kernel.  The transform does leave the issue stream, but an SM runs 3 independent instruction streams here instead
+// of 12, and the scalar search code around the transform (staging, bookkeeping, reductions) issues at one instruction per
+// ~10 clk; the path is selectable (fme_config.k2Path), FME_K2_PATH_AUTO stays on SWAR.
 //
 // Served here: uni-prediction records with Hadamard distortion (lossless PUs inside such packs get their SAD from the
 // staged region, TEncSearch.cpp:5258).  SAD mode and bi-predictive records stay on k2_refine.cu.
