@@ -611,7 +611,7 @@ def banded_leg(fme, torch, dist, dev, stream, rank, world, local, steps, warmup)
             eng.upload_ref_device_u8(s_, d_refs[i][s_].data_ptr(), W4K)
         eng.int_surface_device(d_full[i].data_ptr(), n_full)
     torch.cuda.synchronize(dev)
-    d_band, n_band, rows_band = [], [], []
+    d_band, n_band, rows_band, org_rows_band = [], [], [], []
     for i, (_, _, rc) in enumerate(sets):
         full = d_full[i].cpu().numpy().view(fme.PU_DTYPE).reshape(-1).copy()
         full["flags"] = 0
@@ -619,6 +619,7 @@ def banded_leg(fme, torch, dist, dev, stream, rank, world, local, steps, warmup)
         mine = np.ascontiguousarray(full[fme.pu_list.band_mask_balanced(full, rank, world, W4K)])
         n_band.append(len(mine))
         rows_band.append(fme.pu_list.referenced_rows(mine))   # the plane rows this rank's PUs can read (from its records)
+        org_rows_band.append(fme.pu_list.source_rows(mine))   # ... and the source rows
         d_band.append(torch.from_numpy(mine.view(np.uint8).reshape(len(mine), -1).copy()).to(dev))
     d_res = torch.zeros((n_full, 16), dtype=torch.uint8, device=dev)
     torch.cuda.synchronize(dev)
@@ -637,14 +638,14 @@ def banded_leg(fme, torch, dist, dev, stream, rank, world, local, steps, warmup)
             pending.pop(i).wait()           # compute stream waits for frame i's reference (issued a step ago)
         # K1 only on the plane rows this band's PUs reference (exact: the range comes from the band's own records)
         eng.upload_ref_device_u8_rows(slot, d_refs[k][slot].data_ptr(), W4K, rows_band[k][0], rows_band[k][1])
-        eng.upload_org_device_u8(d_org[k].data_ptr(), W4K)
+        eng.upload_org_device_u8_rows(d_org[k].data_ptr(), W4K, org_rows_band[k][0], org_rows_band[k][1])
         issue_bcast(i + 1)                  # next frame's reference travels while this band is searched
         eng.submit_device(d_band[k].data_ptr(), n_band[k], d_res.data_ptr(), fme.MODE_BOTH)
 
     def step_compute(i):                     # the band's kernels alone (no broadcast): per-rank balance
         k, slot = i % n_sets, i % N_REFS
         eng.upload_ref_device_u8_rows(slot, d_refs[k][slot].data_ptr(), W4K, rows_band[k][0], rows_band[k][1])
-        eng.upload_org_device_u8(d_org[k].data_ptr(), W4K)
+        eng.upload_org_device_u8_rows(d_org[k].data_ptr(), W4K, org_rows_band[k][0], org_rows_band[k][1])
         eng.submit_device(d_band[k].data_ptr(), n_band[k], d_res.data_ptr(), fme.MODE_BOTH)
 
     def step_full(i):

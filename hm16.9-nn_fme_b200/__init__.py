@@ -32,7 +32,7 @@ EXPORTS = [
     "fme_create", "fme_destroy", "fme_last_error", "fme_version", "fme_set_stream", "fme_synchronize",
     "fme_set_nn_weights", "fme_load_nn_csv_dir", "fme_set_slice", "fme_upload_ref", "fme_upload_ref_u8",
     "fme_upload_org", "fme_upload_org_u8", "fme_submit", "fme_submit_async", "fme_submit_heads", "fme_submit_heads_async", "fme_submit_heads_grids", "fme_submit_heads_grids_async", "fme_submit_compact", "fme_submit_compact_async", "fme_wait_oldest", "fme_submit_device", "fme_interp_slot",
-    "fme_upload_ref_device_u8", "fme_upload_ref_device_u8_rows", "fme_upload_org_device_u8", "fme_int_surface_device", "fme_filter_hor",
+    "fme_upload_ref_device_u8", "fme_upload_ref_device_u8_rows", "fme_upload_org_device_u8", "fme_upload_org_device_u8_rows", "fme_int_surface_device", "fme_filter_hor",
     "fme_filter_ver", "fme_dist", "fme_mv_cost", "fme_upload_ref_chroma", "fme_upload_ref_chroma_u8", "fme_upload_ref_yuv420_u8", "fme_upload_org_yuv420_u8", "fme_mc", "fme_mc_bi", "fme_pred_error", "fme_cand_cost", "fme_cand_cost_device", "fme_mc_luma_compact",
     "fme_mc_luma_compact_device", "fme_download_plane",
     "fme_last_kernel_ms", "fme_launch_count", "fme_set_profiling",
@@ -114,6 +114,7 @@ def load_library():
     lib.fme_upload_ref_device_u8.argtypes = [vp, i32, vp, i32]
     lib.fme_upload_ref_device_u8_rows.argtypes = [vp, i32, vp, i32, i32, i32]
     lib.fme_upload_org_device_u8.argtypes = [vp, vp, i32]
+    lib.fme_upload_org_device_u8_rows.argtypes = [vp, vp, i32, i32, i32]
     lib.fme_int_surface_device.argtypes = [vp, vp, i32]
     lib.fme_filter_hor.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32]
     lib.fme_filter_ver.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32]
@@ -217,6 +218,9 @@ class Fme:
 
     def upload_org_device_u8(self, dev_ptr, pitch):
         self._check(self.lib.fme_upload_org_device_u8(self.h, C.c_void_p(dev_ptr), pitch))
+
+    def upload_org_device_u8_rows(self, dev_ptr, pitch, row_begin, row_end):
+        self._check(self.lib.fme_upload_org_device_u8_rows(self.h, C.c_void_p(dev_ptr), pitch, int(row_begin), int(row_end)))
 
     def upload_ref_device_u8_rows(self, slot, d_ptr, pitch, row_begin, row_end):
         self._check(self.lib.fme_upload_ref_device_u8_rows(self.h, slot, C.c_void_p(d_ptr), pitch, int(row_begin), int(row_end)))

@@ -701,6 +701,20 @@ int fme_upload_org_device_u8(fme_ctx* c, const uint8_t* d_y, int pitch) {
   return FME_OK;
 }
 
+int fme_upload_org_device_u8_rows(fme_ctx* c, const uint8_t* d_y, int pitch, int rowBegin, int rowEnd) {
+  if (!c || !d_y || pitch < c->g.W) return fail(FME_ERR_INVALID, "bad device picture");
+  if (rowBegin < 0) rowBegin = 0;
+  if (rowEnd > c->g.H) rowEnd = c->g.H;
+  if (rowEnd <= rowBegin) return fail(FME_ERR_INVALID, "empty row range");
+  CU_CHECK(cudaSetDevice(c->cfg.device));
+  int idx, rc;
+  if ((rc = begin_org_upload(c, c->stream, &idx))) return rc;
+  CU_CHECK(cudaMemcpy2DAsync(c->d_org + (size_t)rowBegin * c->g.orgPitch, c->g.orgPitch, d_y + (size_t)rowBegin * pitch, pitch,
+                             c->g.W, rowEnd - rowBegin, cudaMemcpyDeviceToDevice, c->stream));
+  c->orgValid = true;
+  return FME_OK;
+}
+
 extern "C++" {
 template <typename T>
 static int upload_ref_chroma_host(fme_ctx* c, int slot, const T* cb, const T* cr, int stride) {

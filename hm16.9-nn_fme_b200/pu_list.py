@@ -223,6 +223,15 @@ def band_of_pus_balanced(recs, band, n_bands, width, ctu=64):
     return recs[band_mask_balanced(recs, band, n_bands, width, ctu)]
 
 
+def source_rows(recs):
+    """Picture-row range [begin, end) of the SOURCE picture the records read (rows y .. y + h - 1 of every PU): what a rank
+    of the banded mode has to upload (fme_upload_org_device_u8_rows)."""
+    if len(recs) == 0:
+        return 0, 0
+    y = recs["y"].astype(np.int64)
+    return int(y.min()), int((y + recs["h"]).max())
+
+
 def referenced_rows(recs):
     """Picture-row range [begin, end) of the sub-pel planes the records can read (banded mode: the rows a rank has to
     interpolate).  A PU at row y with integer MV my and height h reads plane rows y + my - 1 .. y + my + h - 1 in K2 (half-

@@ -265,6 +265,10 @@ int fme_upload_org_device_u8(fme_ctx* ctx, const uint8_t* d_y, int pitch);
  * keeps its previous content.  Exact as long as the range covers every row the submitted PUs reference: a PU at row y with
  * integer MV my and height h reads plane rows y + my - 1 .. y + my + h.  d_y must be 4-byte aligned, read in place. */
 int fme_upload_ref_device_u8_rows(fme_ctx* ctx, int slot, const uint8_t* d_y, int pitch, int picRowBegin, int picRowEnd);
+/* Source picture rows [rowBegin, rowEnd) only (clamped to the picture): in the banded mode a rank's PUs read nothing but
+ * their own rows of the source (K2 and K0: rows y .. y + h - 1 of a PU at row y), so copying the whole picture on every
+ * rank is work that does not shrink with the number of ranks.  The other rows of the ctx's source buffer are undefined. */
+int fme_upload_org_device_u8_rows(fme_ctx* ctx, const uint8_t* d_y, int pitch, int rowBegin, int rowEnd);
 /* K0: fill fme_pu.err[] of device-resident records from the 3x3 integer error surface
  * (xTZ8PointSquareSearch(save=true) metric, TEncSearch.cpp:1085-1166, 5037-5050). */
 int fme_int_surface_device(fme_ctx* ctx, fme_pu* d_pus, int n);

@@ -1084,6 +1084,7 @@ def test_row_range_interpolation_serves_a_band_exactly():
         e.set_slice(lam)
         e.upload_org(org)
     d_refs = [torch.from_numpy(r).cuda() for r in refs]
+    d_org = torch.from_numpy(org).cuda()
     for s in range(2):
         full.upload_ref(s, refs[s])
         part.upload_ref(s, other[s])           # stale content everywhere
@@ -1094,6 +1095,11 @@ def test_row_range_interpolation_serves_a_band_exactly():
         for s in range(2):
             part.upload_ref(s, other[s])
             part.upload_ref_device_u8_rows(s, d_refs[s].data_ptr(), W, lo, hi)
+        # the source picture too: only the band's own rows, over a buffer holding another picture
+        olo, ohi = fme.pu_list.source_rows(mine)
+        assert 0 <= olo < ohi <= H and ohi - olo < H
+        part.upload_org(other[0])
+        part.upload_org_device_u8_rows(d_org.data_ptr(), W, olo, ohi)
         want = full.submit(mine, fme.MODE_BOTH)
         got = part.submit(mine, fme.MODE_BOTH)
         for f in ("halfX", "halfY", "qterX", "qterY", "cost", "nnClass"):
