@@ -59,8 +59,11 @@ __global__ void k2_count(const fme_pu* __restrict__ pus, int n, int* __restrict_
     const int c = k2_key_of(p, wantBi);
     keys[i] = (short)c;
     if (errOnGpuCount && (p.flags & FME_PU_ERR_ON_GPU)) atomicAdd(&s_flagged, 1);
-    if (c >= 0) atomicAdd(&s_cnt[c], 1);
-    else if (res && (!fme_hevc_pu_shape(p.w, p.h) || ((p.flags & FME_PU_BI) && !biServed)))
+    // neighbouring records mostly share their key (raster CU order): one shared-memory atomic per distinct key per warp
+    const unsigned peers = __match_any_sync(__activemask(), c);
+    if (c >= 0) {
+      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_cnt[c], __popc(peers));
+    } else if (res && (!fme_hevc_pu_shape(p.w, p.h) || ((p.flags & FME_PU_BI) && !biServed)))
       *reinterpret_cast<uint2*>(&res[i]) = make_uint2(0u, 0xffffffffu);
   }
   __syncthreads();
@@ -115,7 +118,8 @@ __global__ void k2_scatter(const short* __restrict__ keys, int n, const int* __r
   __syncthreads();
   for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const int c = keys[i];
-    if (c >= 0) atomicAdd(&s_cnt[c], 1);
+    const unsigned peers = __match_any_sync(__activemask(), c);
+    if (c >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_cnt[c], __popc(peers));
   }
   __syncthreads();
   for (int i = threadIdx.x; i < FME_K2_KEYS; i += blockDim.x) {
@@ -125,7 +129,13 @@ __global__ void k2_scatter(const short* __restrict__ keys, int n, const int* __r
   __syncthreads();
   for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const int c = keys[i];
-    if (c >= 0) order[s_base[c] + atomicAdd(&s_cnt[c], 1)] = i;
+    const unsigned act = __activemask();
+    const unsigned peers = __match_any_sync(act, c);
+    const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+    int base = 0;
+    if (c >= 0 && lane == leader) base = atomicAdd(&s_cnt[c], __popc(peers));
+    base = __shfl_sync(act, base, leader);
+    if (c >= 0) order[s_base[c] + base + __popc(peers & ((1u << lane) - 1u))] = i;
   }
 }
 
