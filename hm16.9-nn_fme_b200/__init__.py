@@ -58,7 +58,7 @@ class FmeConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("margin", C.c_int32),
                 ("bitDepth", C.c_int32), ("numRefSlots", C.c_int32), ("maxPUs", C.c_int32), ("useHadME", C.c_int32),
                 ("fen", C.c_int32), ("nnFma", C.c_int32), ("biPred", C.c_int32), ("k2Path", C.c_int32),
-                ("k1Path", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("k1Path", C.c_int32), ("k3Fuse", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class FmeError(RuntimeError):
@@ -139,13 +139,15 @@ class Fme:
     """One engine context (= one encoder instance's TEncSearch for the fractional-ME path)."""
 
     def __init__(self, width, height, num_ref_slots=4, max_pus=1 << 20, margin=80, use_had=True, fen=True, device=0,
-                 nn_fma=False, bi_pred=False, k2_path=None, k1_path=None):
+                 nn_fma=False, bi_pred=False, k2_path=None, k1_path=None, k3_fuse=None):
         self.lib = load_library()
         if k2_path is None:   # FME_K2_PATH=1|2|3 runs a whole test / bench session on one K2 path (all are bit-identical)
             k2_path = int(os.environ.get("FME_K2_PATH", "0"))
         if k1_path is None:   # FME_K1_PATH=1|2 likewise for the plane builder
             k1_path = int(os.environ.get("FME_K1_PATH", "0"))
-        self.cfg = FmeConfig(device=device, width=width, height=height, margin=margin, bitDepth=8,
+        if k3_fuse is None:   # FME_K3_FUSE=1 folds K3's work items into the K2 kernel (fme_config.k3Fuse, experimental)
+            k3_fuse = os.environ.get("FME_K3_FUSE", "0") == "1"
+        self.cfg = FmeConfig(device=device, width=width, height=height, margin=margin, bitDepth=8, k3Fuse=1 if k3_fuse else 0,
                              numRefSlots=num_ref_slots, maxPUs=max_pus, useHadME=int(use_had), fen=int(fen),
                              nnFma=int(nn_fma), biPred=int(bi_pred), k2Path=int(k2_path), k1Path=int(k1_path))
         self.h = C.c_void_p()

@@ -244,18 +244,25 @@ int run_search(fme_ctx* c, fme_pu* d_pus, int n, fme_result* d_out, int mode, bo
     return fail(FME_ERR_STATE, "fme_submit(STD) needs fme_upload_org and fme_set_slice first");
   if ((mode & FME_MODE_NN) && !c->nnValid) return fail(FME_ERR_STATE, "fme_submit(NN) needs fme_set_nn_weights first");
   if (mode != FME_MODE_BOTH) CU_CHECK(fme_launch_clear_results(d_out, n, c->stream, &c->launches));
+  // fme_config.k3Fuse (experimental, off by default): both passes over the same records, the shipped net shape, no K0
+  // between them -> K3's work items ride inside the K2 kernel (k2_refine.cu)
+  bool nnDone = false;
+  const FmeNnHeader& nh = c->nnHeader;
+  const bool fusable = mode == FME_MODE_BOTH && !k0BehindK2 && c->cfg.k3Fuse == 1 && nh.nOut == 49 && nh.nEmb == 2 &&
+                       nh.embDim == 4 && nh.nHidden == 2 && nh.hidden[0] == 22 && nh.hidden[1] == 20;
+  const FmeK2NnFuse nnFuse = {c->d_nn, c->cfg.nnFma, nh.outSigmoid ? 36.7368f : 3.0e38f};
   if (mode & FME_MODE_STD) {
     StageTimer t(c, 1);
     CU_CHECK(fme_launch_k2(c->g, c->d_planes, c->d_org, d_pus, n, d_out, c->costLut, c->cfg.useHadME, c->cfg.biPred,
                            c->cfg.k2Path == FME_K2_PATH_AUTO ? FME_K2_PATH_DEFAULT : c->cfg.k2Path, c->k2, c->numSMs, c->stream,
-                           &c->launches));
+                           &c->launches, fusable ? &nnFuse : nullptr, &nnDone));
   }
   if (k0BehindK2) {
     StageTimer t(c, 3);
     CU_CHECK(fme_launch_k0(c->g, c->d_planes, c->d_org, d_pus, n, c->cfg.fen, c->stream, &c->launches, c->k2.workCounter + 1));
   }
   dbg_stamp(c, 5);
-  if (mode & FME_MODE_NN) {
+  if ((mode & FME_MODE_NN) && !nnDone) {
     StageTimer t(c, 2);
     CU_CHECK(fme_launch_k3(d_pus, n, d_out, c->d_nn, c->nnBytes, c->nnHeader, c->cfg.nnFma, c->stream, &c->launches));
   }
@@ -311,6 +318,7 @@ int fme_create(const fme_config* cfg, fme_ctx** out) {
   if (cfg->maxPUs < 1) return fail(FME_ERR_INVALID, "maxPUs must be positive");
   if (cfg->k2Path < FME_K2_PATH_AUTO || cfg->k2Path > FME_K2_PATH_UMMA) return fail(FME_ERR_INVALID, "k2Path out of range");
   if (cfg->k1Path < FME_K1_PATH_AUTO || cfg->k1Path > FME_K1_PATH_UMMA) return fail(FME_ERR_INVALID, "k1Path out of range");
+  if (cfg->k3Fuse < 0 || cfg->k3Fuse > 1) return fail(FME_ERR_INVALID, "k3Fuse must be 0 or 1");
 
   int nDev = 0;
   if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) {

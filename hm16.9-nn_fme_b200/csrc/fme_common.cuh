@@ -100,9 +100,16 @@ cudaError_t fme_launch_k1(const FmeGeom& g, const uint8_t* d_pic, int picPitch, 
                           int numSMs, int rowBegin, int rowEnd, int path, cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_pad_chroma(const FmeGeom& g, const uint8_t* d_pic, int picPitch, uint8_t* d_plane,
                                   cudaStream_t s, int64_t* launches);
+// K3's work folded into the K2 kernel (k2_refine.cu): the FMNN blob on the device (shipped 17-22-20-49 shape only).
+struct FmeK2NnFuse {
+  const float* d_blob;
+  int fma;         // fme_config.nnFma
+  float outClamp;  // 53 ln 2 for sigmoid-output nets, +inf otherwise (as in k3_nn_fixed)
+};
 cudaError_t fme_launch_k2(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_pu* d_pus, int n,
                           fme_result* d_res, const FmeCostLut& costLut, int useHad, int biPred, int k2Path,
-                          const FmeK2Scratch& sc, int numSMs, cudaStream_t s, int64_t* launches);
+                          const FmeK2Scratch& sc, int numSMs, cudaStream_t s, int64_t* launches,
+                          const FmeK2NnFuse* nn = nullptr, bool* nnDone = nullptr);
 cudaError_t fme_launch_k3(const fme_pu* d_pus, int n, fme_result* d_res, const float* d_nn, size_t nnBytes,
                           const FmeNnHeader& h, int fma, cudaStream_t s, int64_t* launches);
 cudaError_t fme_launch_k0(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, fme_pu* d_pus, int n,

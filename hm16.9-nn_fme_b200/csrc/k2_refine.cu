@@ -22,6 +22,7 @@
 //   * per-PU sums by xor-shuffles over the PU's power-of-two lane group, MV cost from an exact host-built LUT,
 //     first-minimum argmin in the reference's table order (TEncSearch.cpp:212-236, strict < at :1634).
 #include "k2_common.cuh"
+#include "k3_common.cuh"
 
 namespace {
 
@@ -1208,14 +1209,28 @@ __device__ __noinline__ bool k2_group_mma(int w, int h, const int* __restrict__ 
 template <int PATH>
 constexpr int k2_warps() { return PATH == 2 ? FME_K2_WARPS_GROUP : K2_WARPS; }
 
-template <bool BI, int PATH>
+// NNF != 0 (uni-prediction SWAR kernel only): K3's work rides along as extra work items -- NN_pred for 64 list-order PUs per
+// item (k3_common.cuh NnWarpNet, the shipped 17-22-20-49 shape; NNF 1 exact, 2 fused multiply-add), one after every R SATD
+// packs.  The idea: an NN item is independent fp32 work that needs nothing but the records, so it could fill the issue
+// slots the integer packs leave idle (K2 alone issues on 67 % of the cycles).  Measured (fme_config.k3Fuse = 1, off by
+// default): the results are identical, but a pack body (23 KB) and the NN item's code do not fit the SM's 32 KB instruction
+// cache together -- 1.365 ms per 1080p frame with the stand-alone kernel's unrolling (48 KB of NN code,
+// stall_no_instruction 3.0 per issue), 0.961 ms with the compact item below (25 KB), against 0.757 + 0.143 ms apart.
+using K2Nn = NnWarpNet<2, 22, 20, 49, false>;
+using K2NnFma = NnWarpNet<2, 22, 20, 49, true>;
+static_assert(K2Nn::ACT_WORDS * 4 <= K2_SMEM_PER_WARP, "the activation transpose of an NN item lives in the warp's staging slice");
+
+template <bool BI, int PATH, int NNF = 0>
 __global__ void __launch_bounds__(k2_warps<PATH>() * 32, 1)
 k2_refine(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, const uint8_t* __restrict__ planes,
           const uint8_t* __restrict__ org, const FmeGeom g, const FmeCostLut costLutG, int useHad,
           const int* __restrict__ order, const int* __restrict__ classOffset, const int* __restrict__ packOffset,
-          int* __restrict__ workCounter) {
+          int* __restrict__ workCounter, int nPus, const float* __restrict__ nnBlob, float nnOutClamp) {
   constexpr int mmaGroups = PATH == 2 ? 1 : 0;
   extern __shared__ __align__(16) uint8_t dynSmem[];
+  constexpr int kWarps = PATH == 2 ? FME_K2_WARPS_GROUP : K2_WARPS;
+  [[maybe_unused]] float* const s_net = reinterpret_cast<float*>(dynSmem + kWarps * K2_SMEM_PER_WARP);
+  if constexpr (NNF != 0) K2Nn::load(s_net, nnBlob);   // (same image for both arithmetic modes)
   __shared__ uint32_t s_lut[FME_COST_LUT_SIZE];
   __shared__ int s_packOff[FME_K2_KEYS + 1];
   __shared__ int s_classOff[FME_K2_KEYS + 1];
@@ -1230,14 +1245,32 @@ k2_refine(const fme_pu* __restrict__ pus, fme_result* __restrict__ res, const ui
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* smem = dynSmem + warp * K2_SMEM_PER_WARP;
   const int totalPacks = s_packOff[FME_K2_KEYS];
+  // work items: the packs, and with NNF groups of R packs followed by one NN item
+  [[maybe_unused]] const int nnItems = (nPus + K2Nn::PUS - 1) / K2Nn::PUS;
+  [[maybe_unused]] const int nnR = max(1, totalPacks / max(nnItems, 1));
+  const int totalItems = NNF != 0 ? max((totalPacks + nnR - 1) / nnR, nnItems) * (nnR + 1) : totalPacks;
 
   // dynamic pack scheduler; the next pack index is requested while the current pack is processed
   int nextPack = 0;
   if (lane == 0) nextPack = atomicAdd(workCounter, 1);
   while (true) {
-    const int pack = __shfl_sync(0xffffffffu, nextPack, 0);
-    if (pack >= totalPacks) break;
+    const int item = __shfl_sync(0xffffffffu, nextPack, 0);
+    if (item >= totalItems) break;
     if (lane == 0) nextPack = atomicAdd(workCounter, 1);
+    int pack = item;
+    if constexpr (NNF != 0) {
+      const int q = item / (nnR + 1), r = item - q * (nnR + 1);
+      if (r == nnR) {
+        if (q < nnItems) {
+          if constexpr (NNF == 2) K2NnFma::warp_item(s_net, reinterpret_cast<float*>(smem), pus, res, q * K2Nn::PUS, nPus, lane, nnOutClamp);
+          else K2Nn::warp_item(s_net, reinterpret_cast<float*>(smem), pus, res, q * K2Nn::PUS, nPus, lane, nnOutClamp);
+          __syncwarp();
+        }
+        continue;
+      }
+      pack = q * nnR + r;
+      if (pack >= totalPacks) continue;
+    }
     // schedule position of this pack: the last v with packOff[v] <= pack (binary search, uniform across the warp);
     // position v holds shape class 63 - (v & 63) of slot group v >> 6 (k2_scatter)
     int v = 0;
@@ -1454,19 +1487,20 @@ cudaError_t fme_k2_bin(const fme_pu* d_pus, int n, fme_result* d_res, int wantBi
   return cudaGetLastError();
 }
 
-template <bool BI, int PATH>
+template <bool BI, int PATH, int NNF = 0>
 static cudaError_t launch_k2_pass(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_pu* d_pus, int n,
                                   fme_result* d_res, const FmeCostLut& costLut, int useHad, int biServed, const FmeK2Scratch& sc,
-                                  int numSMs, cudaStream_t s, int64_t* launches) {
+                                  int numSMs, cudaStream_t s, int64_t* launches, const FmeK2NnFuse* nn = nullptr) {
   cudaError_t e = fme_k2_bin(d_pus, n, BI ? nullptr : d_res, BI ? 1 : 0, biServed, sc, PATH == 2 ? 1 : 0, numSMs, s, launches);
   if (e != cudaSuccess) return e;
-  const int smemBytes = k2_warps<PATH>() * K2_SMEM_PER_WARP;
+  const int smemBytes = k2_warps<PATH>() * K2_SMEM_PER_WARP + (NNF != 0 ? K2Nn::WORDS * 4 : 0);
   // the opt-in to > 48 KB dynamic shared memory is a per-device, per-function attribute; setting it is cheap and
   // idempotent, so it is simply set before every launch (no shared state between host threads / contexts)
-  e = cudaFuncSetAttribute(k2_refine<BI, PATH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
+  e = cudaFuncSetAttribute(k2_refine<BI, PATH, NNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
   if (e != cudaSuccess) return e;
-  k2_refine<BI, PATH><<<numSMs, k2_warps<PATH>() * 32, smemBytes, s>>>(d_pus, d_res, d_planes, d_org, g, costLut, useHad,
-                                                                      sc.order, sc.classOffset, sc.packOffset, sc.workCounter);
+  k2_refine<BI, PATH, NNF><<<numSMs, k2_warps<PATH>() * 32, smemBytes, s>>>(
+      d_pus, d_res, d_planes, d_org, g, costLut, useHad, sc.order, sc.classOffset, sc.packOffset, sc.workCounter, n,
+      nn ? nn->d_blob : nullptr, nn ? nn->outClamp : 0.f);
   ++*launches;
   return cudaGetLastError();
 }
@@ -1477,11 +1511,22 @@ static cudaError_t launch_k2_pass(const FmeGeom& g, const uint8_t* d_planes, con
 // the SWAR kernels.
 // biPred != 0: a second binning + refinement pass serves the bi-predictive refinement records (FME_PU_BI); with
 // biPred == 0 such records are left untouched (the synchronous entry points reject them).
+// nn != nullptr: the caller also wants NN_pred for the same records and the net has the shipped shape; *nnDone is set when
+// the pass that ran carried K3's work along (the SWAR kernel), otherwise the caller launches K3 itself.
 cudaError_t fme_launch_k2(const FmeGeom& g, const uint8_t* d_planes, const uint8_t* d_org, const fme_pu* d_pus, int n,
                           fme_result* d_res, const FmeCostLut& costLut, int useHad, int biPred, int k2Path,
-                          const FmeK2Scratch& sc, int numSMs, cudaStream_t s, int64_t* launches) {
+                          const FmeK2Scratch& sc, int numSMs, cudaStream_t s, int64_t* launches, const FmeK2NnFuse* nn,
+                          bool* nnDone) {
+  if (nnDone) *nnDone = false;
   if (n <= 0) return cudaSuccess;
   cudaError_t e;
+  if (nn && nnDone && (!useHad || k2Path == FME_K2_PATH_SWAR)) {
+    e = nn->fma ? launch_k2_pass<false, 0, 2>(g, d_planes, d_org, d_pus, n, d_res, costLut, useHad, biPred, sc, numSMs, s, launches, nn)
+                : launch_k2_pass<false, 0, 1>(g, d_planes, d_org, d_pus, n, d_res, costLut, useHad, biPred, sc, numSMs, s, launches, nn);
+    *nnDone = e == cudaSuccess;
+    if (e != cudaSuccess || !biPred) return e;
+    return launch_k2_pass<true, 0>(g, d_planes, d_org, d_pus, n, d_res, costLut, useHad, biPred, sc, numSMs, s, launches);
+  }
 #define K2_UNI(PATH) launch_k2_pass<false, PATH>(g, d_planes, d_org, d_pus, n, d_res, costLut, useHad, biPred, sc, numSMs, s, launches)
   if (!useHad || k2Path == FME_K2_PATH_SWAR) e = K2_UNI(0);
   else if (k2Path == FME_K2_PATH_MMA_PACK) e = K2_UNI(1);

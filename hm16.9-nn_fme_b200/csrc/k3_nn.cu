@@ -17,39 +17,12 @@
 // broadcast LDS.128 (one wavefront for the whole warp), hidden activations go through a [unit][thread]
 // shared-memory transpose so that the output-unit loop can stay a runtime loop (small code, no local memory).
 // Generic path: any FMNN blob (up to 4 hidden layers of <= 64 units), one PU per thread, local-memory vectors.
-#include "fme_common.cuh"
+#include "k3_common.cuh"
 
 namespace {
 
 constexpr int K3_THREADS = 128;
 constexpr int K3_MAX_WIDTH = 64;  // widest layer supported (inputs or hidden units)
-
-__device__ __forceinline__ int emb_index(int v, bool isHeight) {
-  switch (v) {
-    case 4: return 1;
-    case 8: return 2;
-    case 16: return isHeight ? 3 : 4;  // TEncSearch.cpp:96 vs :108
-    case 12: return isHeight ? 4 : 3;  // TEncSearch.cpp:97 vs :107
-    case 24: return 5;
-    case 32: return 6;
-    case 64: return 7;
-    default: return 0;
-  }
-}
-
-// TEncSearch.cpp:136-193: class -> per-axis (half, quarter)
-__device__ __forceinline__ void store_class(fme_result* r, int best) {
-  int qx = best % 7, qy = best / 7;
-  const int kHalf = (0 << 0) | (0 << 2) | (1 << 4) | (1 << 6) | (1 << 8) | (2 << 10) | (2 << 12);  // +1 biased
-  const int kQter = (0 << 0) | (1 << 2) | (0 << 4) | (1 << 6) | (2 << 8) | (1 << 10) | (2 << 12);  // +1 biased
-  int8_t hx = 0, hy = 0, tx = 0, ty = 0;
-  if (best >= 0 && best <= 48) {
-    hx = (int8_t)(((kHalf >> (2 * qx)) & 3) - 1); tx = (int8_t)(((kQter >> (2 * qx)) & 3) - 1);
-    hy = (int8_t)(((kHalf >> (2 * qy)) & 3) - 1); ty = (int8_t)(((kQter >> (2 * qy)) & 3) - 1);
-  }
-  r->nnHalfX = hx; r->nnHalfY = hy; r->nnQterX = tx; r->nnQterY = ty;
-  r->nnClass = (uint8_t)best;
-}
 
 // ------------------------------------------------------------------------------------------------
 // generic path
@@ -122,74 +95,6 @@ __global__ void __launch_bounds__(K3_THREADS) k3_nn_pred(const fme_pu* __restric
 // ------------------------------------------------------------------------------------------------
 // fast path: compile-time layer sizes
 // ------------------------------------------------------------------------------------------------
-constexpr int K3F_THREADS = 128;
-constexpr int K3F_NPU = 2;  // PUs per thread
-
-__host__ __device__ constexpr int pad4(int v) { return (v + 3) & ~3; }
-
-// One dense layer for NPU input vectors held in registers.  sW: rows padded to pad4(IN) floats, 16-byte aligned.
-// emit(o, acc[NPU]) receives the pre-activation W x + b of unit o (ascending-k, mul then add).
-template <bool FMA, int IN, int OUT, typename Emit>
-__device__ __forceinline__ void dense_rows(const float* __restrict__ sW, const float* __restrict__ sb,
-                                           const float (&x)[K3F_NPU][IN], Emit emit) {
-  constexpr int IN4 = pad4(IN);
-#pragma unroll 4  // four output units in flight: measured best of 1 / 2 / 4 / 7 / 10
-  for (int o = 0; o < OUT; ++o) {
-    const float4* wr = reinterpret_cast<const float4*>(sW + o * IN4);
-    float acc[K3F_NPU];
-#pragma unroll
-    for (int q = 0; q < IN4 / 4; ++q) {
-      const float4 wv = wr[q];  // broadcast LDS.128
-      const float wk[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int k = 4 * q + t;
-        if (k < IN) {
-#pragma unroll
-          for (int u = 0; u < K3F_NPU; ++u) {
-            if (FMA) {  // opt-in relaxed mode (fme_config.nnFma): one rounding per tap
-              acc[u] = (k == 0) ? __fmul_rn(wk[t], x[u][k]) : __fmaf_rn(wk[t], x[u][k], acc[u]);
-            } else {
-              const float prod = __fmul_rn(wk[t], x[u][k]);
-              acc[u] = (k == 0) ? prod : __fadd_rn(acc[u], prod);
-            }
-          }
-        }
-      }
-    }
-    const float bo = sb[o];
-#pragma unroll
-    for (int u = 0; u < K3F_NPU; ++u) acc[u] = __fadd_rn(acc[u], bo);
-    emit(o, acc);
-  }
-}
-
-// shared-memory image of one layer
-template <int IN, int OUT>
-struct LayerSmem {
-  static constexpr int IN4 = pad4(IN);
-  static constexpr int WORDS = OUT * IN4 + 3 * pad4(OUT);
-  __device__ static const float* W(const float* s) { return s; }
-  __device__ static const float* b(const float* s) { return s + OUT * IN4; }
-  __device__ static const float* g(const float* s) { return s + OUT * IN4 + pad4(OUT); }
-  __device__ static const float* be(const float* s) { return s + OUT * IN4 + 2 * pad4(OUT); }
-  // blob layout: W[OUT][IN] b[OUT] gamma[OUT] beta[OUT] (gamma/beta absent for the output layer)
-  __device__ static void load(float* s, const float* __restrict__ blob, bool hasBn) {
-    for (int i = threadIdx.x; i < OUT * IN4; i += blockDim.x) {
-      int o = i / IN4, k = i - o * IN4;
-      s[i] = k < IN ? blob[o * IN + k] : 0.0f;
-    }
-    for (int i = threadIdx.x; i < OUT; i += blockDim.x) {
-      s[OUT * IN4 + i] = blob[OUT * IN + i];
-      if (hasBn) {
-        s[OUT * IN4 + pad4(OUT) + i] = blob[OUT * IN + OUT + i];
-        s[OUT * IN4 + 2 * pad4(OUT) + i] = blob[OUT * IN + 2 * OUT + i];
-      }
-    }
-  }
-  __host__ __device__ static constexpr int blob_words_bn() { return OUT * IN + 3 * OUT; }
-};
-
 // NH hidden layers of sizes H1,H2,(H3); NEMB = 0 or 2 embedding tables of 8 x 4.
 template <int NEMB, int H1, int H2, int H3, int NOUT, bool FMA>
 __global__ void __launch_bounds__(K3F_THREADS) k3_nn_fixed(const fme_pu* __restrict__ pus, int n,

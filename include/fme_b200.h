@@ -79,7 +79,11 @@ typedef struct fme_config {
                            fastest measured), _DP4A (integer dot products on the CUDA cores), _MMA (both filter stages
                            as exact mma.sync products against Toeplitz tap matrices), _UMMA (experimental: the vertical
                            stage on tcgen05.mma with the accumulator in TMEM; never picked by AUTO) */
-  int32_t reserved[3];
+  int32_t k3Fuse;       /* 0 (default): K3 is its own launch behind K2.  1 (experimental): when one submit runs both passes
+                           over the same records with the shipped 17-22-20-49 net, K3's work items ride inside the persistent
+                           K2 kernel as extra work items (same arithmetic, same results).  Measured slower: the two code
+                           bodies do not fit the 32 KB instruction cache of an SM together */
+  int32_t reserved[2];
 } fme_config;
 #define FME_K1_PATH_AUTO 0
 #define FME_K1_PATH_DP4A 1

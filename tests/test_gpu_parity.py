@@ -1358,3 +1358,38 @@ def test_compact_44_byte_records_equal_full_records(small):
     badg = big.copy(); badg["pu"][0] = len(recs)
     with pytest.raises(fme.FmeError):
         eng.submit_compact(comp, badg, fme.MODE_BOTH)
+
+
+@pytest.mark.gpu
+def test_k3_fused_into_k2_gives_the_same_results():
+    """fme_config.k3Fuse = 1 (experimental): NN_pred work items inside the persistent K2 kernel (k2_refine.cu NNF) -- every
+    field of every result equals the two-launch default, exact and nnFma arithmetic, ragged PU counts, the heads path (K0 in
+    front) and a batch with unservable records; the MODE_STD / MODE_NN submits of a fused ctx are unaffected."""
+    W, H = 416, 240
+    org, refs, motions = fme.pu_list.synth_frames(W, H, n_refs=2, seed=31)
+    recs = fme.pu_list.make_records(W, H, motions, seed=8, amp=True)
+    frame = ob.CpuFrame(org, refs)
+    frame.oracle_fill_surface(recs)
+    recs["flags"][::13] |= fme.PU_LOSSLESS
+    lam = fme.pu_list.slice_lambda(22)
+    blob = fme.nn_weights.load_blob(22)
+    FIELDS = ("halfX", "halfY", "qterX", "qterY", "cost", "nnHalfX", "nnHalfY", "nnQterX", "nnQterY", "nnClass")
+    same = lambda a, b: all(np.array_equal(a[f], b[f]) for f in FIELDS)   # (the pad bytes of fme_result are never written)
+    for fma in (False, True):
+        engs = []
+        for fuse in (False, True):
+            e = fme.Fme(W, H, num_ref_slots=2, max_pus=len(recs), nn_fma=fma, k3_fuse=fuse)
+            e.set_nn_weights(blob); e.set_slice(lam); e.upload_org(org)
+            for s in range(2):
+                e.upload_ref(s, refs[s])
+            engs.append(e)
+        plain, fused = engs
+        for n in (len(recs), len(recs) - 37, 65, 1):
+            a = plain.submit(recs[:n], fme.MODE_BOTH)
+            b = fused.submit(recs[:n], fme.MODE_BOTH)
+            assert same(a, b), (fma, n)
+        heads = fme.pu_list.heads_of(recs)
+        assert same(plain.submit_heads(heads, fme.MODE_BOTH), fused.submit_heads(heads, fme.MODE_BOTH))
+        for mode in (fme.MODE_STD, fme.MODE_NN):
+            assert same(plain.submit(recs, mode), fused.submit(recs, mode))
+        plain.close(); fused.close()
