@@ -130,6 +130,29 @@ public:
     if (!m_queue.empty()) check(fme_submit(m_ctx, &m_queue[0], Int(m_queue.size()), &m_results[0], mode));
     m_queue.clear();
   }
+  // The same flush over the bus-friendlier 44-byte records (fme_submit_compact): array_e / C travel as 24-bit values, the
+  // PUs whose surface needs 32 bits (only possible above 256 luma samples) go in the full-grid list.  Uni-prediction
+  // queues whose PUs all carry their surface; anything else falls back to flush().
+  Void flushCompact(Int mode = FME_MODE_BOTH)
+  {
+    for (size_t i = 0; i < m_queue.size(); i++)
+      if (m_queue[i].flags & (FME_PU_BI | FME_PU_ERR_ON_GPU)) { flush(mode); return; }
+    m_results.resize(m_queue.size());
+    m_compact.resize(m_queue.size());
+    m_big.clear();
+    for (size_t i = 0; i < m_queue.size(); i++)
+      if (fme_pu_compact_pack(&m_queue[i], &m_compact[i]))
+      {
+        fme_err_grid g;
+        g.pu = Int(i);
+        for (Int k = 0; k < 9; k++) g.err[k] = m_queue[i].err[k];
+        m_big.push_back(g);
+      }
+    if (!m_queue.empty())
+      check(fme_submit_compact(m_ctx, &m_compact[0], Int(m_compact.size()), m_big.empty() ? NULL : &m_big[0], Int(m_big.size()),
+                               &m_results[0], mode));
+    m_queue.clear();
+  }
   const fme_result& result(Int ticket) const { return m_results[ticket]; }
 
   // ---- immediate mode: the reference's own signatures ----------------------------------------------------
@@ -211,6 +234,8 @@ private:
   std::vector<const TComPicYuv*> m_refPics;
   std::vector<fme_pu>            m_queue;
   std::vector<fme_result>        m_results;
+  std::vector<fme_pu_compact>    m_compact;
+  std::vector<fme_err_grid>      m_big;
   UInt                           m_zeroErr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 

@@ -75,6 +75,24 @@ int main(int argc, char** argv)
   fme.flush(FME_MODE_BOTH);
   std::vector<fme_result> batched(nPUs);
   for (int i = 0; i < nPUs; i++) batched[i] = fme.result(ticket[i]);
+  // ---- the same batch through the 44-byte compact records (flushCompact): identical results ----
+  for (int i = 0; i < nPUs; i++)
+  {
+    const fme_pu& p = pus[i];
+    UInt e8[8];
+    for (int k = 0; k < 4; k++) { e8[k] = p.err[k]; e8[4 + k] = p.err[5 + k]; }
+    ticket[i] = fme.enqueue(p.x, p.y, p.w, p.h, p.refSlot, TComMv(p.mvIntX, p.mvIntY), TComMv(p.mvPredX, p.mvPredY), e8,
+                            p.err[4], (p.flags & FME_PU_LOSSLESS) != 0);
+  }
+  fme.flushCompact(FME_MODE_BOTH);
+  for (int i = 0; i < nPUs; i++)
+  {
+    const fme_result& a = batched[i];
+    const fme_result& b = fme.result(ticket[i]);
+    if (a.halfX != b.halfX || a.halfY != b.halfY || a.qterX != b.qterX || a.qterY != b.qterY || a.cost != b.cost ||
+        a.nnHalfX != b.nnHalfX || a.nnHalfY != b.nnHalfY || a.nnQterX != b.nnQterX || a.nnQterY != b.nnQterY || a.nnClass != b.nnClass)
+      fail("flushCompact vs flush", i);
+  }
   FILE* o = fopen(argv[2], "wb");
   if (!o) { perror(argv[2]); return 2; }
   fwrite(&batched[0], sizeof(fme_result), nPUs, o);
