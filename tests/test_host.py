@@ -137,3 +137,32 @@ def test_balanced_bands_partition_the_list_and_even_out_the_work():
             rows = np.array([px[(recs["y"] // 64 >= lo) & (recs["y"] // 64 < hi)].sum()
                              for lo, hi in (fme.pu_list.band_rows(b, nb, H) for b in range(nb))], np.float64)
             assert work.max() / work.mean() < 1.01 < rows.max() / rows.mean()
+
+
+def test_band_row_ranges_and_compact_records():
+    """Host helpers of the banded mode and the 44-byte record format: a band's source rows are exactly the rows its PUs
+    cover, its referenced plane rows contain every row a search can touch (integer MV, +-1 row for the half- / quarter-pel
+    regions); compact_of keeps every grid below 2^24 in the record and routes the others to the full-grid list."""
+    W, H = 416, 240
+    _, _, motions = fme.pu_list.synth_frames(W, H, n_refs=2, seed=3)
+    recs = fme.pu_list.make_records(W, H, motions, seed=4, amp=True)
+    for band in range(3):
+        mine = recs[fme.pu_list.band_mask_balanced(recs, band, 3, W)]
+        lo, hi = fme.pu_list.source_rows(mine)
+        assert lo == int(mine["y"].min()) and hi == int((mine["y"].astype(int) + mine["h"]).max()) and 0 <= lo < hi <= H
+        rlo, rhi = fme.pu_list.referenced_rows(mine)
+        top = mine["y"].astype(int) + mine["mvIntY"]
+        assert rlo <= int(top.min()) - 1 and rhi >= int((top + mine["h"]).max()) + 1
+    assert fme.pu_list.source_rows(recs[:0]) == (0, 0)
+    r = recs[:5].copy()
+    r["err"] = 0
+    r["err"][0, 8] = (1 << 24) - 1      # fits
+    r["err"][1, 0] = 1 << 24            # does not
+    r["err"][3, 4] = 0xffffffff
+    comp, big = fme.pu_list.compact_of(r)
+    assert list(big["pu"]) == [1, 3] and np.array_equal(big["err"], r["err"][[1, 3]])
+    e24 = comp["err24"].reshape(5, 9, 3).astype(np.uint32)
+    val = e24[:, :, 0] | (e24[:, :, 1] << 8) | (e24[:, :, 2] << 16)
+    assert np.array_equal(val, r["err"] & 0xffffff)
+    for f in fme.HEAD_DTYPE.names:
+        assert np.array_equal(comp[f], r[f])
