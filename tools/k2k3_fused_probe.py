@@ -1,5 +1,6 @@
+"""K2 + K3 over one 1080p PU list: mode BOTH (two launches, or K3 inside K2 with FME_K3_FUSE=1) against STD and NN alone."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, fme_loader
 fme = fme_loader.load()
 W, H = 1920, 1080
